@@ -1,0 +1,166 @@
+"""ctypes binding for the CPU ORACLE (test infrastructure only).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
+this module.  The product package (warp3d_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libw3d_oracle.so")
+
+
+class _Model(C.Structure):
+    _fields_ = [
+        ("nelblk", C.c_int32), ("noelem", C.c_int32), ("nonode", C.c_int32), ("nodof", C.c_int32),
+        ("elblks", C.c_void_p), ("props", C.c_void_p), ("matprp", C.c_void_p), ("nmat", C.c_int32),
+        ("c", C.c_void_p), ("edest", C.c_void_p), ("cdest", C.c_void_p), ("hist_size", C.c_void_p),
+        ("eps_bbar", C.c_double), ("qbar_flag", C.c_int32), ("dt", C.c_double),
+        ("total_model_time", C.c_double), ("beta_fact", C.c_double),
+        ("extrapolated_du", C.c_int32), ("adaptive_flag", C.c_int32),
+        ("fpconstant_data", C.c_int32), ("cp", C.c_void_p),
+    ]
+
+
+class _State(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("history", "history1", "eps_n", "eps_n1", "urcs_n", "urcs_n1", "rot_n", "rot_n1",
+                 "cep", "estiff", "element_vol")]
+
+
+class _Scalars(C.Structure):
+    _fields_ = [("internal_energy", C.c_double), ("plastic_work", C.c_double),
+                ("sum_ifv", C.c_double), ("num_term_ifv", C.c_int64),
+                ("material_cut_step", C.c_int32)]
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (g++, -ffp-contract=off)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if (not force and os.path.exists(_LIB)
+            and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in srcs)):
+        return _LIB
+    subprocess.run(["make", "-C", _HERE, "libw3d_oracle.so"], check=True, capture_output=True)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.w3do_drive_eps_sig_internal_forces.restype = C.c_int32
+        _lib.w3do_tanstf.restype = C.c_int32
+        _lib.w3do_block_offset.restype = C.c_int64
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Oracle:
+    """Runs the oracle on a warp3d_b200.model.Model + State (arrays are used in place)."""
+
+    def __init__(self, model, nthreads=1):
+        self.model = model
+        self.nthreads = int(nthreads)
+        m = model
+        self._keep = [np.ascontiguousarray(x) for x in
+                      (m.elblks, m.props, m.matprp, m.c, m.edest, m.cdest, m.hist_size)]
+        self._cm = _Model()
+        self.sync_globals()
+
+    def sync_globals(self):
+        m, cm = self.model, self._cm
+        cm.nelblk, cm.noelem, cm.nonode, cm.nodof = m.nelblk, m.noelem, m.nonode, m.nodof
+        (cm.elblks, cm.props, cm.matprp, cm.c, cm.edest, cm.cdest,
+         cm.hist_size) = [_ptr(x) for x in self._keep]
+        cm.nmat = self._keep[2].shape[0]
+        cm.eps_bbar = m.eps_bbar
+        cm.qbar_flag = int(m.qbar_flag)
+        cm.dt = m.dt
+        cm.total_model_time = m.total_model_time
+        cm.beta_fact = m.beta_fact
+        cm.extrapolated_du = int(m.extrapolated_du)
+        cm.adaptive_flag = int(m.adaptive_flag)
+        cm.fpconstant_data = 1
+        cm.cp = None
+
+    @staticmethod
+    def _cstate(st):
+        cs = _State()
+        for n in st.NAMES:
+            a = getattr(st, n)
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+            setattr(cs, n, _ptr(a))
+        return cs
+
+    def eps_sig_ifv(self, state, step, itr, u, du):
+        """drive_eps_sig_internal_forces: returns (ifv, scalars dict)."""
+        self.sync_globals()
+        ifv = np.zeros(self.model.nodof)
+        sc = _Scalars()
+        cs = self._cstate(state)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        du = np.ascontiguousarray(du, dtype=np.float64)
+        rc = lib().w3do_drive_eps_sig_internal_forces(
+            C.byref(self._cm), C.byref(cs), C.c_int32(step), C.c_int32(itr), _ptr(u), _ptr(du),
+            _ptr(ifv), C.byref(sc), C.c_int32(self.nthreads))
+        if rc:
+            raise RuntimeError(f"oracle fatal condition {rc}")
+        return ifv, dict(internal_energy=sc.internal_energy, plastic_work=sc.plastic_work,
+                         sum_ifv=sc.sum_ifv, num_term_ifv=sc.num_term_ifv,
+                         material_cut_step=bool(sc.material_cut_step))
+
+    def tanstf(self, state, step, itr, u, du):
+        self.sync_globals()
+        cs = self._cstate(state)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        du = np.ascontiguousarray(du, dtype=np.float64)
+        rc = lib().w3do_tanstf(C.byref(self._cm), C.byref(cs), C.c_int32(step), C.c_int32(itr),
+                               _ptr(u), _ptr(du), C.c_int32(self.nthreads))
+        if rc:
+            raise RuntimeError(f"oracle fatal condition {rc}")
+        return state.estiff
+
+    def update(self, state):
+        cs = self._cstate(state)
+        lib().w3do_update(C.byref(self._cm), C.byref(cs))
+
+    def adaptive_save(self, state):
+        cs = self._cstate(state)
+        lib().w3do_adaptive_save(C.byref(self._cm), C.byref(cs))
+
+    def adaptive_reset(self, state):
+        cs = self._cstate(state)
+        lib().w3do_adaptive_reset(C.byref(self._cm), C.byref(cs))
+
+
+def quad2(gpn):
+    v = [C.c_double() for _ in range(4)]
+    lib().w3do_quad2(C.c_int32(gpn), *[C.byref(x) for x in v])
+    return tuple(x.value for x in v)
+
+
+def deriv2(xi, eta, zeta):
+    out = [np.zeros(8) for _ in range(3)]
+    lib().w3do_deriv2(C.c_double(xi), C.c_double(eta), C.c_double(zeta), *[_ptr(x) for x in out])
+    return out
+
+
+def cp_icp(n):
+    utsz = (n * n + n) // 2
+    cp = np.zeros(n, dtype=np.int32)
+    dcp = np.zeros(n, dtype=np.int32)
+    icp = np.zeros((2, utsz), dtype=np.int32)   # Fortran (utsz, 2)
+    lib().w3do_cp_icp(C.c_int32(n), _ptr(cp), _ptr(dcp), _ptr(icp))
+    return cp, dcp, icp

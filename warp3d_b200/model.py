@@ -1,0 +1,259 @@
+"""Host-side mirror of the reference's global data for the element-block hot path.
+
+Everything here is *input data* for the engine, laid out exactly as the reference's Fortran
+modules hold it (column-major arrays, 1-based index tables), so the same arrays can be handed
+to the C ABI (``include/w3d_engine.h``) that a Fortran caller would bind:
+
+* ``elblks(0:3, nelblk)``            -- src/inelbk.f:47-52, auto blocking src/inelbk.f:282-345
+* ``props/iprops/lprops(mxelpr, noelem)`` (one 4-byte table, three views) -- src/mod_main.f:41-46,
+  rows filled as src/elprp.f:715-935 (elprp2, l3disop) does
+* ``edest/cdest (totdof, span)``     -- src/reopen.f:1200-1408 (all u, all v, all w ordering)
+* blocked state arrays               -- src/mod_eleblocks.f:52-131
+
+The synthetic structured hex8 meshes follow SURVEY.md section 8(d).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+MXVL = 128     # param_def: mxvl
+MXELPR = 43    # param_def: mxelpr
+MXMTPR = 300   # param_def: mxmtpr
+NSTR = 6
+NSTRS = 9
+HIST_SIZE = {1: 11, 5: 14}   # mm01.f:976, mm05.f:4136
+CEP_SIZE = 21
+
+# WARP3D hex8 (l3disop) node ordering in (xi, eta, zeta) -- src/derivs.f:283-343
+HEX8_NODE_SIGNS = np.array(
+    [(-1, -1, +1), (-1, -1, -1), (-1, +1, -1), (-1, +1, +1),
+     (+1, -1, +1), (+1, -1, -1), (+1, +1, -1), (+1, +1, +1)], dtype=np.int64)
+
+
+@dataclass
+class Material:
+    """One entry of the reference's material table (src/inmat.f), bilinear (mm01) subset."""
+    mat_type: int = 1
+    e: float = 200.0e9
+    nu: float = 0.3
+    yld_pt: float = 400.0e6
+    tan_e: float = 2.0e9
+    beta: float = 1.0
+    linear_elastic: bool = False
+    extra: dict = field(default_factory=dict)   # mm05: matprp(55:64); mm10: crystal data
+
+
+@dataclass
+class Model:
+    nonode: int
+    noelem: int
+    nodof: int
+    nelblk: int
+    c: np.ndarray          # (nodof,) float64 coordinates
+    incid: np.ndarray      # (noelem, 8) int32, 1-based nodes, WARP3D ordering
+    elblks: np.ndarray     # (nelblk, 4) int32 rows = [span, felem, domain, 0]  (Fortran (0:3,blk))
+    props: np.ndarray      # (noelem, MXELPR) int32 words (Fortran (mxelpr, noelem))
+    matprp: np.ndarray     # (nmat, MXMTPR) float32
+    edest: np.ndarray      # concatenated per block (span, 24) int32 (Fortran (24, span))
+    cdest: np.ndarray
+    hist_size: np.ndarray  # (nelblk,) int32
+    materials: list
+    eps_bbar: float = 0.0
+    qbar_flag: bool = True
+    dt: float = 1.0
+    total_model_time: float = 0.0
+    beta_fact: float = 1.0
+    extrapolated_du: bool = False
+    adaptive_flag: bool = True
+    grid: tuple = ()
+
+    # ---- sizes of the blocked arrays (doubles) ----
+    def span(self, blk):
+        return int(self.elblks[blk, 0])
+
+    def felem(self, blk):
+        return int(self.elblks[blk, 1])
+
+    def sizes(self):
+        spans = self.elblks[:, 0].astype(np.int64)
+        return dict(
+            history=int((spans * 8 * self.hist_size).sum()),
+            eps=int(spans.sum() * 8 * NSTR), urcs=int(spans.sum() * 8 * NSTRS),
+            rot=int(spans.sum() * 8 * 9), cep=int(spans.sum() * 8 * CEP_SIZE),
+            estiff=int(spans.sum() * 300), element_vol=int(spans.sum()))
+
+    def block_offsets(self, per_elem):
+        """offsets (doubles) of each block in an array with per_elem doubles per element."""
+        spans = self.elblks[:, 0].astype(np.int64)
+        per = np.asarray(per_elem, dtype=np.int64) * spans
+        off = np.zeros(self.nelblk + 1, dtype=np.int64)
+        np.cumsum(per, out=off[1:])
+        return off
+
+
+@dataclass
+class State:
+    """Blocked state in the reference's layouts, blocks concatenated in block order."""
+    history: np.ndarray
+    history1: np.ndarray
+    eps_n: np.ndarray
+    eps_n1: np.ndarray
+    urcs_n: np.ndarray
+    urcs_n1: np.ndarray
+    rot_n: np.ndarray
+    rot_n1: np.ndarray
+    cep: np.ndarray
+    estiff: np.ndarray
+    element_vol: np.ndarray
+
+    NAMES = ("history", "history1", "eps_n", "eps_n1", "urcs_n", "urcs_n1", "rot_n", "rot_n1",
+             "cep", "estiff", "element_vol")
+
+    def copy(self):
+        return State(**{k: getattr(self, k).copy() for k in self.NAMES})
+
+
+def new_state(model: Model) -> State:
+    """history_cep_init / rotation_init (src/reopen.f:1015-1176, 1841-1960): zeros, R = I."""
+    sz = model.sizes()
+    z = lambda n: np.zeros(n, dtype=np.float64)
+    rot = np.zeros((sz["rot"] // 9, 9), dtype=np.float64)
+    rot[:, 0] = 1.0
+    rot[:, 4] = 1.0
+    rot[:, 8] = 1.0
+    return State(history=z(sz["history"]), history1=z(sz["history"]), eps_n=z(sz["eps"]),
+                 eps_n1=z(sz["eps"]), urcs_n=z(sz["urcs"]), urcs_n1=z(sz["urcs"]),
+                 rot_n=rot.reshape(-1).copy(), rot_n1=rot.reshape(-1).copy(), cep=z(sz["cep"]),
+                 estiff=z(sz["estiff"]), element_vol=z(sz["element_vol"]))
+
+
+def _f32_bits(x) -> np.ndarray:
+    return np.asarray(x, dtype=np.float32).view(np.int32)
+
+
+def simple_blocking(noelem, keys, auto_size=MXVL):
+    """inelbk_simple_blocking (src/inelbk.f:282-345, 497-548): sequential pass, new block when
+    full or when (etype, matnum, geonl, intord, intnum, bbar) differ. keys: (noelem, k) ints."""
+    blocks = []
+    felem, size = 1, 1
+    for element in range(2, noelem + 1):
+        size += 1
+        newblk = size > auto_size
+        if not newblk and not np.array_equal(keys[element - 1], keys[felem - 1]):
+            newblk = True
+        if not newblk:
+            continue
+        blocks.append((size - 1, felem))
+        felem, size = element, 1
+    blocks.append((size, felem))
+    return blocks
+
+
+def build_structured_hex8(nx, ny, nz, materials=None, elem_material=None, geonl=True, bbar=True,
+                          h=1.0, block_size=MXVL, numprocs=1, coord_jitter=0.0, seed=0,
+                          **globals_) -> Model:
+    """Structured box of nx*ny*nz hex8 unit cubes, nodes and elements numbered x-fastest."""
+    materials = materials or [Material()]
+    nnx, nny, nnz = nx + 1, ny + 1, nz + 1
+    nonode = nnx * nny * nnz
+    noelem = nx * ny * nz
+    nodof = 3 * nonode
+    k, j, i = np.meshgrid(np.arange(nnz), np.arange(nny), np.arange(nnx), indexing="ij")
+    coords = np.stack([i.ravel(), j.ravel(), k.ravel()], axis=1).astype(np.float64) * h
+    if coord_jitter:
+        rng = np.random.default_rng(seed)
+        interior = ((i.ravel() > 0) & (i.ravel() < nx) & (j.ravel() > 0) & (j.ravel() < ny)
+                    & (k.ravel() > 0) & (k.ravel() < nz))
+        coords[interior] += rng.uniform(-coord_jitter, coord_jitter, (int(interior.sum()), 3)) * h
+    c = coords.reshape(-1).copy()
+
+    ek, ej, ei = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    ei, ej, ek = ei.ravel(), ej.ravel(), ek.ravel()
+    incid = np.empty((noelem, 8), dtype=np.int32)
+    for a, (sx, sy, sz) in enumerate(HEX8_NODE_SIGNS):
+        ni = ei + (sx > 0)
+        nj = ej + (sy > 0)
+        nk = ek + (sz > 0)
+        incid[:, a] = (nk * nny + nj) * nnx + ni + 1
+
+    if elem_material is None:
+        elem_material = np.ones(noelem, dtype=np.int32)
+    elem_material = np.asarray(elem_material, dtype=np.int32)
+
+    # ---- material table (src/inmat.f rows) and element property table (src/elprp.f:715-935)
+    matprp = np.zeros((len(materials), MXMTPR), dtype=np.float32)
+    for mi, mat in enumerate(materials):
+        matprp[mi, 0] = mat.e
+        matprp[mi, 1] = mat.nu
+        matprp[mi, 2] = mat.beta
+        matprp[mi, 3] = mat.tan_e
+        matprp[mi, 4] = mat.yld_pt
+        matprp[mi, 8] = mat.mat_type
+        for row, val in mat.extra.get("matprp", {}).items():
+            matprp[mi, row - 1] = val
+    props = np.zeros((noelem, MXELPR), dtype=np.int32)
+    props[:, 0] = 2              # type l3disop
+    props[:, 1] = 8              # nodes
+    props[:, 2] = 24 * 65536 + 6
+    props[:, 3] = 3              # dof / node
+    props[:, 4] = 1              # integration order 2x2x2
+    props[:, 5] = 8              # number of gauss points
+    props[:, 10] = 6
+    mi = elem_material - 1
+    e32 = matprp[mi, 0]
+    et32 = matprp[mi, 3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        h32 = ((e32 * et32) / (e32 - et32)).astype(np.float32)   # real*4 arithmetic, elprp.f:866
+    props[:, 6] = _f32_bits(e32)
+    props[:, 7] = _f32_bits(matprp[mi, 1])
+    props[:, 13] = _f32_bits(matprp[mi, 2])
+    props[:, 14] = _f32_bits(h32)
+    props[:, 16] = np.where(np.array([materials[k].linear_elastic for k in mi]), -1, 0)
+    props[:, 17] = -1 if geonl else 0      # ifort .true. = -1
+    props[:, 18] = -1 if bbar else 0
+    props[:, 22] = _f32_bits(matprp[mi, 4])
+    props[:, 24] = matprp[mi, 8].astype(np.int32)
+    props[:, 37] = elem_material
+    props[:, 41] = -1
+
+    keys = np.stack([props[:, 0], props[:, 37], props[:, 17], props[:, 4], props[:, 5],
+                     props[:, 18]], axis=1)
+    blocks = simple_blocking(noelem, keys, block_size)
+    nelblk = len(blocks)
+    elblks = np.zeros((nelblk, 4), dtype=np.int32)
+    for b, (span, felem) in enumerate(blocks):
+        elblks[b, 0] = span
+        elblks[b, 1] = felem
+    if numprocs > 1:                     # round-robin, src/inelbk.f:368-378
+        elblks[:, 2] = np.arange(nelblk) % numprocs
+
+    # edest / cdest: dstmap(node) = 3*(node-1)+1 ; ordering all u, all v, all w
+    base = 3 * (incid.astype(np.int64) - 1) + 1        # (noelem, 8)
+    dest = np.concatenate([base, base + 1, base + 2], axis=1).astype(np.int32)  # (noelem, 24)
+    edest = dest.reshape(-1).copy()
+    cdest = edest.copy()
+    hist_size = np.array([HIST_SIZE.get(int(props[f - 1, 24]), 0) for _, f in blocks],
+                         dtype=np.int32)
+    for b, (_, f) in enumerate(blocks):
+        mt = materials[int(props[f - 1, 37]) - 1]
+        if "hist_size" in mt.extra:
+            hist_size[b] = mt.extra["hist_size"]
+    return Model(nonode=nonode, noelem=noelem, nodof=nodof, nelblk=nelblk, c=c, incid=incid,
+                 elblks=elblks, props=props, matprp=matprp, edest=edest, cdest=cdest,
+                 hist_size=hist_size, materials=materials, grid=(nx, ny, nz), **globals_)
+
+
+def smooth_displacement(model: Model, strain=1.0e-3, seed=1, noise=1.0e-4, axis=0):
+    """Uniaxial stretch along `axis` with lateral Poisson contraction plus a seeded perturbation
+    (SURVEY 8(d)).  Returns a (nodof,) vector."""
+    xyz = model.c.reshape(-1, 3)
+    u = np.zeros_like(xyz)
+    nu = 0.3
+    for a in range(3):
+        u[:, a] = (strain if a == axis else -nu * strain) * xyz[:, a]
+    if noise:
+        rng = np.random.default_rng(seed)
+        u += rng.uniform(-1.0, 1.0, u.shape) * noise * strain * 10.0
+    return u.reshape(-1).copy()
