@@ -1,0 +1,151 @@
+/*
+ * w3d_engine.h -- C ABI of the B200 (sm_100a) element-block engine.
+ *
+ * This is the drop-in boundary for WARP3D's element-block hot path.  The reference has no FFI at
+ * this level (no iso_c_binding anywhere in src/); the seam is the body of the two OpenMP block
+ * loops and the block part of the n+1 -> n rollover.  Each entry point below cites the reference
+ * code it replaces (paths relative to the reference tree's src/).  The Fortran side binds these
+ * with ISO_C_BINDING (see INTEGRATION.md for the interface block and the patched call sites).
+ *
+ * Conventions
+ *   - plain C: int32_t, int64_t, float, double and pointers to them; no C++/torch types.
+ *   - arrays are in the reference's own (Fortran, column-major) layouts; index tables hold the
+ *     reference's 1-based indices unchanged.
+ *   - the caller owns every host array; the engine copies what it needs during the call.
+ *   - return value: 0 = ok; >0 = a condition on which the reference would call die_abort
+ *     (W3D_ERR_*).  A requested adaptive step cut is data (material_cut_step), not an error.
+ *   - one handle per GPU / MPI rank; calls on one handle are not re-entrant.
+ *   - there is no CPU fallback: every entry point fails with W3D_ERR_CUDA when no sm_100
+ *     device / driver is usable.
+ */
+#ifndef W3D_ENGINE_H
+#define W3D_ENGINE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W3D_ABI_VERSION 1
+
+/* error codes (return values) */
+#define W3D_OK             0
+#define W3D_ERR_CUDA       1  /* CUDA runtime/driver failure or no device                       */
+#define W3D_ERR_CONFIG     2  /* inconsistent tables in w3d_engine_config                       */
+#define W3D_ERR_UNSUPPORTED 3 /* element type / material model / option outside the engine scope */
+#define W3D_ERR_ARG        4  /* bad argument (null pointer, block index out of range, ...)      */
+#define W3D_ERR_MM01_LAMBDA 5 /* mm01_general: negative plastic multiplier (mm01.f:878-881)      */
+#define W3D_ERR_DETF       6  /* det F <= 0 and the step is not adaptive (rstgp1.f:136-145)      */
+
+/* which = selector for w3d_push_state / w3d_pull_state.  Layout per block as in
+ * mod_eleblocks.f:52-131 (blk is 1-based like the reference's block numbers):
+ *   HIST_N/HIST_N1  history_blocks / history1_blocks (hist_size, ngp, span)
+ *   EPS_N/EPS_N1    eps_n_blocks / eps_n1_blocks     (6, ngp, span)
+ *   URCS_N/URCS_N1  urcs_n_blocks / urcs_n1_blocks   (9, ngp, span)
+ *   ROT_N/ROT_N1    rot_n_blocks / rot_n1_blocks     (9, ngp, span)
+ *   CEP             cep_blocks(blk)%vector           (21, span, ngp)   [rstgp1.f:5366]
+ *   ESTIFF          estiff_blocks(blk)%ptr           (utsz, span)      [tanstf.f:422]
+ *   ELEM_VOL        element_vol_blocks(blk)%ptr      (span)
+ */
+enum {
+  W3D_HIST_N = 0, W3D_HIST_N1 = 1, W3D_EPS_N = 2, W3D_EPS_N1 = 3, W3D_URCS_N = 4,
+  W3D_URCS_N1 = 5, W3D_ROT_N = 6, W3D_ROT_N1 = 7, W3D_CEP = 8, W3D_ESTIFF = 9,
+  W3D_ELEM_VOL = 10
+};
+
+/* Model description handed over once, after the reference has read its input and run the
+ * *_init routines (reopen.f:1015-1408, setup.f:268-276, inelbk.f:282-345).                      */
+typedef struct w3d_engine_config {
+  int32_t abi_version;       /* W3D_ABI_VERSION                                                  */
+  int32_t mxvl, mxelpr, mxmtpr;          /* param_def:20-60                                      */
+  int32_t nelblk, noelem, nonode, nodof; /* mod_main.f global_data                               */
+  int32_t myid, numprocs;    /* MPI rank / domain count; the engine owns blocks whose
+                                elblks(2,blk) == myid (drive_eps_sig_internal_forces.f:166)      */
+  const int32_t *elblks;     /* (0:3, nelblk): span, felem, domain, -   (inelbk.f:47-52)         */
+  const void    *props;      /* (mxelpr, noelem) 4-byte words, props/iprops/lprops aliases
+                                (mod_main.f:41-46); rows used: 1,2,4,5,6,7,8,14,15,17,18,19,23,
+                                25,38 (drive_eps_sig_internal_forces.f:448-461, rknstr.f:1036-1059)*/
+  const float   *matprp;     /* (mxmtpr, nmat) real*4 material table, may be NULL                */
+  int32_t        nmat;
+  const double  *c;          /* (nodof) nodal coordinates (mod_main.f:48)                        */
+  const int32_t *edest;      /* per-block (totdof, span) tables concatenated in block order
+                                (edest_blocks, reopen.f:1315-1408)                               */
+  const int32_t *cdest;      /* same for cdest_blocks (reopen.f:1200-1293)                       */
+  const int32_t *history_blk_list; /* (nelblk) history words per Gauss point                     */
+  double  eps_bbar;          /* global_data eps_bbar                                             */
+  int32_t qbar_flag;         /* global_data qbar_flag ("consistent q")                           */
+  double  beta_fact;         /* global_data beta_fact                                            */
+  int32_t adaptive_flag;     /* global_data adaptive_flag                                        */
+  int32_t device;            /* CUDA device ordinal, -1 = current device                         */
+} w3d_engine_config;
+
+/* scalars the stress/ifv pass returns (drive_eps_sig_internal_forces.f:210-226, 316-319) */
+typedef struct w3d_scalars {
+  double  internal_energy;   /* sum of block_energies                                            */
+  double  plastic_work;      /* sum of block_plastic_work                                        */
+  double  sum_ifv;           /* sum |f_e| over all element force terms (addifv.f:104-110)        */
+  int64_t num_term_ifv;      /* number of terms in sum_ifv                                       */
+  int32_t material_cut_step; /* 1 = some Gauss point asked for an adaptive step cut              */
+  int32_t reserved;
+} w3d_scalars;
+
+typedef struct w3d_engine w3d_engine;   /* opaque */
+
+/* Build the device-side model: block tables, index maps, property vectors, zeroed state with
+ * R = I (history_cep_init / rotation_init, reopen.f:1015-1176).                                 */
+int32_t w3d_engine_create(const w3d_engine_config *cfg, w3d_engine **handle);
+int32_t w3d_engine_destroy(w3d_engine *handle);
+/* last error text for this handle (or for a failed create when handle == NULL) */
+const char *w3d_engine_last_error(const w3d_engine *handle);
+
+/* Replaces drive_eps_sig_internal_forces.f:115-349 (allocate_ifv, the OMP block loop over
+ * do_nleps_block -> dupstr / dupstr_blocked / rknstr / rstgp1|rstgp2 / mm01+cnst1 / rplstr /
+ * rknifv / gpifv1, the scalar reductions and the addifv scatter).  u, du, ifv are (nodof) host
+ * vectors; ifv is overwritten with this engine's (this rank's) contribution, already scaled by
+ * beta_fact, and zeroed when material_cut_step is set (:253-263).                               */
+int32_t w3d_eps_sig_ifv(w3d_engine *h, int32_t step, int32_t iter, int32_t extrapolated_du,
+                        const double *u, const double *du, double *ifv, w3d_scalars *out);
+
+/* Replaces tanstf.f:56-95 (estiff_allocate + the OMP block loop over do_nlek_block -> dptstf /
+ * dptstf_blocks / rktstf / gptns1 / bdbtgen / ctran1 / kgstiff / rktstf_do_transpose).  u, du
+ * may be NULL to reuse the vectors of the last w3d_eps_sig_ifv call.  estiff, when not NULL,
+ * receives every owned block's (utsz, span) matrix, blocks concatenated in block order
+ * (offsets: w3d_block_offset); NULL keeps the result on the device (w3d_pull_state).           */
+int32_t w3d_tanstf(w3d_engine *h, int32_t step, int32_t iter, const double *u, const double *du,
+                   double *estiff);
+
+/* Replaces the block part of update (update.f:75-93): history, eps, urcs  n+1 -> n.             */
+int32_t w3d_update(w3d_engine *h);
+/* adaptive_save (mnralg.f:1258-1310): rot n+1 -> n.                                             */
+int32_t w3d_adaptive_save(w3d_engine *h);
+/* adaptive_reset (mnralg.f:1335-1401): history, rot, eps, urcs  n -> n+1.                       */
+int32_t w3d_adaptive_reset(w3d_engine *h);
+
+/* Move one block of blocked state between the reference's host arrays and the device
+ * (restart store.f/reopen.f, output ou*.f, J-integral di*.f read these).  blk is 1-based.      */
+int32_t w3d_push_state(w3d_engine *h, int32_t which, int32_t blk, const double *src);
+int32_t w3d_pull_state(w3d_engine *h, int32_t which, int32_t blk, double *dst);
+/* offset in doubles of block blk (1-based; blk = nelblk+1 gives the total) inside an array that
+ * concatenates all blocks of kind `which` in block order.                                       */
+int64_t w3d_block_offset(const w3d_engine *h, int32_t which, int32_t blk);
+
+/* ---- device-resident variants (no host<->device copies inside) --------------------------------
+ * The engine owns device copies of u, du and ifv.  A caller that already lives on the GPU (the
+ * NCCL layer, a device-side residual/assembly) fills u/du through these pointers, runs the
+ * resident passes and reads ifv / scalars back when it needs them.                              */
+int32_t w3d_device_vectors(w3d_engine *h, double **d_u, double **d_du, double **d_ifv);
+int32_t w3d_eps_sig_ifv_resident(w3d_engine *h, int32_t step, int32_t iter,
+                                 int32_t extrapolated_du);
+int32_t w3d_tanstf_resident(w3d_engine *h, int32_t step, int32_t iter);
+/* scalars of the last resident stress pass (synchronises the engine's stream) */
+int32_t w3d_last_scalars(w3d_engine *h, w3d_scalars *out);
+/* the CUDA stream (cudaStream_t as void*) every engine kernel is launched on */
+void   *w3d_engine_stream(w3d_engine *h);
+int32_t w3d_engine_synchronize(w3d_engine *h);
+/* number of kernels the engine has launched since create (bench.py: gpu_launches) */
+int64_t w3d_engine_launch_count(const w3d_engine *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W3D_ENGINE_H */

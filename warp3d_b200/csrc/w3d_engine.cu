@@ -1,0 +1,653 @@
+// w3d_engine.cu -- host side of the B200 element-block engine and its C ABI (include/w3d_engine.h).
+//
+// The engine mirrors the reference's block contract on the host (elblks, props, edest/cdest,
+// history_blk_list) and keeps all blocked state resident in HBM as structure-of-arrays.  Blocks
+// that share (material model, geonl, bbar, history size) form a *segment*; every pass is one
+// kernel launch per segment.  There is no CPU code path for the arithmetic: if CUDA is not
+// usable every entry point returns W3D_ERR_CUDA.
+#include "../../include/w3d_engine.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "w3d_stress_kernel.cuh"
+#include "w3d_tanstf_kernel.cuh"
+
+using namespace w3d;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      return fail(W3D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),         \
+                  __FILE__, __LINE__);                                                          \
+    }                                                                                           \
+  } while (0)
+
+struct Segment {
+  int mat_type = 0, hist_size = 0;
+  bool geonl = false, bbar = false;
+  int nslots = 0, ncta = 0;
+  long long ng = 0;                 // nslots * 8
+  std::vector<int> blocks;          // 0-based block numbers in block order
+  // device
+  CtaDesc *d_cta = nullptr;
+  int32_t *d_edest = nullptr, *d_cdest = nullptr;
+  float *d_eprops = nullptr;
+  double *eps_n = nullptr, *eps_n1 = nullptr, *urcs_n = nullptr, *urcs_n1 = nullptr,
+         *rot_n = nullptr, *rot_n1 = nullptr, *cep = nullptr, *hist_n = nullptr,
+         *hist_n1 = nullptr, *elem_vol = nullptr, *partials = nullptr;
+};
+
+struct BlockInfo {
+  int span = 0, felem = 0, domain = 0;
+  bool owned = false;
+  int seg = -1;
+  int slot0 = 0;        // segment-relative first slot
+  long long epos0 = 0;  // unpadded element position among owned blocks
+  int elem_type = 0, nnode = 0, ndof = 0, int_order = 0, ngp = 0, mat_type = 0, matnum = 0,
+      hist_size = 0, totdof = 0, utsz = 0;
+  bool geonl = false, bbar = false;
+  long long tab_off = 0;  // offset (ints) of this block's edest/cdest table in the caller's arrays
+};
+
+}  // namespace
+
+struct w3d_engine {
+  w3d_engine_config cfg{};
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<BlockInfo> blocks;
+  std::vector<Segment> segs;
+  long long n_owned_elems = 0;
+  double *d_c = nullptr, *d_u = nullptr, *d_du = nullptr, *d_ifv = nullptr;
+  double *d_estiff = nullptr;       // (300, n_owned_elems)
+  double *d_scal = nullptr;         // [4]
+  int *d_flags = nullptr;           // [2]
+  double *d_stage = nullptr;        // push/pull staging (one block)
+  size_t stage_doubles = 0;
+  double *h_pin = nullptr;          // pinned: [0..3] scalars, then 2 ints of flags
+  int64_t launches = 0;
+  w3d_scalars last{};
+  bool have_vectors = false;
+
+  int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+namespace {
+
+inline int32_t iprop(const w3d_engine_config &c, int row, int elem) {
+  int32_t v;
+  std::memcpy(&v, (const char *)c.props + 4 * ((size_t)(elem - 1) * c.mxelpr + (row - 1)), 4);
+  return v;
+}
+inline float rprop(const w3d_engine_config &c, int row, int elem) {
+  float v;
+  std::memcpy(&v, (const char *)c.props + 4 * ((size_t)(elem - 1) * c.mxelpr + (row - 1)), 4);
+  return v;
+}
+// ifort logicals: .true. has the low bit set
+inline bool lprop(const w3d_engine_config &c, int row, int elem) { return (iprop(c, row, elem) & 1) != 0; }
+
+// quad2 (getgpts.f:642-718) and deriv2 (derivs.f:283-343): WARP3D point and node ordering
+void shape_tables(double (*tab)[8][8]) {
+  const double l1 = 0.5773502691896257645;
+  static const int sx[8] = {-1, -1, 1, 1, -1, -1, 1, 1};
+  static const int sy[8] = {-1, 1, -1, 1, -1, 1, -1, 1};
+  static const int sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+  for (int gp = 0; gp < 8; ++gp) {
+    const double xi = sx[gp] * l1, eta = sy[gp] * l1, zeta = sz[gp] * l1;
+    const double one = 1.0, one25 = 0.125;
+    const double xp = one + xi, ep = one + eta, zp = one + zeta;
+    const double xm_ = one - xi, em = one - eta, zm = one - zeta;
+    double nxi[8], neta[8], nzeta[8];
+    nxi[0] = -em * zp * one25; neta[0] = -xm_ * zp * one25; nzeta[0] = xm_ * em * one25;
+    nxi[1] = -em * zm * one25; neta[1] = -xm_ * zm * one25; nzeta[1] = -xm_ * em * one25;
+    nxi[2] = -ep * zm * one25; neta[2] = xm_ * zm * one25;  nzeta[2] = -xm_ * ep * one25;
+    nxi[3] = -ep * zp * one25; neta[3] = xm_ * zp * one25;  nzeta[3] = xm_ * ep * one25;
+    nxi[4] = em * zp * one25;  neta[4] = -xp * zp * one25;  nzeta[4] = xp * em * one25;
+    nxi[5] = em * zm * one25;  neta[5] = -xp * zm * one25;  nzeta[5] = -xp * em * one25;
+    nxi[6] = ep * zm * one25;  neta[6] = xp * zm * one25;   nzeta[6] = -xp * ep * one25;
+    nxi[7] = ep * zp * one25;  neta[7] = xp * zp * one25;   nzeta[7] = xp * ep * one25;
+    for (int j = 0; j < 8; ++j) { tab[0][j][gp] = nxi[j]; tab[1][j][gp] = neta[j]; tab[2][j][gp] = nzeta[j]; }
+  }
+}
+
+// ---- layout conversion kernels: one reference block <-> the segment's SoA arrays ---------------
+// reference (nprm, ngp=8, span)  <->  soa[k*ng + (slot0+i)*8 + gp]
+__global__ void k_block_to_soa(const double *blk, double *soa, long long ng, int slot0, int span,
+                               int nprm, int cep_layout) {
+  const int n = nprm * 8 * span;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    int k, gp, i;
+    if (cep_layout) { k = t % nprm; i = (t / nprm) % span; gp = t / (nprm * span); }   // (21,span,ngp)
+    else { k = t % nprm; gp = (t / nprm) % 8; i = t / (nprm * 8); }                    // (nprm,ngp,span)
+    soa[(long long)k * ng + (long long)(slot0 + i) * 8 + gp] = blk[t];
+  }
+}
+__global__ void k_soa_to_block(double *blk, const double *soa, long long ng, int slot0, int span,
+                               int nprm, int cep_layout) {
+  const int n = nprm * 8 * span;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    int k, gp, i;
+    if (cep_layout) { k = t % nprm; i = (t / nprm) % span; gp = t / (nprm * span); }
+    else { k = t % nprm; gp = (t / nprm) % 8; i = t / (nprm * 8); }
+    blk[t] = soa[(long long)k * ng + (long long)(slot0 + i) * 8 + gp];
+  }
+}
+// R = I for every Gauss point (rotation_init, reopen.f:1841-1960)
+__global__ void k_rot_identity(double *rot, long long ng) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ng;
+       t += (long long)gridDim.x * blockDim.x) {
+    rot[0 * ng + t] = 1.0; rot[4 * ng + t] = 1.0; rot[8 * ng + t] = 1.0;
+  }
+}
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t n) {
+  cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+  return e;
+}
+
+int nprm_of(const w3d_engine *h, int which, const BlockInfo &b) {
+  (void)h;
+  switch (which) {
+    case W3D_HIST_N: case W3D_HIST_N1: return b.hist_size;
+    case W3D_EPS_N: case W3D_EPS_N1: return 6;
+    case W3D_URCS_N: case W3D_URCS_N1: return 9;
+    case W3D_ROT_N: case W3D_ROT_N1: return 9;
+    case W3D_CEP: return 21;
+    default: return 0;
+  }
+}
+double *soa_of(Segment &s, int which) {
+  switch (which) {
+    case W3D_HIST_N: return s.hist_n;   case W3D_HIST_N1: return s.hist_n1;
+    case W3D_EPS_N: return s.eps_n;     case W3D_EPS_N1: return s.eps_n1;
+    case W3D_URCS_N: return s.urcs_n;   case W3D_URCS_N1: return s.urcs_n1;
+    case W3D_ROT_N: return s.rot_n;     case W3D_ROT_N1: return s.rot_n1;
+    case W3D_CEP: return s.cep;
+    default: return nullptr;
+  }
+}
+long long block_doubles(int which, const BlockInfo &b) {
+  switch (which) {
+    case W3D_HIST_N: case W3D_HIST_N1: return (long long)b.hist_size * b.ngp * b.span;
+    case W3D_EPS_N: case W3D_EPS_N1: return 6LL * b.ngp * b.span;
+    case W3D_URCS_N: case W3D_URCS_N1: case W3D_ROT_N: case W3D_ROT_N1: return 9LL * b.ngp * b.span;
+    case W3D_CEP: return 21LL * b.ngp * b.span;
+    case W3D_ESTIFF: return (long long)b.utsz * b.span;
+    case W3D_ELEM_VOL: return b.span;
+    default: return -1;
+  }
+}
+
+void free_all(w3d_engine *h) {
+  for (auto &s : h->segs) {
+    cudaFree(s.d_cta); cudaFree(s.d_edest); cudaFree(s.d_cdest); cudaFree(s.d_eprops);
+    cudaFree(s.eps_n); cudaFree(s.eps_n1); cudaFree(s.urcs_n); cudaFree(s.urcs_n1);
+    cudaFree(s.rot_n); cudaFree(s.rot_n1); cudaFree(s.cep); cudaFree(s.hist_n);
+    cudaFree(s.hist_n1); cudaFree(s.elem_vol); cudaFree(s.partials);
+  }
+  cudaFree(h->d_c); cudaFree(h->d_u); cudaFree(h->d_du); cudaFree(h->d_ifv);
+  cudaFree(h->d_estiff); cudaFree(h->d_scal); cudaFree(h->d_flags); cudaFree(h->d_stage);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+int create_impl(w3d_engine *h) {
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  const w3d_engine_config &c = h->cfg;
+  if (c.abi_version != W3D_ABI_VERSION) return fail(W3D_ERR_CONFIG, "abi_version %d != %d", c.abi_version, W3D_ABI_VERSION);
+  if (!c.elblks || !c.props || !c.c || !c.edest || !c.cdest || !c.history_blk_list)
+    return fail(W3D_ERR_ARG, "null table in w3d_engine_config");
+  if (c.nelblk <= 0 || c.noelem <= 0 || c.nodof <= 0 || c.mxelpr < 38)
+    return fail(W3D_ERR_CONFIG, "bad sizes nelblk=%d noelem=%d nodof=%d mxelpr=%d", c.nelblk, c.noelem, c.nodof, c.mxelpr);
+
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) return fail(W3D_ERR_CUDA, "no CUDA device");
+  if (c.device >= 0) { CUDA_TRY(cudaSetDevice(c.device)); }
+  CUDA_TRY(cudaGetDevice(&h->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10) return fail(W3D_ERR_CUDA, "device %d is sm_%d%d; this engine is built for sm_100a only", h->device, prop.major, prop.minor);
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+  // ---- block table (do_nleps_block reads the same props rows, :448-461) and segments
+  h->blocks.resize(c.nelblk);
+  long long tab = 0, epos = 0;
+  for (int blk = 0; blk < c.nelblk; ++blk) {
+    BlockInfo &b = h->blocks[blk];
+    b.span = c.elblks[4 * blk + 0];
+    b.felem = c.elblks[4 * blk + 1];
+    b.domain = c.elblks[4 * blk + 2];
+    if (b.span <= 0 || b.felem < 1 || b.felem + b.span - 1 > c.noelem)
+      return fail(W3D_ERR_CONFIG, "block %d: span %d felem %d outside 1..%d", blk + 1, b.span, b.felem, c.noelem);
+    if (c.mxvl > 0 && b.span > c.mxvl) return fail(W3D_ERR_CONFIG, "block %d: span %d > mxvl %d", blk + 1, b.span, c.mxvl);
+    const int fe = b.felem;
+    b.elem_type = iprop(c, 1, fe); b.nnode = iprop(c, 2, fe); b.ndof = iprop(c, 4, fe);
+    b.int_order = iprop(c, 5, fe); b.ngp = iprop(c, 6, fe);
+    b.geonl = lprop(c, 18, fe); b.bbar = lprop(c, 19, fe);
+    b.mat_type = iprop(c, 25, fe); b.matnum = iprop(c, 38, fe);
+    b.totdof = b.nnode * b.ndof;
+    b.utsz = (b.totdof * b.totdof - b.totdof) / 2 + b.totdof;
+    b.hist_size = c.history_blk_list[blk];
+    b.tab_off = tab;
+    tab += (long long)b.totdof * b.span;
+    b.owned = (c.numprocs <= 1) || (b.domain == c.myid);
+    if (!b.owned) continue;
+    if (b.elem_type != 2 || b.nnode != 8 || b.ndof != 3 || b.ngp != 8)
+      return fail(W3D_ERR_UNSUPPORTED, "block %d: element type %d (%d nodes, %d points): only hex8 l3disop 2x2x2", blk + 1, b.elem_type, b.nnode, b.ngp);
+    if (b.mat_type != 1)
+      return fail(W3D_ERR_UNSUPPORTED, "block %d: material model %d not built yet (mm01 only)", blk + 1, b.mat_type);
+    if (b.mat_type == 1 && b.hist_size != 11)
+      return fail(W3D_ERR_CONFIG, "block %d: mm01 history size %d != 11", blk + 1, b.hist_size);
+    int sidx = -1;
+    for (size_t s = 0; s < h->segs.size(); ++s) {
+      const Segment &sg = h->segs[s];
+      if (sg.mat_type == b.mat_type && sg.geonl == b.geonl && sg.bbar == b.bbar && sg.hist_size == b.hist_size) { sidx = (int)s; break; }
+    }
+    if (sidx < 0) {
+      Segment sg;
+      sg.mat_type = b.mat_type; sg.geonl = b.geonl; sg.bbar = b.bbar; sg.hist_size = b.hist_size;
+      h->segs.push_back(sg);
+      sidx = (int)h->segs.size() - 1;
+    }
+    Segment &sg = h->segs[sidx];
+    b.seg = sidx;
+    b.slot0 = sg.nslots;
+    b.epos0 = epos;
+    sg.nslots += ((b.span + EPC - 1) / EPC) * EPC;
+    sg.blocks.push_back(blk);
+    epos += b.span;
+  }
+  h->n_owned_elems = epos;
+
+  // ---- global vectors
+  CUDA_TRY(dalloc(&h->d_c, (size_t)c.nodof));
+  CUDA_TRY(dalloc(&h->d_u, (size_t)c.nodof));
+  CUDA_TRY(dalloc(&h->d_du, (size_t)c.nodof));
+  CUDA_TRY(dalloc(&h->d_ifv, (size_t)c.nodof));
+  CUDA_TRY(cudaMemcpy(h->d_c, c.c, sizeof(double) * c.nodof, cudaMemcpyHostToDevice));
+  CUDA_TRY(dalloc(&h->d_estiff, (size_t)h->n_owned_elems * 300));
+  CUDA_TRY(dalloc(&h->d_scal, 4));
+  CUDA_TRY(dalloc(&h->d_flags, 2));
+  CUDA_TRY(cudaMallocHost((void **)&h->h_pin, 8 * sizeof(double)));
+  {
+    double tab3[3][8][8];
+    shape_tables(tab3);
+    CUDA_TRY(cudaMemcpyToSymbol(c_shape, tab3, sizeof tab3));
+  }
+
+  // ---- per-segment tables and state
+  size_t max_blk_doubles = 0;
+  for (auto &sg : h->segs) {
+    sg.ng = (long long)sg.nslots * 8;
+    sg.ncta = sg.nslots / EPC;
+    std::vector<CtaDesc> cta(sg.ncta);
+    std::vector<int32_t> ed((size_t)sg.nslots * 24), cdv((size_t)sg.nslots * 24);
+    std::vector<float> ep((size_t)sg.nslots * EPROP, 0.0f);
+    int ci = 0;
+    for (int blk : sg.blocks) {
+      const BlockInfo &b = h->blocks[blk];
+      for (int i0 = 0; i0 < b.span; i0 += EPC) {
+        CtaDesc &d = cta[ci++];
+        d.slot0 = b.slot0 + i0;
+        d.nvalid = (b.span - i0 < EPC) ? b.span - i0 : EPC;
+        d.blk_slot0 = b.slot0;
+        d.epos0 = (int)(b.epos0 + i0);
+      }
+      const int padded = ((b.span + EPC - 1) / EPC) * EPC;
+      for (int i = 0; i < padded; ++i) {
+        const int src = (i < b.span) ? i : b.span - 1;       // padding repeats the last element
+        const int elem = b.felem + src;
+        const size_t slot = (size_t)b.slot0 + i;
+        for (int j = 0; j < 24; ++j) {
+          const int32_t e = c.edest[b.tab_off + (size_t)src * 24 + j];
+          const int32_t cc = c.cdest[b.tab_off + (size_t)src * 24 + j];
+          if (e < 1 || e > c.nodof || cc < 1 || cc > c.nodof)
+            return fail(W3D_ERR_CONFIG, "block %d element %d: edest/cdest entry %d outside 1..nodof", blk + 1, elem, j + 1);
+          ed[slot * 24 + j] = e;
+          cdv[slot * 24 + j] = cc;
+        }
+        // setup_mm01_rknstr (rknstr.f:1018-1066): real*4 props widened on the device
+        float *p = &ep[slot * EPROP];
+        p[0] = rprop(c, 7, elem); p[1] = rprop(c, 8, elem); p[2] = rprop(c, 14, elem);
+        p[3] = rprop(c, 15, elem); p[4] = rprop(c, 23, elem); p[5] = lprop(c, 17, elem) ? 1.0f : 0.0f;
+      }
+      for (int w = 0; w <= W3D_ELEM_VOL; ++w) {
+        const long long n = block_doubles(w, b);
+        if (n > 0 && (size_t)n > max_blk_doubles) max_blk_doubles = (size_t)n;
+      }
+    }
+    CUDA_TRY(dalloc(&sg.d_cta, (size_t)sg.ncta));
+    CUDA_TRY(cudaMemcpy(sg.d_cta, cta.data(), sizeof(CtaDesc) * sg.ncta, cudaMemcpyHostToDevice));
+    CUDA_TRY(dalloc(&sg.d_edest, ed.size()));
+    CUDA_TRY(cudaMemcpy(sg.d_edest, ed.data(), sizeof(int32_t) * ed.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(dalloc(&sg.d_cdest, cdv.size()));
+    CUDA_TRY(cudaMemcpy(sg.d_cdest, cdv.data(), sizeof(int32_t) * cdv.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(dalloc(&sg.d_eprops, ep.size()));
+    CUDA_TRY(cudaMemcpy(sg.d_eprops, ep.data(), sizeof(float) * ep.size(), cudaMemcpyHostToDevice));
+    const size_t ng = (size_t)sg.ng;
+    CUDA_TRY(dalloc(&sg.eps_n, 6 * ng));   CUDA_TRY(dalloc(&sg.eps_n1, 6 * ng));
+    CUDA_TRY(dalloc(&sg.urcs_n, 9 * ng));  CUDA_TRY(dalloc(&sg.urcs_n1, 9 * ng));
+    CUDA_TRY(dalloc(&sg.rot_n, 9 * ng));   CUDA_TRY(dalloc(&sg.rot_n1, 9 * ng));
+    CUDA_TRY(dalloc(&sg.cep, 21 * ng));
+    CUDA_TRY(dalloc(&sg.hist_n, (size_t)sg.hist_size * ng));
+    CUDA_TRY(dalloc(&sg.hist_n1, (size_t)sg.hist_size * ng));
+    CUDA_TRY(dalloc(&sg.elem_vol, (size_t)sg.nslots));
+    CUDA_TRY(dalloc(&sg.partials, (size_t)sg.ncta * 4));
+    k_rot_identity<<<148 * 4, 256, 0, h->stream>>>(sg.rot_n, sg.ng);
+    k_rot_identity<<<148 * 4, 256, 0, h->stream>>>(sg.rot_n1, sg.ng);
+    h->launches += 2;
+  }
+  h->stage_doubles = max_blk_doubles;
+  CUDA_TRY(dalloc(&h->d_stage, h->stage_doubles));
+  CUDA_TRY(cudaFuncSetAttribute(k_tanstf<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPC * ELREC * 8));
+  CUDA_TRY(cudaFuncSetAttribute(k_tanstf<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPC * ELREC * 8));
+  CUDA_TRY(cudaFuncSetAttribute(k_tanstf<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPC * ELREC * 8));
+  CUDA_TRY(cudaFuncSetAttribute(k_tanstf<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPC * ELREC * 8));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaGetLastError());
+  return W3D_OK;
+}
+
+template <int MAT>
+void launch_stress(const Segment &sg, const StressArgs &a, cudaStream_t st) {
+  if (sg.geonl) {
+    if (sg.bbar) k_eps_sig_ifv<MAT, true, true><<<sg.ncta, TPB, 0, st>>>(a);
+    else k_eps_sig_ifv<MAT, true, false><<<sg.ncta, TPB, 0, st>>>(a);
+  } else {
+    if (sg.bbar) k_eps_sig_ifv<MAT, false, true><<<sg.ncta, TPB, 0, st>>>(a);
+    else k_eps_sig_ifv<MAT, false, false><<<sg.ncta, TPB, 0, st>>>(a);
+  }
+}
+
+int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  const w3d_engine_config &c = h->cfg;
+  CUDA_TRY(cudaMemsetAsync(h->d_ifv, 0, sizeof(double) * c.nodof, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->stream));
+  int first = 1;
+  for (auto &sg : h->segs) {
+    StressArgs a{};
+    a.cta = sg.d_cta; a.edest = sg.d_edest; a.cdest = sg.d_cdest; a.eprops = sg.d_eprops;
+    a.c = h->d_c; a.u = h->d_u; a.du = h->d_du; a.ifv = h->d_ifv;
+    a.eps_n = sg.eps_n; a.urcs_n = sg.urcs_n; a.hist_n = sg.hist_n;
+    a.eps_n1 = sg.eps_n1; a.urcs_n1 = sg.urcs_n1; a.rot_n1 = sg.rot_n1; a.hist_n1 = sg.hist_n1;
+    a.cep = sg.cep; a.elem_vol = sg.elem_vol; a.partials = sg.partials; a.flags = h->d_flags;
+    a.ng = sg.ng; a.eps_bbar = c.eps_bbar; a.beta_fact = c.beta_fact;
+    a.step = step; a.iter = iter;
+    a.nonlinear_update = (iter >= 1 || extrapolated_du) ? 1 : 0;
+    a.update_coords = (sg.geonl && !(step == 1 && iter == 0)) ? 1 : 0;
+    a.adaptive = (c.adaptive_flag && step > 1) ? 1 : 0;
+    a.hist_size = sg.hist_size;
+    launch_stress<1>(sg, a, h->stream);
+    k_reduce_partials<<<1, 256, 0, h->stream>>>(sg.partials, sg.ncta, h->d_scal, first ? 0 : 1);
+    h->launches += 2;
+    first = 0;
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->have_vectors = true;
+  return W3D_OK;
+}
+
+int fetch_scalars(w3d_engine *h, w3d_scalars *out) {
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  CUDA_TRY(cudaMemcpyAsync(h->h_pin, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->h_pin + 4, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  int flags[2];
+  std::memcpy(flags, h->h_pin + 4, sizeof flags);
+  w3d_scalars s{};
+  s.material_cut_step = flags[0] ? 1 : 0;
+  if (!s.material_cut_step) {
+    s.internal_energy = h->h_pin[0];
+    s.plastic_work = h->h_pin[1];
+    s.sum_ifv = h->h_pin[2];
+    s.num_term_ifv = 24 * (int64_t)h->n_owned_elems;
+  }
+  h->last = s;
+  if (out) *out = s;
+  if (flags[1] == W3D_ERR_MM01_LAMBDA) return fail(W3D_ERR_MM01_LAMBDA, "mm01_general: lambda_deltat is negative (mm01.f:878)");
+  if (flags[1] == W3D_ERR_DETF) return fail(W3D_ERR_DETF, "det F <= 0 and the step is not adaptive (rstgp1.f:136-145)");
+  if (flags[1]) return fail(flags[1], "device-side fatal condition %d", flags[1]);
+  return W3D_OK;
+}
+
+int tanstf_resident(w3d_engine *h, int step, int iter) {
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  (void)step; (void)iter;
+  const w3d_engine_config &c = h->cfg;
+  for (auto &sg : h->segs) {
+    TanstfArgs a{};
+    a.cta = sg.d_cta; a.edest = sg.d_edest; a.cdest = sg.d_cdest;
+    a.c = h->d_c; a.u = h->d_u; a.du = h->d_du;
+    a.urcs_n1 = sg.urcs_n1; a.rot_n1 = sg.rot_n1; a.cep = sg.cep;
+    a.estiff = h->d_estiff; a.ng = sg.ng; a.eps_bbar = c.eps_bbar; a.beta_fact = c.beta_fact;
+    a.qbar = c.qbar_flag ? 1 : 0;
+    const size_t shm = (size_t)EPC * ELREC * 8;
+    if (sg.geonl) {
+      if (sg.bbar) k_tanstf<true, true><<<sg.ncta, TPB, shm, h->stream>>>(a);
+      else k_tanstf<true, false><<<sg.ncta, TPB, shm, h->stream>>>(a);
+    } else {
+      if (sg.bbar) k_tanstf<false, true><<<sg.ncta, TPB, shm, h->stream>>>(a);
+      else k_tanstf<false, false><<<sg.ncta, TPB, shm, h->stream>>>(a);
+    }
+    h->launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return W3D_OK;
+}
+
+int copy_state(w3d_engine *h, int from, int to) {
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  for (auto &sg : h->segs) {
+    const double *src = soa_of(sg, from);
+    double *dst = soa_of(sg, to);
+    const size_t n = (size_t)nprm_of(h, from, h->blocks[sg.blocks[0]]) * (size_t)sg.ng;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return W3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t w3d_engine_create(const w3d_engine_config *cfg, w3d_engine **handle) {
+  if (!cfg || !handle) { g_create_error = "null argument"; return W3D_ERR_ARG; }
+  *handle = nullptr;
+  w3d_engine *h = new w3d_engine();
+  h->cfg = *cfg;
+  const int rc = create_impl(h);
+  if (rc != W3D_OK) {
+    g_create_error = h->err;
+    free_all(h);
+    delete h;
+    return rc;
+  }
+  // the engine keeps no pointer into caller memory after create
+  h->cfg.elblks = nullptr; h->cfg.props = nullptr; h->cfg.matprp = nullptr; h->cfg.c = nullptr;
+  h->cfg.edest = nullptr; h->cfg.cdest = nullptr; h->cfg.history_blk_list = nullptr;
+  *handle = h;
+  return W3D_OK;
+}
+
+int32_t w3d_engine_destroy(w3d_engine *h) {
+  if (!h) return W3D_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_all(h);
+  delete h;
+  return W3D_OK;
+}
+
+const char *w3d_engine_last_error(const w3d_engine *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t w3d_eps_sig_ifv(w3d_engine *h, int32_t step, int32_t iter, int32_t extrapolated_du,
+                        const double *u, const double *du, double *ifv, w3d_scalars *out) {
+  if (!h || !u || !du || !ifv) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t nb = sizeof(double) * h->cfg.nodof;
+  CUDA_TRY(cudaMemcpyAsync(h->d_u, u, nb, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_du, du, nb, cudaMemcpyHostToDevice, h->stream));
+  int rc = stress_resident(h, step, iter, extrapolated_du);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ifv, h->d_ifv, nb, cudaMemcpyDeviceToHost, h->stream));
+  w3d_scalars s;
+  rc = fetch_scalars(h, &s);
+  if (s.material_cut_step) std::memset(ifv, 0, nb);   // :253-263
+  if (out) *out = s;
+  return rc;
+}
+
+int32_t w3d_tanstf(w3d_engine *h, int32_t step, int32_t iter, const double *u, const double *du,
+                   double *estiff) {
+  if (!h) return W3D_ERR_ARG;
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t nb = sizeof(double) * h->cfg.nodof;
+  if (u && du) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_u, u, nb, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_du, du, nb, cudaMemcpyHostToDevice, h->stream));
+    h->have_vectors = true;
+  } else if (!h->have_vectors) {
+    return fail(W3D_ERR_ARG, "w3d_tanstf: u/du are NULL and no displacement vectors are resident");
+  }
+  const int rc = tanstf_resident(h, step, iter);
+  if (rc) return rc;
+  if (estiff)
+    CUDA_TRY(cudaMemcpyAsync(estiff, h->d_estiff, sizeof(double) * 300 * (size_t)h->n_owned_elems, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return W3D_OK;
+}
+
+int32_t w3d_update(w3d_engine *h) {
+  if (!h) return W3D_ERR_ARG;
+  cudaSetDevice(h->device);
+  int rc = copy_state(h, W3D_HIST_N1, W3D_HIST_N);
+  if (!rc) rc = copy_state(h, W3D_EPS_N1, W3D_EPS_N);
+  if (!rc) rc = copy_state(h, W3D_URCS_N1, W3D_URCS_N);
+  return rc;
+}
+int32_t w3d_adaptive_save(w3d_engine *h) {
+  if (!h) return W3D_ERR_ARG;
+  cudaSetDevice(h->device);
+  return copy_state(h, W3D_ROT_N1, W3D_ROT_N);
+}
+int32_t w3d_adaptive_reset(w3d_engine *h) {
+  if (!h) return W3D_ERR_ARG;
+  cudaSetDevice(h->device);
+  int rc = copy_state(h, W3D_HIST_N, W3D_HIST_N1);
+  if (!rc) rc = copy_state(h, W3D_ROT_N, W3D_ROT_N1);
+  if (!rc) rc = copy_state(h, W3D_EPS_N, W3D_EPS_N1);
+  if (!rc) rc = copy_state(h, W3D_URCS_N, W3D_URCS_N1);
+  return rc;
+}
+
+static int state_xfer(w3d_engine *h, int which, int blk1, double *host, bool push) {
+  if (!h || !host) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  if (blk1 < 1 || blk1 > (int)h->blocks.size()) return fail(W3D_ERR_ARG, "block %d out of range", blk1);
+  const BlockInfo &b = h->blocks[blk1 - 1];
+  if (!b.owned) return fail(W3D_ERR_ARG, "block %d is not owned by this engine (domain %d)", blk1, b.domain);
+  const long long n = block_doubles(which, b);
+  if (n < 0) return fail(W3D_ERR_ARG, "unknown state selector %d", which);
+  if (n == 0) return W3D_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  Segment &sg = h->segs[b.seg];
+  const auto kind = push ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  if (which == W3D_ESTIFF || which == W3D_ELEM_VOL) {
+    double *dev = (which == W3D_ESTIFF) ? h->d_estiff + (size_t)b.epos0 * 300 : sg.elem_vol + b.slot0;
+    if (push) CUDA_TRY(cudaMemcpyAsync(dev, host, n * sizeof(double), kind, h->stream));
+    else CUDA_TRY(cudaMemcpyAsync(host, dev, n * sizeof(double), kind, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return W3D_OK;
+  }
+  double *soa = soa_of(sg, which);
+  const int nprm = nprm_of(h, which, b);
+  const int grid = (int)((n + 255) / 256);
+  if (push) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_stage, host, n * sizeof(double), kind, h->stream));
+    k_block_to_soa<<<grid, 256, 0, h->stream>>>(h->d_stage, soa, sg.ng, b.slot0, b.span, nprm, which == W3D_CEP);
+  } else {
+    k_soa_to_block<<<grid, 256, 0, h->stream>>>(h->d_stage, soa, sg.ng, b.slot0, b.span, nprm, which == W3D_CEP);
+    CUDA_TRY(cudaMemcpyAsync(host, h->d_stage, n * sizeof(double), kind, h->stream));
+  }
+  h->launches += 1;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaGetLastError());
+  return W3D_OK;
+}
+
+int32_t w3d_push_state(w3d_engine *h, int32_t which, int32_t blk, const double *src) {
+  return state_xfer(h, which, blk, const_cast<double *>(src), true);
+}
+int32_t w3d_pull_state(w3d_engine *h, int32_t which, int32_t blk, double *dst) {
+  return state_xfer(h, which, blk, dst, false);
+}
+
+int64_t w3d_block_offset(const w3d_engine *h, int32_t which, int32_t blk) {
+  if (!h || blk < 1 || blk > (int)h->blocks.size() + 1) return -1;
+  int64_t off = 0;
+  for (int k = 0; k < blk - 1; ++k) {
+    if (!h->blocks[k].owned) continue;
+    const long long n = block_doubles(which, h->blocks[k]);
+    if (n < 0) return -1;
+    off += n;
+  }
+  return off;
+}
+
+int32_t w3d_device_vectors(w3d_engine *h, double **d_u, double **d_du, double **d_ifv) {
+  if (!h) return W3D_ERR_ARG;
+  if (d_u) *d_u = h->d_u;
+  if (d_du) *d_du = h->d_du;
+  if (d_ifv) *d_ifv = h->d_ifv;
+  h->have_vectors = true;
+  return W3D_OK;
+}
+int32_t w3d_eps_sig_ifv_resident(w3d_engine *h, int32_t step, int32_t iter, int32_t extrapolated_du) {
+  if (!h) return W3D_ERR_ARG;
+  cudaSetDevice(h->device);
+  return stress_resident(h, step, iter, extrapolated_du);
+}
+int32_t w3d_tanstf_resident(w3d_engine *h, int32_t step, int32_t iter) {
+  if (!h) return W3D_ERR_ARG;
+  cudaSetDevice(h->device);
+  return tanstf_resident(h, step, iter);
+}
+int32_t w3d_last_scalars(w3d_engine *h, w3d_scalars *out) {
+  if (!h) return W3D_ERR_ARG;
+  cudaSetDevice(h->device);
+  return fetch_scalars(h, out);
+}
+void *w3d_engine_stream(w3d_engine *h) { return h ? (void *)h->stream : nullptr; }
+int32_t w3d_engine_synchronize(w3d_engine *h) {
+  if (!h) return W3D_ERR_ARG;
+  cudaSetDevice(h->device);
+  return cudaStreamSynchronize(h->stream) == cudaSuccess ? W3D_OK : h->fail(W3D_ERR_CUDA, "stream synchronize failed");
+}
+int64_t w3d_engine_launch_count(const w3d_engine *h) { return h ? h->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,412 @@
+// w3d_stress_kernel.cuh -- fused strain recovery / material update / internal force kernel.
+//
+// One launch replaces, for every owned hex8 block of one segment (same material model, geonl and
+// B-bar flags), the reference chain
+//   dupstr (dupstr.f:82-88) + dupstr_blocked (drive_eps_sig_internal_forces.f:1699-1754)
+//   rknstr_geonl / rknstr_sm_displ (rknstr.f:455-614) with vol_terms/vol_avg
+//   rstgp1 / rstgp2 (rstgp1.f:19-598): gtmat1, gtlsn1, qmply1, rstgp1_update_strains
+//   drive_01_update (rstgp1.f:614-984): mm01 + cnst1 + rstgp1_store_cep, or linear-elastic iter 0
+//   rstgp1_b energy integration (rstgp1.f:5189-5241)
+//   rplstr (rplstr.f:15-93)
+//   rknifv_std + gpifv1 (rknifv.f:141-215, gpifv1.f:16-165)
+//   addifv_standard (addifv.f:86-113)
+// Thread = (element, Gauss point).  HBM traffic per Gauss point: read eps_n 48 + urcs_n 72 +
+// hist_n 88, write eps_n1 48 + urcs_n1 72 + rot_n1 72 + hist_n1 88 + cep 168 (B), plus the
+// element's index maps / coordinates / displacements and 24 force atomics.
+#pragma once
+#include "w3d_device.cuh"
+#include "w3d_mm01.cuh"
+
+namespace w3d {
+
+struct StressArgs {
+  const CtaDesc *cta;
+  const int32_t *edest, *cdest;   // [slot][24], 1-based
+  const float *eprops;            // [slot][EPROP]: e, nu, beta, hprime, yld, lnelas
+  const double *c, *u, *du;       // (nodof)
+  double *ifv;                    // (nodof), atomically accumulated
+  const double *eps_n, *urcs_n, *hist_n;
+  double *eps_n1, *urcs_n1, *rot_n1, *hist_n1, *cep, *elem_vol;
+  double *partials;               // [ncta][4]: internal energy, plastic work, sum |f|, -
+  int *flags;                     // [0] material_cut_step, [1] fatal code
+  long long ng;                   // component stride of the state arrays (Gauss-point slots)
+  double eps_bbar, beta_fact;
+  int step, iter;
+  int nonlinear_update;           // iter >= 1 or extrapolated_du (rstgp1.f:835)
+  int update_coords;              // geonl and not (step 1, iter 0)  (:1722-1754)
+  int adaptive;                   // adaptive_flag and step > 1 (rstgp1.f:136-145)
+  int hist_size;
+};
+
+// parent-space shape function derivatives of the 8 Gauss points: [dir][node][gp], filled by the
+// host with the reference's quad2 / deriv2 tables (getgpts.f:642-718, derivs.f:283-343)
+__constant__ double c_shape[3][8][8];
+
+template <int MAT, bool GEONL, bool BBAR>
+__global__ void __launch_bounds__(TPB) k_eps_sig_ifv(const StressArgs a) {
+  __shared__ double sN[3][8][8];
+  __shared__ double sC[EPC][24], sU[EPC][24], sDU[EPC][24];
+  __shared__ double sRed[TPB / 32][3];
+
+  const int tid = threadIdx.x;
+  for (int k = tid; k < 192; k += TPB) (&sN[0][0][0])[k] = (&c_shape[0][0][0])[k];
+
+  const CtaDesc cd = a.cta[blockIdx.x];
+  const int el = tid >> 3, gp = tid & 7;
+  const bool valid = el < cd.nvalid;
+  const int slot = cd.slot0 + (valid ? el : cd.nvalid - 1);
+  const long long g = (long long)slot * 8 + gp;
+  const long long ng = a.ng;
+
+  // ---- gather: lane gp fetches node gp of its element (dofs node, 8+node, 16+node)
+  int dofs[3];
+  {
+    const int32_t *ed = a.edest + (size_t)slot * 24;
+    const int32_t *cdst = a.cdest + (size_t)slot * 24;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int d = ed[k * 8 + gp] - 1;
+      dofs[k] = d;
+      sU[el][k * 8 + gp] = a.u[d];
+      sDU[el][k * 8 + gp] = a.du[d];
+      sC[el][k * 8 + gp] = a.c[cdst[k * 8 + gp] - 1];
+    }
+  }
+  __syncthreads();
+
+  double nx[8], ne[8], nz[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { nx[j] = sN[0][j][gp]; ne[j] = sN[1][j][gp]; nz[j] = sN[2][j][gp]; }
+
+  const double *C = sC[el], *U = sU[el], *DU = sDU[el];
+  const double beta_b = (1.0 - a.eps_bbar) * (1.0 / 3.0);   // bmod.f: beta = (1-eps)/3
+  const double weight = 1.0;                                 // quad2: w = 1
+
+  bool error = false;
+  double R1[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  double dfn1 = 1.0, dj0;
+  double uddt[6];
+
+  if (GEONL) {
+    // ---- gtmat1 (gtmat1.f:17-190): F at n+1 and n+1/2 from the undeformed configuration
+    double X[8], Y[8], Z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { X[j] = C[j]; Y[j] = C[8 + j]; Z[j] = C[16 + j]; }
+    double G0[3][3];
+    jacobian<true>(nx, ne, nz, X, Y, Z, G0, dj0);
+    double t1[9], th[9];   // theta at n+1, n+1/2 (tcomp1, gtmat1.f:522-584)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { t1[k] = 0.0; th[k] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double tx = xa(xa(xm(G0[0][0], nx[j]), xm(G0[0][1], ne[j])), xm(G0[0][2], nz[j]));
+      const double ty = xa(xa(xm(G0[1][0], nx[j]), xm(G0[1][1], ne[j])), xm(G0[1][2], nz[j]));
+      const double tz = xa(xa(xm(G0[2][0], nx[j]), xm(G0[2][1], ne[j])), xm(G0[2][2], nz[j]));
+      const double u0 = U[j], v0 = U[8 + j], w0 = U[16 + j];
+      const double du = DU[j], dv = DU[8 + j], dw = DU[16 + j];
+      const double u1 = xa(u0, du), v1 = xa(v0, dv), w1 = xa(w0, dw);          // uen1
+      const double uh = xa(u0, xm(0.5, du)), vh = xa(v0, xm(0.5, dv)), wh = xa(w0, xm(0.5, dw));
+      t1[0] = xa(t1[0], xm(tx, u1)); t1[1] = xa(t1[1], xm(tx, v1)); t1[2] = xa(t1[2], xm(tx, w1));
+      t1[3] = xa(t1[3], xm(ty, u1)); t1[4] = xa(t1[4], xm(ty, v1)); t1[5] = xa(t1[5], xm(ty, w1));
+      t1[6] = xa(t1[6], xm(tz, u1)); t1[7] = xa(t1[7], xm(tz, v1)); t1[8] = xa(t1[8], xm(tz, w1));
+      th[0] = xa(th[0], xm(tx, uh)); th[1] = xa(th[1], xm(tx, vh)); th[2] = xa(th[2], xm(tx, wh));
+      th[3] = xa(th[3], xm(ty, uh)); th[4] = xa(th[4], xm(ty, vh)); th[5] = xa(th[5], xm(ty, wh));
+      th[6] = xa(th[6], xm(tz, uh)); th[7] = xa(th[7], xm(tz, vh)); th[8] = xa(th[8], xm(tz, wh));
+    }
+    // fcomp1 (gtmat1.f:601-674)
+    double F1[3][3], Fh[3][3];
+    F1[0][0] = xa(t1[0], 1.0); F1[0][1] = t1[3]; F1[0][2] = t1[6];
+    F1[1][0] = t1[1]; F1[1][1] = xa(t1[4], 1.0); F1[1][2] = t1[7];
+    F1[2][0] = t1[2]; F1[2][1] = t1[5]; F1[2][2] = xa(t1[8], 1.0);
+    Fh[0][0] = xa(th[0], 1.0); Fh[0][1] = th[3]; Fh[0][2] = th[6];
+    Fh[1][0] = th[1]; Fh[1][1] = xa(th[4], 1.0); Fh[1][2] = th[7];
+    Fh[2][0] = th[2]; Fh[2][1] = th[5]; Fh[2][2] = xa(th[8], 1.0);
+    {
+      const double f1 = xs(xm(F1[1][1], F1[2][2]), xm(F1[1][2], F1[2][1]));
+      const double f2 = xs(xm(F1[1][0], F1[2][2]), xm(F1[1][2], F1[2][0]));
+      const double f3 = xs(xm(F1[1][0], F1[2][1]), xm(F1[1][1], F1[2][0]));
+      dfn1 = xa(xs(xm(F1[0][0], f1), xm(F1[0][1], f2)), xm(F1[0][2], f3));
+      const double h1 = xs(xm(Fh[1][1], Fh[2][2]), xm(Fh[1][2], Fh[2][1]));
+      const double h2 = xs(xm(Fh[1][0], Fh[2][2]), xm(Fh[1][2], Fh[2][0]));
+      const double h3 = xs(xm(Fh[1][0], Fh[2][1]), xm(Fh[1][1], Fh[2][0]));
+      const double dfh = xa(xs(xm(Fh[0][0], h1), xm(Fh[0][1], h2)), xm(Fh[0][2], h3));
+      error = !(dfn1 > 1.0e-20) || !(dfh > 1.0e-20);
+    }
+    double Rh[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (!error) {
+      polar_rotation(F1, R1);
+      polar_rotation(Fh, Rh);
+    }
+    // ---- strain increment on the mid-step configuration (rknstr_geonl, gtlsn1)
+    if (a.update_coords) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        X[j] = (C[j] + U[j]) + 0.5 * DU[j];
+        Y[j] = (C[8 + j] + U[8 + j]) + 0.5 * DU[8 + j];
+        Z[j] = (C[16 + j] + U[16 + j]) + 0.5 * DU[16 + j];
+      }
+    }
+    double Gm[3][3], djm;
+    jacobian<false>(nx, ne, nz, X, Y, Z, Gm, djm);
+    double ddt[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double bx = Gm[0][0] * nx[j] + Gm[0][1] * ne[j] + Gm[0][2] * nz[j];
+      const double by = Gm[1][0] * nx[j] + Gm[1][1] * ne[j] + Gm[1][2] * nz[j];
+      const double bz = Gm[2][0] * nx[j] + Gm[2][1] * ne[j] + Gm[2][2] * nz[j];
+      const double du = DU[j], dv = DU[8 + j], dw = DU[16 + j];
+      ddt[0] = fma(bx, du, ddt[0]);
+      ddt[1] = fma(by, dv, ddt[1]);
+      ddt[2] = fma(bz, dw, ddt[2]);
+      ddt[3] += by * du + bx * dv;
+      ddt[4] += bz * dv + by * dw;
+      ddt[5] += bz * du + bx * dw;
+    }
+    if (BBAR) {
+      // mean-dilatation B-bar (vol_terms / vol_avg / bmod): eps_kk -> eps_kk + beta (thbar - th)
+      const double thgp = ddt[0] + ddt[1] + ddt[2];
+      const double vol = sum8(djm);
+      const double thbar = sum8(djm * thgp) / vol;
+      const double corr = beta_b * (thbar - thgp);
+      ddt[0] += corr; ddt[1] += corr; ddt[2] += corr;
+    }
+    double q[6][6];
+    getrm1_opt1(Rh, q);
+    qmply(q, ddt, uddt);
+  } else {
+    // ---- rknstr_sm_displ + rstgp2: B on the undeformed configuration
+    double X[8], Y[8], Z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { X[j] = C[j]; Y[j] = C[8 + j]; Z[j] = C[16 + j]; }
+    double G0[3][3];
+    jacobian<false>(nx, ne, nz, X, Y, Z, G0, dj0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) uddt[k] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double bx = G0[0][0] * nx[j] + G0[0][1] * ne[j] + G0[0][2] * nz[j];
+      const double by = G0[1][0] * nx[j] + G0[1][1] * ne[j] + G0[1][2] * nz[j];
+      const double bz = G0[2][0] * nx[j] + G0[2][1] * ne[j] + G0[2][2] * nz[j];
+      const double du = DU[j], dv = DU[8 + j], dw = DU[16 + j];
+      uddt[0] = fma(bx, du, uddt[0]);
+      uddt[1] = fma(by, dv, uddt[1]);
+      uddt[2] = fma(bz, dw, uddt[2]);
+      uddt[3] += by * du + bx * dv;
+      uddt[4] += bz * dv + by * dw;
+      uddt[5] += bz * du + bx * dw;
+    }
+    if (BBAR) {
+      const double thgp = uddt[0] + uddt[1] + uddt[2];
+      const double vol = sum8(dj0);
+      const double thbar = sum8(dj0 * thgp) / vol;
+      const double corr = beta_b * (thbar - thgp);
+      uddt[0] += corr; uddt[1] += corr; uddt[2] += corr;
+    }
+  }
+
+  // ---- rstgp1_update_strains (rstgp1.f:4983-5005): total strain at n+1
+  double eps1[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) eps1[k] = a.eps_n[k * ng + g] + uddt[k];
+
+  // ---- material update
+  double cgn[9], cgn1[9], cep[21];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cgn[k] = a.urcs_n[k * ng + g];
+  int fatal = 0;
+  double h1[11];
+  if (MAT == 1) {
+    const float *ep = a.eprops + (size_t)slot * EPROP;
+    Mm01Props pr;
+    pr.e = (double)ep[0]; pr.nu = (double)ep[1]; pr.beta = (double)ep[2];
+    pr.hprime = (double)ep[3]; pr.yld = (double)ep[4]; pr.lnelas = ep[5] != 0.0f;
+    if (a.nonlinear_update) {
+      double h[11], rtse[6];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) h[k] = a.hist_n[k * ng + g];
+      double h11_first = h[10];
+      if (1.0 - pr.beta != 0.0) h11_first = a.hist_n[10 * ng + (long long)cd.blk_slot0 * 8 + gp];
+      fatal = mm01_update(a.step, pr, cgn, cgn1, uddt, h, h1, rtse, h11_first);
+      cnst1_cep21(pr, rtse, h1, cep);
+    } else {
+      // drive_01_update_a/_b: linear-elastic [D] and stress for iteration 0
+      elastic_cep21(pr.e, pr.nu, cep);
+      const double c2 = cep[0], c4 = cep[1], c3 = cep[9];
+      cgn1[0] = cgn[0] + (c2 * uddt[0] + c4 * uddt[1] + c4 * uddt[2]);
+      cgn1[1] = cgn[1] + (c4 * uddt[0] + c2 * uddt[1] + c4 * uddt[2]);
+      cgn1[2] = cgn[2] + (c4 * uddt[0] + c4 * uddt[1] + c2 * uddt[2]);
+      cgn1[3] = cgn[3] + c3 * uddt[3];
+      cgn1[4] = cgn[4] + c3 * uddt[4];
+      cgn1[5] = cgn[5] + c3 * uddt[5];
+      cgn1[6] = 0.0; cgn1[7] = 0.0; cgn1[8] = 0.0;   // local urcs_blk_n1 is zero-initialised
+    }
+  }
+
+  // a Gauss point with det F <= 0 asks for a step cut; its state is not written
+  const bool store = valid && !error;
+  if (error && valid) {
+    atomicOr(&a.flags[0], 1);
+    if (!a.adaptive) atomicMax(&a.flags[1], 6);
+  }
+  if (fatal && store) atomicMax(&a.flags[1], fatal);
+
+  // ---- rplstr (rplstr.f:15-93) + rstgp1_store_cep
+  if (store) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.urcs_n1[k * ng + g] = cgn1[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a.eps_n1[k * ng + g] = eps1[k];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) a.cep[k * ng + g] = cep[k];
+    if (a.iter > 0) {
+      if (GEONL) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) a.rot_n1[(c * 3 + r) * ng + g] = R1[r][c];
+      }
+      if (MAT == 1 && a.nonlinear_update) {
+#pragma unroll
+        for (int k = 0; k < 11; ++k) a.hist_n1[k * ng + g] = h1[k];
+      }
+    }
+  }
+
+  // ---- rstgp1_b: energy integration over the undeformed volume
+  double en = 0.0, pw = 0.0;
+  if (a.iter != 0 && store) {
+    const double factor = (GEONL ? dfn1 * dj0 : dj0) * a.beta_fact * weight;
+    en = cgn1[6] * factor;
+    pw = cgn1[7] * factor;
+  }
+
+  // ---- internal force on the n+1 configuration (rknifv_std, gpifv1)
+  double sig[6];
+  if (GEONL) {
+    double q[6][6];
+    getrm1_opt2(R1, q);
+    const double t6[6] = {cgn1[0], cgn1[1], cgn1[2], cgn1[3], cgn1[4], cgn1[5]};
+    qmply(q, t6, sig);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sig[k] = cgn1[k];
+  }
+  if (error) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sig[k] = 0.0;
+  }
+  double G1[3][3], dj1;
+  {
+    double X[8], Y[8], Z[8];
+    if (GEONL && a.update_coords) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        X[j] = (C[j] + U[j]) + DU[j];
+        Y[j] = (C[8 + j] + U[8 + j]) + DU[8 + j];
+        Z[j] = (C[16 + j] + U[16 + j]) + DU[16 + j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { X[j] = C[j]; Y[j] = C[8 + j]; Z[j] = C[16 + j]; }
+    }
+    jacobian<false>(nx, ne, nz, X, Y, Z, G1, dj1);
+  }
+  const double wdj = weight * dj1;
+  double evol = sum8(wdj);
+  double s[6];
+  if (BBAR) {
+    // B-bar^T sigma = B^T (sigma - beta p m) + beta (P/V) sum_gp B_vol^T : fold the mean
+    // dilatation part into a modified stress so no nodal volume terms are exchanged
+    const double p = sig[0] + sig[1] + sig[2];
+    const double pbar = sum8(p * wdj) / sum8(dj1);
+    const double add = beta_b * (pbar * dj1 - p * wdj);
+    s[0] = sig[0] * wdj + add; s[1] = sig[1] * wdj + add; s[2] = sig[2] * wdj + add;
+  } else {
+    s[0] = sig[0] * wdj; s[1] = sig[1] * wdj; s[2] = sig[2] * wdj;
+  }
+  s[3] = sig[3] * wdj; s[4] = sig[4] * wdj; s[5] = sig[5] * wdj;
+
+  double f[24];   // [node*3 + comp]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double bx = G1[0][0] * nx[j] + G1[0][1] * ne[j] + G1[0][2] * nz[j];
+    const double by = G1[1][0] * nx[j] + G1[1][1] * ne[j] + G1[1][2] * nz[j];
+    const double bz = G1[2][0] * nx[j] + G1[2][1] * ne[j] + G1[2][2] * nz[j];
+    f[j * 3 + 0] = bx * s[0] + by * s[3] + bz * s[5];
+    f[j * 3 + 1] = by * s[1] + bx * s[3] + bz * s[4];
+    f[j * 3 + 2] = bz * s[2] + by * s[4] + bx * s[5];
+  }
+  // reduce-scatter over the 8 Gauss-point lanes: lane n ends with node n's 3 force components
+  {
+    const bool hi4 = (gp & 4) != 0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const double send = hi4 ? f[k] : f[12 + k];
+      const double keep = hi4 ? f[12 + k] : f[k];
+      f[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const bool hi2 = (gp & 2) != 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double send = hi2 ? f[k] : f[6 + k];
+      const double keep = hi2 ? f[6 + k] : f[k];
+      f[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const bool hi1 = (gp & 1) != 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double send = hi1 ? f[k] : f[3 + k];
+      const double keep = hi1 ? f[3 + k] : f[k];
+      f[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+  }
+  // ---- addifv_standard: scatter with FP64 reductions at L2, sum |f| for the convergence test
+  double sabs = 0.0;
+  if (valid) {
+    sabs = fabs(f[0]) + fabs(f[1]) + fabs(f[2]);
+    const double bf = a.beta_fact;
+    atomicAdd(&a.ifv[dofs[0]], bf * f[0]);
+    atomicAdd(&a.ifv[dofs[1]], bf * f[1]);
+    atomicAdd(&a.ifv[dofs[2]], bf * f[2]);
+    if (gp == 0) a.elem_vol[slot] = evol;
+  }
+
+  // ---- per-CTA partial sums, reduced in a fixed order by k_reduce_partials
+  en = warp_sum(en); pw = warp_sum(pw); sabs = warp_sum(sabs);
+  if ((tid & 31) == 0) { sRed[tid >> 5][0] = en; sRed[tid >> 5][1] = pw; sRed[tid >> 5][2] = sabs; }
+  __syncthreads();
+  if (tid < 3) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < TPB / 32; ++w) v += sRed[w][tid];
+    a.partials[(size_t)blockIdx.x * 4 + tid] = v;
+  }
+}
+
+// deterministic final reduction of the per-CTA partials: one CTA, fixed tree
+__global__ void __launch_bounds__(256) k_reduce_partials(const double *partials, int ncta,
+                                                         double *out /*[4]*/, int accumulate) {
+  __shared__ double s[3][256];
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  for (int i = threadIdx.x; i < ncta; i += 256) {
+    v0 += partials[(size_t)i * 4 + 0];
+    v1 += partials[(size_t)i * 4 + 1];
+    v2 += partials[(size_t)i * 4 + 2];
+  }
+  s[0][threadIdx.x] = v0; s[1][threadIdx.x] = v1; s[2][threadIdx.x] = v2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s[0][threadIdx.x] += s[0][threadIdx.x + o];
+      s[1][threadIdx.x] += s[1][threadIdx.x + o];
+      s[2][threadIdx.x] += s[2][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) {
+    const double r = s[threadIdx.x][0];
+    out[threadIdx.x] = accumulate ? out[threadIdx.x] + r : r;
+  }
+}
+
+}  // namespace w3d

@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's block drivers, bound to the C ABI in include/w3d_engine.h.
+
+The method names follow the reference subroutines they stand in for
+(``drive_eps_sig_internal_forces`` src/drive_eps_sig_internal_forces.f:20, ``tanstf``
+src/tanstf.f:17, ``update`` src/update.f:75-93, ``adaptive_save`` / ``adaptive_reset``
+src/mnralg.f:1258-1420).  Everything numerical happens in ``libw3d_engine.so`` (hand-written
+sm_100a CUDA); this module only marshals the reference-layout arrays through ctypes exactly as a
+Fortran ISO_C_BINDING caller would.  There is no CPU fallback: a missing library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .model import MXELPR, MXMTPR, MXVL, Model, State
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libw3d_engine.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+ABI_VERSION = 1
+(HIST_N, HIST_N1, EPS_N, EPS_N1, URCS_N, URCS_N1, ROT_N, ROT_N1, CEP, ESTIFF, ELEM_VOL) = range(11)
+_STATE_WHICH = dict(history=HIST_N, history1=HIST_N1, eps_n=EPS_N, eps_n1=EPS_N1, urcs_n=URCS_N,
+                    urcs_n1=URCS_N1, rot_n=ROT_N, rot_n1=ROT_N1, cep=CEP, estiff=ESTIFF,
+                    element_vol=ELEM_VOL)
+
+EXPORTS = (
+    "w3d_engine_create", "w3d_engine_destroy", "w3d_engine_last_error", "w3d_eps_sig_ifv",
+    "w3d_tanstf", "w3d_update", "w3d_adaptive_save", "w3d_adaptive_reset", "w3d_push_state",
+    "w3d_pull_state", "w3d_block_offset", "w3d_device_vectors", "w3d_eps_sig_ifv_resident",
+    "w3d_tanstf_resident", "w3d_last_scalars", "w3d_engine_stream", "w3d_engine_synchronize",
+    "w3d_engine_launch_count",
+)
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"w3d_engine error {code}: {msg}")
+        self.code = code
+
+
+class _Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("mxvl", C.c_int32), ("mxelpr", C.c_int32),
+        ("mxmtpr", C.c_int32), ("nelblk", C.c_int32), ("noelem", C.c_int32),
+        ("nonode", C.c_int32), ("nodof", C.c_int32), ("myid", C.c_int32),
+        ("numprocs", C.c_int32), ("elblks", C.c_void_p), ("props", C.c_void_p),
+        ("matprp", C.c_void_p), ("nmat", C.c_int32), ("c", C.c_void_p), ("edest", C.c_void_p),
+        ("cdest", C.c_void_p), ("history_blk_list", C.c_void_p), ("eps_bbar", C.c_double),
+        ("qbar_flag", C.c_int32), ("beta_fact", C.c_double), ("adaptive_flag", C.c_int32),
+        ("device", C.c_int32),
+    ]
+
+
+class _Scalars(C.Structure):
+    _fields_ = [("internal_energy", C.c_double), ("plastic_work", C.c_double),
+                ("sum_ifv", C.c_double), ("num_term_ifv", C.c_int64),
+                ("material_cut_step", C.c_int32), ("reserved", C.c_int32)]
+
+
+def build(force=False, verbose=False):
+    """Compile libw3d_engine.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "w3d_engine.h"))
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return LIB_PATH
+    r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError("building libw3d_engine.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the engine library; raise (never fall back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(-1, f"{LIB_PATH} is missing: run __graft_entry__.build() "
+                                  "(there is no CPU fallback for this path)")
+        L = C.CDLL(LIB_PATH)
+        L.w3d_engine_last_error.restype = C.c_char_p
+        L.w3d_engine_last_error.argtypes = [C.c_void_p]
+        L.w3d_block_offset.restype = C.c_int64
+        L.w3d_block_offset.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.w3d_engine_launch_count.restype = C.c_int64
+        L.w3d_engine_launch_count.argtypes = [C.c_void_p]
+        L.w3d_engine_stream.restype = C.c_void_p
+        L.w3d_engine_stream.argtypes = [C.c_void_p]
+        for name in ("w3d_engine_create", "w3d_engine_destroy", "w3d_eps_sig_ifv", "w3d_tanstf",
+                     "w3d_update", "w3d_adaptive_save", "w3d_adaptive_reset", "w3d_push_state",
+                     "w3d_pull_state", "w3d_device_vectors", "w3d_eps_sig_ifv_resident",
+                     "w3d_tanstf_resident", "w3d_last_scalars", "w3d_engine_synchronize"):
+            getattr(L, name).restype = C.c_int32
+        L.w3d_engine_create.argtypes = [C.c_void_p, C.c_void_p]
+        L.w3d_engine_destroy.argtypes = [C.c_void_p]
+        L.w3d_eps_sig_ifv.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
+        L.w3d_tanstf.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]
+        for name in ("w3d_update", "w3d_adaptive_save", "w3d_adaptive_reset",
+                     "w3d_engine_synchronize"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.w3d_push_state.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.w3d_pull_state.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.w3d_device_vectors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.w3d_eps_sig_ifv_resident.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+        L.w3d_tanstf_resident.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.w3d_last_scalars.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+class Engine:
+    """One engine instance = one GPU = one MPI rank's share of the element blocks."""
+
+    def __init__(self, model: Model, device: int = -1, myid: int = 0, numprocs: int = 1):
+        self.model = model
+        self._L = lib()
+        m = model
+        keep = [np.ascontiguousarray(x) for x in
+                (m.elblks.astype(np.int32), m.props.astype(np.int32), m.matprp.astype(np.float32),
+                 m.c.astype(np.float64), m.edest.astype(np.int32), m.cdest.astype(np.int32),
+                 m.hist_size.astype(np.int32))]
+        cfg = _Config()
+        cfg.abi_version = ABI_VERSION
+        cfg.mxvl, cfg.mxelpr, cfg.mxmtpr = max(MXVL, int(m.elblks[:, 0].max())), MXELPR, MXMTPR
+        cfg.nelblk, cfg.noelem, cfg.nonode, cfg.nodof = m.nelblk, m.noelem, m.nonode, m.nodof
+        cfg.myid, cfg.numprocs = myid, numprocs
+        (cfg.elblks, cfg.props, cfg.matprp, cfg.c, cfg.edest, cfg.cdest,
+         cfg.history_blk_list) = [_ptr(x) for x in keep]
+        cfg.nmat = keep[2].shape[0]
+        cfg.eps_bbar = m.eps_bbar
+        cfg.qbar_flag = int(m.qbar_flag)
+        cfg.beta_fact = m.beta_fact
+        cfg.adaptive_flag = int(m.adaptive_flag)
+        cfg.device = device
+        h = C.c_void_p()
+        rc = self._L.w3d_engine_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise EngineError(rc, self._L.w3d_engine_last_error(None).decode())
+        self._h = h
+        self.myid, self.numprocs = myid, numprocs
+        owned = np.ones(m.nelblk, dtype=bool) if numprocs <= 1 else (m.elblks[:, 2] == myid)
+        self.owned_blocks = np.nonzero(owned)[0]
+        self.n_owned_elems = int(m.elblks[owned, 0].sum())
+
+    # ---- plumbing
+    def _check(self, rc):
+        if rc:
+            raise EngineError(rc, self._L.w3d_engine_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.w3d_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self._L.w3d_engine_launch_count(self._h))
+
+    @property
+    def stream(self):
+        return int(self._L.w3d_engine_stream(self._h) or 0)
+
+    def synchronize(self):
+        self._check(self._L.w3d_engine_synchronize(self._h))
+
+    # ---- the reference's drivers
+    def drive_eps_sig_internal_forces(self, step, itr, u, du, ifv=None):
+        """Strain recovery, material update, internal forces for all owned blocks.
+        Returns (ifv, scalars) like the oracle; ifv is this rank's contribution."""
+        u, du = _f64(u), _f64(du)
+        if ifv is None:
+            ifv = np.empty(self.model.nodof)
+        sc = _Scalars()
+        rc = self._L.w3d_eps_sig_ifv(self._h, step, itr, int(self.model.extrapolated_du), _ptr(u),
+                                     _ptr(du), _ptr(ifv), C.byref(sc))
+        self._check(rc)
+        return ifv, self._scalars(sc)
+
+    @staticmethod
+    def _scalars(sc):
+        return dict(internal_energy=sc.internal_energy, plastic_work=sc.plastic_work,
+                    sum_ifv=sc.sum_ifv, num_term_ifv=sc.num_term_ifv,
+                    material_cut_step=bool(sc.material_cut_step))
+
+    def tanstf(self, step, itr, u=None, du=None, out=None, to_host=True):
+        """Element tangent stiffnesses (300, span) per owned block, blocks concatenated."""
+        if u is not None:
+            u, du = _f64(u), _f64(du)
+        if to_host and out is None:
+            out = np.empty(self.n_owned_elems * 300)
+        rc = self._L.w3d_tanstf(self._h, step, itr, _ptr(u), _ptr(du),
+                                _ptr(out) if to_host else None)
+        self._check(rc)
+        return out
+
+    def update(self):
+        self._check(self._L.w3d_update(self._h))
+
+    def adaptive_save(self):
+        self._check(self._L.w3d_adaptive_save(self._h))
+
+    def adaptive_reset(self):
+        self._check(self._L.w3d_adaptive_reset(self._h))
+
+    # ---- device-resident passes (bench, NCCL layer)
+    def device_vectors(self):
+        pu, pdu, pf = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._L.w3d_device_vectors(self._h, C.byref(pu), C.byref(pdu), C.byref(pf)))
+        return pu.value, pdu.value, pf.value
+
+    def eps_sig_ifv_resident(self, step, itr):
+        self._check(self._L.w3d_eps_sig_ifv_resident(self._h, step, itr,
+                                                     int(self.model.extrapolated_du)))
+
+    def tanstf_resident(self, step, itr):
+        self._check(self._L.w3d_tanstf_resident(self._h, step, itr))
+
+    def last_scalars(self):
+        sc = _Scalars()
+        self._check(self._L.w3d_last_scalars(self._h, C.byref(sc)))
+        return self._scalars(sc)
+
+    # ---- blocked state in the reference layouts
+    def block_offset(self, which, blk1):
+        return int(self._L.w3d_block_offset(self._h, which, blk1))
+
+    def _owned_offsets(self, name):
+        """offsets of every block inside the model-wide concatenated array `name` (State)."""
+        m = self.model
+        per = dict(history=8 * m.hist_size.astype(np.int64), history1=8 * m.hist_size.astype(np.int64),
+                   eps_n=48, eps_n1=48, urcs_n=72, urcs_n1=72, rot_n=72, rot_n1=72, cep=168,
+                   estiff=300, element_vol=1)[name]
+        return m.block_offsets(per)
+
+    def push_state(self, state: State, names=None):
+        for name in names or State.NAMES:
+            if name == "estiff":
+                continue
+            a = getattr(state, name)
+            off = self._owned_offsets(name)
+            for blk in self.owned_blocks:
+                seg = a[off[blk]:off[blk + 1]]
+                if seg.size:
+                    self._check(self._L.w3d_push_state(self._h, _STATE_WHICH[name], int(blk) + 1,
+                                                       _ptr(seg)))
+
+    def pull_state(self, state: State, names=None):
+        for name in names or State.NAMES:
+            a = getattr(state, name)
+            off = self._owned_offsets(name)
+            for blk in self.owned_blocks:
+                seg = a[off[blk]:off[blk + 1]]
+                if seg.size:
+                    self._check(self._L.w3d_pull_state(self._h, _STATE_WHICH[name], int(blk) + 1,
+                                                       _ptr(seg)))
+        return state
