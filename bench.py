@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the element-block hot path on B200 (contract: see the task brief).
+
+A *step* is one global Newton iteration over every owned element block of the workload:
+the strain-recovery / material-update / internal-force pass (w3d_eps_sig_ifv) followed by the
+element tangent-stiffness pass (w3d_tanstf).  Workload: BASELINE.json configs[3], the synthetic
+structured 2M-element hex8 mesh with mm01 (geonl, B-bar), state at n prepared by one converged
+load step so that about half of the Gauss points are plastic in the timed iteration.
+
+  value   Gauss-point updates/s with u, du and all state resident in HBM (whole job, all ranks)
+  e2e     same metric through the host-buffer C-ABI calls (H2D of u, du; D2H of ifv and estiff)
+  roofline, cpu_baseline, clocks: as the brief defines them.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, OpenMP over blocks
+like the reference) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, ny, nz)
+    "hex8_2m_mm01": (200, 100, 100),       # BASELINE.json configs[3]: 2 000 000 elements
+    "hex8_256k_mm01": (64, 64, 64),        # smaller variant for quick checks
+}
+CPU_SAMPLE = (64, 50, 50)                  # 160 000 elements of the same mesh/material/loading
+METRIC = "gauss_point_updates_per_s_per_newton_iteration"
+UNIT = "GP/s"
+# algorithmic HBM bytes per Gauss point (DESIGN.md "Kernels")
+BYTES_PER_GP_STRESS = 776.0
+BYTES_PER_GP_TANSTF = 708.0
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            w = [x.strip() for x in line.split(",")]
+            if len(w) < 9:
+                continue
+            try:
+                sm.append(float(w[1])); smax.append(float(w[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), w[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def prepare_cpu_case(dims, nthreads):
+    """Same mesh family, material and load path as the GPU workload, on the oracle."""
+    from oracle.oracle_py import Oracle
+    from warp3d_b200 import build_structured_hex8, graded_stretch, new_state
+    m = build_structured_hex8(*dims)
+    U = graded_stretch(m)
+    orc = Oracle(m, nthreads=nthreads)
+    st = new_state(m)
+    z = np.zeros(m.nodof)
+    orc.eps_sig_ifv(st, 1, 0, z, 0.5 * U)
+    orc.eps_sig_ifv(st, 1, 1, z, 0.5 * U)
+    orc.update(st); orc.adaptive_save(st)
+    orc.eps_sig_ifv(st, 2, 0, 0.5 * U, 0.5 * U)
+    return m, orc, st, 0.5 * U, 0.5 * U
+
+
+def cpu_pass(m, orc, st, u, du):
+    t0 = time.perf_counter()
+    orc.eps_sig_ifv(st, 2, 1, u, du)
+    t1 = time.perf_counter()
+    orc.tanstf(st, 2, 1, u, du)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def cpu_baseline(nrep=3):
+    cores = os.cpu_count() or 1
+    m, orc, st, u, du = prepare_cpu_case(CPU_SAMPLE, cores)
+    cpu_pass(m, orc, st, u, du)
+    ts = [cpu_pass(m, orc, st, u, du) for _ in range(nrep)]
+    t_s = float(np.mean([a for a, _ in ts])); t_k = float(np.mean([b for _, b in ts]))
+    ngp = m.noelem * 8
+    return dict(value=ngp / (t_s + t_k), unit=UNIT, cores=cores, kind="port",
+                sample=f"{m.noelem} elements ({CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} sub-box of the same "
+                       f"mesh, material and load path), {nrep} passes, oracle/ C++ restatement with OpenMP over blocks",
+                stress_gp_per_s=ngp / t_s, stiffness_elem_per_s=m.noelem / t_k)
+
+
+def reference_arm(args):
+    """The reference's own CPU algorithm for the path (oracle port; the Fortran cannot be built
+    here: no Fortran compiler, needs ifort+MKL), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    m, orc, st, u, du = prepare_cpu_case(CPU_SAMPLE, cores)
+    for _ in range(args.warmup):
+        cpu_pass(m, orc, st, u, du)
+    t0 = time.perf_counter()
+    ts = [cpu_pass(m, orc, st, u, du) for _ in range(args.steps)]
+    total = time.perf_counter() - t0
+    ngp = m.noelem * 8
+    value = ngp * args.steps / total
+    t_s = float(np.mean([a for a, _ in ts])); t_k = float(np.mean([b for _, b in ts]))
+    sample = (f"{m.noelem} elements per step ({CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} sub-box of the "
+              f"2M workload), oracle/ port of the reference path, OpenMP over blocks")
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * total / args.steps, higher_is_better=True,
+                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=args.workload, cpu_sample_elements=m.noelem, material="mm01 bilinear",
+                            formulation="geonl+bbar"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
+                                  stress_gp_per_s=ngp / t_s, stiffness_elem_per_s=m.noelem / t_k),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def engine_arm(args):
+    import torch
+    import torch.distributed as dist
+    from warp3d_b200 import build_structured_hex8, graded_stretch
+    from warp3d_b200.distributed import DomainEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    dims = WORKLOADS[args.workload]
+    model = build_structured_hex8(*dims)
+    U = graded_stretch(model)
+    de = DomainEngine(model, rank, world, device=local)
+    eng = de.engine
+    nodof, nel_own = model.nodof, eng.n_owned_elems
+    ngp_total = model.noelem * 8
+
+    def pinned(n):
+        return torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
+
+    u_h, du_h, ifv_h = pinned(nodof), pinned(nodof), pinned(nodof)
+    est_h = pinned(nel_own * 300)
+
+    # ---- state preparation: load step 1 (elastic-plastic), converge, roll over; step 2 iter 0
+    u_h[:] = 0.0; du_h[:] = 0.5 * U
+    de.drive_eps_sig_internal_forces(1, 0, u_h, du_h, ifv_h)
+    de.drive_eps_sig_internal_forces(1, 1, u_h, du_h, ifv_h)
+    de.update(); de.adaptive_save()
+    u_h[:] = 0.5 * U
+    de.drive_eps_sig_internal_forces(2, 0, u_h, du_h, ifv_h)
+    _, sc = de.drive_eps_sig_internal_forces(2, 1, u_h, du_h, ifv_h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    S = de.stream
+
+    # ---- resident timing: K steps bracketed by barrier + synchronize, CUDA events on the stream
+    for _ in range(max(args.warmup, 3)):
+        de.eps_sig_ifv_resident(2, 1); de.tanstf_resident(2, 1)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    l0 = eng.launch_count
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    ev[0].record(S)
+    for k in range(args.steps):
+        de.eps_sig_ifv_resident(2, 1)
+        ev[2 * k + 1].record(S)
+        de.tanstf_resident(2, 1)
+        ev[2 * k + 2].record(S)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    t_stress = float(np.mean([ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]))
+    t_tan = float(np.mean([ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)]))
+
+    # ---- end-to-end timing through the host-buffer calls (pinned host memory)
+    for _ in range(2):
+        de.drive_eps_sig_internal_forces(2, 1, u_h, du_h, ifv_h); de.tanstf(2, 1, est_h)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nrep_e2e = max(2, min(args.steps, 5))
+    e0.record(S)
+    w0 = time.perf_counter()
+    for _ in range(nrep_e2e):
+        de.drive_eps_sig_internal_forces(2, 1, u_h, du_h, ifv_h)
+        de.tanstf(2, 1, est_h)
+    e1.record(S)
+    barrier()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - w0) / nrep_e2e
+    e2e_ms = e0.elapsed_time(e1) / nrep_e2e
+
+    t = torch.tensor([total_ms, t_stress, t_tan, e2e_ms, e2e_wall_ms, float(launches)], dtype=torch.float64,
+                     device="cuda")
+    if world > 1:
+        tl = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        launches = int(tl[5].item())
+    total_ms, t_stress, t_tan, e2e_ms, e2e_wall_ms = [float(x) for x in t[:5].tolist()]
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        ms_per_step = total_ms / args.steps
+        value = ngp_total / (ms_per_step * 1e-3)
+        # dominant kernel = the one with the longer average launch; per-launch units = owned GPs
+        ngp_own = nel_own * 8
+        k_name, k_ms, k_bytes = (("k_tanstf", t_tan, BYTES_PER_GP_TANSTF) if t_tan >= t_stress
+                                 else ("k_eps_sig_ifv", t_stress, BYTES_PER_GP_STRESS))
+        ach = ngp_own * k_bytes / (k_ms * 1e-3) / 1e9
+        other = ("k_eps_sig_ifv", t_stress, BYTES_PER_GP_STRESS) if k_name == "k_tanstf" else ("k_tanstf", t_tan, BYTES_PER_GP_TANSTF)
+        fp64_peak = None
+        pk = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
+        if os.path.exists(pk):
+            with open(pk) as f:
+                fp64_peak = json.load(f).get("dfma_tflops")
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+            ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+            data="synthetic",
+            config=dict(workload=args.workload, elements=model.noelem, gauss_points=ngp_total, blocks=model.nelblk,
+                        nodof=nodof, material="mm01 bilinear (E=200e9 as real*4, nu=0.3, yld=400e6, tan_e=E/100)",
+                        formulation="hex8 l3disop 2x2x2, geonl, bbar", l2="inputs_exceed_l2 (state 16 GB >> 126 MB)",
+                        partition=f"{world} contiguous block slabs, NCCL all-reduce of ifv" if world > 1 else "single GPU",
+                        step="w3d_eps_sig_ifv + w3d_tanstf (one Newton iteration)"),
+            stress_pass=dict(ms=t_stress, gp_updates_per_s=ngp_total / (t_stress * 1e-3)),
+            stiffness_pass=dict(ms=t_tan, element_stiffnesses_per_s=model.noelem / (t_tan * 1e-3)),
+            roofline=dict(bound="hbm", kernel=k_name, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                          peak_kind=f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)", traffic=None,
+                          bytes_per_gp=k_bytes, launch_ms=k_ms,
+                          other_kernel=dict(kernel=other[0], launch_ms=other[1],
+                                            achieved=ngp_own * other[2] / (other[1] * 1e-3) / 1e9,
+                                            frac=ngp_own * other[2] / (other[1] * 1e-3) / 1e9 / peak),
+                          fp64_peak_tflops=fp64_peak),
+            e2e=dict(value=ngp_total / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, wall_ms_per_step=e2e_wall_ms,
+                     h2d_bytes_per_step=2 * 8 * nodof * world, d2h_bytes_per_step=8 * nodof * world + 8 * 300 * model.noelem,
+                     note="pinned host buffers; u,du in; ifv and estiff(300,span) blocks out"),
+            gpu_launches=launches, clocks=clocks,
+            plastic_check=dict(plastic_work=sc["plastic_work"], internal_energy=sc["internal_energy"]),
+        )
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    de.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="hex8_2m_mm01", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        engine_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,6 +134,12 @@ int64_t w3d_block_offset(const w3d_engine *h, int32_t which, int32_t blk);
  * NCCL layer, a device-side residual/assembly) fills u/du through these pointers, runs the
  * resident passes and reads ifv / scalars back when it needs them.                              */
 int32_t w3d_device_vectors(w3d_engine *h, double **d_u, double **d_du, double **d_ifv);
+/* host -> device copy of u and du (nodof each) / device -> host copy of ifv, on the engine's
+ * stream, returning after completion.  Together with the resident passes these let a caller put
+ * its own exchange step (NCCL sum of ifv) between the kernel and the copy back.                 */
+int32_t w3d_upload_displacements(w3d_engine *h, const double *u, const double *du);
+int32_t w3d_download_ifv(w3d_engine *h, double *ifv);
+int32_t w3d_download_estiff(w3d_engine *h, double *estiff);
 int32_t w3d_eps_sig_ifv_resident(w3d_engine *h, int32_t step, int32_t iter,
                                  int32_t extrapolated_du);
 int32_t w3d_tanstf_resident(w3d_engine *h, int32_t step, int32_t iter);

@@ -627,6 +627,33 @@ int32_t w3d_device_vectors(w3d_engine *h, double **d_u, double **d_du, double **
   h->have_vectors = true;
   return W3D_OK;
 }
+int32_t w3d_upload_displacements(w3d_engine *h, const double *u, const double *du) {
+  if (!h || !u || !du) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t nb = sizeof(double) * h->cfg.nodof;
+  CUDA_TRY(cudaMemcpyAsync(h->d_u, u, nb, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_du, du, nb, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->have_vectors = true;
+  return W3D_OK;
+}
+int32_t w3d_download_ifv(w3d_engine *h, double *ifv) {
+  if (!h || !ifv) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(ifv, h->d_ifv, sizeof(double) * h->cfg.nodof, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return W3D_OK;
+}
+int32_t w3d_download_estiff(w3d_engine *h, double *estiff) {
+  if (!h || !estiff) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(estiff, h->d_estiff, sizeof(double) * 300 * (size_t)h->n_owned_elems, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return W3D_OK;
+}
 int32_t w3d_eps_sig_ifv_resident(w3d_engine *h, int32_t step, int32_t iter, int32_t extrapolated_du) {
   if (!h) return W3D_ERR_ARG;
   cudaSetDevice(h->device);

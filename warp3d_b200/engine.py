@@ -32,7 +32,8 @@ EXPORTS = (
     "w3d_tanstf", "w3d_update", "w3d_adaptive_save", "w3d_adaptive_reset", "w3d_push_state",
     "w3d_pull_state", "w3d_block_offset", "w3d_device_vectors", "w3d_eps_sig_ifv_resident",
     "w3d_tanstf_resident", "w3d_last_scalars", "w3d_engine_stream", "w3d_engine_synchronize",
-    "w3d_engine_launch_count",
+    "w3d_engine_launch_count", "w3d_upload_displacements", "w3d_download_ifv",
+    "w3d_download_estiff",
 )
 
 
@@ -98,7 +99,8 @@ def lib():
         for name in ("w3d_engine_create", "w3d_engine_destroy", "w3d_eps_sig_ifv", "w3d_tanstf",
                      "w3d_update", "w3d_adaptive_save", "w3d_adaptive_reset", "w3d_push_state",
                      "w3d_pull_state", "w3d_device_vectors", "w3d_eps_sig_ifv_resident",
-                     "w3d_tanstf_resident", "w3d_last_scalars", "w3d_engine_synchronize"):
+                     "w3d_tanstf_resident", "w3d_last_scalars", "w3d_engine_synchronize",
+                     "w3d_upload_displacements", "w3d_download_ifv", "w3d_download_estiff"):
             getattr(L, name).restype = C.c_int32
         L.w3d_engine_create.argtypes = [C.c_void_p, C.c_void_p]
         L.w3d_engine_destroy.argtypes = [C.c_void_p]
@@ -115,6 +117,9 @@ def lib():
         L.w3d_eps_sig_ifv_resident.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.w3d_tanstf_resident.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.w3d_last_scalars.argtypes = [C.c_void_p, C.c_void_p]
+        L.w3d_upload_displacements.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.w3d_download_ifv.argtypes = [C.c_void_p, C.c_void_p]
+        L.w3d_download_estiff.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -233,6 +238,22 @@ class Engine:
         pu, pdu, pf = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self._L.w3d_device_vectors(self._h, C.byref(pu), C.byref(pdu), C.byref(pf)))
         return pu.value, pdu.value, pf.value
+
+    def upload_displacements(self, u, du):
+        u, du = _f64(u), _f64(du)
+        self._check(self._L.w3d_upload_displacements(self._h, _ptr(u), _ptr(du)))
+
+    def download_ifv(self, ifv=None):
+        if ifv is None:
+            ifv = np.empty(self.model.nodof)
+        self._check(self._L.w3d_download_ifv(self._h, _ptr(ifv)))
+        return ifv
+
+    def download_estiff(self, out=None):
+        if out is None:
+            out = np.empty(self.n_owned_elems * 300)
+        self._check(self._L.w3d_download_estiff(self._h, _ptr(out)))
+        return out
 
     def eps_sig_ifv_resident(self, step, itr):
         self._check(self._L.w3d_eps_sig_ifv_resident(self._h, step, itr,

@@ -134,20 +134,20 @@ def _f32_bits(x) -> np.ndarray:
 
 
 def simple_blocking(noelem, keys, auto_size=MXVL):
-    """inelbk_simple_blocking (src/inelbk.f:282-345, 497-548): sequential pass, new block when
-    full or when (etype, matnum, geonl, intord, intnum, bbar) differ. keys: (noelem, k) ints."""
+    """inelbk_simple_blocking (src/inelbk.f:282-345, 497-548): sequential pass over the elements;
+    a new block opens when the current one is full or when (etype, matnum, geonl, intord, intnum,
+    bbar) differ from the block's first element.  keys: (noelem, k) ints.  Returns a list of
+    (span, felem) with 1-based felem.  Vectorised: runs of equal keys are cut into full blocks."""
+    keys = np.asarray(keys)
+    change = np.ones(noelem, dtype=bool)
+    if noelem > 1:
+        change[1:] = (keys[1:] != keys[:-1]).any(axis=1)
+    starts = np.nonzero(change)[0]
+    ends = np.append(starts[1:], noelem)
     blocks = []
-    felem, size = 1, 1
-    for element in range(2, noelem + 1):
-        size += 1
-        newblk = size > auto_size
-        if not newblk and not np.array_equal(keys[element - 1], keys[felem - 1]):
-            newblk = True
-        if not newblk:
-            continue
-        blocks.append((size - 1, felem))
-        felem, size = element, 1
-    blocks.append((size, felem))
+    for s, e in zip(starts.tolist(), ends.tolist()):
+        for f in range(s, e, auto_size):
+            blocks.append((min(auto_size, e - f), f + 1))
     return blocks
 
 
@@ -257,3 +257,32 @@ def smooth_displacement(model: Model, strain=1.0e-3, seed=1, noise=1.0e-4, axis=
         rng = np.random.default_rng(seed)
         u += rng.uniform(-1.0, 1.0, u.shape) * noise * strain * 10.0
     return u.reshape(-1).copy()
+
+
+def graded_stretch(model: Model, eps_lo=1.0e-3, eps_hi=3.0e-3, seed=1, noise=1.0e-4, nu=0.3):
+    """Benchmark displacement field: uniaxial stretch along x whose axial strain
+    grows linearly from eps_lo at x=0 to eps_hi at x=L (so that about half of the Gauss points of
+    the default mm01 material, yield strain 2e-3, are plastic), Poisson contraction in y and z,
+    plus a seeded perturbation of relative size `noise`.  Returns a (nodof,) vector."""
+    xyz = model.c.reshape(-1, 3)
+    L = float(xyz[:, 0].max()) or 1.0
+    x = xyz[:, 0]
+    eps = eps_lo + (eps_hi - eps_lo) * x / L
+    u = np.empty_like(xyz)
+    u[:, 0] = eps_lo * x + (eps_hi - eps_lo) * x * x / (2.0 * L)
+    u[:, 1] = -nu * eps * xyz[:, 1]
+    u[:, 2] = -nu * eps * xyz[:, 2]
+    if noise:
+        rng = np.random.default_rng(seed)
+        u += rng.uniform(-1.0, 1.0, u.shape) * noise * eps_hi
+    return u.reshape(-1).copy()
+
+
+def slab_domains(model: Model, numprocs: int) -> np.ndarray:
+    """Contiguous block -> rank map (x-fastest element numbering makes these z-slabs of the
+    structured meshes), balanced by element count.  Replaces the reference's round-robin default
+    (src/inelbk.f:368-378), which makes every node an interface node.  Returns elblks(2,:)."""
+    spans = model.elblks[:, 0].astype(np.int64)
+    cum = np.cumsum(spans) - spans // 2
+    dom = np.minimum((cum * numprocs) // int(spans.sum()), numprocs - 1)
+    return dom.astype(np.int32)
