@@ -1,0 +1,62 @@
+"""Committed golden vectors (tests/golden/*.npz, produced by tests/golden/make_golden.py from the
+oracle): the oracle must still reproduce them (CPU), and the CUDA engine must match them through
+the C ABI at 1e-10 (GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+from common import RTOL, history_views, relerr
+from golden import make_golden as mg
+from warp3d_b200 import new_state
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _check(name, got, tol):
+    ref = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    assert set(ref.files) == set(got)
+    for key in ref.files:
+        a, b = got[key], ref[key]
+        if key.endswith("_history1"):
+            m, _ = mg.build(name)
+            fa, ia = history_views(m, a); fb, ib = history_views(m, b)
+            assert np.array_equal(ia, ib), key
+            for col in range(fa.shape[1]):
+                assert relerr(fa[:, col], fb[:, col]) <= tol, (key, col)
+        elif key.endswith("_scalars"):
+            assert np.all(np.abs(a - b) <= tol * np.maximum(np.abs(b), 1e-300)), key
+        elif key.endswith("_estiff"):
+            a2, b2 = a.reshape(-1, 300), b.reshape(-1, 300)
+            assert (np.abs(a2 - b2).max(axis=1) / np.abs(b2).max(axis=1)).max() <= tol, key
+        else:
+            assert relerr(a, b) <= tol, (key, relerr(a, b))
+
+
+@pytest.mark.parametrize("name", sorted(mg.CASES))
+def test_oracle_reproduces_golden(name):
+    _check(name, mg.run(name, mg.OracleRun), 1e-13)
+
+
+class EngineRun:
+    def __init__(self, m):
+        from warp3d_b200.engine import Engine
+        self.m, self.e = m, Engine(m)
+
+    def eps_sig_ifv(self, *a):
+        return self.e.drive_eps_sig_internal_forces(*a)
+
+    def tanstf(self, *a):
+        return self.e.tanstf(*a)
+
+    def state(self):
+        return self.e.pull_state(new_state(self.m))
+
+    def update(self):
+        self.e.update(); self.e.adaptive_save()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(mg.CASES))
+def test_engine_matches_golden(name):
+    _check(name, mg.run(name, EngineRun), RTOL)

@@ -1,0 +1,59 @@
+"""Host-side integer tables must be bit-exact with the reference's rules."""
+import numpy as np
+
+from warp3d_b200 import build_structured_hex8, slab_domains
+from warp3d_b200.model import HEX8_NODE_SIGNS, simple_blocking
+
+
+def _blocking_sequential(noelem, keys, auto_size):
+    """literal restatement of inelbk_simple_blocking (src/inelbk.f:282-345, 497-548)"""
+    blocks, felem, size = [], 1, 1
+    for element in range(2, noelem + 1):
+        size += 1
+        newblk = size > auto_size or not np.array_equal(keys[element - 1], keys[felem - 1])
+        if not newblk:
+            continue
+        blocks.append((size - 1, felem))
+        felem, size = element, 1
+    blocks.append((size, felem))
+    return blocks
+
+
+def test_auto_blocking_matches_the_sequential_rule():
+    rng = np.random.default_rng(3)
+    for n, bs in ((1, 128), (127, 128), (128, 128), (129, 128), (1000, 64), (333, 7)):
+        keys = np.cumsum(rng.random(n) < 0.02).reshape(-1, 1) % 3
+        assert simple_blocking(n, keys, bs) == _blocking_sequential(n, keys, bs)
+
+
+def test_block_table_and_dest_maps():
+    m = build_structured_hex8(5, 4, 3, block_size=16)
+    assert m.noelem == 60 and m.nonode == 6 * 5 * 4 and m.nodof == 3 * m.nonode
+    assert list(m.elblks[:, 0]) == [16, 16, 16, 12] and list(m.elblks[:, 1]) == [1, 17, 33, 49]
+    ed = m.edest.reshape(-1, 24)
+    # all u, all v, all w ordering: edest(j)=dstmap(node_j), edest(8+j)=+1, edest(16+j)=+2
+    assert np.array_equal(ed[:, :8], 3 * (m.incid - 1) + 1)
+    assert np.array_equal(ed[:, 8:16], ed[:, :8] + 1) and np.array_equal(ed[:, 16:], ed[:, :8] + 2)
+    # node ordering gives a positive Jacobian for the unit cube with WARP3D's parent coordinates
+    x = m.c.reshape(-1, 3)[m.incid[0] - 1]
+    assert np.allclose((x - x.mean(0)) * 2, HEX8_NODE_SIGNS)
+
+
+def test_props_table_is_the_reference_word_layout():
+    m = build_structured_hex8(2, 2, 2)
+    p = m.props
+    assert p.dtype == np.int32 and p.shape[1] == 43
+    assert p[0, 0] == 2 and p[0, 1] == 8 and p[0, 3] == 3 and p[0, 5] == 8 and p[0, 24] == 1
+    assert p[0, 6:8].view(np.float32)[0] == np.float32(200.0e9)      # E is real*4
+    e, et = np.float32(200.0e9), np.float32(2.0e9)
+    assert p[0, 14:15].view(np.float32)[0] == np.float32((e * et) / (e - et))   # H' in real*4 arithmetic
+    assert p[0, 17] & 1 and p[0, 18] & 1
+
+
+def test_slab_domains_are_contiguous_and_balanced():
+    m = build_structured_hex8(20, 10, 10)           # 2000 elements, 16 blocks
+    for nproc in (2, 4, 8):
+        d = slab_domains(m, nproc)
+        assert np.all(np.diff(d) >= 0) and d[0] == 0 and d[-1] == nproc - 1
+        counts = np.bincount(d, weights=m.elblks[:, 0], minlength=nproc)
+        assert counts.max() - counts.min() <= 2 * 128

@@ -197,7 +197,7 @@ class Engine:
     # ---- the reference's drivers
     def drive_eps_sig_internal_forces(self, step, itr, u, du, ifv=None):
         """Strain recovery, material update, internal forces for all owned blocks.
-        Returns (ifv, scalars) like the oracle; ifv is this rank's contribution."""
+        Returns (ifv, scalars); ifv is this rank's contribution."""
         u, du = _f64(u), _f64(du)
         if ifv is None:
             ifv = np.empty(self.model.nodof)
