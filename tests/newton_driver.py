@@ -60,7 +60,7 @@ class EngineBackend:
 
 def solve_steps(model, backend, fixed_dofs, fixed_increments, nsteps, tol=1e-10, maxit=12):
     """Displacement-controlled load steps.  fixed_increments[step] gives the imposed increment
-    on fixed_dofs.  Returns (u, log) where log[step] = list of residual norms per iteration."""
+    on fixed_dofs.  Returns (u, log) where log[step] = list of (residual norm, reaction norm) per iteration."""
     n = model.nodof
     free = np.setdiff1d(np.arange(n), fixed_dofs)
     u = np.zeros(n)
@@ -81,7 +81,7 @@ def solve_steps(model, backend, fixed_dofs, fixed_increments, nsteps, tol=1e-10,
             assert not sc["material_cut_step"]
             rn = float(np.linalg.norm(ifv[free]))
             ref = float(np.linalg.norm(ifv[fixed_dofs])) or 1.0
-            norms.append(rn)
+            norms.append((rn, ref))
             if rn <= tol * ref:
                 break
             K = assemble(model, backend.tanstf(step, it, u, du))

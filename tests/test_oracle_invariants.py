@@ -159,5 +159,5 @@ def test_uniaxial_bilinear_closed_form_and_quadratic_newton_convergence():
     for norms in log:
         assert len(norms) <= 6
     # quadratic contraction in the plastic steps: r_{k+1} <~ C r_k^2 (relative)
-    r = np.array(log[1])
+    r = np.array(log[1])[:, 0]
     assert r[-1] < 1e-9 * r[0] or len(r) <= 3

@@ -45,16 +45,18 @@ __device__ __forceinline__ int mm01_update(int step, const Mm01Props &pr, double
   {
     const double htol = 0.000001, root3 = sqrt(3.0), root2 = sqrt(2.0), yld_tol = 0.0000001;
     const double deps_vol = deps[0] + deps[1] + deps[2];
-    const double eps_mean = deps_vol / three;
+    const double eps_mean = deps_vol * (one / three);
     const double de1 = deps[0] - eps_mean, de2 = deps[1] - eps_mean, de3 = deps[2] - eps_mean;
     const double de4 = deps[3], de5 = deps[4], de6 = deps[5];
-    const double g_n = ym_n / two / (one + nu_n);
-    const double een1 = (cgn[0] - nu_n * (cgn[1] + cgn[2])) / ym_n;
-    const double een2 = (cgn[1] - nu_n * (cgn[0] + cgn[2])) / ym_n;
-    const double een3 = (cgn[2] - nu_n * (cgn[0] + cgn[1])) / ym_n;
-    const double een4 = cgn[3] / g_n, een5 = cgn[4] / g_n, een6 = cgn[5] / g_n;
+    // one reciprocal each for 1/E and 1/G instead of six IEEE divisions (<= 1 ulp difference)
+    const double iym = one / ym_n;
+    const double ig = (two * (one + nu_n)) * iym;
+    const double een1 = (cgn[0] - nu_n * (cgn[1] + cgn[2])) * iym;
+    const double een2 = (cgn[1] - nu_n * (cgn[0] + cgn[2])) * iym;
+    const double een3 = (cgn[2] - nu_n * (cgn[0] + cgn[1])) * iym;
+    const double een4 = cgn[3] * ig, een5 = cgn[4] * ig, een6 = cgn[5] * ig;
     eps_vol_n1 = een1 + een2 + een3 + deps_vol;
-    const double eps_mean_n = (een1 + een2 + een3) / three;
+    const double eps_mean_n = (een1 + een2 + een3) * (one / three);
     const double e1 = (een1 - eps_mean_n) + de1;
     const double e2 = (een2 - eps_mean_n) + de2;
     const double e3 = (een3 - eps_mean_n) + de3;
@@ -216,27 +218,29 @@ __device__ __forceinline__ void cnst1_cep21(const Mm01Props &pr, const double (&
   const double gbar = g * bb;
   const double albar = k - two * gbar / three;
   const double thbar = two * g * gambar;
-  c[0] = (albar + two * gbar - thbar * (r1 * r1) / mrtsq);   // 1,1
-  c[1] = (albar - thbar * r1 * r2 / mrtsq);                  // 2,1
-  c[2] = (albar + two * gbar - thbar * (r2 * r2) / mrtsq);   // 2,2
-  c[3] = (albar - thbar * r1 * r3 / mrtsq);                  // 3,1
-  c[4] = (albar - thbar * r3 * r2 / mrtsq);                  // 3,2
-  c[5] = (albar + two * gbar - thbar * (r3 * r3) / mrtsq);   // 3,3
-  c[6] = -(thbar * r1 * r4 / mrtsq);                         // 4,1
-  c[7] = -(thbar * r2 * r4 / mrtsq);                         // 4,2
-  c[8] = -(thbar * r3 * r4 / mrtsq);                         // 4,3
-  c[9] = (gbar - thbar * (r4 * r4) / mrtsq);                 // 4,4
-  c[10] = -(thbar * r1 * r5 / mrtsq);                        // 5,1
-  c[11] = -(thbar * r2 * r5 / mrtsq);                        // 5,2
-  c[12] = -(thbar * r3 * r5 / mrtsq);                        // 5,3
-  c[13] = -(thbar * r4 * r5 / mrtsq);                        // 5,4
-  c[14] = (gbar - thbar * (r5 * r5) / mrtsq);                // 5,5
-  c[15] = -(thbar * r1 * r6 / mrtsq);                        // 6,1
-  c[16] = -(thbar * r2 * r6 / mrtsq);                        // 6,2
-  c[17] = -(thbar * r3 * r6 / mrtsq);                        // 6,3
-  c[18] = -(thbar * r4 * r6 / mrtsq);                        // 6,4
-  c[19] = -(thbar * r5 * r6 / mrtsq);                        // 6,5
-  c[20] = (gbar - thbar * (r6 * r6) / mrtsq);                // 6,6
+  const double t = thbar / mrtsq;            // one division instead of 21
+  const double dg = albar + two * gbar;
+  c[0] = dg - t * (r1 * r1);      // 1,1
+  c[1] = albar - t * (r1 * r2);   // 2,1
+  c[2] = dg - t * (r2 * r2);      // 2,2
+  c[3] = albar - t * (r1 * r3);   // 3,1
+  c[4] = albar - t * (r3 * r2);   // 3,2
+  c[5] = dg - t * (r3 * r3);      // 3,3
+  c[6] = -(t * (r1 * r4));        // 4,1
+  c[7] = -(t * (r2 * r4));        // 4,2
+  c[8] = -(t * (r3 * r4));        // 4,3
+  c[9] = gbar - t * (r4 * r4);    // 4,4
+  c[10] = -(t * (r1 * r5));       // 5,1
+  c[11] = -(t * (r2 * r5));       // 5,2
+  c[12] = -(t * (r3 * r5));       // 5,3
+  c[13] = -(t * (r4 * r5));       // 5,4
+  c[14] = gbar - t * (r5 * r5);   // 5,5
+  c[15] = -(t * (r1 * r6));       // 6,1
+  c[16] = -(t * (r2 * r6));       // 6,2
+  c[17] = -(t * (r3 * r6));       // 6,3
+  c[18] = -(t * (r4 * r6));       // 6,4
+  c[19] = -(t * (r5 * r6));       // 6,5
+  c[20] = gbar - t * (r6 * r6);   // 6,6
 }
 
 }  // namespace w3d

@@ -42,8 +42,95 @@ struct StressArgs {
 // host with the reference's quad2 / deriv2 tables (getgpts.f:642-718, derivs.f:283-343)
 __constant__ double c_shape[3][8][8];
 
+#ifndef STRESS_MIN_CTAS
+#define STRESS_MIN_CTAS 4   // register cap 128/thread -> 4 CTAs (16 warps) per SM
+#endif
+
+// Jacobian with the node loop kept rolled: shape derivatives and coordinates are re-read from
+// shared memory each trip, so only the 9 accumulators are live (register pressure, not smem
+// bandwidth, limits this kernel).  MODE 0: X = c ; 1: X = (c+u)+du/2 ; 2: X = (c+u)+du.
+template <bool EXACT, int MODE>
+__device__ __forceinline__ void jacobian_smem(const double (*sN)[8][8], int gp, const double *C,
+                                              const double *U, const double *DU,
+                                              double (&G)[3][3], double &dj) {
+  double J[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) J[r][c] = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const double nx = sN[0][j][gp], ne = sN[1][j][gp], nz = sN[2][j][gp];
+    double x = C[j], y = C[8 + j], z = C[16 + j];
+    if (MODE == 1) {
+      x = (x + U[j]) + 0.5 * DU[j]; y = (y + U[8 + j]) + 0.5 * DU[8 + j]; z = (z + U[16 + j]) + 0.5 * DU[16 + j];
+    } else if (MODE == 2) {
+      x = (x + U[j]) + DU[j]; y = (y + U[8 + j]) + DU[8 + j]; z = (z + U[16 + j]) + DU[16 + j];
+    }
+    if (EXACT) {
+      J[0][0] = xa(J[0][0], xm(nx, x)); J[0][1] = xa(J[0][1], xm(nx, y)); J[0][2] = xa(J[0][2], xm(nx, z));
+      J[1][0] = xa(J[1][0], xm(ne, x)); J[1][1] = xa(J[1][1], xm(ne, y)); J[1][2] = xa(J[1][2], xm(ne, z));
+      J[2][0] = xa(J[2][0], xm(nz, x)); J[2][1] = xa(J[2][1], xm(nz, y)); J[2][2] = xa(J[2][2], xm(nz, z));
+    } else {
+      J[0][0] = fma(nx, x, J[0][0]); J[0][1] = fma(nx, y, J[0][1]); J[0][2] = fma(nx, z, J[0][2]);
+      J[1][0] = fma(ne, x, J[1][0]); J[1][1] = fma(ne, y, J[1][1]); J[1][2] = fma(ne, z, J[1][2]);
+      J[2][0] = fma(nz, x, J[2][0]); J[2][1] = fma(nz, y, J[2][1]); J[2][2] = fma(nz, z, J[2][2]);
+    }
+  }
+  if (EXACT) {
+    const double j1 = xs(xm(J[1][1], J[2][2]), xm(J[1][2], J[2][1]));
+    const double j2 = xs(xm(J[1][0], J[2][2]), xm(J[1][2], J[2][0]));
+    const double j3 = xs(xm(J[1][0], J[2][1]), xm(J[1][1], J[2][0]));
+    dj = xa(xs(xm(J[0][0], j1), xm(J[0][1], j2)), xm(J[0][2], j3));
+    G[0][0] = __ddiv_rn(j1, dj);
+    G[1][0] = __ddiv_rn(-j2, dj);
+    G[2][0] = __ddiv_rn(j3, dj);
+    G[0][1] = __ddiv_rn(xs(xm(J[2][1], J[0][2]), xm(J[0][1], J[2][2])), dj);
+    G[1][1] = __ddiv_rn(xs(xm(J[0][0], J[2][2]), xm(J[2][0], J[0][2])), dj);
+    G[2][1] = __ddiv_rn(xs(xm(J[0][1], J[2][0]), xm(J[0][0], J[2][1])), dj);
+    G[0][2] = __ddiv_rn(xs(xm(J[0][1], J[1][2]), xm(J[0][2], J[1][1])), dj);
+    G[1][2] = __ddiv_rn(xs(xm(J[0][2], J[1][0]), xm(J[0][0], J[1][2])), dj);
+    G[2][2] = __ddiv_rn(xs(xm(J[0][0], J[1][1]), xm(J[0][1], J[1][0])), dj);
+  } else {
+    const double j1 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    const double j2 = J[1][0] * J[2][2] - J[1][2] * J[2][0];
+    const double j3 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    dj = J[0][0] * j1 - J[0][1] * j2 + J[0][2] * j3;
+    const double r = 1.0 / dj;
+    G[0][0] = j1 * r; G[1][0] = -j2 * r; G[2][0] = j3 * r;
+    G[0][1] = (J[2][1] * J[0][2] - J[0][1] * J[2][2]) * r;
+    G[1][1] = (J[0][0] * J[2][2] - J[2][0] * J[0][2]) * r;
+    G[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
+    G[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
+    G[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
+    G[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
+  }
+}
+
+// strain increment  B(G) * due  with the node loop rolled (gtlsn1.f:25-82 without the B-bar part)
+__device__ __forceinline__ void strain_increment(const double (*sN)[8][8], int gp,
+                                                 const double (&G)[3][3], const double *DU,
+                                                 double (&d)[6]) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) d[k] = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const double nx = sN[0][j][gp], ne = sN[1][j][gp], nz = sN[2][j][gp];
+    const double bx = G[0][0] * nx + G[0][1] * ne + G[0][2] * nz;
+    const double by = G[1][0] * nx + G[1][1] * ne + G[1][2] * nz;
+    const double bz = G[2][0] * nx + G[2][1] * ne + G[2][2] * nz;
+    const double du = DU[j], dv = DU[8 + j], dw = DU[16 + j];
+    d[0] = fma(bx, du, d[0]);
+    d[1] = fma(by, dv, d[1]);
+    d[2] = fma(bz, dw, d[2]);
+    d[3] = fma(by, du, fma(bx, dv, d[3]));
+    d[4] = fma(bz, dv, fma(by, dw, d[4]));
+    d[5] = fma(bz, du, fma(bx, dw, d[5]));
+  }
+}
+
 template <int MAT, bool GEONL, bool BBAR>
-__global__ void __launch_bounds__(TPB) k_eps_sig_ifv(const StressArgs a) {
+__global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const StressArgs a) {
   __shared__ double sN[3][8][8];
   __shared__ double sC[EPC][24], sU[EPC][24], sDU[EPC][24];
   __shared__ double sRed[TPB / 32][3];
@@ -74,127 +161,89 @@ __global__ void __launch_bounds__(TPB) k_eps_sig_ifv(const StressArgs a) {
   }
   __syncthreads();
 
-  double nx[8], ne[8], nz[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { nx[j] = sN[0][j][gp]; ne[j] = sN[1][j][gp]; nz[j] = sN[2][j][gp]; }
-
   const double *C = sC[el], *U = sU[el], *DU = sDU[el];
   const double beta_b = (1.0 - a.eps_bbar) * (1.0 / 3.0);   // bmod.f: beta = (1-eps)/3
   const double weight = 1.0;                                 // quad2: w = 1
 
   bool error = false;
   double R1[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-  double dfn1 = 1.0, dj0;
+  double efac;          // detF * detJ0 * beta_fact * w  (rstgp1_b)
   double uddt[6];
 
   if (GEONL) {
     // ---- gtmat1 (gtmat1.f:17-190): F at n+1 and n+1/2 from the undeformed configuration
-    double X[8], Y[8], Z[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { X[j] = C[j]; Y[j] = C[8 + j]; Z[j] = C[16 + j]; }
-    double G0[3][3];
-    jacobian<true>(nx, ne, nz, X, Y, Z, G0, dj0);
-    double t1[9], th[9];   // theta at n+1, n+1/2 (tcomp1, gtmat1.f:522-584)
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { t1[k] = 0.0; th[k] = 0.0; }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double tx = xa(xa(xm(G0[0][0], nx[j]), xm(G0[0][1], ne[j])), xm(G0[0][2], nz[j]));
-      const double ty = xa(xa(xm(G0[1][0], nx[j]), xm(G0[1][1], ne[j])), xm(G0[1][2], nz[j]));
-      const double tz = xa(xa(xm(G0[2][0], nx[j]), xm(G0[2][1], ne[j])), xm(G0[2][2], nz[j]));
-      const double u0 = U[j], v0 = U[8 + j], w0 = U[16 + j];
-      const double du = DU[j], dv = DU[8 + j], dw = DU[16 + j];
-      const double u1 = xa(u0, du), v1 = xa(v0, dv), w1 = xa(w0, dw);          // uen1
-      const double uh = xa(u0, xm(0.5, du)), vh = xa(v0, xm(0.5, dv)), wh = xa(w0, xm(0.5, dw));
-      t1[0] = xa(t1[0], xm(tx, u1)); t1[1] = xa(t1[1], xm(tx, v1)); t1[2] = xa(t1[2], xm(tx, w1));
-      t1[3] = xa(t1[3], xm(ty, u1)); t1[4] = xa(t1[4], xm(ty, v1)); t1[5] = xa(t1[5], xm(ty, w1));
-      t1[6] = xa(t1[6], xm(tz, u1)); t1[7] = xa(t1[7], xm(tz, v1)); t1[8] = xa(t1[8], xm(tz, w1));
-      th[0] = xa(th[0], xm(tx, uh)); th[1] = xa(th[1], xm(tx, vh)); th[2] = xa(th[2], xm(tx, wh));
-      th[3] = xa(th[3], xm(ty, uh)); th[4] = xa(th[4], xm(ty, vh)); th[5] = xa(th[5], xm(ty, wh));
-      th[6] = xa(th[6], xm(tz, uh)); th[7] = xa(th[7], xm(tz, vh)); th[8] = xa(th[8], xm(tz, wh));
-    }
-    // fcomp1 (gtmat1.f:601-674)
-    double F1[3][3], Fh[3][3];
-    F1[0][0] = xa(t1[0], 1.0); F1[0][1] = t1[3]; F1[0][2] = t1[6];
-    F1[1][0] = t1[1]; F1[1][1] = xa(t1[4], 1.0); F1[1][2] = t1[7];
-    F1[2][0] = t1[2]; F1[2][1] = t1[5]; F1[2][2] = xa(t1[8], 1.0);
-    Fh[0][0] = xa(th[0], 1.0); Fh[0][1] = th[3]; Fh[0][2] = th[6];
-    Fh[1][0] = th[1]; Fh[1][1] = xa(th[4], 1.0); Fh[1][2] = th[7];
-    Fh[2][0] = th[2]; Fh[2][1] = th[5]; Fh[2][2] = xa(th[8], 1.0);
+    double Rh[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
     {
+      double G0[3][3], dj0;
+      jacobian_smem<true, 0>(sN, gp, C, U, DU, G0, dj0);
+      double t1[9], th[9];   // theta at n+1, n+1/2 (tcomp1, gtmat1.f:522-584)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { t1[k] = 0.0; th[k] = 0.0; }
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        const double nx = sN[0][j][gp], ne = sN[1][j][gp], nz = sN[2][j][gp];
+        const double tx = xa(xa(xm(G0[0][0], nx), xm(G0[0][1], ne)), xm(G0[0][2], nz));
+        const double ty = xa(xa(xm(G0[1][0], nx), xm(G0[1][1], ne)), xm(G0[1][2], nz));
+        const double tz = xa(xa(xm(G0[2][0], nx), xm(G0[2][1], ne)), xm(G0[2][2], nz));
+        const double u0 = U[j], v0 = U[8 + j], w0 = U[16 + j];
+        const double du = DU[j], dv = DU[8 + j], dw = DU[16 + j];
+        const double u1 = xa(u0, du), v1 = xa(v0, dv), w1 = xa(w0, dw);          // uen1
+        const double uh = xa(u0, xm(0.5, du)), vh = xa(v0, xm(0.5, dv)), wh = xa(w0, xm(0.5, dw));
+        t1[0] = xa(t1[0], xm(tx, u1)); t1[1] = xa(t1[1], xm(tx, v1)); t1[2] = xa(t1[2], xm(tx, w1));
+        t1[3] = xa(t1[3], xm(ty, u1)); t1[4] = xa(t1[4], xm(ty, v1)); t1[5] = xa(t1[5], xm(ty, w1));
+        t1[6] = xa(t1[6], xm(tz, u1)); t1[7] = xa(t1[7], xm(tz, v1)); t1[8] = xa(t1[8], xm(tz, w1));
+        th[0] = xa(th[0], xm(tx, uh)); th[1] = xa(th[1], xm(tx, vh)); th[2] = xa(th[2], xm(tx, wh));
+        th[3] = xa(th[3], xm(ty, uh)); th[4] = xa(th[4], xm(ty, vh)); th[5] = xa(th[5], xm(ty, wh));
+        th[6] = xa(th[6], xm(tz, uh)); th[7] = xa(th[7], xm(tz, vh)); th[8] = xa(th[8], xm(tz, wh));
+      }
+      // fcomp1 (gtmat1.f:601-674)
+      double F1[3][3], Fh[3][3];
+      F1[0][0] = xa(t1[0], 1.0); F1[0][1] = t1[3]; F1[0][2] = t1[6];
+      F1[1][0] = t1[1]; F1[1][1] = xa(t1[4], 1.0); F1[1][2] = t1[7];
+      F1[2][0] = t1[2]; F1[2][1] = t1[5]; F1[2][2] = xa(t1[8], 1.0);
+      Fh[0][0] = xa(th[0], 1.0); Fh[0][1] = th[3]; Fh[0][2] = th[6];
+      Fh[1][0] = th[1]; Fh[1][1] = xa(th[4], 1.0); Fh[1][2] = th[7];
+      Fh[2][0] = th[2]; Fh[2][1] = th[5]; Fh[2][2] = xa(th[8], 1.0);
       const double f1 = xs(xm(F1[1][1], F1[2][2]), xm(F1[1][2], F1[2][1]));
       const double f2 = xs(xm(F1[1][0], F1[2][2]), xm(F1[1][2], F1[2][0]));
       const double f3 = xs(xm(F1[1][0], F1[2][1]), xm(F1[1][1], F1[2][0]));
-      dfn1 = xa(xs(xm(F1[0][0], f1), xm(F1[0][1], f2)), xm(F1[0][2], f3));
+      const double dfn1 = xa(xs(xm(F1[0][0], f1), xm(F1[0][1], f2)), xm(F1[0][2], f3));
       const double h1 = xs(xm(Fh[1][1], Fh[2][2]), xm(Fh[1][2], Fh[2][1]));
       const double h2 = xs(xm(Fh[1][0], Fh[2][2]), xm(Fh[1][2], Fh[2][0]));
       const double h3 = xs(xm(Fh[1][0], Fh[2][1]), xm(Fh[1][1], Fh[2][0]));
       const double dfh = xa(xs(xm(Fh[0][0], h1), xm(Fh[0][1], h2)), xm(Fh[0][2], h3));
       error = !(dfn1 > 1.0e-20) || !(dfh > 1.0e-20);
-    }
-    double Rh[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    if (!error) {
-      polar_rotation(F1, R1);
-      polar_rotation(Fh, Rh);
-    }
-    // ---- strain increment on the mid-step configuration (rknstr_geonl, gtlsn1)
-    if (a.update_coords) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        X[j] = (C[j] + U[j]) + 0.5 * DU[j];
-        Y[j] = (C[8 + j] + U[8 + j]) + 0.5 * DU[8 + j];
-        Z[j] = (C[16 + j] + U[16 + j]) + 0.5 * DU[16 + j];
+      efac = dfn1 * dj0 * a.beta_fact * weight;
+      if (!error) {
+        polar_rotation(F1, R1);
+        polar_rotation(Fh, Rh);
       }
     }
-    double Gm[3][3], djm;
-    jacobian<false>(nx, ne, nz, X, Y, Z, Gm, djm);
-    double ddt[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double bx = Gm[0][0] * nx[j] + Gm[0][1] * ne[j] + Gm[0][2] * nz[j];
-      const double by = Gm[1][0] * nx[j] + Gm[1][1] * ne[j] + Gm[1][2] * nz[j];
-      const double bz = Gm[2][0] * nx[j] + Gm[2][1] * ne[j] + Gm[2][2] * nz[j];
-      const double du = DU[j], dv = DU[8 + j], dw = DU[16 + j];
-      ddt[0] = fma(bx, du, ddt[0]);
-      ddt[1] = fma(by, dv, ddt[1]);
-      ddt[2] = fma(bz, dw, ddt[2]);
-      ddt[3] += by * du + bx * dv;
-      ddt[4] += bz * dv + by * dw;
-      ddt[5] += bz * du + bx * dw;
-    }
-    if (BBAR) {
-      // mean-dilatation B-bar (vol_terms / vol_avg / bmod): eps_kk -> eps_kk + beta (thbar - th)
-      const double thgp = ddt[0] + ddt[1] + ddt[2];
-      const double vol = sum8(djm);
-      const double thbar = sum8(djm * thgp) / vol;
-      const double corr = beta_b * (thbar - thgp);
-      ddt[0] += corr; ddt[1] += corr; ddt[2] += corr;
+    // ---- strain increment on the mid-step configuration (rknstr_geonl, gtlsn1)
+    double ddt[6];
+    {
+      double Gm[3][3], djm;
+      if (a.update_coords) jacobian_smem<false, 1>(sN, gp, C, U, DU, Gm, djm);
+      else jacobian_smem<false, 0>(sN, gp, C, U, DU, Gm, djm);
+      strain_increment(sN, gp, Gm, DU, ddt);
+      if (BBAR) {
+        // mean-dilatation B-bar (vol_terms / vol_avg / bmod): eps_kk -> eps_kk + beta (thbar - th)
+        const double thgp = ddt[0] + ddt[1] + ddt[2];
+        const double vol = sum8(djm);
+        const double thbar = sum8(djm * thgp) / vol;
+        const double corr = beta_b * (thbar - thgp);
+        ddt[0] += corr; ddt[1] += corr; ddt[2] += corr;
+      }
     }
     double q[6][6];
     getrm1_opt1(Rh, q);
     qmply(q, ddt, uddt);
   } else {
     // ---- rknstr_sm_displ + rstgp2: B on the undeformed configuration
-    double X[8], Y[8], Z[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { X[j] = C[j]; Y[j] = C[8 + j]; Z[j] = C[16 + j]; }
-    double G0[3][3];
-    jacobian<false>(nx, ne, nz, X, Y, Z, G0, dj0);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) uddt[k] = 0.0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double bx = G0[0][0] * nx[j] + G0[0][1] * ne[j] + G0[0][2] * nz[j];
-      const double by = G0[1][0] * nx[j] + G0[1][1] * ne[j] + G0[1][2] * nz[j];
-      const double bz = G0[2][0] * nx[j] + G0[2][1] * ne[j] + G0[2][2] * nz[j];
-      const double du = DU[j], dv = DU[8 + j], dw = DU[16 + j];
-      uddt[0] = fma(bx, du, uddt[0]);
-      uddt[1] = fma(by, dv, uddt[1]);
-      uddt[2] = fma(bz, dw, uddt[2]);
-      uddt[3] += by * du + bx * dv;
-      uddt[4] += bz * dv + by * dw;
-      uddt[5] += bz * du + bx * dw;
-    }
+    double G0[3][3], dj0;
+    jacobian_smem<false, 0>(sN, gp, C, U, DU, G0, dj0);
+    efac = dj0 * a.beta_fact * weight;
+    strain_increment(sN, gp, G0, DU, uddt);
     if (BBAR) {
       const double thgp = uddt[0] + uddt[1] + uddt[2];
       const double vol = sum8(dj0);
@@ -204,29 +253,49 @@ __global__ void __launch_bounds__(TPB) k_eps_sig_ifv(const StressArgs a) {
     }
   }
 
-  // ---- rstgp1_update_strains (rstgp1.f:4983-5005): total strain at n+1
-  double eps1[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) eps1[k] = a.eps_n[k * ng + g] + uddt[k];
+  // a Gauss point with det F <= 0 asks for a step cut; its state is not written
+  const bool store = valid && !error;
+  if (error && valid) {
+    atomicOr(&a.flags[0], 1);
+    if (!a.adaptive) atomicMax(&a.flags[1], 6);
+  }
 
-  // ---- material update
-  double cgn[9], cgn1[9], cep[21];
+  // ---- rstgp1_update_strains (rstgp1.f:4983-5005): total strain at n+1, stored at once
 #pragma unroll
-  for (int k = 0; k < 9; ++k) cgn[k] = a.urcs_n[k * ng + g];
+  for (int k = 0; k < 6; ++k) {
+    const double e1 = a.eps_n[k * ng + g] + uddt[k];
+    if (store) a.eps_n1[k * ng + g] = e1;
+  }
+  if (store && GEONL && a.iter > 0) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a.rot_n1[(c * 3 + r) * ng + g] = R1[r][c];
+  }
+
+  // ---- material update; rplstr stores (rplstr.f:15-93) + rstgp1_store_cep issued as soon as the
+  //      values exist so their registers die early
+  double cgn1[9];
   int fatal = 0;
-  double h1[11];
   if (MAT == 1) {
+    double cgn[9], cep[21];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) cgn[k] = a.urcs_n[k * ng + g];
     const float *ep = a.eprops + (size_t)slot * EPROP;
     Mm01Props pr;
     pr.e = (double)ep[0]; pr.nu = (double)ep[1]; pr.beta = (double)ep[2];
     pr.hprime = (double)ep[3]; pr.yld = (double)ep[4]; pr.lnelas = ep[5] != 0.0f;
     if (a.nonlinear_update) {
-      double h[11], rtse[6];
+      double h[11], h1[11], rtse[6];
 #pragma unroll
       for (int k = 0; k < 11; ++k) h[k] = a.hist_n[k * ng + g];
       double h11_first = h[10];
       if (1.0 - pr.beta != 0.0) h11_first = a.hist_n[10 * ng + (long long)cd.blk_slot0 * 8 + gp];
       fatal = mm01_update(a.step, pr, cgn, cgn1, uddt, h, h1, rtse, h11_first);
+      if (store && a.iter > 0) {
+#pragma unroll
+        for (int k = 0; k < 11; ++k) a.hist_n1[k * ng + g] = h1[k];
+      }
       cnst1_cep21(pr, rtse, h1, cep);
     } else {
       // drive_01_update_a/_b: linear-elastic [D] and stress for iteration 0
@@ -240,98 +309,62 @@ __global__ void __launch_bounds__(TPB) k_eps_sig_ifv(const StressArgs a) {
       cgn1[5] = cgn[5] + c3 * uddt[5];
       cgn1[6] = 0.0; cgn1[7] = 0.0; cgn1[8] = 0.0;   // local urcs_blk_n1 is zero-initialised
     }
-  }
-
-  // a Gauss point with det F <= 0 asks for a step cut; its state is not written
-  const bool store = valid && !error;
-  if (error && valid) {
-    atomicOr(&a.flags[0], 1);
-    if (!a.adaptive) atomicMax(&a.flags[1], 6);
+    if (store) {
+#pragma unroll
+      for (int k = 0; k < 21; ++k) a.cep[k * ng + g] = cep[k];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a.urcs_n1[k * ng + g] = cgn1[k];
+    }
   }
   if (fatal && store) atomicMax(&a.flags[1], fatal);
 
-  // ---- rplstr (rplstr.f:15-93) + rstgp1_store_cep
-  if (store) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) a.urcs_n1[k * ng + g] = cgn1[k];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) a.eps_n1[k * ng + g] = eps1[k];
-#pragma unroll
-    for (int k = 0; k < 21; ++k) a.cep[k * ng + g] = cep[k];
-    if (a.iter > 0) {
-      if (GEONL) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) a.rot_n1[(c * 3 + r) * ng + g] = R1[r][c];
-      }
-      if (MAT == 1 && a.nonlinear_update) {
-#pragma unroll
-        for (int k = 0; k < 11; ++k) a.hist_n1[k * ng + g] = h1[k];
-      }
-    }
-  }
-
   // ---- rstgp1_b: energy integration over the undeformed volume
   double en = 0.0, pw = 0.0;
-  if (a.iter != 0 && store) {
-    const double factor = (GEONL ? dfn1 * dj0 : dj0) * a.beta_fact * weight;
-    en = cgn1[6] * factor;
-    pw = cgn1[7] * factor;
-  }
+  if (a.iter != 0 && store) { en = cgn1[6] * efac; pw = cgn1[7] * efac; }
 
   // ---- internal force on the n+1 configuration (rknifv_std, gpifv1)
-  double sig[6];
-  if (GEONL) {
-    double q[6][6];
-    getrm1_opt2(R1, q);
-    const double t6[6] = {cgn1[0], cgn1[1], cgn1[2], cgn1[3], cgn1[4], cgn1[5]};
-    qmply(q, t6, sig);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) sig[k] = cgn1[k];
-  }
-  if (error) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) sig[k] = 0.0;
-  }
-  double G1[3][3], dj1;
+  double s[6];
+  double evol;
+  double G1[3][3];
   {
-    double X[8], Y[8], Z[8];
-    if (GEONL && a.update_coords) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        X[j] = (C[j] + U[j]) + DU[j];
-        Y[j] = (C[8 + j] + U[8 + j]) + DU[8 + j];
-        Z[j] = (C[16 + j] + U[16 + j]) + DU[16 + j];
-      }
+    double sig[6];
+    if (GEONL) {
+      double q[6][6];
+      getrm1_opt2(R1, q);
+      const double t6[6] = {cgn1[0], cgn1[1], cgn1[2], cgn1[3], cgn1[4], cgn1[5]};
+      qmply(q, t6, sig);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { X[j] = C[j]; Y[j] = C[8 + j]; Z[j] = C[16 + j]; }
+      for (int k = 0; k < 6; ++k) sig[k] = cgn1[k];
     }
-    jacobian<false>(nx, ne, nz, X, Y, Z, G1, dj1);
+    if (error) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) sig[k] = 0.0;
+    }
+    double dj1;
+    if (GEONL && a.update_coords) jacobian_smem<false, 2>(sN, gp, C, U, DU, G1, dj1);
+    else jacobian_smem<false, 0>(sN, gp, C, U, DU, G1, dj1);
+    const double wdj = weight * dj1;
+    evol = sum8(wdj);
+    double add = 0.0;
+    if (BBAR) {
+      // B-bar^T sigma = B^T (sigma - beta p m) + beta (P/V) sum_gp B_vol^T : fold the mean
+      // dilatation part into a modified stress so no nodal volume terms are exchanged
+      const double p = sig[0] + sig[1] + sig[2];
+      const double pbar = sum8(p * wdj) / sum8(dj1);
+      add = beta_b * (pbar * dj1 - p * wdj);
+    }
+    s[0] = fma(sig[0], wdj, add); s[1] = fma(sig[1], wdj, add); s[2] = fma(sig[2], wdj, add);
+    s[3] = sig[3] * wdj; s[4] = sig[4] * wdj; s[5] = sig[5] * wdj;
   }
-  const double wdj = weight * dj1;
-  double evol = sum8(wdj);
-  double s[6];
-  if (BBAR) {
-    // B-bar^T sigma = B^T (sigma - beta p m) + beta (P/V) sum_gp B_vol^T : fold the mean
-    // dilatation part into a modified stress so no nodal volume terms are exchanged
-    const double p = sig[0] + sig[1] + sig[2];
-    const double pbar = sum8(p * wdj) / sum8(dj1);
-    const double add = beta_b * (pbar * dj1 - p * wdj);
-    s[0] = sig[0] * wdj + add; s[1] = sig[1] * wdj + add; s[2] = sig[2] * wdj + add;
-  } else {
-    s[0] = sig[0] * wdj; s[1] = sig[1] * wdj; s[2] = sig[2] * wdj;
-  }
-  s[3] = sig[3] * wdj; s[4] = sig[4] * wdj; s[5] = sig[5] * wdj;
 
   double f[24];   // [node*3 + comp]
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const double bx = G1[0][0] * nx[j] + G1[0][1] * ne[j] + G1[0][2] * nz[j];
-    const double by = G1[1][0] * nx[j] + G1[1][1] * ne[j] + G1[1][2] * nz[j];
-    const double bz = G1[2][0] * nx[j] + G1[2][1] * ne[j] + G1[2][2] * nz[j];
+    const double nx = sN[0][j][gp], ne = sN[1][j][gp], nz = sN[2][j][gp];
+    const double bx = G1[0][0] * nx + G1[0][1] * ne + G1[0][2] * nz;
+    const double by = G1[1][0] * nx + G1[1][1] * ne + G1[1][2] * nz;
+    const double bz = G1[2][0] * nx + G1[2][1] * ne + G1[2][2] * nz;
     f[j * 3 + 0] = bx * s[0] + by * s[3] + bz * s[5];
     f[j * 3 + 1] = by * s[1] + bx * s[3] + bz * s[4];
     f[j * 3 + 2] = bz * s[2] + by * s[4] + bx * s[5];
