@@ -46,6 +46,17 @@ __constant__ double c_shape[3][8][8];
 #define STRESS_MIN_CTAS 4   // register cap 128/thread -> 4 CTAs (16 warps) per SM
 #endif
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): state at n streams in while the
+// kinematics run, so no warp waits on HBM latency when the material update starts
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+constexpr int NSTATE_IN = 6 + 9 + 11;   // eps_n, urcs_n, hist_n (mm01) per Gauss point
+
 // Jacobian with the node loop kept rolled: shape derivatives and coordinates are re-read from
 // shared memory each trip, so only the 9 accumulators are live (register pressure, not smem
 // bandwidth, limits this kernel).  MODE 0: X = c ; 1: X = (c+u)+du/2 ; 2: X = (c+u)+du.
@@ -134,6 +145,7 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
   __shared__ double sN[3][8][8];
   __shared__ double sC[EPC][24], sU[EPC][24], sDU[EPC][24];
   __shared__ double sRed[TPB / 32][3];
+  __shared__ double sSt[NSTATE_IN][TPB];   // state at n, [component][thread]: conflict free
 
   const int tid = threadIdx.x;
   for (int k = tid; k < 192; k += TPB) (&sN[0][0][0])[k] = (&c_shape[0][0][0])[k];
@@ -144,6 +156,17 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
   const int slot = cd.slot0 + (valid ? el : cd.nvalid - 1);
   const long long g = (long long)slot * 8 + gp;
   const long long ng = a.ng;
+
+  // ---- start streaming this Gauss point's state at n into shared memory
+#pragma unroll
+  for (int k = 0; k < 6; ++k) cp_async8(&sSt[k][tid], a.eps_n + k * ng + g);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cp_async8(&sSt[6 + k][tid], a.urcs_n + k * ng + g);
+  if (MAT == 1) {
+#pragma unroll
+    for (int k = 0; k < 11; ++k) cp_async8(&sSt[15 + k][tid], a.hist_n + k * ng + g);
+  }
+  cp_async_commit();
 
   // ---- gather: lane gp fetches node gp of its element (dofs node, 8+node, 16+node)
   int dofs[3];
@@ -215,8 +238,24 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
       error = !(dfn1 > 1.0e-20) || !(dfh > 1.0e-20);
       efac = dfn1 * dj0 * a.beta_fact * weight;
       if (!error) {
-        polar_rotation(F1, R1);
-        polar_rotation(Fh, Rh);
+        // one copy of the (large) polar-decomposition code, executed twice: keeps the kernel
+        // within the instruction cache
+#pragma unroll 1
+        for (int w = 0; w < 2; ++w) {
+          double F[3][3], R[3][3];
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) F[r][c] = w ? Fh[r][c] : F1[r][c];
+          polar_rotation(F, R);
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (w == 0) R1[r][c] = R[r][c];
+              else Rh[r][c] = R[r][c];
+            }
+        }
       }
     }
     // ---- strain increment on the mid-step configuration (rknstr_geonl, gtlsn1)
@@ -261,9 +300,10 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
   }
 
   // ---- rstgp1_update_strains (rstgp1.f:4983-5005): total strain at n+1, stored at once
+  cp_async_wait_all();   // each thread reads back only what it copied itself
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    const double e1 = a.eps_n[k * ng + g] + uddt[k];
+    const double e1 = sSt[k][tid] + uddt[k];
     if (store) a.eps_n1[k * ng + g] = e1;
   }
   if (store && GEONL && a.iter > 0) {
@@ -280,7 +320,7 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
   if (MAT == 1) {
     double cgn[9], cep[21];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) cgn[k] = a.urcs_n[k * ng + g];
+    for (int k = 0; k < 9; ++k) cgn[k] = sSt[6 + k][tid];
     const float *ep = a.eprops + (size_t)slot * EPROP;
     Mm01Props pr;
     pr.e = (double)ep[0]; pr.nu = (double)ep[1]; pr.beta = (double)ep[2];
@@ -288,7 +328,7 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
     if (a.nonlinear_update) {
       double h[11], h1[11], rtse[6];
 #pragma unroll
-      for (int k = 0; k < 11; ++k) h[k] = a.hist_n[k * ng + g];
+      for (int k = 0; k < 11; ++k) h[k] = sSt[15 + k][tid];
       double h11_first = h[10];
       if (1.0 - pr.beta != 0.0) h11_first = a.hist_n[10 * ng + (long long)cd.blk_slot0 * 8 + gp];
       fatal = mm01_update(a.step, pr, cgn, cgn1, uddt, h, h1, rtse, h11_first);

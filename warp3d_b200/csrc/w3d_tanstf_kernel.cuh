@@ -46,8 +46,12 @@ __device__ __forceinline__ int utpos(int r, int c) {
   return (hi * (hi + 1)) / 2 + lo;
 }
 
+#ifndef TANSTF_MIN_CTAS
+#define TANSTF_MIN_CTAS 3   // register cap 168/thread; 3 x 70 KB of shared memory per SM
+#endif
+
 template <bool GEONL, bool BBAR>
-__global__ void __launch_bounds__(TPB) k_tanstf(const TanstfArgs a) {
+__global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArgs a) {
   extern __shared__ double smem[];
   __shared__ double sN[3][8][8];
   const int tid = threadIdx.x;
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(TPB) k_tanstf(const TanstfArgs a) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) acc[d][i][j] = 0.0;
   const int nblk = (l < 4) ? 5 : 4;   // pairs {l, l+4} belong to lanes 0..3
+  double SV[3] = {0.0, 0.0, 0.0};     // sum over Gauss points of m^T D* Bbar_l  (B-bar only)
 
 #pragma unroll 1
   for (int p = 0; p < 8; ++p) {
@@ -241,28 +246,29 @@ __global__ void __launch_bounds__(TPB) k_tanstf(const TanstfArgs a) {
     }
 #pragma unroll
     for (int cl = 0; cl < 3; ++cl) sv[cl] = DB[cl][0] + DB[cl][1] + DB[cl][2];
-    // partner nodes
+    if (BBAR) {
+      // partner row  Bbar_a = B_a + m g_a^T,  g_a = beta (V_a - N_a):  the N_a part of g_a is
+      // folded into the first three entries of DB, the V_a part (constant over the Gauss points)
+      // is applied once after the loop through SV = sum_gp sv.
+#pragma unroll
+      for (int cl = 0; cl < 3; ++cl) {
+        SV[cl] += sv[cl];
+        const double bs = beta_b * sv[cl];
+        DB[cl][0] -= bs; DB[cl][1] -= bs; DB[cl][2] -= bs;
+      }
+    }
+    // partner nodes: 27 FMAs per 3x3 block, accumulators are the FMA addends
 #pragma unroll
     for (int d = 0; d < 5; ++d) {
       if (d < nblk) {
         const int an = (l + d) & 7;
         const double ax = pr[an * 3 + 0], ay = pr[an * 3 + 1], az = pr[an * 3 + 2];
-        double hx = 0, hy = 0, hz = 0;
-        if (BBAR) {
-          hx = beta_b * (sV[an * 3 + 0] - ax);
-          hy = beta_b * (sV[an * 3 + 1] - ay);
-          hz = beta_b * (sV[an * 3 + 2] - az);
-        }
 #pragma unroll
         for (int cl = 0; cl < 3; ++cl) {
           const double *v = DB[cl];
-          double ku = ax * v[0] + ay * v[3] + az * v[5];
-          double kv = ay * v[1] + ax * v[3] + az * v[4];
-          double kw = az * v[2] + ay * v[4] + ax * v[5];
-          if (BBAR) { ku = fma(hx, sv[cl], ku); kv = fma(hy, sv[cl], kv); kw = fma(hz, sv[cl], kw); }
-          acc[d][0][cl] += ku;
-          acc[d][1][cl] += kv;
-          acc[d][2][cl] += kw;
+          acc[d][0][cl] = fma(az, v[5], fma(ay, v[3], fma(ax, v[0], acc[d][0][cl])));
+          acc[d][1][cl] = fma(az, v[4], fma(ax, v[3], fma(ay, v[1], acc[d][1][cl])));
+          acc[d][2][cl] = fma(ax, v[5], fma(ay, v[4], fma(az, v[2], acc[d][2][cl])));
         }
         if (GEONL && !BBAR) {
           // kgstiff (kg1.f:16-160) without B-bar: per-point gradients
@@ -270,6 +276,21 @@ __global__ void __launch_bounds__(TPB) k_tanstf(const TanstfArgs a) {
           const double gtg = ax * Nx * s0 + ay * Ny * s1 + az * Nz * s2 + (ax * Ny + Nx * ay) * s3 +
                              (ay * Nz + Ny * az) * s4 + (ax * Nz + Nx * az) * s5;
           acc[d][0][0] += gtg; acc[d][1][1] += gtg; acc[d][2][2] += gtg;
+        }
+      }
+    }
+  }
+  if (BBAR) {
+    // the V_a part of the partner rows: K(a,l) += beta V_a (x) SV
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      if (d < nblk) {
+        const int an = (l + d) & 7;
+#pragma unroll
+        for (int ca = 0; ca < 3; ++ca) {
+          const double bv = beta_b * sV[an * 3 + ca];
+#pragma unroll
+          for (int cl = 0; cl < 3; ++cl) acc[d][ca][cl] = fma(bv, SV[cl], acc[d][ca][cl]);
         }
       }
     }

@@ -18,7 +18,7 @@ import numpy as np
 from .model import MXELPR, MXMTPR, MXVL, Model, State
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libw3d_engine.so")
+LIB_PATH = os.environ.get("W3D_ENGINE_LIB") or os.path.join(_HERE, "libw3d_engine.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ABI_VERSION = 1
