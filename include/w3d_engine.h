@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define W3D_ABI_VERSION 1
+#define W3D_ABI_VERSION 2
 
 /* error codes (return values) */
 #define W3D_OK             0
@@ -77,7 +77,23 @@ typedef struct w3d_engine_config {
   double  beta_fact;         /* global_data beta_fact                                            */
   int32_t adaptive_flag;     /* global_data adaptive_flag                                        */
   int32_t device;            /* CUDA device ordinal, -1 = current device                         */
+  /* ---- crystal plasticity (mm10) input; NULL / 0 when no block uses material model 10.
+   * crystal_types holds the c_array(cnum) fields the path reads (mod_crystals.f:148-236) as
+   * records of W3D_CRYSTAL_TYPE_DOUBLES doubles: elast_stiff(6,6) row-major, bi(48,3), ni(48,3)
+   * row-major [system][xyz], then harden_n, tau_y, tau_v, voche_m, theta_o, k_o, b, iD_v,
+   * eps_dot_o_y, atol, atol1, rtol, rtol1, then (as doubles) nslip, num_hard, h_type, tang_calc,
+   * miter, solver, alter_mode.  elem_cnum / elem_angles give, per element and crystal, the
+   * crystal number (1-based) and the Kocks angles exactly as setup_mm10_rknstr resolves them
+   * from imatprp(104:107), crystal_input and angle_input (rknstr.f:1690-1720).                   */
+  const double  *crystal_types;
+  int32_t        n_crystal_types;
+  int32_t        cp_ncrystals;     /* crystals per Gauss point, imatprp(101,matnum)              */
+  const int32_t *elem_cnum;        /* (cp_ncrystals, noelem)                                     */
+  const double  *elem_angles;      /* (3, cp_ncrystals, noelem)                                  */
+  int32_t        cp_angle_type;    /* 1 = degrees, 2 = radians (imatprp(103)); Kocks convention  */
+  int32_t        asymmetric_assembly; /* main_data asymmetric_assembly (mm10_a.f:1165)           */
 } w3d_engine_config;
+#define W3D_CRYSTAL_TYPE_DOUBLES 344
 
 /* scalars the stress/ifv pass returns (drive_eps_sig_internal_forces.f:210-226, 316-319) */
 typedef struct w3d_scalars {
@@ -97,6 +113,9 @@ int32_t w3d_engine_create(const w3d_engine_config *cfg, w3d_engine **handle);
 int32_t w3d_engine_destroy(w3d_engine *handle);
 /* last error text for this handle (or for a failed create when handle == NULL) */
 const char *w3d_engine_last_error(const w3d_engine *handle);
+
+/* global_data dt (time increment of the load step); read by rate-dependent models (mm10).       */
+int32_t w3d_set_time_step(w3d_engine *h, double dt);
 
 /* Replaces drive_eps_sig_internal_forces.f:115-349 (allocate_ifv, the OMP block loop over
  * do_nleps_block -> dupstr / dupstr_blocked / rknstr / rstgp1|rstgp2 / mm01+cnst1 / rplstr /

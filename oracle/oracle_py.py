@@ -27,6 +27,11 @@ class _Model(C.Structure):
     ]
 
 
+class _Cp(C.Structure):
+    _fields_ = [("ncrystals", C.c_int32), ("nslip", C.c_int32), ("num_hard", C.c_int32),
+                ("asymmetric_assembly", C.c_int32), ("props", C.c_void_p)]
+
+
 class _State(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("history", "history1", "eps_n", "eps_n1", "urcs_n", "urcs_n1", "rot_n", "rot_n1",
@@ -60,7 +65,23 @@ def lib():
         _lib.w3do_drive_eps_sig_internal_forces.restype = C.c_int32
         _lib.w3do_tanstf.restype = C.c_int32
         _lib.w3do_block_offset.restype = C.c_int64
+        _lib.w3do_mm10_props_doubles.restype = C.c_int32
+        _lib.w3do_mm10_hist_size.restype = C.c_int32
     return _lib
+
+
+def mm10_props(model):
+    """per (element, crystal) property records = setup_mm10_rknstr (rknstr.f:1568-2027)."""
+    L = lib()
+    pd = L.w3do_mm10_props_doubles()
+    n = model.noelem * model.ncrystals
+    out = np.zeros((n, pd))
+    cn = np.ascontiguousarray(model.elem_cnum.reshape(-1), dtype=np.int32)
+    ang = np.ascontiguousarray(model.elem_angles.reshape(-1), dtype=np.float64)
+    ct = np.ascontiguousarray(model.crystal_types, dtype=np.float64)
+    L.w3do_mm10_setup_props_batch(_ptr(ct), _ptr(cn), _ptr(ang), C.c_int64(n),
+                                  C.c_int32(model.angle_type), _ptr(out))
+    return out
 
 
 def _ptr(a):
@@ -77,6 +98,15 @@ class Oracle:
         self._keep = [np.ascontiguousarray(x) for x in
                       (m.elblks, m.props, m.matprp, m.c, m.edest, m.cdest, m.hist_size)]
         self._cm = _Model()
+        self._cp = None
+        if getattr(m, "crystal_types", None) is not None:
+            self._cp_props = mm10_props(m)
+            self._cp = _Cp()
+            self._cp.ncrystals = m.ncrystals
+            self._cp.nslip = int(m.crystal_types[0, 337])
+            self._cp.num_hard = int(m.crystal_types[0, 338])
+            self._cp.asymmetric_assembly = int(m.asymmetric_assembly)
+            self._cp.props = _ptr(self._cp_props)
         self.sync_globals()
 
     def sync_globals(self):
@@ -93,7 +123,7 @@ class Oracle:
         cm.extrapolated_du = int(m.extrapolated_du)
         cm.adaptive_flag = int(m.adaptive_flag)
         cm.fpconstant_data = 1
-        cm.cp = None
+        cm.cp = C.cast(C.pointer(self._cp), C.c_void_p) if self._cp is not None else None
 
     @staticmethod
     def _cstate(st):

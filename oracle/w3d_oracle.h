@@ -53,6 +53,14 @@ typedef struct w3do_model {
   const void *cp;          /* struct w3do_cp*, see w3d_oracle_cp.h                                       */
 } w3do_model;
 
+/* crystal-plasticity data (mm10): per (element, crystal) property records produced by
+ * w3do_mm10_setup_props == setup_mm10_rknstr (rknstr.f:1568-2027).  One record is
+ * W3DO_MM10_PROPS_DOUBLES doubles (w3d_mm10::Props<12>); all elements carry `ncrystals`.        */
+typedef struct w3do_cp {
+  int32_t ncrystals, nslip, num_hard, asymmetric_assembly;
+  const double *props;     /* (noelem, ncrystals, W3DO_MM10_PROPS_DOUBLES) */
+} w3do_cp;
+
 /* Blocked state, concatenated over blocks in block order; per-block pieces are in the reference
  * layouts: history (H,ngp,span), eps (6,ngp,span), urcs (9,ngp,span), rot (9,ngp,span),
  * cep (21,span,ngp) [note span before gp], estiff (utsz,span), element_vol (span).
@@ -94,6 +102,14 @@ void w3do_adaptive_reset(const w3do_model *m, w3do_state *s);
 /* offsets (in doubles) of block blk (0-based) inside the concatenated arrays; which:
  * 0 history, 1 eps, 2 urcs, 3 rot, 4 cep, 5 estiff, 6 element_vol, 7 edest/cdest (in int32s)    */
 int64_t w3do_block_offset(const w3do_model *m, int32_t blk, int32_t which);
+
+/* mm10: number of doubles in one property record; fill one record from a crystal-type table
+ * entry (w3d_mm10::CrystalType laid out as doubles, see oracle_py.py) and Kocks angles.          */
+int32_t w3do_mm10_props_doubles(void);
+int32_t w3do_mm10_crystal_type_doubles(void);
+void w3do_mm10_setup_props(const double *crystal_type, const double *angles, int32_t angle_type,
+                           double *props_out);
+int32_t w3do_mm10_hist_size(int32_t nslip, int32_t num_hard, int32_t ncrystals);
 
 /* small pieces exposed for unit tests */
 void w3do_quad2(int32_t gpn, double *xi, double *eta, double *zeta, double *w);

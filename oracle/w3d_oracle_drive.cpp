@@ -17,6 +17,7 @@
 #include <omp.h>
 #endif
 #include "w3d_oracle_internal.h"
+#include "../warp3d_b200/csrc/w3d_mm10_core.h"   // single-source mm10 core (see its header)
 
 namespace w3do {
 
@@ -207,6 +208,116 @@ static void drive_01_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
   store_cep(span, gpn, gbl_cep, cep.data());
 }
 
+// drive_10_update (rstgp1.f:4327-4513) -> mm10 (mm10_a.f:29).  The per-Gauss-point crystal update
+// is the single-source core shared with the engine (warp3d_b200/csrc/w3d_mm10_core.h, see its
+// header for why); this wrapper supplies the reference's block-local layouts.
+static void drive_10_update(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int gpn,
+                            int step, int iter, const double *uddt_displ, bool &material_cut_step,
+                            int *fatal) {
+  using namespace w3d_mm10;
+  const int span = bi.span;
+  const w3do_cp *cp = (const w3do_cp *)m->cp;
+  if (!cp || cp->nslip > 12 || cp->num_hard != 1) { *fatal = 3; return; }
+  const Layout L = Layout::make(cp->nslip, cp->num_hard);
+  if (L.size(cp->ncrystals) != bi.hist_size) { *fatal = 5; return; }
+  // small displacement analysis: rotations set to identity at the first point (:4408-4421)
+  if (!bi.geonl && gpn == 1) {
+    std::fill(lw.rot_blk_n1.begin(), lw.rot_blk_n1.end(), 0.0);
+    for (int igp = 0; igp < bi.ngp; ++igp)
+      for (int i = 0; i < mxvl; ++i) {
+        lw.rot_blk_n1[((size_t)igp * 9 + 0) * mxvl + i] = 1.0;
+        lw.rot_blk_n1[((size_t)igp * 9 + 4) * mxvl + i] = 1.0;
+        lw.rot_blk_n1[((size_t)igp * 9 + 8) * mxvl + i] = 1.0;
+      }
+  }
+  bool iter_0_extrapolate_off = false;
+  if (iter == 0) {
+    iter_0_extrapolate_off = m->extrapolated_du == 0;
+    if (step == 1) iter_0_extrapolate_off = true;
+  }
+  double *urcs_n = &lw.urcs_blk_n[(size_t)(gpn - 1) * nstrs * mxvl];
+  double *urcs_n1 = &lw.urcs_blk_n1[(size_t)(gpn - 1) * nstrs * mxvl];
+  const double *rot = &lw.rot_blk_n1[(size_t)(gpn - 1) * 9 * mxvl];
+  double *hist = &lw.elem_hist[(size_t)(gpn - 1) * bi.hist_size * span];
+  double *hist1 = &lw.elem_hist1[(size_t)(gpn - 1) * bi.hist_size * span];
+  const size_t prec = sizeof(Props<12>) / sizeof(double);
+  for (int i = 0; i < span; ++i) {
+    const int elem = bi.felem + i;
+    const Props<12> *P =
+        (const Props<12> *)(cp->props + (size_t)(elem - 1) * cp->ncrystals * prec);
+    double Rur[9], ud[6], cgn[9], cgn1[9];
+    for (int k = 0; k < 9; ++k) Rur[k] = rot[(size_t)k * mxvl + i];
+    for (int k = 0; k < 6; ++k) ud[k] = uddt_displ[(size_t)k * mxvl + i] + 0.0;
+    for (int k = 0; k < 9; ++k) cgn[k] = urcs_n[(size_t)k * mxvl + i];
+    const CHist hn{hist + i, span};
+    const Hist h1{hist1 + i, span};
+    const bool cut = gauss_point_update<12>(step, cp->ncrystals, P, L, hn, h1, Rur, ud, m->dt,
+                                            iter_0_extrapolate_off, cp->asymmetric_assembly != 0,
+                                            cgn, cgn1);
+    if (cut) { material_cut_step = true; return; }
+    for (int k = 0; k < 9; ++k) urcs_n1[(size_t)k * mxvl + i] = cgn1[k];
+  }
+}
+
+// rknstr_finish_cp (rknstr.f:268-296) -> mm10_calc_grads (mm10_a.f:1579): gradient of the elastic
+// rotation by a linear fit over the Gauss points, stored in history at n+1 for every point.
+static void finish_cp(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int step) {
+  using namespace w3d_mm10;
+  const w3do_cp *cp = (const w3do_cp *)m->cp;
+  const int span = bi.span, ngp = bi.ngp, H = bi.hist_size;
+  const Layout L = Layout::make(cp->nslip, cp->num_hard);
+  for (int i = 0; i < span; ++i) {
+    double grads[27];
+    if (cp->ncrystals > 1) {
+      for (int k = 0; k < 27; ++k) grads[k] = 0.0;
+    } else {
+      double rt[8][9], jacinv[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      for (int gp = 0; gp < ngp; ++gp) {
+        double Rp[9], rot[9];
+        for (int k = 0; k < 9; ++k) {
+          // the block-local history at n was initialised at step 1 (Rp = I)
+          Rp[k] = (step == 1) ? ((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0)
+                              : lw.elem_hist[((size_t)gp * H + L.c_Rp(0) + k) * span + i];
+          rot[k] = lw.rot_blk_n1[((size_t)gp * 9 + k) * mxvl + i];
+        }
+        if (bi.geonl) {
+          for (int a = 0; a < 3; ++a)      // mult_type_3t: Rt = Rp * rot^T
+            for (int b = 0; b < 3; ++b)
+              rt[gp][b * 3 + a] = Rp[0 * 3 + a] * rot[0 * 3 + b] + Rp[1 * 3 + a] * rot[1 * 3 + b] +
+                                  Rp[2 * 3 + a] * rot[2 * 3 + b];
+        } else {
+          for (int k = 0; k < 9; ++k) rt[gp][k] = Rp[k];
+        }
+      }
+      if (bi.geonl) {
+        // local_work%jac holds the last Jacobian formed: undeformed configuration, last point
+        double a[3][3];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) a[r][c] = lw.jac[(size_t)(c * 3 + r) * mxvl + i];
+        const double det = a[0][0] * a[1][1] * a[2][2] - a[0][0] * a[1][2] * a[2][1] -
+                           a[0][1] * a[1][0] * a[2][2] + a[0][1] * a[1][2] * a[2][0] +
+                           a[0][2] * a[1][0] * a[2][1] - a[0][2] * a[1][1] * a[2][0];
+        double cof[3][3];
+        cof[0][0] = +(a[1][1] * a[2][2] - a[1][2] * a[2][1]);
+        cof[0][1] = -(a[1][0] * a[2][2] - a[1][2] * a[2][0]);
+        cof[0][2] = +(a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+        cof[1][0] = -(a[0][1] * a[2][2] - a[0][2] * a[2][1]);
+        cof[1][1] = +(a[0][0] * a[2][2] - a[0][2] * a[2][0]);
+        cof[1][2] = -(a[0][0] * a[2][1] - a[0][1] * a[2][0]);
+        cof[2][0] = +(a[0][1] * a[1][2] - a[0][2] * a[1][1]);
+        cof[2][1] = -(a[0][0] * a[1][2] - a[0][2] * a[1][0]);
+        cof[2][2] = +(a[0][0] * a[1][1] - a[0][1] * a[1][0]);
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) jacinv[r][c] = (std::fabs(det) <= 1.0e-10) ? 0.0 : cof[c][r] / det;
+      }
+      calc_grads(rt, bi.geonl, jacinv, grads);
+    }
+    for (int gp = 0; gp < ngp; ++gp)
+      for (int k = 0; k < 27; ++k)
+        lw.elem_hist1[((size_t)gp * H + L.o_gradfe() + k) * span + i] = grads[k];
+  }
+}
+
 // rstgp1 (rstgp1.f:19-332) geonl ; rstgp2 (rstgp1.f:351-598) small strain
 static void rstgp(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int gpn, int step,
                   int iter, double *gbl_cep, double &block_energy, double &block_plastic_work,
@@ -248,6 +359,10 @@ static void rstgp(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int g
   switch (bi.mat_type) {
     case 1:
       drive_01_update(m, bi, lw, gpn, step, iter, uddt.data(), gbl_cep, fatal);
+      break;
+    case 10:
+      drive_10_update(m, bi, lw, gpn, step, iter, uddt.data(), material_cut_step, fatal);
+      if (material_cut_step || *fatal) return;
       break;
     default:
       *fatal = 3;  // material model not in the oracle
@@ -314,6 +429,7 @@ static void rknstr(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int 
           material_cut_step, fatal);
     if (material_cut_step || *fatal) return;
   }
+  if (bi.mat_type == 10) finish_cp(m, bi, lw, step);   // rknstr.f:182
 }
 
 // gpifv1 (gpifv1.f:16-165), solid branch
@@ -463,6 +579,38 @@ void w3do_deriv2(double xi, double eta, double zeta, double *nxi, double *neta, 
   deriv2(xi, eta, zeta, nxi, neta, nzeta);
 }
 void w3do_cp_icp(int32_t n, int32_t *cp, int32_t *dcp, int32_t *icp) { make_cp_icp(n, cp, dcp, icp); }
+
+int32_t w3do_mm10_props_doubles(void) { return (int32_t)(sizeof(w3d_mm10::Props<12>) / sizeof(double)); }
+int32_t w3do_mm10_crystal_type_doubles(void) { return (int32_t)(sizeof(w3d_mm10::CrystalType) / sizeof(double)); }
+int32_t w3do_mm10_hist_size(int32_t nslip, int32_t num_hard, int32_t ncrystals) {
+  return w3d_mm10::Layout::make(nslip, num_hard).size(ncrystals);
+}
+// crystal_type: w3d_mm10::CrystalType with the trailing ints widened to doubles (oracle_py.py)
+void w3do_mm10_setup_props(const double *ctd, const double *angles, int32_t angle_type,
+                           double *props_out) {
+  w3d_mm10::CrystalType ct;
+  const size_t nd = 36 + 144 + 144 + 13;
+  std::memcpy(&ct, ctd, nd * sizeof(double));
+  const double *ti = ctd + nd;
+  ct.nslip = (int)ti[0]; ct.num_hard = (int)ti[1]; ct.h_type = (int)ti[2]; ct.tang_calc = (int)ti[3];
+  ct.miter = (int)ti[4]; ct.solver = (int)ti[5]; ct.alter_mode = (int)ti[6];
+  w3d_mm10::Props<12> P;
+  std::memset(&P, 0, sizeof P);
+  w3d_mm10::setup_props<12>(ct, angles, angle_type, P);
+  std::memcpy(props_out, &P, sizeof P);
+}
+
+// n records at once: cnum (1-based into the table of crystal types), angles (3 per record)
+void w3do_mm10_setup_props_batch(const double *ct_table, const int32_t *cnum, const double *angles,
+                                 int64_t n, int32_t angle_type, double *props_out) {
+  const size_t ctd = sizeof(w3d_mm10::CrystalType) / sizeof(double) + 0;
+  const size_t rec = 36 + 144 + 144 + 13 + 7;
+  (void)ctd;
+  const size_t pd = sizeof(w3d_mm10::Props<12>) / sizeof(double);
+  for (int64_t k = 0; k < n; ++k)
+    w3do_mm10_setup_props(ct_table + (size_t)(cnum[k] - 1) * rec, angles + 3 * k, angle_type,
+                          props_out + (size_t)k * pd);
+}
 
 // drive_eps_sig_internal_forces.f:20-387
 int32_t w3do_drive_eps_sig_internal_forces(const w3do_model *m, w3do_state *s, int32_t step,

@@ -13,6 +13,7 @@
 #include <omp.h>
 #endif
 #include "w3d_oracle_internal.h"
+#include "../warp3d_b200/csrc/w3d_mm10_core.h"
 
 namespace w3do {
 
@@ -263,8 +264,18 @@ static void do_nlek_block(const w3do_model *m, const BlockPtrs &bp, int blk, int
     }
     blcmp1(span, lw.b_block.data(), gama, nxi, neta, nzeta, nnode);
     if (bi.bbar) bmod(lw.b_block.data(), lw.vol_block.data(), span, m->eps_bbar);
-    // drive_01_cnst / drive_05_cnst -> extract_D_symmetric
-    extract_D_symmetric(span, gpn, weight, dj, bp.cep, lw.cep.data());
+    if (bi.mat_type == 10) {
+      // drive_10_cnst (gptns1.f:1371-1410): [D] = history1(1:36) (6x6 column-major) * w * detJ
+      for (int i = 0; i < span; ++i) {
+        const double f = weight * dj[i];
+        const double *h = bp.history1 + ((size_t)i * ngp + (gpn - 1)) * bi.hist_size;
+        for (int c = 1; c <= 6; ++c)
+          for (int r = 1; r <= 6; ++r) Q6(lw.cep, i, r, c) = h[(c - 1) * 6 + (r - 1)] * f;
+      }
+    } else {
+      // drive_01_cnst / drive_05_cnst -> extract_D_symmetric
+      extract_D_symmetric(span, gpn, weight, dj, bp.cep, lw.cep.data());
+    }
     if (bi.geonl)
       ctran1(span, lw.cep.data(), lw.qn1.data(), lw.cs_blk_n1.data(), m->qbar_flag != 0, dj, weight);
     bdbtgen(span, lw.icp.data(), lw.b_block.data(), lw.bd_block.data(), lw.cep.data(),

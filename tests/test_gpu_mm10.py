@@ -1,0 +1,67 @@
+"""GPU parity for the crystal-plasticity path (mm10, Voce hardening, fcc): the engine's three
+launches (kinematics, k_mm10, internal force + curvature fit) through the C ABI against the CPU
+build of the same single-source crystal update wrapped in the oracle's block driver."""
+import numpy as np
+import pytest
+
+from common import RTOL, load_path, relerr
+from warp3d_b200 import (Material, attach_crystals, build_structured_hex8, make_crystal_type,
+                         new_state)
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(nx, ny, nz, ncrystals=1, geonl=True, bbar=True, dt=0.5, **kw):
+    ct = make_crystal_type(e=100000.0, nu=0.3, harden_n=20, tau_y=100.0, tau_v=50.0, theta_o=500.0,
+                           voche_m=1.0)
+    m = build_structured_hex8(nx, ny, nz, materials=[Material(mat_type=10)], geonl=geonl, bbar=bbar,
+                              coord_jitter=0.1, seed=7, dt=dt, **kw)
+    return attach_crystals(m, ct, ncrystals=ncrystals)
+
+
+def _run(m, nsteps=3, strain=2.0e-3, tol=RTOL):
+    from oracle.oracle_py import Oracle
+    from warp3d_b200.engine import Engine
+    eng, orc = Engine(m), Oracle(m)
+    so, sg = new_state(m), new_state(m)
+    eng.push_state(sg)
+    for step, iters in load_path(m, nsteps=nsteps, strain=strain):
+        for itr, u, du in iters:
+            fo, sco = orc.eps_sig_ifv(so, step, itr, u, du)
+            fg, scg = eng.drive_eps_sig_internal_forces(step, itr, u, du)
+            tag = f"step {step} iter {itr}"
+            assert scg["material_cut_step"] == sco["material_cut_step"] is False
+            assert relerr(fg, fo) <= tol, f"{tag}: ifv {relerr(fg, fo):.3e}"
+            for k in ("internal_energy", "plastic_work", "sum_ifv"):
+                assert abs(scg[k] - sco[k]) <= tol * max(abs(sco[k]), 1e-300), (tag, k, scg[k], sco[k])
+            eng.pull_state(sg)
+            for name in ("eps_n1", "urcs_n1", "rot_n1", "element_vol"):
+                e = relerr(getattr(sg, name), getattr(so, name))
+                assert e <= tol, f"{tag}: {name} {e:.3e}"
+            H = int(m.hist_size[0])
+            hg, ho = sg.history1.reshape(-1, H), so.history1.reshape(-1, H)
+            for col in range(H):
+                scale = max(np.abs(ho[:, col]).max(), 1e-12 * np.abs(ho).max())
+                assert np.abs(hg[:, col] - ho[:, col]).max() <= max(tol, 1e-9 if col >= 87 + 30 else tol) * scale, \
+                    f"{tag}: history1 column {col}"
+            ko = orc.tanstf(so, step, itr, u, du).reshape(-1, 300)
+            kg = eng.tanstf(step, itr, u, du).reshape(-1, 300)
+            e = (np.abs(kg - ko).max(axis=1) / np.abs(ko).max(axis=1)).max()
+            assert e <= tol, f"{tag}: estiff {e:.3e}"
+        orc.update(so); orc.adaptive_save(so)
+        eng.update(); eng.adaptive_save()
+    plastic = so.urcs_n.reshape(-1, 9)[:, 8].max()
+    eng.close()
+    return plastic
+
+
+def test_single_crystal_geonl_bbar():
+    assert _run(_model(3, 2, 2, block_size=7)) > 0.0
+
+
+def test_single_crystal_small_strain():
+    assert _run(_model(2, 2, 2, geonl=False), strain=3.0e-3) > 0.0
+
+
+def test_polycrystal_three_crystals_per_point():
+    assert _run(_model(2, 2, 1, ncrystals=3), nsteps=2, strain=3.0e-3) > 0.0

@@ -1,0 +1,73 @@
+// w3d_cp.cu -- mm10 (crystal plasticity) Gauss-point update kernel.  Replaces drive_10_update
+// (rstgp1.f:4327-4513) -> mm10 (mm10_a.f:29): one thread per Gauss point runs all crystals of the
+// point through the shared core (w3d_mm10_core.h): Schmid-tensor set-up, stress predictor and
+// 7x7 Newton update with line search and adaptive sub-incrementation, consistent tangent by
+// Schur complement, plastic rotation update and the output/history terms.
+// Inputs from the PHASE 1 kinematics launch (scratch: R(n+1), strain increment, energy factor).
+#include <cstring>
+
+#include "w3d_cp_kernel.h"
+#include "w3d_mm10_core.h"
+
+namespace w3d {
+
+using namespace w3d_mm10;
+
+template <int NS>
+__global__ void __launch_bounds__(TPB) k_mm10(const CpArgs a) {
+  const int tid = threadIdx.x;
+  const CtaDesc cd = a.cta[blockIdx.x];
+  const int el = tid >> 3, gp = tid & 7;
+  if (el >= cd.nvalid) return;
+  const int slot = cd.slot0 + el;
+  const long long ng = a.ng;
+  const long long g = (long long)slot * 8 + gp;
+  const double efac = a.scratch[15 * ng + g];
+  if (!(efac == efac)) return;   // det F <= 0: step cut already requested by the kinematics
+  double Rur[9], uddt[6], cgn[9], cgn1[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Rur[k] = a.scratch[k * ng + g];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) uddt[k] = a.scratch[(9 + k) * ng + g];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cgn[k] = a.urcs_n[k * ng + g];
+  const Layout L = Layout::make(a.nslip, a.num_hard);
+  const Props<NS> *P = reinterpret_cast<const Props<NS> *>(
+      a.props + (size_t)slot * a.ncrystals * (sizeof(Props<NS>) / sizeof(double)));
+  const CHist hn{a.hist_n + g, ng};
+  const Hist h1{a.hist_n1 + g, ng};
+  const bool cut = gauss_point_update<NS>(a.step, a.ncrystals, P, L, hn, h1, Rur, uddt, a.dt,
+                                          a.iter_0_extrapolate_off != 0, a.asymmetric != 0, cgn, cgn1);
+  if (cut) {
+    atomicOr(&a.flags[0], 1);
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) a.urcs_n1[k * ng + g] = cgn1[k];
+}
+
+int mm10_props_doubles() { return (int)(sizeof(Props<12>) / sizeof(double)); }
+int mm10_hist_size(int nslip, int num_hard, int ncrystals) { return Layout::make(nslip, num_hard).size(ncrystals); }
+void mm10_layout_offsets(int nslip, int num_hard, int *o_gradfe, int *o_Rp0) {
+  const Layout L = Layout::make(nslip, num_hard);
+  *o_gradfe = L.o_gradfe();
+  *o_Rp0 = L.c_Rp(0);
+}
+void mm10_setup_props_host(const double *ctd, const double *angles, int angle_type, double *props_out) {
+  CrystalType ct;
+  const size_t nd = 36 + 144 + 144 + 13;
+  std::memcpy(&ct, ctd, nd * sizeof(double));
+  const double *ti = ctd + nd;
+  ct.nslip = (int)ti[0]; ct.num_hard = (int)ti[1]; ct.h_type = (int)ti[2]; ct.tang_calc = (int)ti[3];
+  ct.miter = (int)ti[4]; ct.solver = (int)ti[5]; ct.alter_mode = (int)ti[6];
+  Props<12> P;
+  std::memset(&P, 0, sizeof P);
+  setup_props<12>(ct, angles, angle_type, P);
+  std::memcpy(props_out, &P, sizeof P);
+}
+cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {
+  k_mm10<12><<<ncta, TPB, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace w3d

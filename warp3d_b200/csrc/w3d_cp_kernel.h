@@ -1,0 +1,29 @@
+// w3d_cp_kernel.h -- interface of the crystal-plasticity (mm10) Gauss-point kernel, compiled in
+// its own translation unit (w3d_cp.cu) with -fmad=false so that the tolerance-terminated local
+// Newton loops see the same IEEE operations as the CPU build of the shared core.
+#pragma once
+#include <cuda_runtime.h>
+#include "w3d_device.cuh"
+
+namespace w3d {
+
+struct CpArgs {
+  const CtaDesc *cta;
+  const double *props;        // [slot][ncrystals][props_doubles]  (w3d_mm10::Props<12>)
+  const double *hist_n, *urcs_n, *scratch;
+  double *hist_n1, *urcs_n1;
+  int *flags;
+  long long ng;
+  double dt;
+  int step, iter_0_extrapolate_off, asymmetric, ncrystals, nslip, num_hard;
+};
+
+int mm10_props_doubles();
+// host: one property record from a crystal-type record (setup_mm10_rknstr, rknstr.f:1568-2027)
+void mm10_setup_props_host(const double *crystal_type_rec, const double *angles, int angle_type,
+                           double *props_out);
+int mm10_hist_size(int nslip, int num_hard, int ncrystals);
+void mm10_layout_offsets(int nslip, int num_hard, int *o_gradfe, int *o_Rp0);
+cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st);
+
+}  // namespace w3d

@@ -15,6 +15,7 @@
 
 #include "w3d_stress_kernel.cuh"
 #include "w3d_tanstf_kernel.cuh"
+#include "w3d_cp_kernel.h"
 
 using namespace w3d;
 
@@ -44,6 +45,9 @@ struct Segment {
   double *eps_n = nullptr, *eps_n1 = nullptr, *urcs_n = nullptr, *urcs_n1 = nullptr,
          *rot_n = nullptr, *rot_n1 = nullptr, *cep = nullptr, *hist_n = nullptr,
          *hist_n1 = nullptr, *elem_vol = nullptr, *partials = nullptr;
+  // crystal plasticity (mm10)
+  double *d_cprops = nullptr, *scratch = nullptr;
+  int ncrystals = 0, nslip = 0, num_hard = 0, o_gradfe = 0, o_Rp0 = 0;
 };
 
 struct BlockInfo {
@@ -76,6 +80,7 @@ struct w3d_engine {
   size_t stage_doubles = 0;
   double *h_pin = nullptr;          // pinned: [0..3] scalars, then 2 ints of flags
   int64_t launches = 0;
+  double dt = 1.0;
   w3d_scalars last{};
   bool have_vectors = false;
 
@@ -205,6 +210,7 @@ void free_all(w3d_engine *h) {
     cudaFree(s.eps_n); cudaFree(s.eps_n1); cudaFree(s.urcs_n); cudaFree(s.urcs_n1);
     cudaFree(s.rot_n); cudaFree(s.rot_n1); cudaFree(s.cep); cudaFree(s.hist_n);
     cudaFree(s.hist_n1); cudaFree(s.elem_vol); cudaFree(s.partials);
+    cudaFree(s.d_cprops); cudaFree(s.scratch);
   }
   cudaFree(h->d_c); cudaFree(h->d_u); cudaFree(h->d_du); cudaFree(h->d_ifv);
   cudaFree(h->d_estiff); cudaFree(h->d_scal); cudaFree(h->d_flags); cudaFree(h->d_stage);
@@ -256,10 +262,20 @@ int create_impl(w3d_engine *h) {
     if (!b.owned) continue;
     if (b.elem_type != 2 || b.nnode != 8 || b.ndof != 3 || b.ngp != 8)
       return fail(W3D_ERR_UNSUPPORTED, "block %d: element type %d (%d nodes, %d points): only hex8 l3disop 2x2x2", blk + 1, b.elem_type, b.nnode, b.ngp);
-    if (b.mat_type != 1)
-      return fail(W3D_ERR_UNSUPPORTED, "block %d: material model %d not built yet (mm01 only)", blk + 1, b.mat_type);
+    if (b.mat_type != 1 && b.mat_type != 10)
+      return fail(W3D_ERR_UNSUPPORTED, "block %d: material model %d not built yet (mm01, mm10)", blk + 1, b.mat_type);
     if (b.mat_type == 1 && b.hist_size != 11)
       return fail(W3D_ERR_CONFIG, "block %d: mm01 history size %d != 11", blk + 1, b.hist_size);
+    if (b.mat_type == 10) {
+      if (!c.crystal_types || !c.elem_cnum || !c.elem_angles || c.cp_ncrystals < 1 || c.n_crystal_types < 1)
+        return fail(W3D_ERR_CONFIG, "block %d uses mm10 but no crystal tables were given", blk + 1);
+      const double *ct0 = c.crystal_types;
+      const int nslip = (int)ct0[337], num_hard = (int)ct0[338], h_type = (int)ct0[339];
+      if (nslip > 12 || num_hard != 1 || h_type != 1)
+        return fail(W3D_ERR_UNSUPPORTED, "block %d: mm10 with nslip %d, num_hard %d, hardening %d (built: <=12 systems, Voce)", blk + 1, nslip, num_hard, h_type);
+      if (b.hist_size != mm10_hist_size(nslip, num_hard, c.cp_ncrystals))
+        return fail(W3D_ERR_CONFIG, "block %d: mm10 history size %d != %d", blk + 1, b.hist_size, mm10_hist_size(nslip, num_hard, c.cp_ncrystals));
+    }
     int sidx = -1;
     for (size_t s = 0; s < h->segs.size(); ++s) {
       const Segment &sg = h->segs[s];
@@ -338,6 +354,36 @@ int create_impl(w3d_engine *h) {
         if (n > 0 && (size_t)n > max_blk_doubles) max_blk_doubles = (size_t)n;
       }
     }
+    if (sg.mat_type == 10) {
+      // setup_mm10_rknstr (rknstr.f:1568-2027) once per (element, crystal): rotation from the
+      // Kocks angles, Schmid tensors and elastic stiffness in the reference frame
+      const int pd = mm10_props_doubles();
+      sg.ncrystals = c.cp_ncrystals;
+      sg.nslip = (int)c.crystal_types[337];
+      sg.num_hard = (int)c.crystal_types[338];
+      mm10_layout_offsets(sg.nslip, sg.num_hard, &sg.o_gradfe, &sg.o_Rp0);
+      std::vector<double> cp((size_t)sg.nslots * sg.ncrystals * pd, 0.0);
+      for (int blk : sg.blocks) {
+        const BlockInfo &b = h->blocks[blk];
+        const int padded = ((b.span + EPC - 1) / EPC) * EPC;
+        for (int i = 0; i < padded; ++i) {
+          const int src = (i < b.span) ? i : b.span - 1;
+          const int elem = b.felem + src;
+          for (int cr = 0; cr < sg.ncrystals; ++cr) {
+            const size_t k = (size_t)(elem - 1) * sg.ncrystals + cr;
+            const int cnum = c.elem_cnum[k];
+            if (cnum < 1 || cnum > c.n_crystal_types)
+              return fail(W3D_ERR_CONFIG, "element %d crystal %d: crystal number %d outside 1..%d", elem, cr + 1, cnum, c.n_crystal_types);
+            mm10_setup_props_host(c.crystal_types + (size_t)(cnum - 1) * W3D_CRYSTAL_TYPE_DOUBLES,
+                                  c.elem_angles + 3 * k, c.cp_angle_type,
+                                  &cp[((size_t)(b.slot0 + i) * sg.ncrystals + cr) * pd]);
+          }
+        }
+      }
+      CUDA_TRY(dalloc(&sg.d_cprops, cp.size()));
+      CUDA_TRY(cudaMemcpy(sg.d_cprops, cp.data(), sizeof(double) * cp.size(), cudaMemcpyHostToDevice));
+      CUDA_TRY(dalloc(&sg.scratch, (size_t)16 * sg.nslots * 8));
+    }
     CUDA_TRY(dalloc(&sg.d_cta, (size_t)sg.ncta));
     CUDA_TRY(cudaMemcpy(sg.d_cta, cta.data(), sizeof(CtaDesc) * sg.ncta, cudaMemcpyHostToDevice));
     CUDA_TRY(dalloc(&sg.d_edest, ed.size()));
@@ -370,14 +416,14 @@ int create_impl(w3d_engine *h) {
   return W3D_OK;
 }
 
-template <int MAT>
+template <int MAT, int PHASE>
 void launch_stress(const Segment &sg, const StressArgs &a, cudaStream_t st) {
   if (sg.geonl) {
-    if (sg.bbar) k_eps_sig_ifv<MAT, true, true><<<sg.ncta, TPB, 0, st>>>(a);
-    else k_eps_sig_ifv<MAT, true, false><<<sg.ncta, TPB, 0, st>>>(a);
+    if (sg.bbar) k_eps_sig_ifv<MAT, true, true, PHASE><<<sg.ncta, TPB, 0, st>>>(a);
+    else k_eps_sig_ifv<MAT, true, false, PHASE><<<sg.ncta, TPB, 0, st>>>(a);
   } else {
-    if (sg.bbar) k_eps_sig_ifv<MAT, false, true><<<sg.ncta, TPB, 0, st>>>(a);
-    else k_eps_sig_ifv<MAT, false, false><<<sg.ncta, TPB, 0, st>>>(a);
+    if (sg.bbar) k_eps_sig_ifv<MAT, false, true, PHASE><<<sg.ncta, TPB, 0, st>>>(a);
+    else k_eps_sig_ifv<MAT, false, false, PHASE><<<sg.ncta, TPB, 0, st>>>(a);
   }
 }
 
@@ -400,9 +446,25 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
     a.update_coords = (sg.geonl && !(step == 1 && iter == 0)) ? 1 : 0;
     a.adaptive = (c.adaptive_flag && step > 1) ? 1 : 0;
     a.hist_size = sg.hist_size;
-    launch_stress<1>(sg, a, h->stream);
+    if (sg.mat_type == 10) {
+      a.scratch = sg.scratch; a.cp_ncrystals = sg.ncrystals; a.cp_o_gradfe = sg.o_gradfe; a.cp_o_Rp = sg.o_Rp0;
+      launch_stress<10, 1>(sg, a, h->stream);
+      CpArgs ca{};
+      ca.cta = sg.d_cta; ca.props = sg.d_cprops; ca.hist_n = sg.hist_n; ca.urcs_n = sg.urcs_n;
+      ca.scratch = sg.scratch; ca.hist_n1 = sg.hist_n1; ca.urcs_n1 = sg.urcs_n1; ca.flags = h->d_flags;
+      ca.ng = sg.ng; ca.dt = h->dt; ca.step = step;
+      ca.iter_0_extrapolate_off = (iter == 0 && (!extrapolated_du || step == 1)) ? 1 : 0;   // rstgp1.f:4453-4457
+      ca.asymmetric = c.asymmetric_assembly ? 1 : 0;
+      ca.ncrystals = sg.ncrystals; ca.nslip = sg.nslip; ca.num_hard = sg.num_hard;
+      CUDA_TRY(launch_mm10(ca, sg.ncta, h->stream));
+      launch_stress<10, 2>(sg, a, h->stream);
+      h->launches += 3;
+    } else {
+      launch_stress<1, 0>(sg, a, h->stream);
+      h->launches += 1;
+    }
     k_reduce_partials<<<1, 256, 0, h->stream>>>(sg.partials, sg.ncta, h->d_scal, first ? 0 : 1);
-    h->launches += 2;
+    h->launches += 1;
     first = 0;
   }
   CUDA_TRY(cudaGetLastError());
@@ -444,6 +506,7 @@ int tanstf_resident(w3d_engine *h, int step, int iter) {
     a.urcs_n1 = sg.urcs_n1; a.rot_n1 = sg.rot_n1; a.cep = sg.cep;
     a.estiff = h->d_estiff; a.ng = sg.ng; a.eps_bbar = c.eps_bbar; a.beta_fact = c.beta_fact;
     a.qbar = c.qbar_flag ? 1 : 0;
+    a.hist_n1 = sg.hist_n1; a.d_from_hist = (sg.mat_type == 10) ? 1 : 0;
     const size_t shm = (size_t)EPC * ELREC * 8;
     if (sg.geonl) {
       if (sg.bbar) k_tanstf<true, true><<<sg.ncta, TPB, shm, h->stream>>>(a);
@@ -488,6 +551,7 @@ int32_t w3d_engine_create(const w3d_engine_config *cfg, w3d_engine **handle) {
   // the engine keeps no pointer into caller memory after create
   h->cfg.elblks = nullptr; h->cfg.props = nullptr; h->cfg.matprp = nullptr; h->cfg.c = nullptr;
   h->cfg.edest = nullptr; h->cfg.cdest = nullptr; h->cfg.history_blk_list = nullptr;
+  h->cfg.crystal_types = nullptr; h->cfg.elem_cnum = nullptr; h->cfg.elem_angles = nullptr;
   *handle = h;
   return W3D_OK;
 }
@@ -539,6 +603,12 @@ int32_t w3d_tanstf(w3d_engine *h, int32_t step, int32_t iter, const double *u, c
   if (estiff)
     CUDA_TRY(cudaMemcpyAsync(estiff, h->d_estiff, sizeof(double) * 300 * (size_t)h->n_owned_elems, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return W3D_OK;
+}
+
+int32_t w3d_set_time_step(w3d_engine *h, double dt) {
+  if (!h) return W3D_ERR_ARG;
+  h->dt = dt;
   return W3D_OK;
 }
 

@@ -16,6 +16,7 @@
 #pragma once
 #include "w3d_device.cuh"
 #include "w3d_mm01.cuh"
+#include "w3d_mm10_core.h"
 
 namespace w3d {
 
@@ -36,6 +37,10 @@ struct StressArgs {
   int update_coords;              // geonl and not (step 1, iter 0)  (:1722-1754)
   int adaptive;                   // adaptive_flag and step > 1 (rstgp1.f:136-145)
   int hist_size;
+  // crystal plasticity (mm10) runs as three launches: PHASE 1 kinematics -> scratch,
+  // k_mm10 material update, PHASE 2 internal force + lattice-curvature fit
+  double *scratch;                // [16][ng]: R(n+1) 9 (column-major), uddt 6, energy factor 1
+  int cp_ncrystals, cp_o_gradfe, cp_o_Rp;   // history offsets (w3d_mm10::Layout)
 };
 
 // parent-space shape function derivatives of the 8 Gauss points: [dir][node][gp], filled by the
@@ -140,7 +145,25 @@ __device__ __forceinline__ void strain_increment(const double (*sN)[8][8], int g
   }
 }
 
-template <int MAT, bool GEONL, bool BBAR>
+// Jacobian matrix only, reference statement order (local_work%jac of jacob1) -- used by the
+// mm10 lattice-curvature fit, which inverts it by cofactors (mm10_a_invert_33)
+__device__ __forceinline__ void jacobian_matrix_exact(const double (*sN)[8][8], int gp,
+                                                      const double *C, double (&J)[3][3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) J[r][c] = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const double nx = sN[0][j][gp], ne = sN[1][j][gp], nz = sN[2][j][gp];
+    const double x = C[j], y = C[8 + j], z = C[16 + j];
+    J[0][0] = xa(J[0][0], xm(nx, x)); J[0][1] = xa(J[0][1], xm(nx, y)); J[0][2] = xa(J[0][2], xm(nx, z));
+    J[1][0] = xa(J[1][0], xm(ne, x)); J[1][1] = xa(J[1][1], xm(ne, y)); J[1][2] = xa(J[1][2], xm(ne, z));
+    J[2][0] = xa(J[2][0], xm(nz, x)); J[2][1] = xa(J[2][1], xm(nz, y)); J[2][2] = xa(J[2][2], xm(nz, z));
+  }
+}
+
+template <int MAT, bool GEONL, bool BBAR, int PHASE = 0>
 __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const StressArgs a) {
   __shared__ double sN[3][8][8];
   __shared__ double sC[EPC][24], sU[EPC][24], sDU[EPC][24];
@@ -158,10 +181,14 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
   const long long ng = a.ng;
 
   // ---- start streaming this Gauss point's state at n into shared memory
+  if (PHASE != 2) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) cp_async8(&sSt[k][tid], a.eps_n + k * ng + g);
+    for (int k = 0; k < 6; ++k) cp_async8(&sSt[k][tid], a.eps_n + k * ng + g);
+  }
+  if (MAT == 1) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) cp_async8(&sSt[6 + k][tid], a.urcs_n + k * ng + g);
+    for (int k = 0; k < 9; ++k) cp_async8(&sSt[6 + k][tid], a.urcs_n + k * ng + g);
+  }
   if (MAT == 1) {
 #pragma unroll
     for (int k = 0; k < 11; ++k) cp_async8(&sSt[15 + k][tid], a.hist_n + k * ng + g);
@@ -193,7 +220,17 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
   double efac;          // detF * detJ0 * beta_fact * w  (rstgp1_b)
   double uddt[6];
 
-  if (GEONL) {
+  if (PHASE == 2) {
+    // kinematics were done by the PHASE 1 launch: reload R(n+1) and the energy factor
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) R1[r][c] = a.scratch[(c * 3 + r) * ng + g];
+    efac = a.scratch[15 * ng + g];
+    error = !(efac == efac);   // NaN marks a point whose det F was not positive
+#pragma unroll
+    for (int k = 0; k < 6; ++k) uddt[k] = 0.0;
+  } else if (GEONL) {
     // ---- gtmat1 (gtmat1.f:17-190): F at n+1 and n+1/2 from the undeformed configuration
     double Rh[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
     {
@@ -301,16 +338,31 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
 
   // ---- rstgp1_update_strains (rstgp1.f:4983-5005): total strain at n+1, stored at once
   cp_async_wait_all();   // each thread reads back only what it copied itself
+  if (PHASE != 2) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const double e1 = sSt[k][tid] + uddt[k];
-    if (store) a.eps_n1[k * ng + g] = e1;
+    for (int k = 0; k < 6; ++k) {
+      const double e1 = sSt[k][tid] + uddt[k];
+      if (store) a.eps_n1[k * ng + g] = e1;
+    }
   }
-  if (store && GEONL && a.iter > 0) {
+  if (PHASE != 2 && store && GEONL && a.iter > 0) {
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int c = 0; c < 3; ++c) a.rot_n1[(c * 3 + r) * ng + g] = R1[r][c];
+  }
+  if (PHASE == 1) {
+    // hand R(n+1), the un-rotated strain increment and the energy factor to k_mm10
+    if (valid) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a.scratch[(c * 3 + r) * ng + g] = R1[r][c];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a.scratch[(9 + k) * ng + g] = uddt[k];
+      a.scratch[15 * ng + g] = error ? __longlong_as_double(0x7ff8000000000000LL) : efac;
+    }
+    return;
   }
 
   // ---- material update; rplstr stores (rplstr.f:15-93) + rstgp1_store_cep issued as soon as the
@@ -354,6 +406,67 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
       for (int k = 0; k < 21; ++k) a.cep[k * ng + g] = cep[k];
 #pragma unroll
       for (int k = 0; k < 9; ++k) a.urcs_n1[k * ng + g] = cgn1[k];
+    }
+  }
+  if (MAT == 10) {
+    // PHASE 2: stresses at n+1 come from k_mm10
+#pragma unroll
+    for (int k = 0; k < 9; ++k) cgn1[k] = a.urcs_n1[k * ng + g];
+    // rknstr_finish_cp / mm10_calc_grads: least-squares gradient of Rp^T R over the 8 points
+    double *sRt = &sSt[0][0];                 // reuse: [el][gp][9]
+    {
+      double Rp[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        Rp[k] = (a.step == 1) ? ((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0)
+                              : a.hist_n[(long long)(a.cp_o_Rp + k) * ng + g];
+      double *rt = sRt + (el * 8 + gp) * 9;
+      if (GEONL) {
+#pragma unroll
+        for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb)   // Rt = Rp * R^T (mult_type_3t), column-major storage
+            rt[bb * 3 + aa] = Rp[0 * 3 + aa] * R1[bb][0] + Rp[1 * 3 + aa] * R1[bb][1] + Rp[2 * 3 + aa] * R1[bb][2];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) rt[k] = Rp[k];
+      }
+    }
+    __syncwarp();
+    if (valid) {
+      double jacinv[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      if (GEONL) {
+        double Jm[3][3];
+        jacobian_matrix_exact(sN, 7, C, Jm);
+        const double det = Jm[0][0] * Jm[1][1] * Jm[2][2] - Jm[0][0] * Jm[1][2] * Jm[2][1] -
+                           Jm[0][1] * Jm[1][0] * Jm[2][2] + Jm[0][1] * Jm[1][2] * Jm[2][0] +
+                           Jm[0][2] * Jm[1][0] * Jm[2][1] - Jm[0][2] * Jm[1][1] * Jm[2][0];
+        double cof[3][3];
+        cof[0][0] = +(Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1]);
+        cof[0][1] = -(Jm[1][0] * Jm[2][2] - Jm[1][2] * Jm[2][0]);
+        cof[0][2] = +(Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0]);
+        cof[1][0] = -(Jm[0][1] * Jm[2][2] - Jm[0][2] * Jm[2][1]);
+        cof[1][1] = +(Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0]);
+        cof[1][2] = -(Jm[0][0] * Jm[2][1] - Jm[0][1] * Jm[2][0]);
+        cof[2][0] = +(Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]);
+        cof[2][1] = -(Jm[0][0] * Jm[1][2] - Jm[0][2] * Jm[1][0]);
+        cof[2][2] = +(Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) jacinv[r][c] = (fabs(det) <= 1.0e-10) ? 0.0 : cof[c][r] / det;
+      }
+      double grads[27];
+      if (a.cp_ncrystals > 1) {
+#pragma unroll
+        for (int k = 0; k < 27; ++k) grads[k] = 0.0;
+      } else {
+        w3d_mm10::calc_grads((const double (*)[9])(sRt + el * 72), GEONL, jacinv, grads);
+      }
+      if (!error) {
+#pragma unroll
+        for (int k = 0; k < 27; ++k) a.hist_n1[(long long)(a.cp_o_gradfe + k) * ng + g] = grads[k];
+      }
     }
   }
   if (fatal && store) atomicMax(&a.flags[1], fatal);

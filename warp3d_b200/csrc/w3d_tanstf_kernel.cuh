@@ -28,6 +28,10 @@ struct TanstfArgs {
   long long ng;
   double eps_bbar, beta_fact;
   int qbar;
+  // mm10 keeps its consistent [D] as a full 6x6 (column-major) in history(1:36) at n+1
+  // (drive_10_cnst, gptns1.f:1371-1410); read the lower triangle from there when set
+  const double *hist_n1;
+  int d_from_hist;
 };
 
 // shared-memory record of one (element, Gauss point): 24 N-derivatives [node][3], 21 D* terms
@@ -113,7 +117,8 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
       for (int r = 0; r < 6; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) {
-          const double v = wdj * a.cep[k * ng + g];
+          const double v = wdj * (a.d_from_hist ? a.hist_n1[(long long)(c * 6 + r) * ng + g]
+                                                : a.cep[k * ng + g]);
           D[r][c] = v; D[c][r] = v;
           ++k;
         }

@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("W3D_ENGINE_LIB") or os.path.join(_HERE, "libw3d_engine.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 (HIST_N, HIST_N1, EPS_N, EPS_N1, URCS_N, URCS_N1, ROT_N, ROT_N1, CEP, ESTIFF, ELEM_VOL) = range(11)
 _STATE_WHICH = dict(history=HIST_N, history1=HIST_N1, eps_n=EPS_N, eps_n1=EPS_N1, urcs_n=URCS_N,
                     urcs_n1=URCS_N1, rot_n=ROT_N, rot_n1=ROT_N1, cep=CEP, estiff=ESTIFF,
@@ -33,7 +33,7 @@ EXPORTS = (
     "w3d_pull_state", "w3d_block_offset", "w3d_device_vectors", "w3d_eps_sig_ifv_resident",
     "w3d_tanstf_resident", "w3d_last_scalars", "w3d_engine_stream", "w3d_engine_synchronize",
     "w3d_engine_launch_count", "w3d_upload_displacements", "w3d_download_ifv",
-    "w3d_download_estiff",
+    "w3d_download_estiff", "w3d_set_time_step",
 )
 
 
@@ -53,6 +53,9 @@ class _Config(C.Structure):
         ("cdest", C.c_void_p), ("history_blk_list", C.c_void_p), ("eps_bbar", C.c_double),
         ("qbar_flag", C.c_int32), ("beta_fact", C.c_double), ("adaptive_flag", C.c_int32),
         ("device", C.c_int32),
+        ("crystal_types", C.c_void_p), ("n_crystal_types", C.c_int32), ("cp_ncrystals", C.c_int32),
+        ("elem_cnum", C.c_void_p), ("elem_angles", C.c_void_p), ("cp_angle_type", C.c_int32),
+        ("asymmetric_assembly", C.c_int32),
     ]
 
 
@@ -120,6 +123,8 @@ def lib():
         L.w3d_upload_displacements.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.w3d_download_ifv.argtypes = [C.c_void_p, C.c_void_p]
         L.w3d_download_estiff.argtypes = [C.c_void_p, C.c_void_p]
+        L.w3d_set_time_step.restype = C.c_int32
+        L.w3d_set_time_step.argtypes = [C.c_void_p, C.c_double]
         _lib = L
     return _lib
 
@@ -157,11 +162,21 @@ class Engine:
         cfg.beta_fact = m.beta_fact
         cfg.adaptive_flag = int(m.adaptive_flag)
         cfg.device = device
+        if getattr(m, "crystal_types", None) is not None:      # mm10 input tables
+            ct = np.ascontiguousarray(m.crystal_types, dtype=np.float64)
+            cn = np.ascontiguousarray(m.elem_cnum, dtype=np.int32)
+            ang = np.ascontiguousarray(m.elem_angles, dtype=np.float64)
+            keep += [ct, cn, ang]
+            cfg.crystal_types, cfg.elem_cnum, cfg.elem_angles = _ptr(ct), _ptr(cn), _ptr(ang)
+            cfg.n_crystal_types, cfg.cp_ncrystals = ct.shape[0], int(m.ncrystals)
+            cfg.cp_angle_type = int(m.angle_type)
+            cfg.asymmetric_assembly = int(m.asymmetric_assembly)
         h = C.c_void_p()
         rc = self._L.w3d_engine_create(C.byref(cfg), C.byref(h))
         if rc:
             raise EngineError(rc, self._L.w3d_engine_last_error(None).decode())
         self._h = h
+        self._check(self._L.w3d_set_time_step(self._h, float(m.dt)))
         self.myid, self.numprocs = myid, numprocs
         owned = np.ones(m.nelblk, dtype=bool) if numprocs <= 1 else (m.elblks[:, 2] == myid)
         self.owned_blocks = np.nonzero(owned)[0]
@@ -195,6 +210,9 @@ class Engine:
         self._check(self._L.w3d_engine_synchronize(self._h))
 
     # ---- the reference's drivers
+    def set_time_step(self, dt):
+        self._check(self._L.w3d_set_time_step(self._h, float(dt)))
+
     def drive_eps_sig_internal_forces(self, step, itr, u, du, ifv=None):
         """Strain recovery, material update, internal forces for all owned blocks.
         Returns (ifv, scalars); ifv is this rank's contribution."""

@@ -68,6 +68,13 @@ class Model:
     extrapolated_du: bool = False
     adaptive_flag: bool = True
     grid: tuple = ()
+    # crystal plasticity (mm10) input, see attach_crystals
+    crystal_types: np.ndarray = None
+    elem_cnum: np.ndarray = None
+    elem_angles: np.ndarray = None
+    ncrystals: int = 0
+    angle_type: int = 1
+    asymmetric_assembly: bool = False
 
     # ---- sizes of the blocked arrays (doubles) ----
     def span(self, blk):
@@ -286,3 +293,88 @@ def slab_domains(model: Model, numprocs: int) -> np.ndarray:
     cum = np.cumsum(spans) - spans // 2
     dom = np.minimum((cum * numprocs) // int(spans.sum()), numprocs - 1)
     return dom.astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# crystal plasticity (mm10) input data: the c_array(cnum) table of src/mod_crystals.f and the
+# per-element crystal numbers / Kocks angles of src/rknstr.f:1690-1720
+# ------------------------------------------------------------------------------------------------
+CRYSTAL_TYPE_DOUBLES = 36 + 144 + 144 + 13 + 7     # w3d_mm10::CrystalType, ints widened to double
+
+
+def fcc_slip_systems():
+    """slip directions bi and plane normals ni of slip_type 1 (fcc), src/mod_crystals.f:441-518."""
+    f = 1.0 / np.sqrt(2.0)
+    bi = np.array([[0, -f, f], [f, 0, -f], [-f, f, 0], [0, f, f], [f, 0, f], [f, -f, 0],
+                   [0, -f, f], [-f, 0, -f], [f, f, 0], [0, f, f], [f, 0, -f], [-f, -f, 0]])
+    g = 1.0 / np.sqrt(3.0)
+    ni = np.array([[g, g, g]] * 3 + [[-g, -g, g]] * 3 + [[-g, g, g]] * 3 + [[g, -g, g]] * 3)
+    return bi, ni
+
+
+def make_crystal_type(e=69000.0, nu=0.33, mu=None, elastic="isotropic", slip="fcc", harden_n=20.0,
+                      tau_y=0.0, tau_v=0.0, voche_m=1.0, theta_o=100.0, k_o=0.0, b=2.87e-7,
+                      iD_v=0.0, eps_dot_o_y=1.0e10, atol=1.0e-5, atol1=1.0e-5, rtol=5.0e-5,
+                      rtol1=1.0e-5, miter=30, alter_mode=False):
+    """One crystal definition = c_array(cnum) after finalize_new_crystal
+    (src/mod_crystals.f:238-417 defaults, :421-1934 derived data).  Returns a
+    (CRYSTAL_TYPE_DOUBLES,) float64 record."""
+    if slip != "fcc":
+        raise NotImplementedError("slip systems other than fcc are not built yet")
+    bi, ni = fcc_slip_systems()
+    nslip = 12
+    if mu is None:
+        mu = e / 2.0 / (1.0 + nu)
+    flex = np.zeros((6, 6))
+    flex[:3, :3] = -nu / e
+    flex[0, 0] = flex[1, 1] = flex[2, 2] = 1.0 / e
+    sh = 2.0 * (1.0 + nu) / e if elastic == "isotropic" else 1.0 / mu     # elastic_type 1 / 2 (cubic)
+    flex[3, 3] = flex[4, 4] = flex[5, 5] = sh
+    stiff = np.linalg.inv(flex)
+    stiff = 0.5 * (stiff + stiff.T)
+    rec = np.zeros(CRYSTAL_TYPE_DOUBLES)
+    rec[0:36] = stiff.reshape(-1)
+    B = np.zeros((48, 3)); N = np.zeros((48, 3))
+    B[:nslip] = bi; N[:nslip] = ni
+    rec[36:180] = B.reshape(-1)
+    rec[180:324] = N.reshape(-1)
+    rec[324:337] = [harden_n, tau_y, tau_v, voche_m, theta_o, k_o, b, iD_v, eps_dot_o_y, atol, atol1,
+                    rtol, rtol1]
+    rec[337:344] = [nslip, 1, 1, 0, miter, 1, 1 if alter_mode else 0]   # nslip, num_hard, h_type, tang_calc, miter, solver, alter_mode
+    return rec
+
+
+def mm10_hist_size(nslip, ncrystals, num_hard=1):
+    """history words per Gauss point, mm10_set_history_locs (src/mm10_d.f:153-330)."""
+    use_max = nslip == 48 or num_hard == 48
+    ls = 48 if use_max else nslip
+    lt = 48 if use_max else num_hard
+    lu = 48 if use_max else 15
+    return (36 + 27 + 9 + 3 + ls) + ncrystals * (30 + ls + lt + lu + lt + 12)
+
+
+def attach_crystals(model: Model, crystal_types, ncrystals=1, seed=20261017, angles=None,
+                    elem_cnum=None, angle_type=1):
+    """Give every element of an mm10 model `ncrystals` crystals: crystal numbers (1-based into
+    crystal_types) and Kocks angles in degrees drawn U(0,360) x U(0,180) x U(0,360).
+    Also sets history_blk_list for the mm10 blocks."""
+    ct = np.atleast_2d(np.asarray(crystal_types, dtype=np.float64))
+    model.crystal_types = np.ascontiguousarray(ct)
+    model.ncrystals = int(ncrystals)
+    model.angle_type = int(angle_type)
+    if angles is None:
+        rng = np.random.default_rng(seed)
+        angles = np.stack([rng.uniform(0, 360, (model.noelem, ncrystals)),
+                           rng.uniform(0, 180, (model.noelem, ncrystals)),
+                           rng.uniform(0, 360, (model.noelem, ncrystals))], axis=2)
+    model.elem_angles = np.ascontiguousarray(np.asarray(angles, dtype=np.float64).reshape(model.noelem, ncrystals, 3))
+    if elem_cnum is None:
+        elem_cnum = np.ones((model.noelem, ncrystals), dtype=np.int32)
+    model.elem_cnum = np.ascontiguousarray(np.asarray(elem_cnum, dtype=np.int32).reshape(model.noelem, ncrystals))
+    nslip = int(ct[0, 337])
+    for b in range(model.nelblk):
+        f = model.felem(b)
+        if int(model.props[f - 1, 24]) == 10:
+            model.hist_size[b] = mm10_hist_size(nslip, ncrystals)
+    model.asymmetric_assembly = False
+    return model
