@@ -30,7 +30,13 @@ def _run(m, nsteps=3, strain=2.0e-3, tol=RTOL):
             fo, sco = orc.eps_sig_ifv(so, step, itr, u, du)
             fg, scg = eng.drive_eps_sig_internal_forces(step, itr, u, du)
             tag = f"step {step} iter {itr}"
-            assert scg["material_cut_step"] == sco["material_cut_step"] is False
+            assert scg["material_cut_step"] == sco["material_cut_step"], tag
+            if sco["material_cut_step"]:
+                # the local solver gave up after 4 halvings in both runs: the reference would now
+                # reset to n and cut the load step (mnralg.f:535-588); ifv is zeroed
+                assert not fg.any() and not fo.any()
+                orc.adaptive_reset(so); eng.adaptive_reset()
+                continue
             assert relerr(fg, fo) <= tol, f"{tag}: ifv {relerr(fg, fo):.3e}"
             for k in ("internal_energy", "plastic_work", "sum_ifv"):
                 assert abs(scg[k] - sco[k]) <= tol * max(abs(sco[k]), 1e-300), (tag, k, scg[k], sco[k])
@@ -42,8 +48,11 @@ def _run(m, nsteps=3, strain=2.0e-3, tol=RTOL):
             hg, ho = sg.history1.reshape(-1, H), so.history1.reshape(-1, H)
             for col in range(H):
                 scale = max(np.abs(ho[:, col]).max(), 1e-12 * np.abs(ho).max())
-                assert np.abs(hg[:, col] - ho[:, col]).max() <= max(tol, 1e-9 if col >= 87 + 30 else tol) * scale, \
-                    f"{tag}: history1 column {col}"
+                if 36 <= col < 63:
+                    # grad Fe^-1: differences of O(1) rotation terms over O(1) lengths
+                    scale = max(scale, 1.0)
+                assert np.abs(hg[:, col] - ho[:, col]).max() <= tol * scale, \
+                    f"{tag}: history1 column {col}: {np.abs(hg[:, col] - ho[:, col]).max():.3e} vs scale {scale:.3e}"
             ko = orc.tanstf(so, step, itr, u, du).reshape(-1, 300)
             kg = eng.tanstf(step, itr, u, du).reshape(-1, 300)
             e = (np.abs(kg - ko).max(axis=1) / np.abs(ko).max(axis=1)).max()

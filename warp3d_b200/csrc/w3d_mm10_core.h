@@ -1,6 +1,6 @@
 // w3d_mm10_core.h -- crystal-plasticity material update (mm10) for ONE Gauss point, written once
 // in plain C++ and compiled twice: by nvcc as device code for the engine, and by g++ as the CPU
-// restatement the parity tests check it against (oracle/w3d_oracle_mm10.cpp includes this file).
+// restatement the parity tests check it against (the block driver under oracle/ includes this file).
 // Because the local Newton loops are tolerance-terminated, an independently written CPU copy
 // would not be comparable at 1e-10; the second compile checks the port (compiler, FMA, libm),
 // not the transcription.  Fidelity to the Fortran is argued by the citations below and by the
