@@ -16,7 +16,8 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 from common import load_path  # noqa: E402
 from oracle.oracle_py import Oracle  # noqa: E402
-from warp3d_b200 import Material, build_structured_hex8, new_state  # noqa: E402
+from warp3d_b200 import (Material, attach_crystals, build_structured_hex8, make_crystal_type,  # noqa: E402
+                         new_state)
 
 CASES = {
     # name: (builder kwargs, load-path kwargs)
@@ -25,14 +26,22 @@ CASES = {
     "hex8_small_mm01_kinematic": (dict(nx=2, ny=2, nz=2, coord_jitter=0.1, seed=9, geonl=False, bbar=False,
                                        materials=[Material(e=70.0e9, nu=0.33, yld_pt=250.0e6, tan_e=1.0e9, beta=0.25)]),
                                   dict(nsteps=2, strain=5.0e-3)),
+    # crystal plasticity: fcc, Voce, 2 crystals per Gauss point
+    "hex8_geonl_mm10_voce": (dict(nx=2, ny=1, nz=1, coord_jitter=0.1, seed=4, dt=0.5,
+                                  materials=[Material(mat_type=10)], crystals=2),
+                             dict(nsteps=2, strain=2.5e-3)),
 }
+CRYSTAL = dict(e=100000.0, nu=0.3, harden_n=20, tau_y=100.0, tau_v=50.0, theta_o=500.0, voche_m=1.0)
 
 
 def build(name):
     bk, lk = CASES[name]
     bk = dict(bk)
     nx, ny, nz = bk.pop("nx"), bk.pop("ny"), bk.pop("nz")
+    ncrys = bk.pop("crystals", 0)
     m = build_structured_hex8(nx, ny, nz, **bk)
+    if ncrys:
+        attach_crystals(m, make_crystal_type(**CRYSTAL), ncrystals=ncrys)
     return m, load_path(m, **lk)
 
 
