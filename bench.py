@@ -28,16 +28,44 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (nx, ny, nz)
-    "hex8_2m_mm01": (200, 100, 100),       # BASELINE.json configs[3]: 2 000 000 elements
-    "hex8_256k_mm01": (64, 64, 64),        # smaller variant for quick checks
+    # name: (dims, material kind, CPU sample dims)
+    "hex8_2m_mm01": ((200, 100, 100), "mm01", (64, 50, 50)),   # BASELINE.json configs[3]
+    "hex8_256k_mm01": ((64, 64, 64), "mm01", (64, 50, 50)),    # smaller variant for quick checks
+    "hex8_1m_mm10": ((100, 100, 100), "mm10", (32, 25, 25)),   # BASELINE.json configs[4]: CP polycrystal
+    "hex8_64k_mm10": ((40, 40, 40), "mm10", (32, 25, 25)),
 }
-CPU_SAMPLE = (64, 50, 50)                  # 160 000 elements of the same mesh/material/loading
+# mm10 workload: fcc (12 slip systems), Voce hardening with the property values of
+# verification/test82/voche_model/warp3d_voche.inp:6-10, one crystal per element, Kocks angles
+# from default_rng(20261017)
+MM10_CRYSTAL = dict(e=150000.0, nu=0.28, harden_n=20.0, voche_m=5.0, theta_o=400.0, tau_y=300.0, tau_v=1200.0)
+
+
+def make_workload(name, dims=None):
+    """Returns (model, du_per_step, nprep): `nprep` converged load steps of increment du prepare
+    the state at n; the timed Newton iteration is iteration 1 of step nprep+1."""
+    from warp3d_b200 import (Material, attach_crystals, build_structured_hex8, graded_stretch,
+                             make_crystal_type)
+    wdims, kind, _ = WORKLOADS[name]
+    dims = dims or wdims
+    if kind == "mm01":
+        m = build_structured_hex8(*dims)
+        return m, 0.5 * graded_stretch(m), 1
+    m = build_structured_hex8(*dims, materials=[Material(mat_type=10)], dt=1.0)
+    attach_crystals(m, make_crystal_type(**MM10_CRYSTAL), ncrystals=1)
+    return m, 0.25 * graded_stretch(m, eps_lo=3.0e-3, eps_hi=9.0e-3), 2
+
+
+def workload_description(name):
+    kind = WORKLOADS[name][1]
+    if kind == "mm01":
+        return dict(material="mm01 bilinear (E=200e9 as real*4, nu=0.3, yld=400e6, tan_e=E/100)",
+                    bytes_stress=776.0, bytes_tanstf=708.0)
+    # per Gauss point: history 2 x 158 x 8, urcs 2 x 72, eps 2 x 48, rot 72, scratch 2 x 128,
+    # crystal properties 1448/8, element vectors 120  (DESIGN.md "mm10")
+    return dict(material="mm10 crystal plasticity: fcc 12 slip, Voce (test82/voche_model values), 1 crystal/element",
+                bytes_stress=2.0 * 158 * 8 + 144 + 96 + 72 + 256 + 181 + 120, bytes_tanstf=72 + 72 + 288 + 396.0)
 METRIC = "gauss_point_updates_per_s_per_newton_iteration"
 UNIT = "GP/s"
-# algorithmic HBM bytes per Gauss point (DESIGN.md "Kernels")
-BYTES_PER_GP_STRESS = 776.0
-BYTES_PER_GP_TANSTF = 708.0
 
 
 def measured_peaks():
@@ -105,36 +133,38 @@ class ClockSampler:
         return out
 
 
-def prepare_cpu_case(dims, nthreads):
+def prepare_cpu_case(workload, nthreads):
     """Same mesh family, material and load path as the GPU workload, on the oracle."""
     from oracle.oracle_py import Oracle
-    from warp3d_b200 import build_structured_hex8, graded_stretch, new_state
-    m = build_structured_hex8(*dims)
-    U = graded_stretch(m)
+    from warp3d_b200 import new_state
+    m, du, nprep = make_workload(workload, WORKLOADS[workload][2])
     orc = Oracle(m, nthreads=nthreads)
     st = new_state(m)
-    z = np.zeros(m.nodof)
-    orc.eps_sig_ifv(st, 1, 0, z, 0.5 * U)
-    orc.eps_sig_ifv(st, 1, 1, z, 0.5 * U)
-    orc.update(st); orc.adaptive_save(st)
-    orc.eps_sig_ifv(st, 2, 0, 0.5 * U, 0.5 * U)
-    return m, orc, st, 0.5 * U, 0.5 * U
+    u = np.zeros(m.nodof)
+    for step in range(1, nprep + 1):
+        orc.eps_sig_ifv(st, step, 0, u, du)
+        orc.eps_sig_ifv(st, step, 1, u, du)
+        orc.update(st); orc.adaptive_save(st)
+        u = u + du
+    orc.eps_sig_ifv(st, nprep + 1, 0, u, du)
+    return m, orc, st, u, du, nprep + 1
 
 
-def cpu_pass(m, orc, st, u, du):
+def cpu_pass(m, orc, st, u, du, step):
     t0 = time.perf_counter()
-    orc.eps_sig_ifv(st, 2, 1, u, du)
+    orc.eps_sig_ifv(st, step, 1, u, du)
     t1 = time.perf_counter()
-    orc.tanstf(st, 2, 1, u, du)
+    orc.tanstf(st, step, 1, u, du)
     t2 = time.perf_counter()
     return t1 - t0, t2 - t1
 
 
-def cpu_baseline(nrep=3):
+def cpu_baseline(workload, nrep=3):
     cores = os.cpu_count() or 1
-    m, orc, st, u, du = prepare_cpu_case(CPU_SAMPLE, cores)
-    cpu_pass(m, orc, st, u, du)
-    ts = [cpu_pass(m, orc, st, u, du) for _ in range(nrep)]
+    CPU_SAMPLE = WORKLOADS[workload][2]
+    m, orc, st, u, du, step = prepare_cpu_case(workload, cores)
+    cpu_pass(m, orc, st, u, du, step)
+    ts = [cpu_pass(m, orc, st, u, du, step) for _ in range(nrep)]
     t_s = float(np.mean([a for a, _ in ts])); t_k = float(np.mean([b for _, b in ts]))
     ngp = m.noelem * 8
     return dict(value=ngp / (t_s + t_k), unit=UNIT, cores=cores, kind="port",
@@ -150,22 +180,23 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    m, orc, st, u, du = prepare_cpu_case(CPU_SAMPLE, cores)
+    CPU_SAMPLE = WORKLOADS[args.workload][2]
+    m, orc, st, u, du, step = prepare_cpu_case(args.workload, cores)
     for _ in range(args.warmup):
-        cpu_pass(m, orc, st, u, du)
+        cpu_pass(m, orc, st, u, du, step)
     t0 = time.perf_counter()
-    ts = [cpu_pass(m, orc, st, u, du) for _ in range(args.steps)]
+    ts = [cpu_pass(m, orc, st, u, du, step) for _ in range(args.steps)]
     total = time.perf_counter() - t0
     ngp = m.noelem * 8
     value = ngp * args.steps / total
     t_s = float(np.mean([a for a, _ in ts])); t_k = float(np.mean([b for _, b in ts]))
     sample = (f"{m.noelem} elements per step ({CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} sub-box of the "
-              f"2M workload), oracle/ port of the reference path, OpenMP over blocks")
+              f"{args.workload} workload), oracle/ port of the reference path, OpenMP over blocks")
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * total / args.steps, higher_is_better=True,
                 scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=args.workload, cpu_sample_elements=m.noelem, material="mm01 bilinear",
-                            formulation="geonl+bbar"),
+                config=dict(workload=args.workload, cpu_sample_elements=m.noelem,
+                            material=workload_description(args.workload)["material"], formulation="geonl+bbar"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
                                   stress_gp_per_s=ngp / t_s, stiffness_elem_per_s=m.noelem / t_k),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -176,7 +207,6 @@ def reference_arm(args):
 def engine_arm(args):
     import torch
     import torch.distributed as dist
-    from warp3d_b200 import build_structured_hex8, graded_stretch
     from warp3d_b200.distributed import DomainEngine
 
     rank = int(os.environ.get("RANK", "0"))
@@ -188,9 +218,9 @@ def engine_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    dims = WORKLOADS[args.workload]
-    model = build_structured_hex8(*dims)
-    U = graded_stretch(model)
+    model, du_step, nprep = make_workload(args.workload)
+    wd = workload_description(args.workload)
+    TS = nprep + 1                      # the timed load step
     de = DomainEngine(model, rank, world, device=local)
     eng = de.engine
     nodof, nel_own = model.nodof, eng.n_owned_elems
@@ -202,14 +232,17 @@ def engine_arm(args):
     u_h, du_h, ifv_h = pinned(nodof), pinned(nodof), pinned(nodof)
     est_h = pinned(nel_own * 300)
 
-    # ---- state preparation: load step 1 (elastic-plastic), converge, roll over; step 2 iter 0
-    u_h[:] = 0.0; du_h[:] = 0.5 * U
-    de.drive_eps_sig_internal_forces(1, 0, u_h, du_h, ifv_h)
-    de.drive_eps_sig_internal_forces(1, 1, u_h, du_h, ifv_h)
-    de.update(); de.adaptive_save()
-    u_h[:] = 0.5 * U
-    de.drive_eps_sig_internal_forces(2, 0, u_h, du_h, ifv_h)
-    _, sc = de.drive_eps_sig_internal_forces(2, 1, u_h, du_h, ifv_h)
+    # ---- state preparation: nprep converged load steps, roll over; then iteration 0 of step TS
+    u_h[:] = 0.0; du_h[:] = du_step
+    for step in range(1, nprep + 1):
+        de.drive_eps_sig_internal_forces(step, 0, u_h, du_h, ifv_h)
+        de.drive_eps_sig_internal_forces(step, 1, u_h, du_h, ifv_h)
+        de.update(); de.adaptive_save()
+        u_h[:] = u_h + du_step
+    de.drive_eps_sig_internal_forces(TS, 0, u_h, du_h, ifv_h)
+    _, sc = de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
+    if sc["material_cut_step"]:
+        raise SystemExit("bench.py: the workload asked for a step cut; timing would be invalid")
 
     def barrier():
         if world > 1:
@@ -220,7 +253,7 @@ def engine_arm(args):
 
     # ---- resident timing: K steps bracketed by barrier + synchronize, CUDA events on the stream
     for _ in range(max(args.warmup, 3)):
-        de.eps_sig_ifv_resident(2, 1); de.tanstf_resident(2, 1)
+        de.eps_sig_ifv_resident(TS, 1); de.tanstf_resident(TS, 1)
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     l0 = eng.launch_count
@@ -228,9 +261,9 @@ def engine_arm(args):
     barrier()
     ev[0].record(S)
     for k in range(args.steps):
-        de.eps_sig_ifv_resident(2, 1)
+        de.eps_sig_ifv_resident(TS, 1)
         ev[2 * k + 1].record(S)
-        de.tanstf_resident(2, 1)
+        de.tanstf_resident(TS, 1)
         ev[2 * k + 2].record(S)
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -241,15 +274,15 @@ def engine_arm(args):
 
     # ---- end-to-end timing through the host-buffer calls (pinned host memory)
     for _ in range(2):
-        de.drive_eps_sig_internal_forces(2, 1, u_h, du_h, ifv_h); de.tanstf(2, 1, est_h)
+        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h); de.tanstf(TS, 1, est_h)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nrep_e2e = max(2, min(args.steps, 5))
     e0.record(S)
     w0 = time.perf_counter()
     for _ in range(nrep_e2e):
-        de.drive_eps_sig_internal_forces(2, 1, u_h, du_h, ifv_h)
-        de.tanstf(2, 1, est_h)
+        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
+        de.tanstf(TS, 1, est_h)
     e1.record(S)
     barrier()
     e2e_wall_ms = 1e3 * (time.perf_counter() - w0) / nrep_e2e
@@ -270,10 +303,11 @@ def engine_arm(args):
         value = ngp_total / (ms_per_step * 1e-3)
         # dominant kernel = the one with the longer average launch; per-launch units = owned GPs
         ngp_own = nel_own * 8
-        k_name, k_ms, k_bytes = (("k_tanstf", t_tan, BYTES_PER_GP_TANSTF) if t_tan >= t_stress
-                                 else ("k_eps_sig_ifv", t_stress, BYTES_PER_GP_STRESS))
+        sname = "k_eps_sig_ifv" if WORKLOADS[args.workload][1] == "mm01" else "k_eps_sig_ifv<phase 1,2> + k_mm10"
+        k_name, k_ms, k_bytes = (("k_tanstf", t_tan, wd["bytes_tanstf"]) if t_tan >= t_stress
+                                 else (sname, t_stress, wd["bytes_stress"]))
         ach = ngp_own * k_bytes / (k_ms * 1e-3) / 1e9
-        other = ("k_eps_sig_ifv", t_stress, BYTES_PER_GP_STRESS) if k_name == "k_tanstf" else ("k_tanstf", t_tan, BYTES_PER_GP_TANSTF)
+        other = (sname, t_stress, wd["bytes_stress"]) if k_name == "k_tanstf" else ("k_tanstf", t_tan, wd["bytes_tanstf"])
         fp64_peak = None
         pk = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
         if os.path.exists(pk):
@@ -284,8 +318,8 @@ def engine_arm(args):
             ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
             data="synthetic",
             config=dict(workload=args.workload, elements=model.noelem, gauss_points=ngp_total, blocks=model.nelblk,
-                        nodof=nodof, material="mm01 bilinear (E=200e9 as real*4, nu=0.3, yld=400e6, tan_e=E/100)",
-                        formulation="hex8 l3disop 2x2x2, geonl, bbar", l2="inputs_exceed_l2 (state 16 GB >> 126 MB)",
+                        nodof=nodof, material=wd["material"],
+                        formulation="hex8 l3disop 2x2x2, geonl, bbar", l2="inputs_exceed_l2 (state >> 126 MB)",
                         partition=f"{world} contiguous block slabs, NCCL all-reduce of ifv" if world > 1 else "single GPU",
                         step="w3d_eps_sig_ifv + w3d_tanstf (one Newton iteration)"),
             stress_pass=dict(ms=t_stress, gp_updates_per_s=ngp_total / (t_stress * 1e-3)),
@@ -304,7 +338,7 @@ def engine_arm(args):
             plastic_check=dict(plastic_work=sc["plastic_work"], internal_energy=sc["internal_energy"]),
         )
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line), flush=True)
     de.close()
     if world > 1:
