@@ -65,8 +65,18 @@ void mm10_setup_props_host(const double *ctd, const double *angles, int angle_ty
   setup_props<12>(ct, angles, angle_type, P);
   std::memcpy(props_out, &P, sizeof P);
 }
+#ifndef MM10_DYN_SMEM
+#define MM10_DYN_SMEM 0   // bytes of (unused) dynamic shared memory: caps the resident CTAs per SM
+#endif
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {
-  k_mm10<12><<<ncta, TPB, 0, st>>>(a);
+  if (MM10_DYN_SMEM > 48 * 1024) {
+    static bool set = false;
+    if (!set) {
+      cudaFuncSetAttribute(k_mm10<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM10_DYN_SMEM);
+      set = true;
+    }
+  }
+  k_mm10<12><<<ncta, TPB, MM10_DYN_SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
