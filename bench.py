@@ -216,6 +216,7 @@ def engine_arm(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     model, du_step, nprep = make_workload(args.workload)
@@ -253,7 +254,7 @@ def engine_arm(args):
 
     # ---- resident timing: K steps bracketed by barrier + synchronize, CUDA events on the stream
     for _ in range(max(args.warmup, 3)):
-        de.eps_sig_ifv_resident(TS, 1); de.tanstf_resident(TS, 1)
+        de.eps_sig_ifv_resident(TS, 1, exchange=args.exchange); de.tanstf_resident(TS, 1)
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     l0 = eng.launch_count
@@ -261,7 +262,7 @@ def engine_arm(args):
     barrier()
     ev[0].record(S)
     for k in range(args.steps):
-        de.eps_sig_ifv_resident(TS, 1)
+        de.eps_sig_ifv_resident(TS, 1, exchange=args.exchange)
         ev[2 * k + 1].record(S)
         de.tanstf_resident(TS, 1)
         ev[2 * k + 2].record(S)
@@ -320,7 +321,8 @@ def engine_arm(args):
             config=dict(workload=args.workload, elements=model.noelem, gauss_points=ngp_total, blocks=model.nelblk,
                         nodof=nodof, material=wd["material"],
                         formulation="hex8 l3disop 2x2x2, geonl, bbar", l2="inputs_exceed_l2 (state >> 126 MB)",
-                        partition=f"{world} contiguous block slabs, NCCL all-reduce of ifv" if world > 1 else "single GPU",
+                        partition=(f"{world} contiguous block slabs; resident pass: NCCL sum of ifv ({args.exchange}), "
+                                   f"e2e pass: full all-reduce") if world > 1 else "single GPU",
                         step="w3d_eps_sig_ifv + w3d_tanstf (one Newton iteration)"),
             stress_pass=dict(ms=t_stress, gp_updates_per_s=ngp_total / (t_stress * 1e-3)),
             stiffness_pass=dict(ms=t_tan, element_stiffnesses_per_s=model.noelem / (t_tan * 1e-3)),
@@ -353,6 +355,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="hex8_2m_mm01", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="interface", choices=["interface", "full"],
+                    help="N>1 resident pass: sum only the dofs shared between ranks, or the whole ifv vector")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -43,15 +43,38 @@ class DomainEngine:
         self.d_u = torch.as_tensor(_DevVec(pu, model.nodof), device=dev)
         self.d_du = torch.as_tensor(_DevVec(pdu, model.nodof), device=dev)
         self._scal = torch.zeros(4, dtype=torch.float64, device=dev)
+        # interface dofs = dofs touched by the blocks of more than one rank (identical, sorted list
+        # on every rank since the block tables are replicated): the only entries of ifv that need
+        # the cross-rank sum when the caller stays on the device
+        self.interface_idx = None
+        if world > 1:
+            off = model.block_offsets(24)
+            ed = model.edest.astype(np.int64) - 1
+            touched = np.zeros((world, model.nodof), dtype=bool)
+            for blk in range(model.nelblk):
+                touched[int(model.elblks[blk, 2]), ed[off[blk]:off[blk + 1]]] = True
+            shared = np.nonzero(touched.sum(axis=0) > 1)[0]
+            self.interface_idx = torch.as_tensor(shared, dtype=torch.int64, device=dev)
+            self._ibuf = torch.zeros(len(shared), dtype=torch.float64, device=dev)
 
     # ---- device-resident Newton-iteration pieces
-    def eps_sig_ifv_resident(self, step, itr):
-        """stress/ifv kernel for the owned blocks, then the NCCL sum of ifv over ranks."""
+    def eps_sig_ifv_resident(self, step, itr, exchange="full"):
+        """stress/ifv kernel for the owned blocks, then the NCCL sum of ifv over ranks.
+        exchange="full": all-reduce of the whole vector (the reference's wmpi_reduce_vec; every
+        rank ends with the complete ifv).  exchange="interface": only the dofs shared between
+        ranks are summed (packed gather -> all-reduce -> scatter); each rank then holds the
+        correct ifv on every dof its own blocks touch, which is all a device-resident caller
+        needs, and the message shrinks from nodof to the slab faces."""
         self.engine.eps_sig_ifv_resident(step, itr)
         if self.world > 1:
             import torch.distributed as dist
             with self.torch.cuda.stream(self.stream):
-                dist.all_reduce(self.d_ifv, op=dist.ReduceOp.SUM, group=self.group)
+                if exchange == "interface":
+                    self.torch.index_select(self.d_ifv, 0, self.interface_idx, out=self._ibuf)
+                    dist.all_reduce(self._ibuf, op=dist.ReduceOp.SUM, group=self.group)
+                    self.d_ifv.index_copy_(0, self.interface_idx, self._ibuf)
+                else:
+                    dist.all_reduce(self.d_ifv, op=dist.ReduceOp.SUM, group=self.group)
 
     def tanstf_resident(self, step, itr):
         self.engine.tanstf_resident(step, itr)
