@@ -36,7 +36,7 @@ struct TanstfArgs {
 
 // shared-memory record of one (element, Gauss point): 24 N-derivatives [node][3], 21 D* terms
 // (lower triangle by rows), 6 = D* m, 6 = sigma w detJ, 1 = detJ
-// (58 doubles used).  Strides are chosen for the 32-bank shared memory: GPREC = 1 (mod 16) spreads
+// (58 doubles used, 58..63 double as the landing zone of the cp.async stress prefetch).  Strides are chosen for the 32-bank shared memory: GPREC = 1 (mod 16) spreads
 // the 8 Gauss points of an element over distinct bank pairs, ELREC = 8 (mod 16) puts the second
 // element of a half-warp 16 banks away.
 constexpr int GPREC = 65;
@@ -72,6 +72,26 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
   double *sV = er + 8 * GPREC;                // V[node][3]
   double *sS = sV + 24;                       // Sbar[6]
 
+  // ---- start streaming this point's [D], R and stresses into its (still unused) record slots:
+  //      cep -> gr[24..44] (overwritten in place by D* later), R -> gr[45..53], t -> gr[58..63]
+  {
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) {
+        cp_async8(gr + 24 + k, a.d_from_hist ? a.hist_n1 + (long long)(c * 6 + r) * ng + g
+                                             : a.cep + (long long)k * ng + g);
+        ++k;
+      }
+    if (GEONL) {
+#pragma unroll
+      for (int q9 = 0; q9 < 9; ++q9) cp_async8(gr + 45 + q9, a.rot_n1 + (long long)q9 * ng + g);
+#pragma unroll
+      for (int q6 = 0; q6 < 6; ++q6) cp_async8(gr + 58 + q6, a.urcs_n1 + (long long)q6 * ng + g);
+    }
+    cp_async_commit();
+  }
   // ---- dptstf: coordinates of node `gp` on the n+1 configuration, staged in the N slots
   {
     const int32_t *ed = a.edest + (size_t)slot * 24;
@@ -110,6 +130,7 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
   const double wdj = 1.0 * dj;   // quad2 weight = 1
   {
     // extract_D_symmetric: D = w detJ cep(21 lower-triangle terms by rows)
+    cp_async_wait_all();   // each thread reads only what it copied itself
     double D[6][6];
     {
       int k = 0;
@@ -117,8 +138,7 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
       for (int r = 0; r < 6; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) {
-          const double v = wdj * (a.d_from_hist ? a.hist_n1[(long long)(c * 6 + r) * ng + g]
-                                                : a.cep[k * ng + g]);
+          const double v = wdj * gr[24 + k];
           D[r][c] = v; D[c][r] = v;
           ++k;
         }
@@ -130,10 +150,9 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) R[r][c] = a.rot_n1[(c * 3 + r) * ng + g];
+        for (int c = 0; c < 3; ++c) R[r][c] = gr[45 + c * 3 + r];
       getrm1_opt2(R, q);
-      const double t6[6] = {a.urcs_n1[0 * ng + g], a.urcs_n1[1 * ng + g], a.urcs_n1[2 * ng + g],
-                            a.urcs_n1[3 * ng + g], a.urcs_n1[4 * ng + g], a.urcs_n1[5 * ng + g]};
+      const double t6[6] = {gr[58], gr[59], gr[60], gr[61], gr[62], gr[63]};
       qmply(q, t6, cs);
       double tc[6][6];
 #pragma unroll
