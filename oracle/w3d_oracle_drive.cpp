@@ -18,6 +18,7 @@
 #endif
 #include "w3d_oracle_internal.h"
 #include "../warp3d_b200/csrc/w3d_mm10_core.h"   // single-source mm10 core (see its header)
+#include "../warp3d_b200/csrc/w3d_mm05_core.h"   // single-source mm05 core (see its header)
 
 namespace w3do {
 
@@ -208,6 +209,57 @@ static void drive_01_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
   store_cep(span, gpn, gbl_cep, cep.data());
 }
 
+// drive_05_update (rstgp1.f:2373-2700) -> mm05 (mm05.f:9) + cnst5 (:1566), nonlinear_hardening
+// option.  Per-point arithmetic = single-source core warp3d_b200/csrc/w3d_mm05_core.h.
+static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int gpn,
+                            int step, int iter, const double *uddt_displ, double *gbl_cep,
+                            bool &material_cut_step, int *fatal) {
+  using namespace w3d_mm05;
+  const int span = bi.span;
+  std::vector<double> cep(mxvl * 36, 0.0);
+  double *urcs_n = &lw.urcs_blk_n[(size_t)(gpn - 1) * nstrs * mxvl];
+  double *urcs_n1 = &lw.urcs_blk_n1[(size_t)(gpn - 1) * nstrs * mxvl];
+  double *hist = &lw.elem_hist[(size_t)(gpn - 1) * bi.hist_size * span];
+  double *hist1 = &lw.elem_hist1[(size_t)(gpn - 1) * bi.hist_size * span];
+  const bool nonlinear_update = iter >= 1 || m->extrapolated_du != 0;
+  const bool adaptive_possible = m->adaptive_flag != 0 && step > 1;
+  if (bi.hist_size != 14 || !m->matprp) { *fatal = 5; return; }
+  if (matprp(m, 58, bi.matnum) <= 0.0f) { *fatal = 3; return; }   // generalized_plasticity: not built
+  for (int i = 0; i < span; ++i) {
+    const int elem = bi.felem + i;
+    Props P;
+    P.e = rprop(m, 7, elem); P.nu = rprop(m, 8, elem); P.sigyld = rprop(m, 23, elem);
+    for (int k = 0; k < 10; ++k) P.mm[k] = matprp(m, 55 + k, bi.matnum);
+    double cgn[9], cgn1[9], ud[6], h[14], h1[14], trial[6];
+    for (int k = 0; k < 9; ++k) { cgn[k] = urcs_n[(size_t)k * mxvl + i]; cgn1[k] = 0.0; }
+    for (int k = 0; k < 6; ++k) ud[k] = uddt_displ[(size_t)k * mxvl + i] + 0.0;
+    for (int k = 0; k < 14; ++k) { h[k] = hist[(size_t)k * span + i]; h1[k] = hist1[(size_t)k * span + i]; }
+    double D[6][6];
+    if (nonlinear_update) {
+      const int rc = fa_update(step, iter, P, cgn, cgn1, ud, h, h1, trial, adaptive_possible);
+      if (rc == CUT) { material_cut_step = true; return; }
+      if (rc != OK) { *fatal = rc; return; }
+      cnst5_fa(P, trial, h1, cgn1, D);
+      for (int k = 0; k < 14; ++k) hist1[(size_t)k * span + i] = h1[k];
+    } else {
+      // drive_05_update_a/_b: linear-elastic [D] and stress for iteration 0 (no history update)
+      const double one = 1.0, two = 2.0;
+      const double c1 = (P.e / ((one + P.nu) * (one - two * P.nu)));
+      const double c2 = (one - P.nu) * c1, c3 = ((one - two * P.nu) / two) * c1, c4 = P.nu * c1;
+      for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) D[r][c] = 0.0;
+      D[0][0] = c2; D[1][1] = c2; D[2][2] = c2; D[3][3] = c3; D[4][4] = c3; D[5][5] = c3;
+      D[0][1] = c4; D[0][2] = c4; D[1][0] = c4; D[2][0] = c4; D[1][2] = c4; D[2][1] = c4;
+      for (int k = 0; k < 6; ++k) {
+        cgn1[k] = cgn[k];
+        for (int mm = 0; mm < 6; ++mm) cgn1[k] = cgn1[k] + D[mm][k] * ud[mm];
+      }
+    }
+    for (int k = 0; k < 9; ++k) urcs_n1[(size_t)k * mxvl + i] = cgn1[k];
+    for (int r = 1; r <= 6; ++r) for (int c = 1; c <= 6; ++c) Q6(cep, i, r, c) = D[r - 1][c - 1];
+  }
+  store_cep(span, gpn, gbl_cep, cep.data());
+}
+
 // drive_10_update (rstgp1.f:4327-4513) -> mm10 (mm10_a.f:29).  The per-Gauss-point crystal update
 // is the single-source core shared with the engine (warp3d_b200/csrc/w3d_mm10_core.h, see its
 // header for why); this wrapper supplies the reference's block-local layouts.
@@ -359,6 +411,10 @@ static void rstgp(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int g
   switch (bi.mat_type) {
     case 1:
       drive_01_update(m, bi, lw, gpn, step, iter, uddt.data(), gbl_cep, fatal);
+      break;
+    case 5:
+      drive_05_update(m, bi, lw, gpn, step, iter, uddt.data(), gbl_cep, material_cut_step, fatal);
+      if (material_cut_step || *fatal) return;
       break;
     case 10:
       drive_10_update(m, bi, lw, gpn, step, iter, uddt.data(), material_cut_step, fatal);

@@ -18,7 +18,8 @@ namespace w3d {
 
 constexpr int EPC = 16;          // elements per CTA
 constexpr int TPB = EPC * 8;     // threads per CTA (one per Gauss point)
-constexpr int EPROP = 8;         // floats per element in the compact property table
+constexpr int EPROP = 16;        // floats per element in the compact property table:
+                                 // e, nu, beta, hprime, yld, lnelas, then matprp(55:64) (mm05)
 
 // one CTA = up to EPC consecutive elements of one reference block
 struct CtaDesc {

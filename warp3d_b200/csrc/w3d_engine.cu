@@ -262,8 +262,15 @@ int create_impl(w3d_engine *h) {
     if (!b.owned) continue;
     if (b.elem_type != 2 || b.nnode != 8 || b.ndof != 3 || b.ngp != 8)
       return fail(W3D_ERR_UNSUPPORTED, "block %d: element type %d (%d nodes, %d points): only hex8 l3disop 2x2x2", blk + 1, b.elem_type, b.nnode, b.ngp);
-    if (b.mat_type != 1 && b.mat_type != 10)
-      return fail(W3D_ERR_UNSUPPORTED, "block %d: material model %d not built yet (mm01, mm10)", blk + 1, b.mat_type);
+    if (b.mat_type != 1 && b.mat_type != 5 && b.mat_type != 10)
+      return fail(W3D_ERR_UNSUPPORTED, "block %d: material model %d not built yet (mm01, mm05, mm10)", blk + 1, b.mat_type);
+    if (b.mat_type == 5) {
+      if (b.hist_size != 14) return fail(W3D_ERR_CONFIG, "block %d: mm05 history size %d != 14", blk + 1, b.hist_size);
+      if (!c.matprp || b.matnum < 1 || b.matnum > c.nmat || c.mxmtpr < 64)
+        return fail(W3D_ERR_CONFIG, "block %d: mm05 needs matprp(55:64) of material %d", blk + 1, b.matnum);
+      if (!(c.matprp[(size_t)(b.matnum - 1) * c.mxmtpr + 57] > 0.0f))
+        return fail(W3D_ERR_UNSUPPORTED, "block %d: mm05 generalized_plasticity option not built yet (nonlinear_hardening only)", blk + 1);
+    }
     if (b.mat_type == 1 && b.hist_size != 11)
       return fail(W3D_ERR_CONFIG, "block %d: mm01 history size %d != 11", blk + 1, b.hist_size);
     if (b.mat_type == 10) {
@@ -348,6 +355,8 @@ int create_impl(w3d_engine *h) {
         float *p = &ep[slot * EPROP];
         p[0] = rprop(c, 7, elem); p[1] = rprop(c, 8, elem); p[2] = rprop(c, 14, elem);
         p[3] = rprop(c, 15, elem); p[4] = rprop(c, 23, elem); p[5] = lprop(c, 17, elem) ? 1.0f : 0.0f;
+        if (b.mat_type == 5)   // setup_mm05_rknstr (rknstr.f:1234-1317): mm05_props = matprp(55:64)
+          for (int k = 0; k < 10; ++k) p[6 + k] = c.matprp[(size_t)(b.matnum - 1) * c.mxmtpr + 54 + k];
       }
       for (int w = 0; w <= W3D_ELEM_VOL; ++w) {
         const long long n = block_doubles(w, b);
@@ -459,6 +468,9 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
       CUDA_TRY(launch_mm10(ca, sg.ncta, h->stream));
       launch_stress<10, 2>(sg, a, h->stream);
       h->launches += 3;
+    } else if (sg.mat_type == 5) {
+      launch_stress<5, 0>(sg, a, h->stream);
+      h->launches += 1;
     } else {
       launch_stress<1, 0>(sg, a, h->stream);
       h->launches += 1;

@@ -17,6 +17,7 @@
 #include "w3d_device.cuh"
 #include "w3d_mm01.cuh"
 #include "w3d_mm10_core.h"
+#include "w3d_mm05_core.h"
 
 namespace w3d {
 
@@ -60,7 +61,7 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_s
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-constexpr int NSTATE_IN = 6 + 9 + 11;   // eps_n, urcs_n, hist_n (mm01) per Gauss point
+constexpr int NSTATE_IN = 6 + 9 + 14;   // eps_n, urcs_n, hist_n (11 mm01 / 14 mm05) per Gauss point
 
 // Jacobian with the node loop kept rolled: shape derivatives and coordinates are re-read from
 // shared memory each trip, so only the 9 accumulators are live (register pressure, not smem
@@ -185,13 +186,11 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
 #pragma unroll
     for (int k = 0; k < 6; ++k) cp_async8(&sSt[k][tid], a.eps_n + k * ng + g);
   }
-  if (MAT == 1) {
+  if (MAT == 1 || MAT == 5) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) cp_async8(&sSt[6 + k][tid], a.urcs_n + k * ng + g);
-  }
-  if (MAT == 1) {
 #pragma unroll
-    for (int k = 0; k < 11; ++k) cp_async8(&sSt[15 + k][tid], a.hist_n + k * ng + g);
+    for (int k = 0; k < (MAT == 1 ? 11 : 14); ++k) cp_async8(&sSt[15 + k][tid], a.hist_n + k * ng + g);
   }
   cp_async_commit();
 
@@ -406,6 +405,64 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
       for (int k = 0; k < 21; ++k) a.cep[k * ng + g] = cep[k];
 #pragma unroll
       for (int k = 0; k < 9; ++k) a.urcs_n1[k * ng + g] = cgn1[k];
+    }
+  }
+  bool mm05_cut = false;
+  if (MAT == 5) {
+    // drive_05_update (rstgp1.f:2373-2700): mm05 nonlinear_hardening + cnst5, or linear-elastic
+    double cgn[9], D[6][6];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) cgn[k] = sSt[6 + k][tid];
+    const float *ep = a.eprops + (size_t)slot * EPROP;
+    w3d_mm05::Props pr;
+    pr.e = (double)ep[0]; pr.nu = (double)ep[1]; pr.sigyld = (double)ep[4];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) pr.mm[k] = (double)ep[6 + k];
+    if (a.nonlinear_update) {
+      double h[14], h1[14], trial[6];
+#pragma unroll
+      for (int k = 0; k < 14; ++k) { h[k] = sSt[15 + k][tid]; h1[k] = 0.0; }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) cgn1[k] = 0.0;
+      const int rc = w3d_mm05::fa_update(a.step, a.iter, pr, cgn, cgn1, uddt, h, h1, trial, a.adaptive != 0);
+      if (rc == w3d_mm05::CUT) mm05_cut = true;
+      else if (rc != w3d_mm05::OK) fatal = rc;
+      w3d_mm05::cnst5_fa(pr, trial, h1, cgn1, D);
+      if (store && !mm05_cut && a.iter > 0) {
+#pragma unroll
+        for (int k = 0; k < 14; ++k) a.hist_n1[k * ng + g] = h1[k];
+      }
+    } else {
+      double c21[21];
+      elastic_cep21(pr.e, pr.nu, c21);
+      const double c2 = c21[0], c4 = c21[1], c3 = c21[9];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) D[r][c] = 0.0;
+      D[0][0] = c2; D[1][1] = c2; D[2][2] = c2; D[3][3] = c3; D[4][4] = c3; D[5][5] = c3;
+      D[1][0] = c4; D[2][0] = c4; D[2][1] = c4;
+      cgn1[0] = cgn[0] + (c2 * uddt[0] + c4 * uddt[1] + c4 * uddt[2]);
+      cgn1[1] = cgn[1] + (c4 * uddt[0] + c2 * uddt[1] + c4 * uddt[2]);
+      cgn1[2] = cgn[2] + (c4 * uddt[0] + c4 * uddt[1] + c2 * uddt[2]);
+      cgn1[3] = cgn[3] + c3 * uddt[3];
+      cgn1[4] = cgn[4] + c3 * uddt[4];
+      cgn1[5] = cgn[5] + c3 * uddt[5];
+      cgn1[6] = 0.0; cgn1[7] = 0.0; cgn1[8] = 0.0;
+    }
+    if (mm05_cut && valid) atomicOr(&a.flags[0], 1);
+    if (store && !mm05_cut) {
+      int k = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) { a.cep[k * ng + g] = D[r][c]; ++k; }
+#pragma unroll
+      for (int q = 0; q < 9; ++q) a.urcs_n1[q * ng + g] = cgn1[q];
+    }
+    if (mm05_cut) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) cgn1[q] = 0.0;
     }
   }
   if (MAT == 10) {

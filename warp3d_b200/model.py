@@ -136,6 +136,19 @@ def new_state(model: Model) -> State:
                  estiff=z(sz["estiff"]), element_vol=z(sz["element_vol"]))
 
 
+def cyclic_fa_material(e=200.0e9, nu=0.3, yld_pt=400.0e6, q_u=100.0e6, b_u=20.0, h_u=10.0e9,
+                       gamma_u=50.0, sig_tol=0.001):
+    """mm05 'cyclic' material, nonlinear_hardening (Frederick-Armstrong) option: the matprp(55:60)
+    rows exactly as src/inmat.f:2003-2040, :2220, :2287 stores them (real*4 arithmetic):
+    q_u, b = sqrt(2/3) b_u, h = (2/3) h_u, option flag +1, gamma = sqrt(2/3) gamma_u, sig_tol."""
+    f = np.float32
+    root23 = np.sqrt(f(2.0) / f(3.0)).astype(np.float32)
+    twothrds = f(2.0) / f(3.0)
+    rows = {55: f(q_u), 56: f(f(b_u) * root23), 57: f(f(h_u) * twothrds), 58: f(1.0),
+            59: f(f(gamma_u) * root23), 60: f(sig_tol)}
+    return Material(mat_type=5, e=e, nu=nu, yld_pt=yld_pt, tan_e=0.0, beta=1.0, extra={"matprp": rows})
+
+
 def _f32_bits(x) -> np.ndarray:
     return np.asarray(x, dtype=np.float32).view(np.int32)
 
