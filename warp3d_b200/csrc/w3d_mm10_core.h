@@ -224,19 +224,7 @@ W3D_HD inline double effective_dg(const double *D) {                            
 // in each of mm10_form_dbarp, mm10_form_wp, mm10_h_voche, mm10_dgdh_voche, ... (3-4 times per
 // residual, each with a pow()).  They are pure functions of (stress, tt), so one evaluation per
 // system per state is bit-identical and is what both builds of this core do.
-template <int NS>
-struct Slips {
-  double rs[NS], si[NS];
-};
-template <int NS>
-W3D_HD inline void eval_slips(const Props<NS> &P, const Work<NS> &w, const double *stress, double tt,
-                              Slips<NS> &s) {
-  const int ns = P.nslip();
-  for (int i = 0; i < ns; ++i) {
-    s.rs[i] = rs_of(w, stress, i);
-    s.si[i] = w.dg / tt * pow(fabs(s.rs[i] / tt), P.rate_n - 1.0) * s.rs[i];
-  }
-}
+//
 // pow(|h_term|, voche_m) with a one-entry memo: without geometric hardening (k_0 = 0) h_term is
 // the same for every slip system
 struct PowMemo {
@@ -248,6 +236,29 @@ W3D_HD inline double hterm_pow(PowMemo &m, double h_term, double voche_m) {
   return m.y;
 }
 
+// All powers of one state come from ONE pow() per slip system, the slip increment's own
+//   pw_i = |rs_i/tt|^(n-1):
+//   dg n / tt^n * |rs_i|^(n-1)             = dg n pw_i / tt              (mm10_dgdt_voche),
+//   dg n / tt^n * |rs_i|^(n-2) * rs_i      = dg n pw_i sign(rs_i) / tt   (mm10_estress_voche),
+// which differs from the reference's separate pow() calls by an ulp or two (as two libm's
+// differ) and takes the Jacobian from 49 pow() per state to none: it is always formed at the
+// state whose residual was evaluated last, so it reuses that evaluation.
+template <int NS>
+struct Slips {
+  double rs[NS], si[NS], pw[NS];
+  PowMemo pm;                       // |h_term|^m of this state, shared by formR2 and formJ
+};
+template <int NS>
+W3D_HD inline void eval_slips(const Props<NS> &P, const Work<NS> &w, const double *stress, double tt,
+                              Slips<NS> &s) {
+  const int ns = P.nslip();
+  for (int i = 0; i < ns; ++i) {
+    s.rs[i] = rs_of(w, stress, i);
+    s.pw[i] = pow(fabs(s.rs[i] / tt), P.rate_n - 1.0);
+    s.si[i] = w.dg / tt * s.pw[i] * s.rs[i];
+  }
+  s.pm.have = false;
+}
 // mm10_form_wp (Voce): w = sum (slipinc + rs tinc iD_v) qc
 template <int NS>
 W3D_HD inline void form_w(const Props<NS> &P, const Work<NS> &w, const Slips<NS> &s,
@@ -285,21 +296,20 @@ W3D_HD inline void formR1(const Props<NS> &P, const Work<NS> &w, const double *s
 }
 // mm10_h_voche (mm10_b.f:1896) and mm10_formR2 (:63); also records curr%tt_rate
 template <int NS>
-W3D_HD inline double formR2(const Props<NS> &P, Work<NS> &w, const Slips<NS> &s, double tt) {
+W3D_HD inline double formR2(const Props<NS> &P, Work<NS> &w, Slips<NS> &s, double tt) {
   double h = 0.0;
   const int ns = P.nslip();
-  PowMemo pm{0.0, 0.0, false};
   for (int i = 0; i < ns; ++i) {
     const double h_term = 1.0 - (tt - P.tau_y) / P.tau_v + w.tau_l[i] / (tt - P.tau_y);
-    h = h + hterm_pow(pm, h_term, P.voche_m) * copysign(1.0, h_term) * fabs(s.si[i]);
+    h = h + hterm_pow(s.pm, h_term, P.voche_m) * copysign(1.0, h_term) * fabs(s.si[i]);
   }
   h = w.n_tt + P.theta_0 * h;
   w.tt_rate = (h - w.n_tt) / w.tinc;
   return tt - h;
 }
 template <int NS>
-W3D_HD inline void formR(const Props<NS> &P, Work<NS> &w, const double *x, double *R) {
-  Slips<NS> s;
+W3D_HD inline void formR(const Props<NS> &P, Work<NS> &w, const double *x, double *R,
+                         Slips<NS> &s) {
   eval_slips(P, w, x, x[6], s);
   formR1(P, w, s, x, R);
   R[6] = formR2(P, w, s, x[6]);
@@ -318,13 +328,11 @@ W3D_HD inline void formJ11(const Props<NS> &P, const Work<NS> &w, const Slips<NS
   for (int r = 0; r < 6; ++r)
     for (int c = 0; c < 6; ++c) J[r][c] = 0.0;
   const int ns = P.nslip();
-  const double ptt = pow(tt, P.rate_n);                           // same value for every system
+  const double dgn = w.dg * P.rate_n / tt;
   for (int i = 0; i < ns; ++i) {
     double sq[6], wv[6];
     symsw(stress, w.qc[i], sq);                                   // mm10_symSWmat column i
-    const double rs = s.rs[i];
-    double dgdt = pow(fabs(rs), P.rate_n - 1.0);                  // mm10_dgdt_voche
-    dgdt = w.dg * P.rate_n / ptt * dgdt;
+    double dgdt = dgn * s.pw[i];                                  // mm10_dgdt_voche
     dgdt = dgdt + w.tinc * P.iD_v;
     for (int r = 0; r < 6; ++r) wv[r] = 2.0 * sq[r];              // mult_type_4
     for (int c = 0; c < 6; ++c)
@@ -343,18 +351,17 @@ W3D_HD inline void formJ11(const Props<NS> &P, const Work<NS> &w, const Slips<NS
   J[5][0] += wp[1]; J[5][2] += -wp[1]; J[5][3] += wp[0]; J[5][4] += -wp[2];
   for (int r = 0; r < 6; ++r) J[r][r] = J[r][r] + 1.0;
 }
-// full 7x7 Jacobian (mm10_formJ, mm10_b.f:909) for Voce with one hardening variable
+// full 7x7 Jacobian (mm10_formJ, mm10_b.f:909) for Voce with one hardening variable; s is the
+// slip evaluation at x
 template <int NS>
-W3D_HD inline void formJ(const Props<NS> &P, const Work<NS> &w, const double *x, double (&J)[7][7]) {
+W3D_HD inline void formJ(const Props<NS> &P, const Work<NS> &w, Slips<NS> &s, const double *x,
+                         double (&J)[7][7]) {
   const double tt = x[6];
-  Slips<NS> s;
-  eval_slips(P, w, x, tt, s);
   formJ11(P, w, s, x, tt, J);
   const int ns = P.nslip();
   for (int r = 0; r < 6; ++r) { J[r][6] = 0.0; J[6][r] = 0.0; }
   double et[6] = {0, 0, 0, 0, 0, 0};
   double etau = 0.0;
-  PowMemo pm{0.0, 0.0, false};
   for (int i = 0; i < ns; ++i) {
     // J12 (mm10_formJ12 + mm10_dgdh_voche)
     double sq[6], tm[6];
@@ -366,10 +373,9 @@ W3D_HD inline void formJ(const Props<NS> &P, const Work<NS> &w, const double *x,
     const double dgdh = -P.rate_n / tt * dgam;
     for (int r = 0; r < 6; ++r) J[r][6] = J[r][6] + 1.0 * tm[r] * dgdh;
     // J21 = -estress (mm10_estress_voche)
-    const double rs = s.rs[i];
     const double h_term = 1.0 - (tt - P.tau_y) / P.tau_v + w.tau_l[i] / (tt - P.tau_y);
-    const double hp = hterm_pow(pm, h_term, P.voche_m);
-    const double f = hp * copysign(1.0, h_term) * pow(fabs(rs), P.rate_n - 2.0) * rs;
+    const double hp = hterm_pow(s.pm, h_term, P.voche_m);
+    const double f = hp * copysign(1.0, h_term) * s.pw[i] * copysign(1.0, s.rs[i]);
     for (int k = 0; k < 6; ++k) et[k] = et[k] + f * w.ms[i][k];
     // J22 (mm10_ehard_voche)
     etau = etau + (P.voche_m * (-1.0 / P.tau_v - w.tau_l[i] / ((tt - P.tau_y) * (tt - P.tau_y))) *
@@ -377,7 +383,7 @@ W3D_HD inline void formJ(const Props<NS> &P, const Work<NS> &w, const double *x,
                    fabs(dgam) * P.rate_n / tt * copysign(1.0, h_term) * copysign(1.0, dgam)) *
                       hp;
   }
-  const double sc = P.theta_0 * w.dg * P.rate_n / pow(tt, P.rate_n);
+  const double sc = P.theta_0 * w.dg * P.rate_n / tt;
   for (int k = 0; k < 6; ++k) J[6][k] = -(sc * et[k]);
   etau = P.theta_0 * etau;
   J[6][6] = 1.0 - etau;
@@ -394,7 +400,7 @@ W3D_HD inline bool any_nan(const double *x, int n) {
 // x = [stress(6), tt]; returns fail.  J holds the last Jacobian formed by the update loop.
 template <int NS>
 W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double &tt, double dtinc,
-                         double (&J)[7][7]) {
+                         double (&J)[7][7], Slips<NS> &s) {
   const double c = 1.0e-4, red = 0.5;
   const int mls = 10, mmin = 1;
   const int miter = P.miter();
@@ -403,6 +409,8 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
   for (int k = 0; k < 6; ++k) x[k] = stress[k];
   x[6] = tt;
   double inR1;
+  // s: slip evaluation of the state whose residual was formed last; on a successful return that
+  // is the converged (stress, tt)
   {  // ---- mm10_solve_predict
     int iter = 0;
     double x1[6], d1[6], d2[6], R1[6];
@@ -425,17 +433,14 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
     t2 = d1[3] * d2[3] + d1[4] * d2[4] + d1[5] * d2[5];
     const double cos_ang = fmax(t1 + t2, 0.0);
     const double x2 = x[6] + cos_ang * w.n_tt_rate * dtinc;
-    formR1(P, w, x1, x2, R1);
+    eval_slips(P, w, x1, x2, s);
+    formR1(P, w, s, x1, R1);
     double nR1 = sqrt(R1[0] * R1[0] + R1[1] * R1[1] + R1[2] * R1[2] + R1[3] * R1[3] +
                       R1[4] * R1[4] + R1[5] * R1[5]);
     inR1 = nR1;
     bool pfail = false;
     while ((nR1 > P.atol1) && (nR1 / inR1 > P.rtol1)) {
-      {
-        Slips<NS> sj;
-        eval_slips(P, w, x1, x2, sj);
-        formJ11(P, w, sj, x1, x2, J);
-      }
+      formJ11(P, w, s, x1, x2, J);              // s: evaluated with R1 at (x1, x2)
       double A[6][6], dx[6][1], wv[6];
       for (int r = 0; r < 6; ++r) {
         dx[r][0] = R1[r];
@@ -456,7 +461,8 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
         const double nlsx = ls1 + ls2 * alpha;
         double xnew[6];
         for (int k = 0; k < 6; ++k) xnew[k] = x1[k] + alpha * dx[k][0];
-        formR1(P, w, xnew, x2, R1);
+        eval_slips(P, w, xnew, x2, s);
+        formR1(P, w, s, xnew, R1);
         dotR1 = R1[0] * R1[0] + R1[1] * R1[1] + R1[2] * R1[2] + R1[3] * R1[3] + R1[4] * R1[4] +
                 R1[5] * R1[5];
         nR1 = sqrt(dotR1);
@@ -482,14 +488,14 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
   {  // ---- mm10_solve_update
     int iter = 0;
     double R[7];
-    formR(P, w, x, R);
+    formR(P, w, x, R, s);
     double dotR = 0.0;
     for (int k = 0; k < 7; ++k) dotR = dotR + R[k] * R[k];
     double nR = sqrt(dotR);
     double inR = nR;
     if (inR == 0.0) inR = inR1;
     while (((nR > P.atol) && (nR / inR > P.rtol)) || (iter < mmin)) {
-      formJ(P, w, x, J);
+      formJ(P, w, s, x, J);                     // s: evaluated with R at x
       double A[7][7], dx[7][1], wv[7];
       for (int r = 0; r < 7; ++r) {
         dx[r][0] = R[r];
@@ -513,7 +519,7 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
         const double nlsx = ls1 + ls2 * alpha;
         double xnew[7];
         for (int k = 0; k < 7; ++k) xnew[k] = x[k] + alpha * dx[k][0];
-        formR(P, w, xnew, R);
+        formR(P, w, xnew, R, s);
         dotR = 0.0;
         for (int k = 0; k < 7; ++k) dotR = dotR + R[k] * R[k];
         nR = sqrt(dotR);
@@ -611,6 +617,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
                        stress[3] * stress[3] + stress[4] * stress[4] + stress[5] * stress[5];
   const bool no_load = (temp2 == 0.0) && (temp1 == 0.0);
   double J[7][7];
+  Slips<NS> sf;   // slips of the converged state; the last solve runs with the full-step D, tinc, dg
   if (iter_0_extrapolate_off || no_load) {
     // mm10_solve_strup_a: elastic stiffness as tangent; stress corrected for creep only
     for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) o.tangent[r][c] = P.stiffness[r][c];
@@ -635,7 +642,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
       w.dg = effective_dg<NS>(w.D);
       if (P.alter_mode_d != 0.0) w.dg = P.eps_dot_0_y * w.tinc;
       tt = w.n_tt;   // "some subroutines modify n%tau_tilde in setup": tt restarts from n
-      fail = solve(P, w, stress, tt, dt * step, J);
+      fail = solve(P, w, stress, tt, dt * step, J, sf);
       if (fail) {
         for (int k = 0; k < 6; ++k) stress[k] = ostress[k];
         tt = ott;
@@ -682,7 +689,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
   // ---- mm10_update_rotation: Rp_{n+1} = exp(wbarp) Rp_n
   {
     double wb[3], W[3][3], A[3][3];
-    form_w(P, w, stress, tt, w.qs, wb);
+    form_w(P, w, sf, w.qs, wb);
     W[0][0] = 0.0; W[0][1] = wb[2]; W[0][2] = wb[1];
     W[1][0] = -wb[2]; W[1][1] = 0.0; W[1][2] = wb[0];
     W[2][0] = -wb[1]; W[2][1] = -wb[0]; W[2][2] = 0.0;
@@ -701,7 +708,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
   // ---- mm10_output (mm10_a.f:3493)
   {
     const double pi = 3.141592653589793, one_eighty = 180.0;
-    for (int i = 0; i < ns; ++i) o.slip_incs[i] = slipinc(P, w, stress, tt, i);
+    for (int i = 0; i < ns; ++i) o.slip_incs[i] = sf.si[i];
     {  // mm10_update_euler_angles
       double w1[3][3], full[3][3];
       mat33_bt(w1, o.Rp, w.R);
@@ -720,7 +727,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
     }
     double ed[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < ns; ++i) {
-      const double dif = rs_of(w, stress, i) * w.tinc * P.iD_v;
+      const double dif = sf.rs[i] * w.tinc * P.iD_v;
       for (int k = 0; k < 6; ++k) ed[k] = ed[k] + dif * w.ms[i][k];
     }
     for (int k = 0; k < 6; ++k) o.ed[k] = ed[k] / w.tinc;
@@ -741,7 +748,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
     for (int i = 0; i < ns; ++i)
       for (int k = 0; k < 6; ++k) dbarp[k] = dbarp[k] + o.slip_incs[i] * w.ms[i][k];
     double wp[3], ewwe[6], ep[6];
-    form_w(P, w, stress, tt, w.qc, wp);
+    form_w(P, w, sf, w.qc, wp);
     symsw(ee, wp, ewwe);
     for (int k = 0; k < 6; ++k) { ep[k] = dbarp[k] + ewwe[k]; o.ep[k] = ep[k] / w.tinc; }
     t1 = ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2];
