@@ -303,9 +303,10 @@ static void drive_10_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
     for (int k = 0; k < 9; ++k) cgn[k] = urcs_n[(size_t)k * mxvl + i];
     const CHist hn{hist + i, span};
     const Hist h1{hist1 + i, span};
+    double slip_store[slip_store_doubles<12>()];
     const bool cut = gauss_point_update<12>(step, cp->ncrystals, P, L, hn, h1, Rur, ud, m->dt,
                                             iter_0_extrapolate_off, cp->asymmetric_assembly != 0,
-                                            cgn, cgn1);
+                                            cgn, cgn1, slip_store, 1);
     if (cut) { material_cut_step = true; return; }
     for (int k = 0; k < 9; ++k) urcs_n1[(size_t)k * mxvl + i] = cgn1[k];
   }

@@ -36,8 +36,10 @@ __global__ void __launch_bounds__(TPB) k_mm10(const CpArgs a) {
       a.props + (size_t)slot * a.ncrystals * (sizeof(Props<NS>) / sizeof(double)));
   const CHist hn{a.hist_n + g, ng};
   const Hist h1{a.hist_n1 + g, ng};
+  extern __shared__ double slip_store[];   // [slip_store_doubles<NS>()][TPB], one column per thread
   const bool cut = gauss_point_update<NS>(a.step, a.ncrystals, P, L, hn, h1, Rur, uddt, a.dt,
-                                          a.iter_0_extrapolate_off != 0, a.asymmetric != 0, cgn, cgn1);
+                                          a.iter_0_extrapolate_off != 0, a.asymmetric != 0, cgn, cgn1,
+                                          slip_store + tid, TPB);
   if (cut) {
     atomicOr(&a.flags[0], 1);
     return;
@@ -65,18 +67,17 @@ void mm10_setup_props_host(const double *ctd, const double *angles, int angle_ty
   setup_props<12>(ct, angles, angle_type, P);
   std::memcpy(props_out, &P, sizeof P);
 }
-#ifndef MM10_DYN_SMEM
-#define MM10_DYN_SMEM 0   // bytes of (unused) dynamic shared memory: caps the resident CTAs per SM
-#endif
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {
-  if (MM10_DYN_SMEM > 48 * 1024) {
-    static bool set = false;
-    if (!set) {
-      cudaFuncSetAttribute(k_mm10<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM10_DYN_SMEM);
-      set = true;
-    }
+  // rotated Schmid data of the crystal being updated: 9 doubles per slip system per thread
+  const int smem = slip_store_doubles<12>() * TPB * (int)sizeof(double);
+  static bool set = false;
+  if (!set) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(k_mm10<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    set = true;
   }
-  k_mm10<12><<<ncta, TPB, MM10_DYN_SMEM, st>>>(a);
+  k_mm10<12><<<ncta, TPB, smem, st>>>(a);
   return cudaGetLastError();
 }
 

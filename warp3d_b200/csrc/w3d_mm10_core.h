@@ -20,10 +20,13 @@
 #pragma once
 #include <math.h>
 
-// Note (round 1 measurement): fully inlined, k_mm10 is ~26 k SASS instructions and ncu shows the
-// warps stalling on instruction fetch; keeping the residual / Jacobian / solver as __noinline__
-// device functions shrinks the code to 16 k instructions but runs 15 % slower (call + stack
-// traffic).  The planned fix is the warp-cooperative redesign in DESIGN.md, not inlining policy.
+// Performance notes (round 1 measurements, 64k-element check): a thread-per-point transcription
+// with every array on the thread's stack is bound by local-memory traffic (6 KB per thread, more
+// than L2 holds for the resident threads: ncu shows ~60 GB of DRAM traffic per launch), not by
+// FP64 issue.  Hence: per-system Schmid data behind a strided pointer (shared memory on the
+// device), results stored straight to history instead of a staging record, sums over slip
+// systems taken before the 6x6 products.  __noinline__ residual/Jacobian functions were tried and
+// are slower (call + stack traffic).
 #if defined(__CUDACC__)
 #define W3D_HD __host__ __device__
 #else
@@ -192,26 +195,32 @@ W3D_HD inline int lu_solve(double (&A)[N][N], double (&B)[N][NRHS], int n, int n
 }
 
 // ---- state of one crystal --------------------------------------------------------------------
+// The rotated Schmid data of the current crystal (ms(6) and one 3-vector q per slip system) sit
+// behind a strided pointer: the engine keeps them in shared memory (stride = threads per CTA, so
+// a warp's accesses are conflict free), the CPU build in a plain array (stride 1).
+//   ms(i,k) = sl[(6 i + k) stride],   q(i,k) = sl[(6 NS + 3 i + k) stride]
+// q holds qc (current-configuration vectors) during the solve and the output terms and is
+// overwritten with qs for the plastic-rotation update at the very end.
 template <int NS>
 struct Work {
   // quantities at n read from history
-  double n_stress[6], n_Rp[3][3], n_R[3][3], n_D[6], n_tt, n_tt_rate, n_gradfe[27];
-  // set up for n+1 (mm10_setup): current Schmid tensors and geometric hardening
-  double R[3][3], ms[NS][6], qs[NS][3], qc[NS][3], tau_l[NS], mu_harden;
+  double n_stress[6], n_Rp[3][3], n_D[6], n_tt, n_tt_rate;
+  // set up for n+1 (mm10_setup): geometric hardening
+  double R[3][3], tau_l[NS], mu_harden;
   // the (sub-)increment being solved: curr%D, curr%tinc, curr%dg
   double D[6], tinc, dg, tt_rate;
+  double *sl;
+  int sls;
+  W3D_HD double &ms(int i, int k) const { return sl[(6 * i + k) * sls]; }
+  W3D_HD double &q(int i, int k) const { return sl[(6 * NS + 3 * i + k) * sls]; }
 };
+template <int NS>
+W3D_HD constexpr int slip_store_doubles() { return 9 * NS; }
 
 template <int NS>
 W3D_HD inline double rs_of(const Work<NS> &w, const double *stress, int i) {   // mm10_rs
-  return stress[0] * w.ms[i][0] + stress[1] * w.ms[i][1] + stress[2] * w.ms[i][2] +
-         stress[3] * w.ms[i][3] + stress[4] * w.ms[i][4] + stress[5] * w.ms[i][5];
-}
-template <int NS>
-W3D_HD inline double slipinc(const Props<NS> &P, const Work<NS> &w, const double *stress, double tt,
-                             int i) {                                          // mm10_slipinc
-  const double rs = rs_of(w, stress, i);
-  return w.dg / tt * pow(fabs(rs / tt), P.rate_n - 1.0) * rs;
+  return stress[0] * w.ms(i, 0) + stress[1] * w.ms(i, 1) + stress[2] * w.ms(i, 2) +
+         stress[3] * w.ms(i, 3) + stress[4] * w.ms(i, 4) + stress[5] * w.ms(i, 5);
 }
 template <int NS>
 W3D_HD inline double effective_dg(const double *D) {                            // mm10_setup :880
@@ -220,11 +229,6 @@ W3D_HD inline double effective_dg(const double *D) {                            
   return sqrt((2.0 / 3.0) * (t1 + 0.5 * t2));
 }
 
-// The reference re-evaluates the resolved shear stress and the slip increment of every system
-// in each of mm10_form_dbarp, mm10_form_wp, mm10_h_voche, mm10_dgdh_voche, ... (3-4 times per
-// residual, each with a pow()).  They are pure functions of (stress, tt), so one evaluation per
-// system per state is bit-identical and is what both builds of this core do.
-//
 // pow(|h_term|, voche_m) with a one-entry memo: without geometric hardening (k_0 = 0) h_term is
 // the same for every slip system
 struct PowMemo {
@@ -236,6 +240,11 @@ W3D_HD inline double hterm_pow(PowMemo &m, double h_term, double voche_m) {
   return m.y;
 }
 
+// The reference re-evaluates the resolved shear stress and the slip increment of every system
+// in each of mm10_form_dbarp, mm10_form_wp, mm10_h_voche, mm10_dgdh_voche, ... (3-4 times per
+// residual, each with a pow()).  They are pure functions of (stress, tt), so one evaluation per
+// system per state is what both builds of this core do.
+//
 // All powers of one state come from ONE pow() per slip system, the slip increment's own
 //   pw_i = |rs_i/tt|^(n-1):
 //   dg n / tt^n * |rs_i|^(n-1)             = dg n pw_i / tt              (mm10_dgdt_voche),
@@ -252,47 +261,43 @@ template <int NS>
 W3D_HD inline void eval_slips(const Props<NS> &P, const Work<NS> &w, const double *stress, double tt,
                               Slips<NS> &s) {
   const int ns = P.nslip();
+  const double dgt = w.dg / tt;
   for (int i = 0; i < ns; ++i) {
     s.rs[i] = rs_of(w, stress, i);
     s.pw[i] = pow(fabs(s.rs[i] / tt), P.rate_n - 1.0);
-    s.si[i] = w.dg / tt * s.pw[i] * s.rs[i];
+    s.si[i] = dgt * s.pw[i] * s.rs[i];
   }
   s.pm.have = false;
 }
-// mm10_form_wp (Voce): w = sum (slipinc + rs tinc iD_v) qc
+
+// mm10_form_wp / mm10_form_wbarp (Voce): w = sum (slipinc + rs tinc iD_v) q
 template <int NS>
-W3D_HD inline void form_w(const Props<NS> &P, const Work<NS> &w, const Slips<NS> &s,
-                          const double (*q)[3], double (&out)[3]) {
+W3D_HD inline void form_w(const Props<NS> &P, const Work<NS> &w, const Slips<NS> &s, double (&out)[3]) {
   out[0] = out[1] = out[2] = 0.0;
   const int ns = P.nslip();
+  const double cv = w.tinc * P.iD_v;
   for (int i = 0; i < ns; ++i) {
-    for (int k = 0; k < 3; ++k) out[k] = out[k] + s.si[i] * q[i][k];
-    for (int k = 0; k < 3; ++k) out[k] = out[k] + s.rs[i] * w.tinc * P.iD_v * q[i][k];
+    const double f = s.si[i] + s.rs[i] * cv;
+    for (int k = 0; k < 3; ++k) out[k] = out[k] + f * w.q(i, k);
   }
 }
 // mm10_formR1 (mm10_b.f:1073): R1 = stress - n%stress - C (D - dbarp) + 2 sym(T W)
 template <int NS>
 W3D_HD inline void formR1(const Props<NS> &P, const Work<NS> &w, const Slips<NS> &s,
                           const double *stress, double *R1) {
-  double dbarp[6] = {0, 0, 0, 0, 0, 0};
+  double dbarp[6] = {0, 0, 0, 0, 0, 0}, wp[3] = {0, 0, 0};
   const int ns = P.nslip();
+  const double cv = w.tinc * P.iD_v;
   for (int i = 0; i < ns; ++i) {
-    const double f = s.rs[i] * w.tinc * P.iD_v + s.si[i];
-    for (int k = 0; k < 6; ++k) dbarp[k] = dbarp[k] + f * w.ms[i][k];
+    const double f = s.rs[i] * cv + s.si[i];
+    for (int k = 0; k < 6; ++k) dbarp[k] = dbarp[k] + f * w.ms(i, k);
+    for (int k = 0; k < 3; ++k) wp[k] = wp[k] + f * w.q(i, k);
   }
-  double wp[3], symTW[6], v1[6], v2[6];
-  form_w(P, w, s, w.qc, wp);
+  double symTW[6], v1[6], v2[6];
   symsw(stress, wp, symTW);
   for (int k = 0; k < 6; ++k) v1[k] = w.D[k] - dbarp[k];
   mv6(v2, P.stiffness, v1);
   for (int k = 0; k < 6; ++k) R1[k] = stress[k] - w.n_stress[k] - v2[k] + 2.0 * symTW[k];
-}
-template <int NS>
-W3D_HD inline void formR1(const Props<NS> &P, const Work<NS> &w, const double *stress, double tt,
-                          double *R1) {
-  Slips<NS> s;
-  eval_slips(P, w, stress, tt, s);
-  formR1(P, w, s, stress, R1);
 }
 // mm10_h_voche (mm10_b.f:1896) and mm10_formR2 (:63); also records curr%tt_rate
 template <int NS>
@@ -314,34 +319,72 @@ W3D_HD inline void formR(const Props<NS> &P, Work<NS> &w, const double *x, doubl
   formR1(P, w, s, x, R);
   R[6] = formR2(P, w, s, x[6]);
 }
+
+// Jacobian of the local system (mm10_formJ, mm10_b.f:909; J11 :177, J12 :281, J21 :377, J22 :439)
+// for Voce with one hardening variable, at the state s was evaluated for.  The reference sums,
+// per slip system, dgdt_i (C ms_i + 2 symsw(T, qc_i)) (x) ms_i and dgdh_i (C ms_i + 2 symsw(T,
+// qc_i)); C and symsw(T, .) are linear, so the sums over systems are taken first:
+//   M  = sum dgdt_i ms_i (x) ms_i   (symmetric),   Q  = sum dgdt_i qc_i (x) ms_i,
+//   a6 = sum dgdh_i ms_i,                           q3 = sum dgdh_i qc_i,
+//   J11 = C M + 2 symsw(T, Q) + Iw + I,             J12 = C a6 + 2 symsw(T, q3)
+// -- the same numbers to rounding with about 40 % of the multiply-adds.  full = false forms J11
+// only (stress predictor).
 template <int NS>
-W3D_HD inline void form_w(const Props<NS> &P, const Work<NS> &w, const double *stress, double tt,
-                          const double (*q)[3], double (&out)[3]) {
-  Slips<NS> s;
-  eval_slips(P, w, stress, tt, s);
-  form_w(P, w, s, q, out);
-}
-// mm10_formJ11 (mm10_b.f:177) for Voce: sum_i dgdt_i (C ms_i + 2 symtq_i) (x) ms_i + Iw + I
-template <int NS>
-W3D_HD inline void formJ11(const Props<NS> &P, const Work<NS> &w, const Slips<NS> &s,
-                           const double *stress, double tt, double (&J)[7][7]) {
-  for (int r = 0; r < 6; ++r)
-    for (int c = 0; c < 6; ++c) J[r][c] = 0.0;
+W3D_HD inline void formJ(const Props<NS> &P, const Work<NS> &w, Slips<NS> &s, const double *stress,
+                         double tt, bool full, double (&J)[7][7]) {
   const int ns = P.nslip();
-  const double dgn = w.dg * P.rate_n / tt;
-  for (int i = 0; i < ns; ++i) {
-    double sq[6], wv[6];
-    symsw(stress, w.qc[i], sq);                                   // mm10_symSWmat column i
-    double dgdt = dgn * s.pw[i];                                  // mm10_dgdt_voche
-    dgdt = dgdt + w.tinc * P.iD_v;
-    for (int r = 0; r < 6; ++r) wv[r] = 2.0 * sq[r];              // mult_type_4
-    for (int c = 0; c < 6; ++c)
-      for (int r = 0; r < 6; ++r) wv[r] = wv[r] + P.stiffness[r][c] * w.ms[i][c];
-    for (int c = 0; c < 6; ++c)                                   // DGER
-      for (int r = 0; r < 6; ++r) J[r][c] = J[r][c] + dgdt * wv[r] * w.ms[i][c];
+  const double dgn = w.dg * P.rate_n / tt, cv = w.tinc * P.iD_v, nott = P.rate_n / tt;
+  double M[6][6], Q[3][6], a6[6], q3[3], et[6], wp[3];
+  for (int r = 0; r < 6; ++r) {
+    for (int c = r; c < 6; ++c) M[r][c] = 0.0;
+    a6[r] = 0.0; et[r] = 0.0;
   }
-  double wp[3];
-  form_w(P, w, s, w.qc, wp);
+  for (int a = 0; a < 3; ++a) {
+    for (int c = 0; c < 6; ++c) Q[a][c] = 0.0;
+    q3[a] = 0.0; wp[a] = 0.0;
+  }
+  double etau = 0.0;
+  for (int i = 0; i < ns; ++i) {
+    double m[6], gm[6], qc[3];
+    for (int k = 0; k < 6; ++k) m[k] = w.ms(i, k);
+    for (int k = 0; k < 3; ++k) qc[k] = w.q(i, k);
+    const double g = dgn * s.pw[i] + cv;                          // mm10_dgdt_voche + viscous term
+    for (int k = 0; k < 6; ++k) gm[k] = g * m[k];
+    for (int r = 0; r < 6; ++r)
+      for (int c = r; c < 6; ++c) M[r][c] = M[r][c] + gm[r] * m[c];
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 6; ++c) Q[a][c] = Q[a][c] + qc[a] * gm[c];
+    const double fw = s.si[i] + s.rs[i] * cv;                     // mm10_form_wp for mm10_IW
+    for (int a = 0; a < 3; ++a) wp[a] = wp[a] + fw * qc[a];
+    if (full) {
+      const double dgam = s.si[i];
+      const double dgdh = -nott * dgam;                           // mm10_dgdh_voche
+      for (int k = 0; k < 6; ++k) a6[k] = a6[k] + dgdh * m[k];
+      for (int a = 0; a < 3; ++a) q3[a] = q3[a] + dgdh * qc[a];
+      // J21 = -estress (mm10_estress_voche)
+      const double h_term = 1.0 - (tt - P.tau_y) / P.tau_v + w.tau_l[i] / (tt - P.tau_y);
+      const double hp = hterm_pow(s.pm, h_term, P.voche_m);
+      const double f = hp * copysign(1.0, h_term) * s.pw[i] * copysign(1.0, s.rs[i]);
+      for (int k = 0; k < 6; ++k) et[k] = et[k] + f * m[k];
+      // J22 (mm10_ehard_voche)
+      etau = etau + (P.voche_m * (-1.0 / P.tau_v - w.tau_l[i] / ((tt - P.tau_y) * (tt - P.tau_y))) *
+                         fabs(dgam) / fabs(h_term) -
+                     fabs(dgam) * nott * copysign(1.0, h_term) * copysign(1.0, dgam)) *
+                        hp;
+    }
+  }
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < r; ++c) M[r][c] = M[c][r];
+  for (int c = 0; c < 6; ++c) {
+    double sq[6];
+    const double qcol[3] = {Q[0][c], Q[1][c], Q[2][c]};
+    symsw(stress, qcol, sq);
+    for (int r = 0; r < 6; ++r) {
+      double v = 2.0 * sq[r];
+      for (int k = 0; k < 6; ++k) v = v + P.stiffness[r][k] * M[k][c];
+      J[r][c] = v;
+    }
+  }
   // mm10_IW (mm10_b.f:1613)
   J[0][3] += 2.0 * wp[2]; J[0][5] += -2.0 * wp[1];
   J[1][3] += 2.0 * wp[2]; J[1][4] += -2.0 * wp[0];
@@ -350,43 +393,19 @@ W3D_HD inline void formJ11(const Props<NS> &P, const Work<NS> &w, const Slips<NS
   J[4][1] += wp[0]; J[4][2] += -wp[0]; J[4][3] += wp[1]; J[4][5] += wp[2];
   J[5][0] += wp[1]; J[5][2] += -wp[1]; J[5][3] += wp[0]; J[5][4] += -wp[2];
   for (int r = 0; r < 6; ++r) J[r][r] = J[r][r] + 1.0;
-}
-// full 7x7 Jacobian (mm10_formJ, mm10_b.f:909) for Voce with one hardening variable; s is the
-// slip evaluation at x
-template <int NS>
-W3D_HD inline void formJ(const Props<NS> &P, const Work<NS> &w, Slips<NS> &s, const double *x,
-                         double (&J)[7][7]) {
-  const double tt = x[6];
-  formJ11(P, w, s, x, tt, J);
-  const int ns = P.nslip();
-  for (int r = 0; r < 6; ++r) { J[r][6] = 0.0; J[6][r] = 0.0; }
-  double et[6] = {0, 0, 0, 0, 0, 0};
-  double etau = 0.0;
-  for (int i = 0; i < ns; ++i) {
-    // J12 (mm10_formJ12 + mm10_dgdh_voche)
-    double sq[6], tm[6];
-    symsw(x, w.qc[i], sq);
-    for (int r = 0; r < 6; ++r) tm[r] = 2.0 * sq[r];
-    for (int c = 0; c < 6; ++c)
-      for (int r = 0; r < 6; ++r) tm[r] = tm[r] + P.stiffness[r][c] * w.ms[i][c];
-    const double dgam = s.si[i];
-    const double dgdh = -P.rate_n / tt * dgam;
-    for (int r = 0; r < 6; ++r) J[r][6] = J[r][6] + 1.0 * tm[r] * dgdh;
-    // J21 = -estress (mm10_estress_voche)
-    const double h_term = 1.0 - (tt - P.tau_y) / P.tau_v + w.tau_l[i] / (tt - P.tau_y);
-    const double hp = hterm_pow(s.pm, h_term, P.voche_m);
-    const double f = hp * copysign(1.0, h_term) * s.pw[i] * copysign(1.0, s.rs[i]);
-    for (int k = 0; k < 6; ++k) et[k] = et[k] + f * w.ms[i][k];
-    // J22 (mm10_ehard_voche)
-    etau = etau + (P.voche_m * (-1.0 / P.tau_v - w.tau_l[i] / ((tt - P.tau_y) * (tt - P.tau_y))) *
-                       fabs(dgam) / fabs(h_term) -
-                   fabs(dgam) * P.rate_n / tt * copysign(1.0, h_term) * copysign(1.0, dgam)) *
-                      hp;
+  if (!full) return;
+  {
+    double sq[6];
+    symsw(stress, q3, sq);
+    for (int r = 0; r < 6; ++r) {
+      double v = 2.0 * sq[r];
+      for (int k = 0; k < 6; ++k) v = v + P.stiffness[r][k] * a6[k];
+      J[r][6] = v;
+    }
   }
-  const double sc = P.theta_0 * w.dg * P.rate_n / tt;
+  const double sc = P.theta_0 * w.dg * nott;
   for (int k = 0; k < 6; ++k) J[6][k] = -(sc * et[k]);
-  etau = P.theta_0 * etau;
-  J[6][6] = 1.0 - etau;
+  J[6][6] = 1.0 - P.theta_0 * etau;
 }
 
 template <int NS>
@@ -421,14 +440,14 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
     double t1 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2];
     double t2 = d1[3] * d1[3] + d1[4] * d1[4] + d1[5] * d1[5];
     if (t1 + t2 == 0.0) { for (int k = 0; k < 6; ++k) d1[k] = 0.0; }
-    else { const double s = sqrt(t1 + t2); for (int k = 0; k < 6; ++k) d1[k] = d1[k] / s; }
+    else { const double sn = sqrt(t1 + t2); for (int k = 0; k < 6; ++k) d1[k] = d1[k] / sn; }
     for (int k = 0; k < 6; ++k) d2[k] = w.n_D[k];
     dtrace = (d2[0] + d2[1] + d2[2]) / 3.0;
     d2[0] -= dtrace; d2[1] -= dtrace; d2[2] -= dtrace;
     t1 = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2];
     t2 = d2[3] * d2[3] + d2[4] * d2[4] + d2[5] * d2[5];
     if (t1 + t2 == 0.0) { for (int k = 0; k < 6; ++k) d2[k] = 0.0; }
-    else { const double s = sqrt(t1 + t2); for (int k = 0; k < 6; ++k) d2[k] = d2[k] / s; }
+    else { const double sn = sqrt(t1 + t2); for (int k = 0; k < 6; ++k) d2[k] = d2[k] / sn; }
     t1 = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
     t2 = d1[3] * d2[3] + d1[4] * d2[4] + d1[5] * d2[5];
     const double cos_ang = fmax(t1 + t2, 0.0);
@@ -440,20 +459,20 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
     inR1 = nR1;
     bool pfail = false;
     while ((nR1 > P.atol1) && (nR1 / inR1 > P.rtol1)) {
-      formJ11(P, w, s, x1, x2, J);              // s: evaluated with R1 at (x1, x2)
+      formJ(P, w, s, x1, x2, false, J);               // s: evaluated with R1 at (x1, x2)
       double A[6][6], dx[6][1], wv[6];
       for (int r = 0; r < 6; ++r) {
         dx[r][0] = R1[r];
         for (int cc = 0; cc < 6; ++cc) A[r][cc] = -J[r][cc];
       }
-      lu_solve<6, 1>(A, dx, 6, 1);
-      double alpha = 1.0;
       double dotR1 = R1[0] * R1[0] + R1[1] * R1[1] + R1[2] * R1[2] + R1[3] * R1[3] +
                      R1[4] * R1[4] + R1[5] * R1[5];
       const double ls1 = 0.5 * dotR1;
       for (int k = 0; k < 6; ++k)   // trans(J11) R1
         wv[k] = J[0][k] * R1[0] + J[1][k] * R1[1] + J[2][k] * R1[2] + J[3][k] * R1[3] +
                 J[4][k] * R1[4] + J[5][k] * R1[5];
+      lu_solve<6, 1>(A, dx, 6, 1);
+      double alpha = 1.0;
       const double ls2 = c * (dx[0][0] * wv[0] + dx[1][0] * wv[1] + dx[2][0] * wv[2] +
                               dx[3][0] * wv[3] + dx[4][0] * wv[4] + dx[5][0] * wv[5]);
       int ls = 0;
@@ -495,22 +514,22 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
     double inR = nR;
     if (inR == 0.0) inR = inR1;
     while (((nR > P.atol) && (nR / inR > P.rtol)) || (iter < mmin)) {
-      formJ(P, w, s, x, J);                     // s: evaluated with R at x
+      formJ(P, w, s, x, x[6], true, J);               // s: evaluated with R at x
       double A[7][7], dx[7][1], wv[7];
       for (int r = 0; r < 7; ++r) {
         dx[r][0] = R[r];
         for (int cc = 0; cc < 7; ++cc) A[r][cc] = -J[r][cc];
       }
-      lu_solve<7, 1>(A, dx, 7, 1);
-      double alpha = 1.0;
       dotR = 0.0;
       for (int k = 0; k < 7; ++k) dotR = dotR + R[k] * R[k];
       const double ls1 = 0.5 * dotR;
       for (int k = 0; k < 7; ++k) {   // trans(J) R
-        double s = 0.0;
-        for (int r = 0; r < 7; ++r) s = s + J[r][k] * R[r];
-        wv[k] = s;
+        double sj = 0.0;
+        for (int r = 0; r < 7; ++r) sj = sj + J[r][k] * R[r];
+        wv[k] = sj;
       }
+      lu_solve<7, 1>(A, dx, 7, 1);
+      double alpha = 1.0;
       double ls2 = 0.0;
       for (int k = 0; k < 7; ++k) ls2 = ls2 + dx[k][0] * wv[k];
       ls2 = c * ls2;
@@ -540,46 +559,48 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
   return fail;
 }
 
-// result of one crystal update (what mm10_a_do_crystal accumulates / mm10_store_cryhist stores)
+// mm10_setup (mm10_a.f:852) for the Voce model.  n_R (R at n) and gradFe at n feed only the
+// geometric-hardening term; they are read straight from history at n (identity / zero at step 1).
 template <int NS>
-struct CrystalOut {
-  double stress[6], tangent[6][6], Rp[3][3], euler[3], eps[6], slip_incs[NS], tt, tt_rate, u[15],
-      ep[6], ed[6], work_inc, p_work_inc, p_strain_inc, p_strain_ten[6];
-};
-
-// mm10_setup (mm10_a.f:852) for the Voce model
-template <int NS>
-W3D_HD inline void setup(const Props<NS> &P, Work<NS> &w) {
-  double tr[3][3], RE[6][6], RW[3][3], RWC[3][3], wk[3][3];
+W3D_HD inline void setup(const Props<NS> &P, Work<NS> &w, bool init, const CHist &hn, const Layout &L) {
+  double tr[3][3];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) tr[i][j] = w.n_Rp[j][i];
-  rt2rve(tr, RE);
-  rt2rvw(tr, RW);
-  mat33(wk, w.R, tr);
-  rt2rvw(wk, RWC);
   const int ns = P.nslip();
-  for (int i = 0; i < ns; ++i) {
-    double a6[6];
-    mv6(a6, RE, P.ms[i]);
-    for (int k = 0; k < 6; ++k) w.ms[i][k] = a6[k];
-    mv3(w.qs[i], RW, P.qs[i]);
-    mv3(w.qc[i], RWC, P.qs[i]);
+  {
+    double RE[6][6], RWC[3][3], wk[3][3];
+    rt2rve(tr, RE);
+    mat33(wk, w.R, tr);
+    rt2rvw(wk, RWC);
+    for (int i = 0; i < ns; ++i) {
+      double a6[6], a3[3];
+      mv6(a6, RE, P.ms[i]);
+      for (int k = 0; k < 6; ++k) w.ms(i, k) = a6[k];
+      mv3(a3, RWC, P.qs[i]);
+      for (int k = 0; k < 3; ++k) w.q(i, k) = a3[k];
+    }
   }
   w.mu_harden = P.stiffness[5][5];   // mm10_setup_voche
   // geometric hardening tau_l from the lattice curvature (Acharya), :925-975
-  double curv[3][3][3];
-  const double *g = w.n_gradfe;     // gradFeinv(i,j,k) column-major: i + 3 j + 9 k
-#define GF(i, j, k) g[(i) + 3 * (j) + 9 * (k)]
+  const double alpha = 1.0 / 3.0;
+  const double cst = P.k_0 * P.burgers * alpha * alpha * w.mu_harden * w.mu_harden / 2.0 / P.theta_0;
+  if (cst == 0.0) {                  // k_0 = 0: no geometric hardening
+    for (int t = 0; t < ns; ++t) w.tau_l[t] = 0.0;
+    return;
+  }
+  double curv[3][3][3], n_R[3][3];
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i) n_R[i][j] = init ? ((i == j) ? 1.0 : 0.0) : hn[L.o_R() + j * 3 + i];
+  // gradFeinv(i,j,k) column-major: i + 3 j + 9 k
+#define GF(i, j, k) (init ? 0.0 : hn[L.o_gradfe() + (i) + 3 * (j) + 9 * (k)])
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j)
       for (int k = 0; k < 3; ++k) curv[i][j][k] = GF(i, j, k) - GF(i, k, j);
 #undef GF
-  const double alpha = 1.0 / 3.0;
-  const double cst = P.k_0 * P.burgers * alpha * alpha * w.mu_harden * w.mu_harden / 2.0 / P.theta_0;
   for (int t = 0; t < ns; ++t) {
     double wv[3], cn[3], tm[3];
     mv3(wv, tr, P.ns[t]);
-    mv3(cn, w.n_R, wv);
+    mv3(cn, n_R, wv);
     for (int i = 0; i < 3; ++i)
       tm[i] = 0.0 + 0.5 * (-curv[i][0][1] * cn[2] + curv[i][0][2] * cn[1] + curv[i][1][0] * cn[2] -
                            curv[i][1][2] * cn[0] - curv[i][2][0] * cn[1] + curv[i][2][1] * cn[0]);
@@ -587,51 +608,79 @@ W3D_HD inline void setup(const Props<NS> &P, Work<NS> &w) {
   }
 }
 
-// One crystal: mm10_a_do_crystal -> mm10_solve_crystal and everything below it.
-// Returns true when the crystal asks for a global step cut (solver failed after 4 halvings).
+// sums over the crystals of one Gauss point (mm10_a_do_crystal accumulates, mm10_a_crystal_avgs
+// divides); the tangent and the slip history are accumulated in history at n+1 directly
+struct PointSums {
+  double sig[6], t_work, p_work, p_strain;
+};
+
+// mm10_store_cryhist for a crystal whose update took the elastic short cut (mm10_solve_strup_a):
+// everything mm10_setup_np1 zeroes stays zero
+template <int NS>
+W3D_HD inline void store_crystal_defaults(const Layout &L, int c, const Hist &h1) {
+  for (int k = 0; k < 3; ++k) h1[L.c_euler(c) + k] = 0.0;
+  for (int k = 0; k < 9; ++k) h1[L.c_Rp(c) + k] = 0.0;
+  for (int k = 0; k < 6; ++k) h1[L.c_eps(c) + k] = 0.0;
+  for (int k = 0; k < L.len_slip; ++k) h1[L.c_slip(c) + k] = 0.0;
+  for (int k = 0; k < L.len_u; ++k) h1[L.c_u(c) + k] = 0.0;
+  for (int k = 0; k < 6; ++k) h1[L.c_ep(c) + k] = 0.0;
+  for (int k = 0; k < 6; ++k) h1[L.c_ed(c) + k] = 0.0;
+}
+
+// One crystal: mm10_a_do_crystal -> mm10_solve_crystal and everything below it, then
+// mm10_store_cryhist: the crystal's record goes straight to history at n+1, its contribution to
+// the point averages into acc / history (tangent: column-major at o_D, stored for crystal 0 and
+// added for the others).  Returns true when the crystal asks for a global step cut (solver failed
+// after 4 halvings).
 template <int NS>
 W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double *uddt, double dt,
-                                  bool iter_0_extrapolate_off, bool asymmetric,
-                                  CrystalOut<NS> &o) {
+                                  bool iter_0_extrapolate_off, bool asymmetric, bool init,
+                                  const Layout &L, int c, const CHist &hn, const Hist &h1,
+                                  PointSums &acc) {
   const int ns = P.nslip();
-  // mm10_setup_np1 defaults for everything mm10_solve_crystal may leave untouched
-  for (int k = 0; k < 6; ++k) { o.stress[k] = 0.0; o.eps[k] = 0.0; o.ep[k] = 0.0; o.ed[k] = 0.0; o.p_strain_ten[k] = 0.0; }
-  for (int i = 0; i < 3; ++i) { o.euler[i] = 0.0; for (int j = 0; j < 3; ++j) o.Rp[i][j] = 0.0; }
-  for (int i = 0; i < NS; ++i) o.slip_incs[i] = 0.0;
-  for (int i = 0; i < 15; ++i) o.u[i] = 0.0;
-  for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) o.tangent[r][c] = 0.0;
-  o.tt = 0.0; o.tt_rate = 0.0; o.work_inc = 0.0; o.p_work_inc = 0.0; o.p_strain_inc = 0.0;
-
   // ---- mm10_solve_strup
   for (int k = 0; k < 6; ++k) w.D[k] = uddt[k];
   w.tinc = dt;
   w.dg = effective_dg<NS>(w.D);
   if (P.alter_mode_d != 0.0) w.dg = P.eps_dot_0_y * w.tinc;
-  setup(P, w);
-  double stress[6], ostress[6];
-  for (int k = 0; k < 6; ++k) { stress[k] = w.n_stress[k]; ostress[k] = stress[k]; }
-  double tt = w.n_tt, ott = tt;
+  setup(P, w, init, hn, L);
+  double stress[6];
+  for (int k = 0; k < 6; ++k) stress[k] = w.n_stress[k];
+  double tt = w.n_tt;
   const double temp1 = uddt[0] * uddt[0] + uddt[1] * uddt[1] + uddt[2] * uddt[2] + uddt[3] * uddt[3] +
                        uddt[4] * uddt[4] + uddt[5] * uddt[5];
   const double temp2 = stress[0] * stress[0] + stress[1] * stress[1] + stress[2] * stress[2] +
                        stress[3] * stress[3] + stress[4] * stress[4] + stress[5] * stress[5];
   const bool no_load = (temp2 == 0.0) && (temp1 == 0.0);
-  double J[7][7];
+  // per-crystal history entries every path stores the same way
+  for (int k = 0; k < 6; ++k) h1[L.c_D(c) + k] = uddt[k];
+  for (int k = 0; k < L.len_tt; ++k) h1[L.c_tt(c) + k] = 0.0;
+  for (int k = 0; k < L.len_rate; ++k) h1[L.c_rate(c) + k] = 0.0;
   Slips<NS> sf;   // slips of the converged state; the last solve runs with the full-step D, tinc, dg
   if (iter_0_extrapolate_off || no_load) {
     // mm10_solve_strup_a: elastic stiffness as tangent; stress corrected for creep only
-    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) o.tangent[r][c] = P.stiffness[r][c];
+    for (int cc = 0; cc < 6; ++cc)
+      for (int r = 0; r < 6; ++r) {
+        const double t = P.stiffness[r][cc];
+        h1[L.o_D() + cc * 6 + r] = (c == 0) ? t : h1[L.o_D() + cc * 6 + r] + t;
+      }
     if (!no_load) {
       double R1[6];
-      formR1(P, w, stress, tt, R1);
+      eval_slips(P, w, stress, tt, sf);
+      formR1(P, w, sf, stress, R1);
       for (int k = 0; k < 6; ++k) stress[k] = stress[k] - R1[k];
     }
-    for (int k = 0; k < 6; ++k) o.stress[k] = stress[k];
-    o.tt = tt;
-    o.tt_rate = 0.0;
+    for (int k = 0; k < 6; ++k) { h1[L.c_stress(c) + k] = stress[k]; acc.sig[k] = acc.sig[k] + stress[k]; }
+    h1[L.c_tt(c)] = tt;
+    h1[L.c_rate(c)] = 0.0;
+    store_crystal_defaults<NS>(L, c, h1);
     return false;
   }
+  double J[7][7];
   {  // mm10_solve_strup_iterate: adaptive sub-incrementation, at most 4 halvings
+    double ostress[6];
+    for (int k = 0; k < 6; ++k) ostress[k] = stress[k];
+    double ott = tt;
     double frac = 0.0, step = 1.0;
     int cuts = 0;
     const int mcuts = 4;
@@ -658,9 +707,9 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
     }
     if (fail || tt != tt || any_nan<NS>(stress, 6)) return true;
   }
-  for (int k = 0; k < 6; ++k) o.stress[k] = stress[k];
-  o.tt = tt;
-  o.tt_rate = w.tt_rate;
+  for (int k = 0; k < 6; ++k) { h1[L.c_stress(c) + k] = stress[k]; acc.sig[k] = acc.sig[k] + stress[k]; }
+  h1[L.c_tt(c)] = tt;
+  h1[L.c_rate(c)] = w.tt_rate;
   // from here on the full-step quantities of np1 apply (np1%D, np1%tinc, np1%dg)
   for (int k = 0; k < 6; ++k) w.D[k] = uddt[k];
   w.tinc = dt;
@@ -674,22 +723,138 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
     double b21[6];
     for (int k = 0; k < 6; ++k) b21[k] = J[6][k] / J[6][6];   // DGESV on the 1x1 J22
     for (int r = 0; r < 6; ++r)
-      for (int c = 0; c < 6; ++c) {
-        JJ[r][c] = J[r][c] + (-1.0) * J[r][6] * b21[c];
-        JR[r][c] = P.stiffness[r][c] - 0.0 - 0.0 * J[r][6];
+      for (int cc = 0; cc < 6; ++cc) {
+        JJ[r][cc] = J[r][cc] + (-1.0) * J[r][6] * b21[cc];
+        JR[r][cc] = P.stiffness[r][cc] - 0.0 - 0.0 * J[r][6];
       }
     lu_solve<6, 6>(JJ, JR, 6, 6);
-    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) o.tangent[r][c] = JR[r][c];
-    if (!asymmetric) {   // mm10_a_make_symm_1
-      double wk[6][6];
-      for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) wk[r][c] = (o.tangent[r][c] + o.tangent[c][r]) * 0.5;
-      for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) o.tangent[r][c] = wk[r][c];
-    }
+    for (int cc = 0; cc < 6; ++cc)
+      for (int r = 0; r < 6; ++r) {
+        // mm10_a_make_symm_1 unless asymmetric assembly
+        const double t = asymmetric ? JR[r][cc] : (JR[r][cc] + JR[cc][r]) * 0.5;
+        h1[L.o_D() + cc * 6 + r] = (c == 0) ? t : h1[L.o_D() + cc * 6 + r] + t;
+      }
   }
-  // ---- mm10_update_rotation: Rp_{n+1} = exp(wbarp) Rp_n
+  // ---- mm10_output (mm10_a.f:3493); the plastic rotation update (mm10_update_rotation) and the
+  //      Euler angles that need it come last, when q can be overwritten with qs
   {
+    double ed[6] = {0, 0, 0, 0, 0, 0};
+    const double cv = w.tinc * P.iD_v;
+    for (int i = 0; i < ns; ++i) {
+      const double dif = sf.rs[i] * cv;
+      for (int k = 0; k < 6; ++k) ed[k] = ed[k] + dif * w.ms(i, k);
+    }
+    for (int k = 0; k < 6; ++k) h1[L.c_ed(c) + k] = ed[k] / w.tinc;
+    double t1 = ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2];
+    double t2 = ed[3] * ed[3] + ed[4] * ed[4] + ed[5] * ed[5];
+    double ed_dot = sqrt(2.0 / 3.0 * (t1 + 0.5 * t2));
+    ed_dot = ed_dot / w.tinc;
+    const double work_inc = stress[0] * w.D[0] + stress[1] * w.D[1] + stress[2] * w.D[2] +
+                            stress[3] * w.D[3] + stress[4] * w.D[4] + stress[5] * w.D[5];
+    // lattice strain: C^-1 stress (DPOSV -> LU here), rotated with R
+    double ee[6];
+    {
+      double S[6][6], ee0[6][1], erot[6][6];
+      for (int r = 0; r < 6; ++r) { ee0[r][0] = stress[r]; for (int cc = 0; cc < 6; ++cc) S[r][cc] = P.stiffness[r][cc]; }
+      lu_solve<6, 1>(S, ee0, 6, 1);
+      rt2rve(w.R, erot);
+      double v[6];
+      for (int k = 0; k < 6; ++k) v[k] = ee0[k][0];
+      mv6(ee, erot, v);
+    }
+    double dbarp[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < ns; ++i)
+      for (int k = 0; k < 6; ++k) dbarp[k] = dbarp[k] + sf.si[i] * w.ms(i, k);
+    double wp[3], ewwe[6], ep[6];
+    form_w(P, w, sf, wp);
+    symsw(ee, wp, ewwe);
+    for (int k = 0; k < 6; ++k) { ep[k] = dbarp[k] + ewwe[k]; h1[L.c_ep(c) + k] = ep[k] / w.tinc; }
+    t1 = ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2];
+    t2 = ep[3] * ep[3] + ep[4] * ep[4] + ep[5] * ep[5];
+    double ep_dot = sqrt(2.0 / 3.0 * (t1 + 0.5 * t2));
+    ep_dot = ep_dot / w.tinc;
+    for (int k = 0; k < 6; ++k) ep[k] = ep[k] + ed[k];
+    t1 = ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2];
+    t2 = ep[3] * ep[3] + ep[4] * ep[4] + ep[5] * ep[5];
+    const double p_strain_inc = sqrt(2.0 / 3.0 * (t1 + 0.5 * t2));
+    const double p_work_inc = stress[0] * ep[0] + stress[1] * ep[1] + stress[2] * ep[2] +
+                              stress[3] * ep[3] + stress[4] * ep[4] + stress[5] * ep[5];
+    for (int k = 0; k < 6; ++k) h1[L.c_eps(c) + k] = ee[k];
+    const double ec_dot = p_strain_inc / w.tinc;
+    double n_eff;
+    if (ec_dot > 0.0) {
+      for (int k = 0; k < 6; ++k) ep[k] = ep[k] / w.tinc;
+      n_eff = 0.0;
+      const double dgn = w.dg * P.rate_n / tt;
+      for (int i = 0; i < ns; ++i) {
+        const double rs = sf.rs[i];
+        const double dgdt = dgn * sf.pw[i] + cv;
+        t1 = w.ms(i, 0) * ep[0] + w.ms(i, 1) * ep[1] + w.ms(i, 2) * ep[2];
+        t2 = w.ms(i, 3) * ep[3] + w.ms(i, 4) * ep[4] + w.ms(i, 5) * ep[5];
+        const double ec_slip = t1 + 0.5 * t2;
+        t1 = rs * dgdt / ec_dot;
+        t2 = ec_slip / ec_dot / w.tinc;
+        n_eff = n_eff + (2.0 / 3.0) * t1 * t2;
+      }
+    } else {
+      n_eff = 1.0e10;
+    }
+    double s_trace = (stress[0] + stress[1] + stress[2]) / 3.0;
+    double se[6];
+    for (int k = 0; k < 6; ++k) se[k] = stress[k];
+    se[0] -= s_trace; se[1] -= s_trace; se[2] -= s_trace;
+    t1 = se[0] * se[0] + se[1] * se[1] + se[2] * se[2];
+    t2 = se[3] * se[3] + se[4] * se[4] + se[5] * se[5];
+    s_trace = sqrt(1.5 * (t1 + 2.0 * t2));
+    double B_eff;
+    if (ec_dot < 1.0e-100) B_eff = 0.0;
+    else if (n_eff > 100.0) B_eff = -1.0;
+    else B_eff = ec_dot / pow(s_trace, n_eff);
+    // total slip increments (plastic + viscous), the most active system and the number active
+    double maxslip = 0.0;
+    int sysID = 0;
+    for (int i = 0; i < ns; ++i) {
+      const double inc = sf.si[i] + sf.rs[i] * cv;
+      h1[L.c_slip(c) + i] = inc;
+      h1[L.o_sliphist() + i] = h1[L.o_sliphist() + i] + inc;
+      const double cur = fabs(inc);
+      if (cur > maxslip) { maxslip = cur; sysID = i + 1; }
+    }
+    for (int k = ns; k < L.len_slip; ++k) h1[L.c_slip(c) + k] = 0.0;
+    int numAct = 0;
+    const double thresh = 0.1 * maxslip;
+    for (int i = 0; i < ns; ++i)
+      if (fabs(sf.si[i] + sf.rs[i] * cv) >= thresh) numAct = numAct + 1;
+    // uhist (15 used entries of len_u)
+    for (int k = 0; k < L.len_u; ++k) h1[L.c_u(c) + k] = 0.0;
+    h1[L.c_u(c) + 5] = maxslip / w.tinc;
+    h1[L.c_u(c) + 6] = (double)sysID;
+    h1[L.c_u(c) + 7] = (double)numAct;
+    h1[L.c_u(c) + 10] = ep_dot;
+    h1[L.c_u(c) + 11] = n_eff;
+    h1[L.c_u(c) + 12] = s_trace;
+    h1[L.c_u(c) + 13] = B_eff;
+    h1[L.c_u(c) + 14] = ed_dot;
+    acc.t_work = acc.t_work + work_inc;
+    acc.p_work = acc.p_work + p_work_inc;
+    acc.p_strain = acc.p_strain + p_strain_inc;
+  }
+  // ---- mm10_update_rotation: Rp_{n+1} = exp(wbarp) Rp_n, then mm10_update_euler_angles
+  {
+    double Rp[3][3];
+    {
+      double tr[3][3], RW[3][3];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) tr[i][j] = w.n_Rp[j][i];
+      rt2rvw(tr, RW);
+      for (int i = 0; i < ns; ++i) {
+        double a3[3];
+        mv3(a3, RW, P.qs[i]);
+        for (int k = 0; k < 3; ++k) w.q(i, k) = a3[k];          // q := qs
+      }
+    }
     double wb[3], W[3][3], A[3][3];
-    form_w(P, w, sf, w.qs, wb);
+    form_w(P, w, sf, wb);
     W[0][0] = 0.0; W[0][1] = wb[2]; W[0][2] = wb[1];
     W[1][0] = -wb[2]; W[1][1] = 0.0; W[1][2] = wb[0];
     W[2][0] = -wb[1]; W[2][1] = -wb[0]; W[2][2] = 0.0;
@@ -703,115 +868,25 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
       for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[i][j] = ca * WW[i][j] + sa * W[i][j];
     }
     A[0][0] += 1.0; A[1][1] += 1.0; A[2][2] += 1.0;
-    mat33(o.Rp, A, w.n_Rp);
-  }
-  // ---- mm10_output (mm10_a.f:3493)
-  {
+    mat33(Rp, A, w.n_Rp);
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) h1[L.c_Rp(c) + j * 3 + i] = Rp[i][j];
     const double pi = 3.141592653589793, one_eighty = 180.0;
-    for (int i = 0; i < ns; ++i) o.slip_incs[i] = sf.si[i];
-    {  // mm10_update_euler_angles
-      double w1[3][3], full[3][3];
-      mat33_bt(w1, o.Rp, w.R);
-      mat33(full, P.g, w1);
-      double psi = atan2(full[2][1], full[2][0]);
-      if (psi < 0.0) psi = psi + 2.0 * pi;
-      double phi = atan2(full[1][2], full[0][2]);
-      if (phi < 0.0) phi = phi + 2.0 * pi;
-      if (full[2][2] > 1.0) full[2][2] = 1.0;
-      const double theta = acos(full[2][2]);
-      if ((int)P.angle_type_d == 1) {
-        o.euler[0] = one_eighty / pi * psi; o.euler[1] = one_eighty / pi * theta; o.euler[2] = one_eighty / pi * phi;
-      } else {
-        o.euler[0] = psi; o.euler[1] = theta; o.euler[2] = phi;
-      }
-    }
-    double ed[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < ns; ++i) {
-      const double dif = sf.rs[i] * w.tinc * P.iD_v;
-      for (int k = 0; k < 6; ++k) ed[k] = ed[k] + dif * w.ms[i][k];
-    }
-    for (int k = 0; k < 6; ++k) o.ed[k] = ed[k] / w.tinc;
-    double t1 = ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2];
-    double t2 = ed[3] * ed[3] + ed[4] * ed[4] + ed[5] * ed[5];
-    double ed_dot = sqrt(2.0 / 3.0 * (t1 + 0.5 * t2));
-    ed_dot = ed_dot / w.tinc;
-    o.u[14] = ed_dot;
-    o.work_inc = stress[0] * w.D[0] + stress[1] * w.D[1] + stress[2] * w.D[2] + stress[3] * w.D[3] +
-                 stress[4] * w.D[4] + stress[5] * w.D[5];
-    // lattice strain: C^-1 stress (DPOSV -> LU here), rotated with R
-    double S[6][6], ee0[6][1], erot[6][6], ee[6];
-    for (int r = 0; r < 6; ++r) { ee0[r][0] = stress[r]; for (int c = 0; c < 6; ++c) S[r][c] = P.stiffness[r][c]; }
-    lu_solve<6, 1>(S, ee0, 6, 1);
-    rt2rve(w.R, erot);
-    { double v[6]; for (int k = 0; k < 6; ++k) v[k] = ee0[k][0]; mv6(ee, erot, v); }
-    double dbarp[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < ns; ++i)
-      for (int k = 0; k < 6; ++k) dbarp[k] = dbarp[k] + o.slip_incs[i] * w.ms[i][k];
-    double wp[3], ewwe[6], ep[6];
-    form_w(P, w, sf, w.qc, wp);
-    symsw(ee, wp, ewwe);
-    for (int k = 0; k < 6; ++k) { ep[k] = dbarp[k] + ewwe[k]; o.ep[k] = ep[k] / w.tinc; }
-    t1 = ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2];
-    t2 = ep[3] * ep[3] + ep[4] * ep[4] + ep[5] * ep[5];
-    double ep_dot = sqrt(2.0 / 3.0 * (t1 + 0.5 * t2));
-    ep_dot = ep_dot / w.tinc;
-    o.u[10] = ep_dot;
-    for (int k = 0; k < 6; ++k) { ep[k] = ep[k] + ed[k]; o.p_strain_ten[k] = ep[k]; }
-    t1 = ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2];
-    t2 = ep[3] * ep[3] + ep[4] * ep[4] + ep[5] * ep[5];
-    o.p_strain_inc = sqrt(2.0 / 3.0 * (t1 + 0.5 * t2));
-    o.p_work_inc = stress[0] * ep[0] + stress[1] * ep[1] + stress[2] * ep[2] + stress[3] * ep[3] +
-                   stress[4] * ep[4] + stress[5] * ep[5];
-    for (int k = 0; k < 6; ++k) o.eps[k] = ee[k];
-    const double ec_dot = o.p_strain_inc / w.tinc;
-    double n_eff;
-    if (ec_dot > 0.0) {
-      for (int k = 0; k < 6; ++k) ep[k] = ep[k] / w.tinc;
-      n_eff = 0.0;
-      for (int i = 0; i < ns; ++i) {
-        const double rs = rs_of(w, stress, i);
-        double dgdt = pow(fabs(rs), P.rate_n - 1.0);
-        dgdt = w.dg * P.rate_n / pow(tt, P.rate_n) * dgdt;
-        dgdt = dgdt + w.tinc * P.iD_v;
-        t1 = w.ms[i][0] * ep[0] + w.ms[i][1] * ep[1] + w.ms[i][2] * ep[2];
-        t2 = w.ms[i][3] * ep[3] + w.ms[i][4] * ep[4] + w.ms[i][5] * ep[5];
-        const double ec_slip = t1 + 0.5 * t2;
-        t1 = rs * dgdt / ec_dot;
-        t2 = ec_slip / ec_dot / w.tinc;
-        n_eff = n_eff + (2.0 / 3.0) * t1 * t2;
-      }
+    double w1[3][3], full[3][3];
+    mat33_bt(w1, Rp, w.R);
+    mat33(full, P.g, w1);
+    double psi = atan2(full[2][1], full[2][0]);
+    if (psi < 0.0) psi = psi + 2.0 * pi;
+    double phi = atan2(full[1][2], full[0][2]);
+    if (phi < 0.0) phi = phi + 2.0 * pi;
+    if (full[2][2] > 1.0) full[2][2] = 1.0;
+    const double theta = acos(full[2][2]);
+    if ((int)P.angle_type_d == 1) {
+      h1[L.c_euler(c) + 0] = one_eighty / pi * psi;
+      h1[L.c_euler(c) + 1] = one_eighty / pi * theta;
+      h1[L.c_euler(c) + 2] = one_eighty / pi * phi;
     } else {
-      n_eff = 1.0e10;
+      h1[L.c_euler(c) + 0] = psi; h1[L.c_euler(c) + 1] = theta; h1[L.c_euler(c) + 2] = phi;
     }
-    o.u[11] = n_eff;
-    double s_trace = (stress[0] + stress[1] + stress[2]) / 3.0;
-    double se[6];
-    for (int k = 0; k < 6; ++k) se[k] = stress[k];
-    se[0] -= s_trace; se[1] -= s_trace; se[2] -= s_trace;
-    t1 = se[0] * se[0] + se[1] * se[1] + se[2] * se[2];
-    t2 = se[3] * se[3] + se[4] * se[4] + se[5] * se[5];
-    s_trace = sqrt(1.5 * (t1 + 2.0 * t2));
-    o.u[12] = s_trace;
-    double B_eff;
-    if (ec_dot < 1.0e-100) B_eff = 0.0;
-    else if (n_eff > 100.0) B_eff = -1.0;
-    else B_eff = ec_dot / pow(s_trace, n_eff);
-    o.u[13] = B_eff;
-    for (int i = 0; i < ns; ++i)
-      o.slip_incs[i] = o.slip_incs[i] + rs_of(w, stress, i) * w.tinc * P.iD_v;
-    double maxslip = 0.0;
-    int sysID = 0;
-    for (int i = 0; i < ns; ++i) {
-      const double cur = fabs(o.slip_incs[i]);
-      if (cur > maxslip) { maxslip = cur; sysID = i + 1; }
-    }
-    o.u[5] = maxslip / w.tinc;
-    o.u[6] = (double)sysID;
-    int numAct = 0;
-    maxslip = 0.1 * maxslip;
-    for (int i = 0; i < ns; ++i)
-      if (fabs(o.slip_incs[i]) >= maxslip) numAct = numAct + 1;
-    o.u[7] = (double)numAct;
   }
   return false;
 }
@@ -819,37 +894,36 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
 // mm10 (mm10_a.f:29): all crystals of one Gauss point.  hn / h1: history at n / n+1;
 // props: ncrystals consecutive Props records of this element; Rur: rot_blk_n1 (R of F = R U at
 // n+1, identity for small strain), column-major 9; uddt: un-rotated strain increment;
-// cgn / cgn1: urcs at n / n+1 (9).  Returns true when a crystal requests a step cut.
+// cgn / cgn1: urcs at n / n+1 (9); sl / sls: slip_store_doubles<NS>() doubles of scratch with
+// element stride sls (Work).  Returns true when a crystal requests a step cut.
 template <int NS>
 W3D_HD inline bool gauss_point_update(int step, int ncrystals, const Props<NS> *props, const Layout &L,
                                       const CHist &hn, const Hist &h1, const double *Rur,
                                       const double *uddt, double dt, bool iter_0_extrapolate_off,
-                                      bool asymmetric, const double *cgn, double *cgn1) {
-  const int ns = L.nslip;
+                                      bool asymmetric, const double *cgn, double *cgn1, double *sl,
+                                      int sls) {
   // At step 1 the reference initialises its block-local copy of history at n
   // (mm10_init_general_hist / _uout_hist / _slip_hist, mm10_init_cc_hist0) and never writes that
   // copy back; the same values are substituted here on the fly, history at n stays untouched.
   const bool init = (step == 1);
-  double sig_avg[6] = {0, 0, 0, 0, 0, 0}, tang_avg[6][6], p_strain_ten[6] = {0, 0, 0, 0, 0, 0};
-  for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) tang_avg[r][c] = 0.0;
-  double t_work_inc = 0.0, p_work_inc = 0.0, p_strain_inc = 0.0;
+  PointSums acc;
+  for (int k = 0; k < 6; ++k) acc.sig[k] = 0.0;
+  acc.t_work = 0.0; acc.p_work = 0.0; acc.p_strain = 0.0;
   // the slip-history sum is accumulated directly into history at n+1 (zeroed first)
   for (int k = 0; k < L.len_slip; ++k) h1[L.o_sliphist() + k] = 0.0;
 
   Work<NS> w;
-  CrystalOut<NS> o;
+  w.sl = sl;
+  w.sls = sls;
   for (int c = 0; c < ncrystals; ++c) {
     const Props<NS> &P = props[c];
     // mm10_copy_cc_hist
     if (init) {
-      for (int k = 0; k < 27; ++k) w.n_gradfe[k] = 0.0;
-      for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) { w.n_R[i][j] = (i == j) ? 1.0 : 0.0; w.n_Rp[i][j] = (i == j) ? 1.0 : 0.0; }
+      for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) w.n_Rp[i][j] = (i == j) ? 1.0 : 0.0;
       for (int k = 0; k < 6; ++k) { w.n_stress[k] = cgn[k]; w.n_D[k] = 0.0; }
       w.n_tt = P.tau_y + 1.0e-5;   // mm10_init_voche
       w.n_tt_rate = 0.0;
     } else {
-      for (int k = 0; k < 27; ++k) w.n_gradfe[k] = hn[L.o_gradfe() + k];
-      for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) w.n_R[i][j] = hn[L.o_R() + j * 3 + i];
       for (int k = 0; k < 6; ++k) w.n_stress[k] = hn[L.c_stress(c) + k];
       for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) w.n_Rp[i][j] = hn[L.c_Rp(c) + j * 3 + i];
       for (int k = 0; k < 6; ++k) w.n_D[k] = hn[L.c_D(c) + k];
@@ -858,41 +932,18 @@ W3D_HD inline bool gauss_point_update(int step, int ncrystals, const Props<NS> *
     }
     for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) w.R[i][j] = Rur[j * 3 + i];
     w.tt_rate = 0.0;
-
-    const bool cut = crystal_update(P, w, uddt, dt, iter_0_extrapolate_off, asymmetric, o);
-    if (cut) return true;
-
-    for (int k = 0; k < 6; ++k) sig_avg[k] = sig_avg[k] + o.stress[k];
-    for (int r = 0; r < 6; ++r) for (int cc = 0; cc < 6; ++cc) tang_avg[r][cc] = tang_avg[r][cc] + o.tangent[r][cc];
-    for (int k = 0; k < ns; ++k) h1[L.o_sliphist() + k] = h1[L.o_sliphist() + k] + o.slip_incs[k];
-    t_work_inc = t_work_inc + o.work_inc;
-    p_work_inc = p_work_inc + o.p_work_inc;
-    p_strain_inc = p_strain_inc + o.p_strain_inc;
-    for (int k = 0; k < 6; ++k) p_strain_ten[k] = p_strain_ten[k] + o.p_strain_ten[k];
-    // mm10_store_cryhist
-    for (int k = 0; k < 6; ++k) h1[L.c_stress(c) + k] = o.stress[k];
-    for (int k = 0; k < 3; ++k) h1[L.c_euler(c) + k] = o.euler[k];
-    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) h1[L.c_Rp(c) + j * 3 + i] = o.Rp[i][j];
-    for (int k = 0; k < 6; ++k) h1[L.c_D(c) + k] = uddt[k];
-    for (int k = 0; k < 6; ++k) h1[L.c_eps(c) + k] = o.eps[k];
-    for (int k = 0; k < L.len_slip; ++k) h1[L.c_slip(c) + k] = (k < NS) ? o.slip_incs[k] : 0.0;
-    for (int k = 0; k < L.len_tt; ++k) h1[L.c_tt(c) + k] = 0.0;
-    h1[L.c_tt(c)] = o.tt;
-    for (int k = 0; k < L.len_u; ++k) h1[L.c_u(c) + k] = (k < 15) ? o.u[k] : 0.0;
-    for (int k = 0; k < L.len_rate; ++k) h1[L.c_rate(c) + k] = 0.0;
-    h1[L.c_rate(c)] = o.tt_rate;
-    for (int k = 0; k < 6; ++k) h1[L.c_ep(c) + k] = o.ep[k];
-    for (int k = 0; k < 6; ++k) h1[L.c_ed(c) + k] = o.ed[k];
+    if (crystal_update(P, w, uddt, dt, iter_0_extrapolate_off, asymmetric, init, L, c, hn, h1, acc))
+      return true;
   }
   // mm10_a_crystal_avgs + mm10_a_store_crystal
   const double rn = (double)ncrystals;
-  for (int k = 0; k < 6; ++k) cgn1[k] = sig_avg[k] / rn;
-  for (int cc = 0; cc < 6; ++cc)
-    for (int r = 0; r < 6; ++r) h1[L.o_D() + cc * 6 + r] = tang_avg[r][cc] / rn;   // column-major
+  for (int k = 0; k < 6; ++k) cgn1[k] = acc.sig[k] / rn;
+  if (ncrystals > 1)
+    for (int k = 0; k < 36; ++k) h1[L.o_D() + k] = h1[L.o_D() + k] / rn;
   for (int k = 0; k < 9; ++k) h1[L.o_R() + k] = Rur[k];
   for (int k = 0; k < L.len_slip; ++k)
     h1[L.o_sliphist() + k] = (init ? 0.0 : hn[L.o_sliphist() + k]) + h1[L.o_sliphist() + k] / rn;
-  t_work_inc = t_work_inc / rn; p_work_inc = p_work_inc / rn; p_strain_inc = p_strain_inc / rn;
+  const double t_work_inc = acc.t_work / rn, p_work_inc = acc.p_work / rn, p_strain_inc = acc.p_strain / rn;
   cgn1[6] = cgn[6] + t_work_inc;
   cgn1[7] = cgn[7] + p_work_inc;
   cgn1[8] = cgn[8] + p_strain_inc;
