@@ -12,7 +12,9 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libw3d_oracle.so")
+# W3D_ORACLE_STATS=1 selects the build with mm10 operation counters (w3d_mm10_core.h, W3D_STAT)
+_STATS = bool(os.environ.get("W3D_ORACLE_STATS"))
+_LIB = os.path.join(_HERE, "libw3d_oracle_stats.so" if _STATS else "libw3d_oracle.so")
 
 
 class _Model(C.Structure):
@@ -50,7 +52,7 @@ def build(force=False):
     if (not force and os.path.exists(_LIB)
             and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in srcs)):
         return _LIB
-    subprocess.run(["make", "-C", _HERE, "libw3d_oracle.so"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", _HERE, os.path.basename(_LIB)], check=True, capture_output=True)
     return _LIB
 
 
@@ -68,6 +70,19 @@ def lib():
         _lib.w3do_mm10_props_doubles.restype = C.c_int32
         _lib.w3do_mm10_hist_size.restype = C.c_int32
     return _lib
+
+
+def mm10_stats(reset=False):
+    """mm10 operation counters of the stats build: slip evaluations, Jacobians, dense solves,
+    crystal updates that ran the solver, sub-increment solves."""
+    if not _STATS:
+        raise RuntimeError("set W3D_ORACLE_STATS=1 before importing the oracle")
+    arr = (C.c_longlong * 8).in_dll(lib(), "w3d_mm10_stats")
+    out = dict(zip(("slip_evals", "jacobians", "solves", "crystal_solves", "subincrement_solves"), list(arr)[:5]))
+    if reset:
+        for k in range(8):
+            arr[k] = 0
+    return out
 
 
 def mm10_props(model):

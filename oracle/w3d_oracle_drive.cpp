@@ -18,6 +18,9 @@
 #endif
 #include "w3d_oracle_internal.h"
 #include "../warp3d_b200/csrc/w3d_mm10_core.h"   // single-source mm10 core (see its header)
+#ifdef W3D_MM10_STATS
+extern "C" { long long w3d_mm10_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }
+#endif
 #include "../warp3d_b200/csrc/w3d_mm05_core.h"   // single-source mm05 core (see its header)
 
 namespace w3do {

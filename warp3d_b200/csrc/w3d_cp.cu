@@ -13,8 +13,11 @@ namespace w3d {
 
 using namespace w3d_mm10;
 
+#ifndef MM10_MIN_CTAS
+#define MM10_MIN_CTAS 2   // resident CTAs per SM the register allocation is sized for
+#endif
 template <int NS>
-__global__ void __launch_bounds__(TPB) k_mm10(const CpArgs a) {
+__global__ void __launch_bounds__(TPB, MM10_MIN_CTAS) k_mm10(const CpArgs a) {
   const int tid = threadIdx.x;
   const CtaDesc cd = a.cta[blockIdx.x];
   const int el = tid >> 3, gp = tid & 7;
@@ -36,10 +39,18 @@ __global__ void __launch_bounds__(TPB) k_mm10(const CpArgs a) {
       a.props + (size_t)slot * a.ncrystals * (sizeof(Props<NS>) / sizeof(double)));
   const CHist hn{a.hist_n + g, ng};
   const Hist h1{a.hist_n1 + g, ng};
+#ifdef W3D_MM10_SLIP_STORE
   extern __shared__ double slip_store[];   // [slip_store_doubles<NS>()][TPB], one column per thread
+  double *const sl = slip_store + tid;
+  const int sls = TPB;
+#else
+  // no slip store on the device: the core recomputes the rotated Schmid data where needed
+  double *const sl = nullptr;
+  const int sls = 0;
+#endif
   const bool cut = gauss_point_update<NS>(a.step, a.ncrystals, P, L, hn, h1, Rur, uddt, a.dt,
                                           a.iter_0_extrapolate_off != 0, a.asymmetric != 0, cgn, cgn1,
-                                          slip_store + tid, TPB);
+                                          sl, sls);
   if (cut) {
     atomicOr(&a.flags[0], 1);
     return;
@@ -68,7 +79,7 @@ void mm10_setup_props_host(const double *ctd, const double *angles, int angle_ty
   std::memcpy(props_out, &P, sizeof P);
 }
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {
-  // rotated Schmid data of the crystal being updated: 9 doubles per slip system per thread
+#ifdef W3D_MM10_SLIP_STORE
   const int smem = slip_store_doubles<12>() * TPB * (int)sizeof(double);
   static bool set = false;
   if (!set) {
@@ -77,6 +88,9 @@ cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     set = true;
   }
+#else
+  const int smem = 0;
+#endif
   k_mm10<12><<<ncta, TPB, smem, st>>>(a);
   return cudaGetLastError();
 }

@@ -29,8 +29,20 @@
 // are slower (call + stack traffic).
 #if defined(__CUDACC__)
 #define W3D_HD __host__ __device__
+#define W3D_ROLLED _Pragma("unroll 1")   // keep a loop rolled on the device: code size, see notes
 #else
 #define W3D_HD
+#define W3D_ROLLED
+#endif
+
+// optional host-side operation counters (oracle built with -DW3D_MM10_STATS; bench.py uses them
+// to state the algorithmic work of a launch): [0] slip evaluations (one pow per system each),
+// [1] Jacobians, [2] 7x7 / 6x6 solves, [3] crystal updates that ran the solver, [4] sub-increment solves
+#if defined(W3D_MM10_STATS) && !defined(__CUDA_ARCH__)
+extern "C" long long w3d_mm10_stats[8];
+#define W3D_STAT(k) __atomic_fetch_add(&w3d_mm10_stats[k], 1LL, __ATOMIC_RELAXED)
+#else
+#define W3D_STAT(k) ((void)0)
 #endif
 
 namespace w3d_mm10 {
@@ -165,6 +177,7 @@ W3D_HD inline void symsw(const double *s, const double *w, double (&sw)[6]) {   
 template <int N, int NRHS>
 W3D_HD inline int lu_solve(double (&A)[N][N], double (&B)[N][NRHS], int n, int nrhs) {
   int info = 0;
+  W3D_ROLLED
   for (int j = 0; j < n; ++j) {
     int p = j;
     double amax = fabs(A[j][j]);
@@ -195,18 +208,19 @@ W3D_HD inline int lu_solve(double (&A)[N][N], double (&B)[N][NRHS], int n, int n
 }
 
 // ---- state of one crystal --------------------------------------------------------------------
-// The rotated Schmid data of the current crystal (ms(6) and one 3-vector q per slip system) sit
-// behind a strided pointer: the engine keeps them in shared memory (stride = threads per CTA, so
-// a warp's accesses are conflict free), the CPU build in a plain array (stride 1).
-//   ms(i,k) = sl[(6 i + k) stride],   q(i,k) = sl[(6 NS + 3 i + k) stride]
-// q holds qc (current-configuration vectors) during the solve and the output terms and is
-// overwritten with qs for the plastic-rotation update at the very end.
+// Schmid data of the current crystal in the unrotated configuration: ms_i = RE ms0_i (6) and the
+// spin vector qc_i = RQ qs0_i (3), with RE / RQ the 6x6 / 3x3 operators of the rotations
+// Rp_n^T and R Rp_n^T (mm10_setup) and ms0 / qs0 the element's reference-frame tables (Props).
+// The CPU build computes them once per crystal into a plain array (sl, stride 1), as the
+// reference does.  The device build recomputes them from RE / RQ wherever a loop over the slip
+// systems needs them (45 multiply-adds per system, bit-identical values): 864 bytes per thread of
+// storage cap the resident warps, the FP64 pipe has the room (see the notes at the top).
 template <int NS>
 struct Work {
   // quantities at n read from history
   double n_stress[6], n_Rp[3][3], n_D[6], n_tt, n_tt_rate;
-  // set up for n+1 (mm10_setup): geometric hardening
-  double R[3][3], tau_l[NS], mu_harden;
+  // set up for n+1 (mm10_setup)
+  double R[3][3], RE[6][6], RQ[3][3], tau_l[NS], mu_harden;
   // the (sub-)increment being solved: curr%D, curr%tinc, curr%dg
   double D[6], tinc, dg, tt_rate;
   double *sl;
@@ -218,9 +232,15 @@ template <int NS>
 W3D_HD constexpr int slip_store_doubles() { return 9 * NS; }
 
 template <int NS>
-W3D_HD inline double rs_of(const Work<NS> &w, const double *stress, int i) {   // mm10_rs
-  return stress[0] * w.ms(i, 0) + stress[1] * w.ms(i, 1) + stress[2] * w.ms(i, 2) +
-         stress[3] * w.ms(i, 3) + stress[4] * w.ms(i, 4) + stress[5] * w.ms(i, 5);
+W3D_HD inline void slip_system(const Props<NS> &P, const Work<NS> &w, int i, double (&m)[6],
+                               double (&q)[3]) {
+#if defined(__CUDA_ARCH__) && !defined(W3D_MM10_SLIP_STORE)
+  mv6(m, w.RE, P.ms[i]);
+  mv3(q, w.RQ, P.qs[i]);
+#else
+  for (int k = 0; k < 6; ++k) m[k] = w.ms(i, k);
+  for (int k = 0; k < 3; ++k) q[k] = w.q(i, k);
+#endif
 }
 template <int NS>
 W3D_HD inline double effective_dg(const double *D) {                            // mm10_setup :880
@@ -229,6 +249,32 @@ W3D_HD inline double effective_dg(const double *D) {                            
   return sqrt((2.0 / 3.0) * (t1 + 0.5 * t2));
 }
 
+// x^e for x >= 0.  The exponents on this path are material constants that are whole numbers in
+// every deck of the reference (rate sensitivity n - 1 = 19 in test82/voche_model, 9..49 in the
+// example problems; Voce exponent m = 1): those are evaluated by binary powering (a handful of
+// multiplies, within a few ulp of pow(), like two libm's differ) -- pow() itself is ~290 SASS
+// instructions per call on the device and was a third of all instructions executed.  Anything
+// else goes to pow().
+struct Power {
+  double e;
+  int ie;      // >= 0: e is this whole number; -1: general exponent
+  W3D_HD static Power make(double e) {
+    Power p;
+    p.e = e;
+    p.ie = (e >= 0.0 && e <= 1024.0 && e == (double)(int)e) ? (int)e : -1;
+    return p;
+  }
+  W3D_HD double operator()(double x) const {
+    if (ie < 0) return pow(x, e);
+    double r = 1.0, b = x;
+    for (int k = ie; k != 0; k >>= 1) {
+      if (k & 1) r = r * b;
+      b = b * b;
+    }
+    return r;
+  }
+};
+
 // pow(|h_term|, voche_m) with a one-entry memo: without geometric hardening (k_0 = 0) h_term is
 // the same for every slip system
 struct PowMemo {
@@ -236,7 +282,7 @@ struct PowMemo {
   bool have;
 };
 W3D_HD inline double hterm_pow(PowMemo &m, double h_term, double voche_m) {
-  if (!(m.have && m.x == h_term)) { m.x = h_term; m.y = pow(fabs(h_term), voche_m); m.have = true; }
+  if (!(m.have && m.x == h_term)) { m.x = h_term; m.y = Power::make(voche_m)(fabs(h_term)); m.have = true; }
   return m.y;
 }
 
@@ -257,42 +303,31 @@ struct Slips {
   double rs[NS], si[NS], pw[NS];
   PowMemo pm;                       // |h_term|^m of this state, shared by formR2 and formJ
 };
+// One pass over the slip systems for the state (stress, tt): resolved shear stresses and slip
+// increments into s (mm10_rs, mm10_slipinc), and mm10_formR1 (mm10_b.f:1073):
+//   R1 = stress - n%stress - C (D - dbarp) + 2 sym(T W),
+// dbarp = sum (slipinc + rs tinc iD_v) ms (mm10_form_dbarp), W from sum (...) qc (mm10_form_wp)
 template <int NS>
-W3D_HD inline void eval_slips(const Props<NS> &P, const Work<NS> &w, const double *stress, double tt,
-                              Slips<NS> &s) {
-  const int ns = P.nslip();
-  const double dgt = w.dg / tt;
-  for (int i = 0; i < ns; ++i) {
-    s.rs[i] = rs_of(w, stress, i);
-    s.pw[i] = pow(fabs(s.rs[i] / tt), P.rate_n - 1.0);
-    s.si[i] = dgt * s.pw[i] * s.rs[i];
-  }
-  s.pm.have = false;
-}
-
-// mm10_form_wp / mm10_form_wbarp (Voce): w = sum (slipinc + rs tinc iD_v) q
-template <int NS>
-W3D_HD inline void form_w(const Props<NS> &P, const Work<NS> &w, const Slips<NS> &s, double (&out)[3]) {
-  out[0] = out[1] = out[2] = 0.0;
-  const int ns = P.nslip();
-  const double cv = w.tinc * P.iD_v;
-  for (int i = 0; i < ns; ++i) {
-    const double f = s.si[i] + s.rs[i] * cv;
-    for (int k = 0; k < 3; ++k) out[k] = out[k] + f * w.q(i, k);
-  }
-}
-// mm10_formR1 (mm10_b.f:1073): R1 = stress - n%stress - C (D - dbarp) + 2 sym(T W)
-template <int NS>
-W3D_HD inline void formR1(const Props<NS> &P, const Work<NS> &w, const Slips<NS> &s,
-                          const double *stress, double *R1) {
+W3D_HD inline void formR1(const Props<NS> &P, const Work<NS> &w, const double *stress, double tt,
+                          Slips<NS> &s, double *R1) {
+  W3D_STAT(0);
   double dbarp[6] = {0, 0, 0, 0, 0, 0}, wp[3] = {0, 0, 0};
   const int ns = P.nslip();
-  const double cv = w.tinc * P.iD_v;
+  const double cv = w.tinc * P.iD_v, dgt = w.dg / tt;
+  const Power rate_pow = Power::make(P.rate_n - 1.0);
   for (int i = 0; i < ns; ++i) {
-    const double f = s.rs[i] * cv + s.si[i];
-    for (int k = 0; k < 6; ++k) dbarp[k] = dbarp[k] + f * w.ms(i, k);
-    for (int k = 0; k < 3; ++k) wp[k] = wp[k] + f * w.q(i, k);
+    double m[6], q[3];
+    slip_system(P, w, i, m, q);
+    const double rs = stress[0] * m[0] + stress[1] * m[1] + stress[2] * m[2] + stress[3] * m[3] +
+                      stress[4] * m[4] + stress[5] * m[5];
+    const double pw = rate_pow(fabs(rs / tt));
+    const double si = dgt * pw * rs;
+    s.rs[i] = rs; s.pw[i] = pw; s.si[i] = si;
+    const double f = rs * cv + si;
+    for (int k = 0; k < 6; ++k) dbarp[k] = dbarp[k] + f * m[k];
+    for (int k = 0; k < 3; ++k) wp[k] = wp[k] + f * q[k];
   }
+  s.pm.have = false;
   double symTW[6], v1[6], v2[6];
   symsw(stress, wp, symTW);
   for (int k = 0; k < 6; ++k) v1[k] = w.D[k] - dbarp[k];
@@ -315,8 +350,7 @@ W3D_HD inline double formR2(const Props<NS> &P, Work<NS> &w, Slips<NS> &s, doubl
 template <int NS>
 W3D_HD inline void formR(const Props<NS> &P, Work<NS> &w, const double *x, double *R,
                          Slips<NS> &s) {
-  eval_slips(P, w, x, x[6], s);
-  formR1(P, w, s, x, R);
+  formR1(P, w, x, x[6], s, R);
   R[6] = formR2(P, w, s, x[6]);
 }
 
@@ -334,6 +368,7 @@ W3D_HD inline void formJ(const Props<NS> &P, const Work<NS> &w, Slips<NS> &s, co
                          double tt, bool full, double (&J)[7][7]) {
   const int ns = P.nslip();
   const double dgn = w.dg * P.rate_n / tt, cv = w.tinc * P.iD_v, nott = P.rate_n / tt;
+  W3D_STAT(1);
   double M[6][6], Q[3][6], a6[6], q3[3], et[6], wp[3];
   for (int r = 0; r < 6; ++r) {
     for (int c = r; c < 6; ++c) M[r][c] = 0.0;
@@ -346,8 +381,7 @@ W3D_HD inline void formJ(const Props<NS> &P, const Work<NS> &w, Slips<NS> &s, co
   double etau = 0.0;
   for (int i = 0; i < ns; ++i) {
     double m[6], gm[6], qc[3];
-    for (int k = 0; k < 6; ++k) m[k] = w.ms(i, k);
-    for (int k = 0; k < 3; ++k) qc[k] = w.q(i, k);
+    slip_system(P, w, i, m, qc);
     const double g = dgn * s.pw[i] + cv;                          // mm10_dgdt_voche + viscous term
     for (int k = 0; k < 6; ++k) gm[k] = g * m[k];
     for (int r = 0; r < 6; ++r)
@@ -452,8 +486,7 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
     t2 = d1[3] * d2[3] + d1[4] * d2[4] + d1[5] * d2[5];
     const double cos_ang = fmax(t1 + t2, 0.0);
     const double x2 = x[6] + cos_ang * w.n_tt_rate * dtinc;
-    eval_slips(P, w, x1, x2, s);
-    formR1(P, w, s, x1, R1);
+    formR1(P, w, x1, x2, s, R1);
     double nR1 = sqrt(R1[0] * R1[0] + R1[1] * R1[1] + R1[2] * R1[2] + R1[3] * R1[3] +
                       R1[4] * R1[4] + R1[5] * R1[5]);
     inR1 = nR1;
@@ -471,6 +504,7 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
       for (int k = 0; k < 6; ++k)   // trans(J11) R1
         wv[k] = J[0][k] * R1[0] + J[1][k] * R1[1] + J[2][k] * R1[2] + J[3][k] * R1[3] +
                 J[4][k] * R1[4] + J[5][k] * R1[5];
+      W3D_STAT(2);
       lu_solve<6, 1>(A, dx, 6, 1);
       double alpha = 1.0;
       const double ls2 = c * (dx[0][0] * wv[0] + dx[1][0] * wv[1] + dx[2][0] * wv[2] +
@@ -480,8 +514,7 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
         const double nlsx = ls1 + ls2 * alpha;
         double xnew[6];
         for (int k = 0; k < 6; ++k) xnew[k] = x1[k] + alpha * dx[k][0];
-        eval_slips(P, w, xnew, x2, s);
-        formR1(P, w, s, xnew, R1);
+        formR1(P, w, xnew, x2, s, R1);
         dotR1 = R1[0] * R1[0] + R1[1] * R1[1] + R1[2] * R1[2] + R1[3] * R1[3] + R1[4] * R1[4] +
                 R1[5] * R1[5];
         nR1 = sqrt(dotR1);
@@ -528,6 +561,7 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
         for (int r = 0; r < 7; ++r) sj = sj + J[r][k] * R[r];
         wv[k] = sj;
       }
+      W3D_STAT(2);
       lu_solve<7, 1>(A, dx, 7, 1);
       double alpha = 1.0;
       double ls2 = 0.0;
@@ -568,17 +602,19 @@ W3D_HD inline void setup(const Props<NS> &P, Work<NS> &w, bool init, const CHist
     for (int j = 0; j < 3; ++j) tr[i][j] = w.n_Rp[j][i];
   const int ns = P.nslip();
   {
-    double RE[6][6], RWC[3][3], wk[3][3];
-    rt2rve(tr, RE);
+    double wk[3][3];
+    rt2rve(tr, w.RE);
     mat33(wk, w.R, tr);
-    rt2rvw(wk, RWC);
+    rt2rvw(wk, w.RQ);
+#if !defined(__CUDA_ARCH__) || defined(W3D_MM10_SLIP_STORE)
     for (int i = 0; i < ns; ++i) {
       double a6[6], a3[3];
-      mv6(a6, RE, P.ms[i]);
+      mv6(a6, w.RE, P.ms[i]);
       for (int k = 0; k < 6; ++k) w.ms(i, k) = a6[k];
-      mv3(a3, RWC, P.qs[i]);
+      mv3(a3, w.RQ, P.qs[i]);
       for (int k = 0; k < 3; ++k) w.q(i, k) = a3[k];
     }
+#endif
   }
   w.mu_harden = P.stiffness[5][5];   // mm10_setup_voche
   // geometric hardening tau_l from the lattice curvature (Acharya), :925-975
@@ -666,8 +702,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
       }
     if (!no_load) {
       double R1[6];
-      eval_slips(P, w, stress, tt, sf);
-      formR1(P, w, sf, stress, R1);
+      formR1(P, w, stress, tt, sf, R1);
       for (int k = 0; k < 6; ++k) stress[k] = stress[k] - R1[k];
     }
     for (int k = 0; k < 6; ++k) { h1[L.c_stress(c) + k] = stress[k]; acc.sig[k] = acc.sig[k] + stress[k]; }
@@ -677,6 +712,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
     return false;
   }
   double J[7][7];
+  W3D_STAT(3);
   {  // mm10_solve_strup_iterate: adaptive sub-incrementation, at most 4 halvings
     double ostress[6];
     for (int k = 0; k < 6; ++k) ostress[k] = stress[k];
@@ -691,6 +727,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
       w.dg = effective_dg<NS>(w.D);
       if (P.alter_mode_d != 0.0) w.dg = P.eps_dot_0_y * w.tinc;
       tt = w.n_tt;   // "some subroutines modify n%tau_tilde in setup": tt restarts from n
+      W3D_STAT(4);
       fail = solve(P, w, stress, tt, dt * step, J, sf);
       if (fail) {
         for (int k = 0; k < 6; ++k) stress[k] = ostress[k];
@@ -736,13 +773,30 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
       }
   }
   // ---- mm10_output (mm10_a.f:3493); the plastic rotation update (mm10_update_rotation) and the
-  //      Euler angles that need it come last, when q can be overwritten with qs
+  //      Euler angles that need it come last
+  double wb[3];
   {
-    double ed[6] = {0, 0, 0, 0, 0, 0};
+    // one pass over the slip systems for mm10_form_dbarp (plastic and viscous parts separately),
+    // mm10_form_wp (qc) and mm10_form_wbarp (qs = RW qs0, for the rotation update below)
+    double ed[6] = {0, 0, 0, 0, 0, 0}, dbarp[6] = {0, 0, 0, 0, 0, 0}, wp[3] = {0, 0, 0};
     const double cv = w.tinc * P.iD_v;
-    for (int i = 0; i < ns; ++i) {
-      const double dif = sf.rs[i] * cv;
-      for (int k = 0; k < 6; ++k) ed[k] = ed[k] + dif * w.ms(i, k);
+    {
+      double tr[3][3], RW[3][3];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) tr[i][j] = w.n_Rp[j][i];
+      rt2rvw(tr, RW);
+      wb[0] = wb[1] = wb[2] = 0.0;
+      for (int i = 0; i < ns; ++i) {
+        double m[6], q[3], qs[3];
+        slip_system(P, w, i, m, q);
+        mv3(qs, RW, P.qs[i]);
+        const double dif = sf.rs[i] * cv;
+        const double f = sf.si[i] + dif;
+        for (int k = 0; k < 6; ++k) ed[k] = ed[k] + dif * m[k];
+        for (int k = 0; k < 6; ++k) dbarp[k] = dbarp[k] + sf.si[i] * m[k];
+        for (int k = 0; k < 3; ++k) wp[k] = wp[k] + f * q[k];
+        for (int k = 0; k < 3; ++k) wb[k] = wb[k] + f * qs[k];
+      }
     }
     for (int k = 0; k < 6; ++k) h1[L.c_ed(c) + k] = ed[k] / w.tinc;
     double t1 = ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2];
@@ -762,11 +816,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
       for (int k = 0; k < 6; ++k) v[k] = ee0[k][0];
       mv6(ee, erot, v);
     }
-    double dbarp[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < ns; ++i)
-      for (int k = 0; k < 6; ++k) dbarp[k] = dbarp[k] + sf.si[i] * w.ms(i, k);
-    double wp[3], ewwe[6], ep[6];
-    form_w(P, w, sf, wp);
+    double ewwe[6], ep[6];
     symsw(ee, wp, ewwe);
     for (int k = 0; k < 6; ++k) { ep[k] = dbarp[k] + ewwe[k]; h1[L.c_ep(c) + k] = ep[k] / w.tinc; }
     t1 = ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2];
@@ -789,8 +839,10 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
       for (int i = 0; i < ns; ++i) {
         const double rs = sf.rs[i];
         const double dgdt = dgn * sf.pw[i] + cv;
-        t1 = w.ms(i, 0) * ep[0] + w.ms(i, 1) * ep[1] + w.ms(i, 2) * ep[2];
-        t2 = w.ms(i, 3) * ep[3] + w.ms(i, 4) * ep[4] + w.ms(i, 5) * ep[5];
+        double m[6], q[3];
+        slip_system(P, w, i, m, q);
+        t1 = m[0] * ep[0] + m[1] * ep[1] + m[2] * ep[2];
+        t2 = m[3] * ep[3] + m[4] * ep[4] + m[5] * ep[5];
         const double ec_slip = t1 + 0.5 * t2;
         t1 = rs * dgdt / ec_dot;
         t2 = ec_slip / ec_dot / w.tinc;
@@ -842,19 +894,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
   // ---- mm10_update_rotation: Rp_{n+1} = exp(wbarp) Rp_n, then mm10_update_euler_angles
   {
     double Rp[3][3];
-    {
-      double tr[3][3], RW[3][3];
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) tr[i][j] = w.n_Rp[j][i];
-      rt2rvw(tr, RW);
-      for (int i = 0; i < ns; ++i) {
-        double a3[3];
-        mv3(a3, RW, P.qs[i]);
-        for (int k = 0; k < 3; ++k) w.q(i, k) = a3[k];          // q := qs
-      }
-    }
-    double wb[3], W[3][3], A[3][3];
-    form_w(P, w, sf, wb);
+    double W[3][3], A[3][3];
     W[0][0] = 0.0; W[0][1] = wb[2]; W[0][2] = wb[1];
     W[1][0] = -wb[2]; W[1][1] = 0.0; W[1][2] = wb[0];
     W[2][0] = -wb[1]; W[2][1] = -wb[0]; W[2][2] = 0.0;
