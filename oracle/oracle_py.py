@@ -78,7 +78,8 @@ def mm10_stats(reset=False):
     if not _STATS:
         raise RuntimeError("set W3D_ORACLE_STATS=1 before importing the oracle")
     arr = (C.c_longlong * 8).in_dll(lib(), "w3d_mm10_stats")
-    out = dict(zip(("slip_evals", "jacobians", "solves", "crystal_solves", "subincrement_solves"), list(arr)[:5]))
+    out = dict(zip(("slip_evals", "jacobians", "solves", "crystal_solves", "subincrement_solves",
+                    "pivoted_solves"), list(arr)[:6]))
     if reset:
         for k in range(8):
             arr[k] = 0

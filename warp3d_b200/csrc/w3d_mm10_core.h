@@ -37,7 +37,8 @@
 
 // optional host-side operation counters (oracle built with -DW3D_MM10_STATS; bench.py uses them
 // to state the algorithmic work of a launch): [0] slip evaluations (one pow per system each),
-// [1] Jacobians, [2] 7x7 / 6x6 solves, [3] crystal updates that ran the solver, [4] sub-increment solves
+// [1] Jacobians, [2] 7x7 / 6x6 solves, [3] crystal updates that ran the solver, [4] sub-increment solves,
+// [5] solves that needed a row interchange (general LU instead of the register-resident one)
 #if defined(W3D_MM10_STATS) && !defined(__CUDA_ARCH__)
 extern "C" long long w3d_mm10_stats[8];
 #define W3D_STAT(k) __atomic_fetch_add(&w3d_mm10_stats[k], 1LL, __ATOMIC_RELAXED)
@@ -177,8 +178,10 @@ W3D_HD inline void symsw(const double *s, const double *w, double (&sw)[6]) {   
 template <int N, int NRHS>
 W3D_HD inline int lu_solve(double (&A)[N][N], double (&B)[N][NRHS], int n, int nrhs) {
   int info = 0;
+  double rinv[N];
   W3D_ROLLED
   for (int j = 0; j < n; ++j) {
+    rinv[j] = 0.0;
     int p = j;
     double amax = fabs(A[j][j]);
     for (int i = j + 1; i < n; ++i)
@@ -189,6 +192,7 @@ W3D_HD inline int lu_solve(double (&A)[N][N], double (&B)[N][NRHS], int n, int n
         for (int k = 0; k < nrhs; ++k) { const double t = B[j][k]; B[j][k] = B[p][k]; B[p][k] = t; }
       }
       const double r = 1.0 / A[j][j];
+      rinv[j] = r;
       for (int i = j + 1; i < n; ++i) A[i][j] *= r;
     } else if (info == 0) {
       info = j + 1;
@@ -201,10 +205,68 @@ W3D_HD inline int lu_solve(double (&A)[N][N], double (&B)[N][NRHS], int n, int n
       for (int j = 0; j < i; ++j) B[i][k] -= A[i][j] * B[j][k];
     for (int i = n - 1; i >= 0; --i) {
       for (int j = i + 1; j < n; ++j) B[i][k] -= A[i][j] * B[j][k];
-      B[i][k] /= A[i][i];
+      B[i][k] *= rinv[i];
     }
   }
   return info;
+}
+// The same elimination when no row interchange is needed (every diagonal entry is already the
+// first largest of its column, the usual case for the Newton matrices here: I + small terms).
+// All indices are compile-time, so A and B live in registers and the code is a straight run of
+// multiply-adds: operation for operation what lu_solve does when its pivot search returns p = j.
+// Returns false -- with A and B destroyed -- as soon as a column would need an interchange; the
+// caller then runs lu_solve on a fresh copy.
+template <int N, int NRHS>
+W3D_HD inline bool lu_solve_nopivot(double (&A)[N][N], double (&B)[N][NRHS]) {
+  double rinv[N];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < N; ++j) {
+    const double amax = fabs(A[j][j]);
+    bool ok = (A[j][j] != 0.0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = j + 1; i < N; ++i) ok = ok && !(fabs(A[i][j]) > amax);
+    if (!ok) return false;
+    const double r = 1.0 / A[j][j];
+    rinv[j] = r;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = j + 1; i < N; ++i) {
+      A[i][j] *= r;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = j + 1; k < N; ++k) A[i][k] -= A[i][j] * A[j][k];
+    }
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < NRHS; ++k) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < N; ++i)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < i; ++j) B[i][k] -= A[i][j] * B[j][k];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = N - 1; i >= 0; --i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = i + 1; j < N; ++j) B[i][k] -= A[i][j] * B[j][k];
+      B[i][k] *= rinv[i];
+    }
+  }
+  return true;
 }
 
 // ---- state of one crystal --------------------------------------------------------------------
@@ -505,7 +567,15 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
         wv[k] = J[0][k] * R1[0] + J[1][k] * R1[1] + J[2][k] * R1[2] + J[3][k] * R1[3] +
                 J[4][k] * R1[4] + J[5][k] * R1[5];
       W3D_STAT(2);
-      lu_solve<6, 1>(A, dx, 6, 1);
+      if (!lu_solve_nopivot<6, 1>(A, dx)) {           // an interchange is needed: general routine
+        W3D_STAT(5);
+        double Ap[6][6];
+        for (int r = 0; r < 6; ++r) {
+          dx[r][0] = R1[r];
+          for (int cc = 0; cc < 6; ++cc) Ap[r][cc] = -J[r][cc];
+        }
+        lu_solve<6, 1>(Ap, dx, 6, 1);
+      }
       double alpha = 1.0;
       const double ls2 = c * (dx[0][0] * wv[0] + dx[1][0] * wv[1] + dx[2][0] * wv[2] +
                               dx[3][0] * wv[3] + dx[4][0] * wv[4] + dx[5][0] * wv[5]);
@@ -562,7 +632,15 @@ W3D_HD inline bool solve(const Props<NS> &P, Work<NS> &w, double *stress, double
         wv[k] = sj;
       }
       W3D_STAT(2);
-      lu_solve<7, 1>(A, dx, 7, 1);
+      if (!lu_solve_nopivot<7, 1>(A, dx)) {           // an interchange is needed: general routine
+        W3D_STAT(5);
+        double Ap[7][7];
+        for (int r = 0; r < 7; ++r) {
+          dx[r][0] = R[r];
+          for (int cc = 0; cc < 7; ++cc) Ap[r][cc] = -J[r][cc];
+        }
+        lu_solve<7, 1>(Ap, dx, 7, 1);
+      }
       double alpha = 1.0;
       double ls2 = 0.0;
       for (int k = 0; k < 7; ++k) ls2 = ls2 + dx[k][0] * wv[k];
