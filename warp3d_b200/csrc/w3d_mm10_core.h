@@ -216,55 +216,58 @@ W3D_HD inline int lu_solve(double (&A)[N][N], double (&B)[N][NRHS], int n, int n
 // multiply-adds: operation for operation what lu_solve does when its pivot search returns p = j.
 // Returns false -- with A and B destroyed -- as soon as a column would need an interchange; the
 // caller then runs lu_solve on a fresh copy.
-template <int N, int NRHS>
-W3D_HD inline bool lu_solve_nopivot(double (&A)[N][N], double (&B)[N][NRHS]) {
-  double rinv[N];
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#define W3D_UNROLL _Pragma("unroll")
+#else
+#define W3D_UNROLL
 #endif
+template <int N>
+W3D_HD inline bool lu_factor_nopivot(double (&A)[N][N], double (&rinv)[N]) {
+  W3D_UNROLL
   for (int j = 0; j < N; ++j) {
     const double amax = fabs(A[j][j]);
     bool ok = (A[j][j] != 0.0);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+    W3D_UNROLL
     for (int i = j + 1; i < N; ++i) ok = ok && !(fabs(A[i][j]) > amax);
     if (!ok) return false;
     const double r = 1.0 / A[j][j];
     rinv[j] = r;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+    W3D_UNROLL
     for (int i = j + 1; i < N; ++i) {
       A[i][j] *= r;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+      W3D_UNROLL
       for (int k = j + 1; k < N; ++k) A[i][k] -= A[i][j] * A[j][k];
     }
   }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+  return true;
+}
+// forward and back substitution with the factors of lu_factor_nopivot, one right-hand side
+template <int N>
+W3D_HD inline void lu_apply(const double (&A)[N][N], const double (&rinv)[N], double (&b)[N]) {
+  W3D_UNROLL
+  for (int i = 0; i < N; ++i) {
+    W3D_UNROLL
+    for (int j = 0; j < i; ++j) b[i] -= A[i][j] * b[j];
+  }
+  W3D_UNROLL
+  for (int i = N - 1; i >= 0; --i) {
+    W3D_UNROLL
+    for (int j = i + 1; j < N; ++j) b[i] -= A[i][j] * b[j];
+    b[i] *= rinv[i];
+  }
+}
+template <int N, int NRHS>
+W3D_HD inline bool lu_solve_nopivot(double (&A)[N][N], double (&B)[N][NRHS]) {
+  double rinv[N];
+  if (!lu_factor_nopivot<N>(A, rinv)) return false;
+  W3D_UNROLL
   for (int k = 0; k < NRHS; ++k) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < N; ++i)
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int j = 0; j < i; ++j) B[i][k] -= A[i][j] * B[j][k];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = N - 1; i >= 0; --i) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int j = i + 1; j < N; ++j) B[i][k] -= A[i][j] * B[j][k];
-      B[i][k] *= rinv[i];
-    }
+    double b[N];
+    W3D_UNROLL
+    for (int i = 0; i < N; ++i) b[i] = B[i][k];
+    lu_apply<N>(A, rinv, b);
+    W3D_UNROLL
+    for (int i = 0; i < N; ++i) B[i][k] = b[i];
   }
   return true;
 }
@@ -373,23 +376,30 @@ template <int NS>
 W3D_HD inline void formR1(const Props<NS> &P, const Work<NS> &w, const double *stress, double tt,
                           Slips<NS> &s, double *R1) {
   W3D_STAT(0);
-  double dbarp[6] = {0, 0, 0, 0, 0, 0}, wp[3] = {0, 0, 0};
+  // ms_i = RE ms0_i and qc_i = RQ qs0_i enter only through stress . ms_i and the two sums, so the
+  // rotations are applied to the stress and to the sums instead of to every system:
+  //   rs_i = (RE^T stress) . ms0_i,   dbarp = RE sum f_i ms0_i,   wp = RQ sum f_i qs0_i
+  double sr[6], a6[6] = {0, 0, 0, 0, 0, 0}, a3[3] = {0, 0, 0};
+  for (int k = 0; k < 6; ++k)
+    sr[k] = w.RE[0][k] * stress[0] + w.RE[1][k] * stress[1] + w.RE[2][k] * stress[2] +
+            w.RE[3][k] * stress[3] + w.RE[4][k] * stress[4] + w.RE[5][k] * stress[5];
   const int ns = P.nslip();
   const double cv = w.tinc * P.iD_v, dgt = w.dg / tt;
   const Power rate_pow = Power::make(P.rate_n - 1.0);
   for (int i = 0; i < ns; ++i) {
-    double m[6], q[3];
-    slip_system(P, w, i, m, q);
-    const double rs = stress[0] * m[0] + stress[1] * m[1] + stress[2] * m[2] + stress[3] * m[3] +
-                      stress[4] * m[4] + stress[5] * m[5];
+    const double rs = sr[0] * P.ms[i][0] + sr[1] * P.ms[i][1] + sr[2] * P.ms[i][2] +
+                      sr[3] * P.ms[i][3] + sr[4] * P.ms[i][4] + sr[5] * P.ms[i][5];
     const double pw = rate_pow(fabs(rs / tt));
     const double si = dgt * pw * rs;
     s.rs[i] = rs; s.pw[i] = pw; s.si[i] = si;
     const double f = rs * cv + si;
-    for (int k = 0; k < 6; ++k) dbarp[k] = dbarp[k] + f * m[k];
-    for (int k = 0; k < 3; ++k) wp[k] = wp[k] + f * q[k];
+    for (int k = 0; k < 6; ++k) a6[k] = a6[k] + f * P.ms[i][k];
+    for (int k = 0; k < 3; ++k) a3[k] = a3[k] + f * P.qs[i][k];
   }
   s.pm.have = false;
+  double dbarp[6], wp[3];
+  mv6(dbarp, w.RE, a6);
+  mv3(wp, w.RQ, a3);
   double symTW[6], v1[6], v2[6];
   symsw(stress, wp, symTW);
   for (int k = 0; k < 6; ++k) v1[k] = w.D[k] - dbarp[k];
@@ -838,11 +848,25 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
     double b21[6];
     for (int k = 0; k < 6; ++k) b21[k] = J[6][k] / J[6][6];   // DGESV on the 1x1 J22
     for (int r = 0; r < 6; ++r)
+      for (int cc = 0; cc < 6; ++cc) JJ[r][cc] = J[r][cc] + (-1.0) * J[r][6] * b21[cc];
+    double rinv[6];
+    if (lu_factor_nopivot<6>(JJ, rinv)) {             // one column of C at a time
       for (int cc = 0; cc < 6; ++cc) {
-        JJ[r][cc] = J[r][cc] + (-1.0) * J[r][6] * b21[cc];
-        JR[r][cc] = P.stiffness[r][cc] - 0.0 - 0.0 * J[r][6];
+        double b[6];
+        for (int r = 0; r < 6; ++r) b[r] = P.stiffness[r][cc] - 0.0 - 0.0 * J[r][6];
+        lu_apply<6>(JJ, rinv, b);
+        for (int r = 0; r < 6; ++r) JR[r][cc] = b[r];
       }
-    lu_solve<6, 6>(JJ, JR, 6, 6);
+    } else {                                          // an interchange is needed: general routine
+      W3D_STAT(5);
+      double Jp[6][6];
+      for (int r = 0; r < 6; ++r)
+        for (int cc = 0; cc < 6; ++cc) {
+          Jp[r][cc] = J[r][cc] + (-1.0) * J[r][6] * b21[cc];
+          JR[r][cc] = P.stiffness[r][cc] - 0.0 - 0.0 * J[r][6];
+        }
+      lu_solve<6, 6>(Jp, JR, 6, 6);
+    }
     for (int cc = 0; cc < 6; ++cc)
       for (int r = 0; r < 6; ++r) {
         // mm10_a_make_symm_1 unless asymmetric assembly
@@ -888,7 +912,12 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
     {
       double S[6][6], ee0[6][1], erot[6][6];
       for (int r = 0; r < 6; ++r) { ee0[r][0] = stress[r]; for (int cc = 0; cc < 6; ++cc) S[r][cc] = P.stiffness[r][cc]; }
-      lu_solve<6, 1>(S, ee0, 6, 1);
+      if (!lu_solve_nopivot<6, 1>(S, ee0)) {
+        W3D_STAT(5);
+        double Sp[6][6];
+        for (int r = 0; r < 6; ++r) { ee0[r][0] = stress[r]; for (int cc = 0; cc < 6; ++cc) Sp[r][cc] = P.stiffness[r][cc]; }
+        lu_solve<6, 1>(Sp, ee0, 6, 1);
+      }
       rt2rve(w.R, erot);
       double v[6];
       for (int k = 0; k < 6; ++k) v[k] = ee0[k][0];
