@@ -340,15 +340,35 @@ struct Power {
   }
 };
 
-// pow(|h_term|, voche_m) with a one-entry memo: without geometric hardening (k_0 = 0) h_term is
-// the same for every slip system
+// Voce hardening term of one slip system (mm10_h_voche, mm10_b.f:1896):
+//   h_term = 1 - (tt - tau_y)/tau_v + tau_l/(tt - tau_y),
+// kept with |h_term|^m and 1/|h_term| in a one-entry memo: without geometric hardening (k_0 = 0)
+// tau_l = 0 and h_term is the same for every slip system.  Divisions by tt - tau_y and by
+// |h_term| are multiplications by reciprocals taken once per state: the operands are often zero
+// or tiny (tau_l = 0, slip increments of inactive systems ~1e-40), which sends every device
+// division down its ~65-instruction slow path.
 struct PowMemo {
-  double x, y;
+  double x, y, rx;   // h_term, |h_term|^m, 1/|h_term|
   bool have;
 };
-W3D_HD inline double hterm_pow(PowMemo &m, double h_term, double voche_m) {
-  if (!(m.have && m.x == h_term)) { m.x = h_term; m.y = Power::make(voche_m)(fabs(h_term)); m.have = true; }
-  return m.y;
+struct HardTerm {
+  double a, inv_d;   // h_term = a + tau_l * inv_d
+};
+template <int NS>
+W3D_HD inline HardTerm hard_term(const Props<NS> &P, double tt) {
+  HardTerm h;
+  const double d = tt - P.tau_y;
+  h.inv_d = 1.0 / d;
+  h.a = 1.0 - d / P.tau_v;
+  return h;
+}
+W3D_HD inline void hterm_eval(PowMemo &m, double h_term, double voche_m) {
+  if (!(m.have && m.x == h_term)) {
+    m.x = h_term;
+    m.y = Power::make(voche_m)(fabs(h_term));
+    m.rx = 1.0 / fabs(h_term);
+    m.have = true;
+  }
 }
 
 // The reference re-evaluates the resolved shear stress and the slip increment of every system
@@ -384,12 +404,12 @@ W3D_HD inline void formR1(const Props<NS> &P, const Work<NS> &w, const double *s
     sr[k] = w.RE[0][k] * stress[0] + w.RE[1][k] * stress[1] + w.RE[2][k] * stress[2] +
             w.RE[3][k] * stress[3] + w.RE[4][k] * stress[4] + w.RE[5][k] * stress[5];
   const int ns = P.nslip();
-  const double cv = w.tinc * P.iD_v, dgt = w.dg / tt;
+  const double cv = w.tinc * P.iD_v, dgt = w.dg / tt, itt = 1.0 / tt;
   const Power rate_pow = Power::make(P.rate_n - 1.0);
   for (int i = 0; i < ns; ++i) {
     const double rs = sr[0] * P.ms[i][0] + sr[1] * P.ms[i][1] + sr[2] * P.ms[i][2] +
                       sr[3] * P.ms[i][3] + sr[4] * P.ms[i][4] + sr[5] * P.ms[i][5];
-    const double pw = rate_pow(fabs(rs / tt));
+    const double pw = rate_pow(fabs(rs * itt));
     const double si = dgt * pw * rs;
     s.rs[i] = rs; s.pw[i] = pw; s.si[i] = si;
     const double f = rs * cv + si;
@@ -411,9 +431,11 @@ template <int NS>
 W3D_HD inline double formR2(const Props<NS> &P, Work<NS> &w, Slips<NS> &s, double tt) {
   double h = 0.0;
   const int ns = P.nslip();
+  const HardTerm ht = hard_term(P, tt);
   for (int i = 0; i < ns; ++i) {
-    const double h_term = 1.0 - (tt - P.tau_y) / P.tau_v + w.tau_l[i] / (tt - P.tau_y);
-    h = h + hterm_pow(s.pm, h_term, P.voche_m) * copysign(1.0, h_term) * fabs(s.si[i]);
+    const double h_term = ht.a + w.tau_l[i] * ht.inv_d;
+    hterm_eval(s.pm, h_term, P.voche_m);
+    h = h + s.pm.y * copysign(1.0, h_term) * fabs(s.si[i]);
   }
   h = w.n_tt + P.theta_0 * h;
   w.tt_rate = (h - w.n_tt) / w.tinc;
@@ -441,6 +463,8 @@ W3D_HD inline void formJ(const Props<NS> &P, const Work<NS> &w, Slips<NS> &s, co
   const int ns = P.nslip();
   const double dgn = w.dg * P.rate_n / tt, cv = w.tinc * P.iD_v, nott = P.rate_n / tt;
   W3D_STAT(1);
+  const HardTerm ht = hard_term(P, tt);
+  const double mitv = -1.0 / P.tau_v;
   double M[6][6], Q[3][6], a6[6], q3[3], et[6], wp[3];
   for (int r = 0; r < 6; ++r) {
     for (int c = r; c < 6; ++c) M[r][c] = 0.0;
@@ -468,13 +492,13 @@ W3D_HD inline void formJ(const Props<NS> &P, const Work<NS> &w, Slips<NS> &s, co
       for (int k = 0; k < 6; ++k) a6[k] = a6[k] + dgdh * m[k];
       for (int a = 0; a < 3; ++a) q3[a] = q3[a] + dgdh * qc[a];
       // J21 = -estress (mm10_estress_voche)
-      const double h_term = 1.0 - (tt - P.tau_y) / P.tau_v + w.tau_l[i] / (tt - P.tau_y);
-      const double hp = hterm_pow(s.pm, h_term, P.voche_m);
+      const double h_term = ht.a + w.tau_l[i] * ht.inv_d;
+      hterm_eval(s.pm, h_term, P.voche_m);
+      const double hp = s.pm.y;
       const double f = hp * copysign(1.0, h_term) * s.pw[i] * copysign(1.0, s.rs[i]);
       for (int k = 0; k < 6; ++k) et[k] = et[k] + f * m[k];
       // J22 (mm10_ehard_voche)
-      etau = etau + (P.voche_m * (-1.0 / P.tau_v - w.tau_l[i] / ((tt - P.tau_y) * (tt - P.tau_y))) *
-                         fabs(dgam) / fabs(h_term) -
+      etau = etau + (P.voche_m * (mitv - w.tau_l[i] * ht.inv_d * ht.inv_d) * fabs(dgam) * s.pm.rx -
                      fabs(dgam) * nott * copysign(1.0, h_term) * copysign(1.0, dgam)) *
                         hp;
     }
