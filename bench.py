@@ -19,6 +19,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import subprocess
 import sys
 import time
 
@@ -171,6 +172,35 @@ def cpu_baseline(workload, nrep=3):
                 sample=f"{m.noelem} elements ({CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} sub-box of the same "
                        f"mesh, material and load path), {nrep} passes, oracle/ C++ restatement with OpenMP over blocks",
                 stress_gp_per_s=ngp / t_s, stiffness_elem_per_s=m.noelem / t_k)
+
+
+def mm10_operation_counts(workload, dims=(16, 16, 16)):
+    """Per-Gauss-point averages of the mm10 solver's operation counters (slip evaluations,
+    Jacobians, dense solves ...) for this workload's material and load path, from the CPU
+    restatement built with -DW3D_MM10_STATS, run in a child process on a small sub-box."""
+    code = ("import json, sys; sys.path.insert(0, %r); import bench; from oracle import oracle_py\n"
+            "bench.WORKLOADS[%r] = bench.WORKLOADS[%r][:2] + (%r,)\n"
+            "m, orc, st, u, du, step = bench.prepare_cpu_case(%r, 4)\n"
+            "oracle_py.mm10_stats(reset=True); orc.eps_sig_ifv(st, step, 1, u, du)\n"
+            "s = oracle_py.mm10_stats(); print(json.dumps({k: v / (m.noelem * 8.0) for k, v in s.items()}))\n"
+            % (ROOT, workload, workload, tuple(dims), workload))
+    env = dict(os.environ, W3D_ORACLE_STATS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
+    return json.loads(out.stdout.strip().split("\n")[-1])
+
+
+def mm10_flops_per_gp(ops, nslip=12, exponent=19):
+    """Algorithmic FP64 flops of one mm10 Gauss-point update (FMA = 2), from the per-operation
+    counts of the algorithm as implemented in w3d_mm10_core.h (DESIGN.md 3.3 lists them):
+    one slip evaluation = residual R1 (+R2), one Jacobian = formJ, one solve = 7x7 LU + line-search
+    bookkeeping, plus the once-per-crystal part (set-up, tangent, output terms, rotation)."""
+    powering = exponent.bit_length() + bin(exponent).count("1")          # multiplies of x^e
+    per_eval = 72 + nslip * (11 + 1 + powering + 2 + 2 + 12 + 6) + 66 + 15 + 24 + 6 + 66 + 24 + nslip * 5
+    per_jac = nslip * 230 + 432 + 168 + 80
+    per_solve = 203 + 84 + 14 + 98 + 30
+    once = 300 + 600 + nslip * 150 + nslip * 110 + 200 + 170 + 200 + 150
+    return (ops["slip_evals"] * per_eval + ops["jacobians"] * per_jac + ops["solves"] * per_solve
+            + ops["crystal_solves"] * once)
 
 
 def reference_arm(args):
@@ -341,6 +371,17 @@ def engine_arm(args):
         )
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.workload)
+            if WORKLOADS[args.workload][1] == "mm10" and fp64_peak:
+                # mm10 is bound by the FP64 pipe, not HBM: state the algorithmic flops too
+                ops = mm10_operation_counts(args.workload)
+                fl = mm10_flops_per_gp(ops)
+                tf = ngp_own * fl / (t_stress * 1e-3) / 1e12
+                line["roofline"]["fp64"] = dict(
+                    bound="fp64", achieved=tf, peak=fp64_peak, unit="TFLOP/s", frac=tf / fp64_peak,
+                    flops_per_gp=fl, operations_per_gp=ops, launch_ms=t_stress,
+                    peak_kind="measured DFMA throughput (tools/fp64_peak.cu, profiles/r01_fp64_peak.json)",
+                    note="algorithmic flops = per-operation counts of the algorithm as implemented "
+                         "(DESIGN.md 3.3) x operation counters of the CPU restatement on a sub-box")
         print(json.dumps(line), flush=True)
     de.close()
     if world > 1:

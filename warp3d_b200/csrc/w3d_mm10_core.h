@@ -870,7 +870,8 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
   {
     double JJ[6][6], JR[6][6];
     double b21[6];
-    for (int k = 0; k < 6; ++k) b21[k] = J[6][k] / J[6][6];   // DGESV on the 1x1 J22
+    const double r66 = 1.0 / J[6][6];
+    for (int k = 0; k < 6; ++k) b21[k] = J[6][k] * r66;       // DGESV on the 1x1 J22
     for (int r = 0; r < 6; ++r)
       for (int cc = 0; cc < 6; ++cc) JJ[r][cc] = J[r][cc] + (-1.0) * J[r][6] * b21[cc];
     double rinv[6];
@@ -924,11 +925,14 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
         for (int k = 0; k < 3; ++k) wb[k] = wb[k] + f * qs[k];
       }
     }
-    for (int k = 0; k < 6; ++k) h1[L.c_ed(c) + k] = ed[k] / w.tinc;
+    // (quotients by tinc, ec_dot and the crystal count are products with reciprocals: many of
+    //  the numerators are zero, see HardTerm)
+    const double itinc = 1.0 / w.tinc;
+    for (int k = 0; k < 6; ++k) h1[L.c_ed(c) + k] = ed[k] * itinc;
     double t1 = ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2];
     double t2 = ed[3] * ed[3] + ed[4] * ed[4] + ed[5] * ed[5];
     double ed_dot = sqrt(2.0 / 3.0 * (t1 + 0.5 * t2));
-    ed_dot = ed_dot / w.tinc;
+    ed_dot = ed_dot * itinc;
     const double work_inc = stress[0] * w.D[0] + stress[1] * w.D[1] + stress[2] * w.D[2] +
                             stress[3] * w.D[3] + stress[4] * w.D[4] + stress[5] * w.D[5];
     // lattice strain: C^-1 stress (DPOSV -> LU here), rotated with R
@@ -949,11 +953,11 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
     }
     double ewwe[6], ep[6];
     symsw(ee, wp, ewwe);
-    for (int k = 0; k < 6; ++k) { ep[k] = dbarp[k] + ewwe[k]; h1[L.c_ep(c) + k] = ep[k] / w.tinc; }
+    for (int k = 0; k < 6; ++k) { ep[k] = dbarp[k] + ewwe[k]; h1[L.c_ep(c) + k] = ep[k] * itinc; }
     t1 = ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2];
     t2 = ep[3] * ep[3] + ep[4] * ep[4] + ep[5] * ep[5];
     double ep_dot = sqrt(2.0 / 3.0 * (t1 + 0.5 * t2));
-    ep_dot = ep_dot / w.tinc;
+    ep_dot = ep_dot * itinc;
     for (int k = 0; k < 6; ++k) ep[k] = ep[k] + ed[k];
     t1 = ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2];
     t2 = ep[3] * ep[3] + ep[4] * ep[4] + ep[5] * ep[5];
@@ -961,10 +965,11 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
     const double p_work_inc = stress[0] * ep[0] + stress[1] * ep[1] + stress[2] * ep[2] +
                               stress[3] * ep[3] + stress[4] * ep[4] + stress[5] * ep[5];
     for (int k = 0; k < 6; ++k) h1[L.c_eps(c) + k] = ee[k];
-    const double ec_dot = p_strain_inc / w.tinc;
+    const double ec_dot = p_strain_inc * itinc;
     double n_eff;
     if (ec_dot > 0.0) {
-      for (int k = 0; k < 6; ++k) ep[k] = ep[k] / w.tinc;
+      for (int k = 0; k < 6; ++k) ep[k] = ep[k] * itinc;
+      const double iec = 1.0 / ec_dot;
       n_eff = 0.0;
       const double dgn = w.dg * P.rate_n / tt;
       for (int i = 0; i < ns; ++i) {
@@ -975,8 +980,8 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
         t1 = m[0] * ep[0] + m[1] * ep[1] + m[2] * ep[2];
         t2 = m[3] * ep[3] + m[4] * ep[4] + m[5] * ep[5];
         const double ec_slip = t1 + 0.5 * t2;
-        t1 = rs * dgdt / ec_dot;
-        t2 = ec_slip / ec_dot / w.tinc;
+        t1 = rs * dgdt * iec;
+        t2 = ec_slip * iec * itinc;
         n_eff = n_eff + (2.0 / 3.0) * t1 * t2;
       }
     } else {
@@ -1010,7 +1015,7 @@ W3D_HD inline bool crystal_update(const Props<NS> &P, Work<NS> &w, const double 
       if (fabs(sf.si[i] + sf.rs[i] * cv) >= thresh) numAct = numAct + 1;
     // uhist (15 used entries of len_u)
     for (int k = 0; k < L.len_u; ++k) h1[L.c_u(c) + k] = 0.0;
-    h1[L.c_u(c) + 5] = maxslip / w.tinc;
+    h1[L.c_u(c) + 5] = maxslip * itinc;
     h1[L.c_u(c) + 6] = (double)sysID;
     h1[L.c_u(c) + 7] = (double)numAct;
     h1[L.c_u(c) + 10] = ep_dot;
@@ -1108,13 +1113,14 @@ W3D_HD inline bool gauss_point_update(int step, int ncrystals, const Props<NS> *
   }
   // mm10_a_crystal_avgs + mm10_a_store_crystal
   const double rn = (double)ncrystals;
-  for (int k = 0; k < 6; ++k) cgn1[k] = acc.sig[k] / rn;
+  const double irn = 1.0 / rn;
+  for (int k = 0; k < 6; ++k) cgn1[k] = acc.sig[k] * irn;
   if (ncrystals > 1)
-    for (int k = 0; k < 36; ++k) h1[L.o_D() + k] = h1[L.o_D() + k] / rn;
+    for (int k = 0; k < 36; ++k) h1[L.o_D() + k] = h1[L.o_D() + k] * irn;
   for (int k = 0; k < 9; ++k) h1[L.o_R() + k] = Rur[k];
   for (int k = 0; k < L.len_slip; ++k)
-    h1[L.o_sliphist() + k] = (init ? 0.0 : hn[L.o_sliphist() + k]) + h1[L.o_sliphist() + k] / rn;
-  const double t_work_inc = acc.t_work / rn, p_work_inc = acc.p_work / rn, p_strain_inc = acc.p_strain / rn;
+    h1[L.o_sliphist() + k] = (init ? 0.0 : hn[L.o_sliphist() + k]) + h1[L.o_sliphist() + k] * irn;
+  const double t_work_inc = acc.t_work * irn, p_work_inc = acc.p_work * irn, p_strain_inc = acc.p_strain * irn;
   cgn1[6] = cgn[6] + t_work_inc;
   cgn1[7] = cgn[7] + p_work_inc;
   cgn1[8] = cgn[8] + p_strain_inc;
