@@ -213,7 +213,7 @@ static void drive_01_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
 }
 
 // drive_05_update (rstgp1.f:2373-2700) -> mm05 (mm05.f:9) + cnst5 (:1566), nonlinear_hardening
-// option.  Per-point arithmetic = single-source core warp3d_b200/csrc/w3d_mm05_core.h.
+// or generalized_plasticity option by the sign of matprp(58).  Per-point arithmetic = single-source core warp3d_b200/csrc/w3d_mm05_core.h.
 static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int gpn,
                             int step, int iter, const double *uddt_displ, double *gbl_cep,
                             bool &material_cut_step, int *fatal) {
@@ -227,7 +227,7 @@ static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
   const bool nonlinear_update = iter >= 1 || m->extrapolated_du != 0;
   const bool adaptive_possible = m->adaptive_flag != 0 && step > 1;
   if (bi.hist_size != 14 || !m->matprp) { *fatal = 5; return; }
-  if (matprp(m, 58, bi.matnum) <= 0.0f) { *fatal = 3; return; }   // generalized_plasticity: not built
+  if (matprp(m, 58, bi.matnum) == 0.0f) { *fatal = 3; return; }   // option flag not set (inmat.f:2220, :2272)
   for (int i = 0; i < span; ++i) {
     const int elem = bi.felem + i;
     Props P;
@@ -239,10 +239,10 @@ static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
     for (int k = 0; k < 14; ++k) { h[k] = hist[(size_t)k * span + i]; h1[k] = hist1[(size_t)k * span + i]; }
     double D[6][6];
     if (nonlinear_update) {
-      const int rc = fa_update(step, iter, P, cgn, cgn1, ud, h, h1, trial, adaptive_possible);
+      const int rc = update(step, iter, P, cgn, cgn1, ud, h, h1, trial, adaptive_possible);
       if (rc == CUT) { material_cut_step = true; return; }
       if (rc != OK) { *fatal = rc; return; }
-      cnst5_fa(P, trial, h1, cgn1, D);
+      cnst5(P, trial, h1, cgn1, D);
       for (int k = 0; k < 14; ++k) hist1[(size_t)k * span + i] = h1[k];
     } else {
       // drive_05_update_a/_b: linear-elastic [D] and stress for iteration 0 (no history update)

@@ -84,3 +84,91 @@ def test_cyclic_hardening_saturates():
     ksat = 0.81649658 * (400.0e6 + 100.0e6)
     assert k0 < kmax <= ksat * (1 + 1e-9)
     assert kmax > k0 + 0.2 * (ksat - k0)
+
+
+# ---- generalized_plasticity option ---------------------------------------------------------------
+from warp3d_b200 import cyclic_gp_material  # noqa: E402
+
+
+def test_gp_matprp_rows_follow_inmat():
+    m = build_structured_hex8(1, 1, 1, materials=[cyclic_gp_material(gp_h_u=350.0, gp_tau=0.25, gp_beta_u=180.0,
+                                                                      gp_delta_u=0.02, sig_tol=0.0005)])
+    r = m.matprp[0, 54:60]
+    f = np.float32
+    # uniaxial values stored unconverted, option flag -1 (inmat.f:2017-2036, :2272)
+    assert list(r) == [f(350.0), f(0.25), f(180.0), f(-1.0), f(0.02), f(0.0005)]
+    assert int(m.hist_size[0]) == 14 and int(m.props[0, 24]) == 5
+
+
+def test_gp_elastic_below_yield_then_smooth_approach_to_the_limit_surface():
+    """Generalized plasticity: elastic inside the yield surface k = sqrt(2/3) sigma_0; beyond it the
+    stress leaves the yield surface and approaches the limit surface (radius k + sqrt(2/3) beta_u,
+    translating with H) with a monotonically decreasing tangent."""
+    mat = cyclic_gp_material()
+    m = build_structured_hex8(1, 1, 1, materials=[mat], geonl=False)
+    o, st = op.Oracle(m), new_state(m)
+    x = m.c.reshape(-1, 3)
+    u = np.zeros(m.nodof)
+    mises, epsp = [], []
+    for step in range(1, 16):
+        de = 1.0e-3                     # yield strain = 60 / 30000 = 2e-3
+        du = np.zeros((m.nonode, 3))
+        du[:, 0] = de * x[:, 0]; du[:, 1] = -0.45 * de * x[:, 1]; du[:, 2] = -0.45 * de * x[:, 2]
+        du = du.reshape(-1)
+        for it in (0, 1, 2):
+            _, sc = o.eps_sig_ifv(st, step, it, u, du)
+            assert not sc["material_cut_step"], step
+        o.update(st); o.adaptive_save(st)
+        u = u + du
+        h = st.history.reshape(-1, 14)
+        s = st.urcs_n.reshape(-1, 9)[:, :6]
+        dev = s.copy(); dev[:, :3] -= s[:, :3].mean(axis=1, keepdims=True)
+        mises.append(np.sqrt(1.5) * np.sqrt((dev[:, :3] ** 2).sum(1) + 2 * (dev[:, 3:] ** 2).sum(1)).max())
+        epsp.append(h[:, 2].max())
+        state = h[:, 3].view(np.int64) & 0xFFFFFFFF
+        if step == 1:
+            assert np.all(state == 3) and np.all(h[:, 0] == 0.0) and epsp[-1] == 0.0
+        else:
+            assert np.all(state == 1) and np.all(h[:, 0] > 0.0)
+            assert 2 <= h[:, 11].max() <= 10                      # sub-increment count, capped at mxsubinc
+            # tau = 0: purely kinematic, the yield surface keeps its size
+            assert np.allclose(h[:, 1], 0.81649658 * 60.0, rtol=1e-12)
+            xi = dev - h[:, 5:11]
+            nrm = np.sqrt((xi[:, :3] ** 2).sum(1) + 2 * (xi[:, 3:] ** 2).sum(1))
+            assert np.all(nrm > h[:, 1])                          # outside the yield surface ...
+            assert np.all(nrm < h[:, 1] + 0.81649658 * 200.0)     # ... inside the limit surface
+    mises, epsp = np.array(mises), np.array(epsp)
+    assert np.all(np.diff(mises) > 0) and np.all(np.diff(epsp[1:]) > 0)
+    slope = np.diff(mises[1:]) / np.diff(epsp[1:])
+    assert np.all(np.diff(slope) < 0)                             # smooth, ever softer approach
+    assert mises[-1] < 60.0 + 200.0 + 400.0 * np.sqrt(2.0 / 3.0) * epsp[-1]
+
+
+def test_gp_consistent_tangent_vs_finite_differences():
+    """cnst5_gp is the tangent of ONE backward-Euler step of the GP return, the update runs up to 10
+    sub-increments with Richardson extrapolation: for a small plastic increment (2 sub-increments)
+    the two agree to 1e-3, which checks the transcriptions of update and tangent against each
+    other; for a large one (10 sub-increments) only to some 20 %, as in the reference."""
+    m = build_structured_hex8(2, 1, 1, materials=[cyclic_gp_material()], geonl=False, coord_jitter=0.05)
+    o = op.Oracle(m)
+    z = np.zeros(m.nodof)
+    st = new_state(m)
+    u1 = smooth_displacement(m, strain=4.0e-3, seed=2)
+    for it in (0, 1, 2):
+        o.eps_sig_ifv(st, 1, it, z, u1)
+    o.update(st); o.adaptive_save(st)
+    d = np.random.default_rng(1).standard_normal(m.nodof)
+    for amp, nsub_max, bound in ((1.5e-4, 2, 5e-3), (1.5e-3, 10, 0.25)):
+        du = smooth_displacement(m, strain=amp, seed=3)
+        s0 = st.copy()
+        f0, sc = o.eps_sig_ifv(s0, 2, 2, u1, du)
+        assert not sc["material_cut_step"]
+        h1 = s0.history1.reshape(-1, 14)
+        assert np.all((h1[:, 3].view(np.int64) & 0xFFFFFFFF) == 1) and h1[:, 11].max() == nsub_max
+        K = assemble(m, o.tanstf(s0, 2, 2, u1, du))
+        assert np.abs(K - K.T).max() <= 1e-12 * np.abs(K).max()
+        hstep = 1e-6 * np.abs(du).max()
+        s1 = st.copy()
+        f1, _ = o.eps_sig_ifv(s1, 2, 2, u1, du + hstep * d)
+        err = np.linalg.norm((f1 - f0) - K @ (hstep * d)) / np.linalg.norm(f1 - f0)
+        assert err < bound, (amp, err)

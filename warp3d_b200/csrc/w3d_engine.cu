@@ -268,8 +268,9 @@ int create_impl(w3d_engine *h) {
       if (b.hist_size != 14) return fail(W3D_ERR_CONFIG, "block %d: mm05 history size %d != 14", blk + 1, b.hist_size);
       if (!c.matprp || b.matnum < 1 || b.matnum > c.nmat || c.mxmtpr < 64)
         return fail(W3D_ERR_CONFIG, "block %d: mm05 needs matprp(55:64) of material %d", blk + 1, b.matnum);
-      if (!(c.matprp[(size_t)(b.matnum - 1) * c.mxmtpr + 57] > 0.0f))
-        return fail(W3D_ERR_UNSUPPORTED, "block %d: mm05 generalized_plasticity option not built yet (nonlinear_hardening only)", blk + 1);
+      // matprp(58) > 0: nonlinear_hardening, < 0: generalized_plasticity (inmat.f:2220, :2272)
+      if (c.matprp[(size_t)(b.matnum - 1) * c.mxmtpr + 57] == 0.0f)
+        return fail(W3D_ERR_CONFIG, "block %d: mm05 option flag matprp(58) of material %d is not set", blk + 1, b.matnum);
     }
     if (b.mat_type == 1 && b.hist_size != 11)
       return fail(W3D_ERR_CONFIG, "block %d: mm01 history size %d != 11", blk + 1, b.hist_size);
@@ -318,6 +319,7 @@ int create_impl(w3d_engine *h) {
     double tab3[3][8][8];
     shape_tables(tab3);
     CUDA_TRY(cudaMemcpyToSymbol(c_shape, tab3, sizeof tab3));
+    CUDA_TRY(mm05_set_shape_table(&tab3[0][0][0], sizeof tab3));
   }
 
   // ---- per-segment tables and state
@@ -469,7 +471,7 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
       launch_stress<10, 2>(sg, a, h->stream);
       h->launches += 3;
     } else if (sg.mat_type == 5) {
-      launch_stress<5, 0>(sg, a, h->stream);
+      CUDA_TRY(launch_stress_mm05(sg.geonl, sg.bbar, sg.ncta, a, h->stream));
       h->launches += 1;
     } else {
       launch_stress<1, 0>(sg, a, h->stream);

@@ -45,8 +45,13 @@ struct StressArgs {
 };
 
 // parent-space shape function derivatives of the 8 Gauss points: [dir][node][gp], filled by the
-// host with the reference's quad2 / deriv2 tables (getgpts.f:642-718, derivs.f:283-343)
-__constant__ double c_shape[3][8][8];
+// host with the reference's quad2 / deriv2 tables (getgpts.f:642-718, derivs.f:283-343).
+// static: one copy per translation unit (w3d_engine.cu and w3d_mm05.cu each upload theirs)
+static __constant__ double c_shape[3][8][8];
+
+// MAT = 5 instantiations live in w3d_mm05.cu
+cudaError_t mm05_set_shape_table(const double *tab3, size_t bytes);
+cudaError_t launch_stress_mm05(bool geonl, bool bbar, int ncta, const struct StressArgs &a, cudaStream_t st);
 
 #ifndef STRESS_MIN_CTAS
 #define STRESS_MIN_CTAS 4   // register cap 128/thread -> 4 CTAs (16 warps) per SM
@@ -424,10 +429,11 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
       for (int k = 0; k < 14; ++k) { h[k] = sSt[15 + k][tid]; h1[k] = 0.0; }
 #pragma unroll
       for (int k = 0; k < 9; ++k) cgn1[k] = 0.0;
-      const int rc = w3d_mm05::fa_update(a.step, a.iter, pr, cgn, cgn1, uddt, h, h1, trial, a.adaptive != 0);
+      // nonlinear_hardening or generalized_plasticity by the sign of matprp(58) (mm05.f:232-254)
+      const int rc = w3d_mm05::update(a.step, a.iter, pr, cgn, cgn1, uddt, h, h1, trial, a.adaptive != 0);
       if (rc == w3d_mm05::CUT) mm05_cut = true;
       else if (rc != w3d_mm05::OK) fatal = rc;
-      w3d_mm05::cnst5_fa(pr, trial, h1, cgn1, D);
+      w3d_mm05::cnst5(pr, trial, h1, cgn1, D);
       if (store && !mm05_cut && a.iter > 0) {
 #pragma unroll
         for (int k = 0; k < 14; ++k) a.hist_n1[k * ng + g] = h1[k];
@@ -627,7 +633,7 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
 }
 
 // deterministic final reduction of the per-CTA partials: one CTA, fixed tree
-__global__ void __launch_bounds__(256) k_reduce_partials(const double *partials, int ncta,
+static __global__ void __launch_bounds__(256) k_reduce_partials(const double *partials, int ncta,
                                                          double *out /*[4]*/, int accumulate) {
   __shared__ double s[3][256];
   double v0 = 0.0, v1 = 0.0, v2 = 0.0;

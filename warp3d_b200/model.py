@@ -149,6 +149,20 @@ def cyclic_fa_material(e=200.0e9, nu=0.3, yld_pt=400.0e6, q_u=100.0e6, b_u=20.0,
     return Material(mat_type=5, e=e, nu=nu, yld_pt=yld_pt, tan_e=0.0, beta=1.0, extra={"matprp": rows})
 
 
+def cyclic_gp_material(e=30000.0, nu=0.3, yld_pt=60.0, gp_h_u=400.0, gp_tau=0.0, gp_beta_u=200.0,
+                       gp_delta_u=0.010, sig_tol=0.0001):
+    """mm05 'cyclic' material, generalized_plasticity option: matprp(55:60) as src/inmat.f:2017-2036,
+    :2272, :2312-2395 stores them -- the uniaxial values unconverted, option flag -1:
+    gp_h_u, gp_tau, gp_beta_u, -1, gp_delta_u, sig_tol; yld_pt is gp_sigma_0 (props(23)).
+    Defaults = the reference's own decks (verification/test39, testP: ksi units).  The option's
+    quadratic for the plastic multiplier is accepted only if |a l^2 + b l + c| <= 1e-6 in
+    absolute terms (mm05.f:2962-2965), which moduli in Pa cannot meet in double precision: with
+    SI-sized numbers the model asks for a step cut, exactly as the Fortran would."""
+    f = np.float32
+    rows = {55: f(gp_h_u), 56: f(gp_tau), 57: f(gp_beta_u), 58: f(-1.0), 59: f(gp_delta_u), 60: f(sig_tol)}
+    return Material(mat_type=5, e=e, nu=nu, yld_pt=yld_pt, tan_e=0.0, beta=1.0, extra={"matprp": rows})
+
+
 def _f32_bits(x) -> np.ndarray:
     return np.asarray(x, dtype=np.float32).view(np.int32)
 
