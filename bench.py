@@ -59,8 +59,12 @@ def make_workload(name, dims=None):
 def workload_description(name):
     kind = WORKLOADS[name][1]
     if kind == "mm01":
+        # FP64 flops per Gauss point: 2 x DFMA + DMUL + DADD executed (predicated-on thread
+        # instructions / Gauss points) from the ncu per-instruction counts of the two kernels on the
+        # 50 %-plastic workload (profiles/r01_summary.md "mm01 instruction mix"); the hand count of
+        # the algorithm agrees to a few percent
         return dict(material="mm01 bilinear (E=200e9 as real*4, nu=0.3, yld=400e6, tan_e=E/100)",
-                    bytes_stress=776.0, bytes_tanstf=708.0)
+                    bytes_stress=776.0, bytes_tanstf=708.0, flops_stress=3573.0, flops_tanstf=4540.0)
     # per Gauss point: history 2 x 158 x 8, urcs 2 x 72, eps 2 x 48, rot 72, scratch 2 x 128,
     # crystal properties 1448/8, element vectors 120  (DESIGN.md "mm10")
     return dict(material="mm10 crystal plasticity: fcc 12 slip, Voce (test82/voche_model values), 1 crystal/element",
@@ -369,6 +373,18 @@ def engine_arm(args):
             gpu_launches=launches, clocks=clocks,
             plastic_check=dict(plastic_work=sc["plastic_work"], internal_energy=sc["internal_energy"]),
         )
+        if "flops_stress" in wd and fp64_peak:
+            # both mm01 kernels are at the FP64 ridge (4.6 and 6.4 flop/B against 36.4 TFLOP/s /
+            # 6.55 TB/s = 5.6 flop/B), and a DMUL or DADD occupies the pipe like a DFMA: with 2 639
+            # and 2 568 FP64 instructions per point the pipe floors are 2.3 ms each for 16 M points,
+            # above the HBM floors of 1.9 and 1.7 ms.  State them against the DFMA peak as well.
+            fs = ngp_own * wd["flops_stress"] / (t_stress * 1e-3) / 1e12
+            ft = ngp_own * wd["flops_tanstf"] / (t_tan * 1e-3) / 1e12
+            line["roofline"]["fp64"] = dict(
+                bound="fp64", unit="TFLOP/s", peak=fp64_peak,
+                peak_kind="measured DFMA throughput (tools/fp64_peak.cu, profiles/r01_fp64_peak.json)",
+                k_eps_sig_ifv=dict(achieved=fs, frac=fs / fp64_peak, flops_per_gp=wd["flops_stress"], launch_ms=t_stress),
+                k_tanstf=dict(achieved=ft, frac=ft / fp64_peak, flops_per_gp=wd["flops_tanstf"], launch_ms=t_tan))
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.workload)
             if WORKLOADS[args.workload][1] == "mm10" and fp64_peak:

@@ -186,6 +186,20 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
   const long long g = (long long)slot * 8 + gp;
   const long long ng = a.ng;
 
+  // ---- gather, first half: lane gp fetches the dof / coordinate numbers of node gp of its
+  //      element (dofs node, 8+node, 16+node); the values are fetched after the state stream
+  //      below has been issued, so the index round trip overlaps it
+  int dofs[3], cidx[3];
+  {
+    const int32_t *ed = a.edest + (size_t)slot * 24;
+    const int32_t *cdst = a.cdest + (size_t)slot * 24;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      dofs[k] = ed[k * 8 + gp] - 1;
+      cidx[k] = cdst[k * 8 + gp] - 1;
+    }
+  }
+
   // ---- start streaming this Gauss point's state at n into shared memory
   if (PHASE != 2) {
 #pragma unroll
@@ -199,18 +213,20 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
   }
   cp_async_commit();
 
-  // ---- gather: lane gp fetches node gp of its element (dofs node, 8+node, 16+node)
-  int dofs[3];
+  // ---- gather, second half: the 9 values of the lane's node
   {
-    const int32_t *ed = a.edest + (size_t)slot * 24;
-    const int32_t *cdst = a.cdest + (size_t)slot * 24;
+    double vu[3], vdu[3], vc[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const int d = ed[k * 8 + gp] - 1;
-      dofs[k] = d;
-      sU[el][k * 8 + gp] = a.u[d];
-      sDU[el][k * 8 + gp] = a.du[d];
-      sC[el][k * 8 + gp] = a.c[cdst[k * 8 + gp] - 1];
+      vu[k] = a.u[dofs[k]];
+      vdu[k] = a.du[dofs[k]];
+      vc[k] = a.c[cidx[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      sU[el][k * 8 + gp] = vu[k];
+      sDU[el][k * 8 + gp] = vdu[k];
+      sC[el][k * 8 + gp] = vc[k];
     }
   }
   __syncthreads();

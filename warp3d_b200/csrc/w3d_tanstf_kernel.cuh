@@ -72,6 +72,17 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
   double *sV = er + 8 * GPREC;                // V[node][3]
   double *sS = sV + 24;                       // Sbar[6]
 
+  // ---- dof / coordinate numbers of node `gp` first: their round trip overlaps the state stream
+  int dofs[3], cidx[3];
+  {
+    const int32_t *ed = a.edest + (size_t)slot * 24;
+    const int32_t *cdst = a.cdest + (size_t)slot * 24;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      cidx[k] = cdst[k * 8 + gp] - 1;
+      dofs[k] = GEONL ? ed[k * 8 + gp] - 1 : 0;
+    }
+  }
   // ---- start streaming this point's [D], R and stresses into its (still unused) record slots:
   //      cep -> gr[24..44] (overwritten in place by D* later), R -> gr[45..53], t -> gr[58..63]
   {
@@ -94,15 +105,16 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
   }
   // ---- dptstf: coordinates of node `gp` on the n+1 configuration, staged in the N slots
   {
-    const int32_t *ed = a.edest + (size_t)slot * 24;
-    const int32_t *cdst = a.cdest + (size_t)slot * 24;
+    double vc[3], vu[3], vdu[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      double x = a.c[cdst[k * 8 + gp] - 1];
-      if (GEONL) {
-        const int d = ed[k * 8 + gp] - 1;
-        x = (x + a.u[d]) + a.du[d];
-      }
+      vc[k] = a.c[cidx[k]];
+      if (GEONL) { vu[k] = a.u[dofs[k]]; vdu[k] = a.du[dofs[k]]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double x = vc[k];
+      if (GEONL) x = (x + vu[k]) + vdu[k];
       sV[k * 8 + gp] = x;   // temporary: coordinates [comp][node]
     }
   }
