@@ -16,11 +16,26 @@ using namespace w3d_mm10;
 #ifndef MM10_MIN_CTAS
 #define MM10_MIN_CTAS 2   // resident CTAs per SM the register allocation is sized for
 #endif
+// property records staged per CTA when they fit (1 448 B per element and crystal for 12 systems)
+constexpr int MM10_PROPS_SMEM_LIMIT = 64 * 1024;
+
 template <int NS>
 __global__ void __launch_bounds__(TPB, MM10_MIN_CTAS) k_mm10(const CpArgs a) {
+  extern __shared__ double sProps[];   // [element of the CTA][crystal][Props<NS>] or unused
   const int tid = threadIdx.x;
   const CtaDesc cd = a.cta[blockIdx.x];
   const int el = tid >> 3, gp = tid & 7;
+  constexpr int REC = (int)(sizeof(Props<NS>) / sizeof(double));
+  const int erec = REC * a.ncrystals;                    // doubles per element
+  const bool staged = (size_t)erec * EPC * sizeof(double) <= (size_t)MM10_PROPS_SMEM_LIMIT;
+  if (staged) {
+    // the 8 lanes of an element read the same record over and over in the slip-system loops:
+    // one coalesced copy into shared memory, then conflict-free broadcast reads
+    const double *src = a.props + (size_t)cd.slot0 * erec;
+    const int n = cd.nvalid * erec;
+    for (int k = tid; k < n; k += TPB) sProps[k] = src[k];
+    __syncthreads();
+  }
   if (el >= cd.nvalid) return;
   const int slot = cd.slot0 + el;
   const long long ng = a.ng;
@@ -35,22 +50,14 @@ __global__ void __launch_bounds__(TPB, MM10_MIN_CTAS) k_mm10(const CpArgs a) {
 #pragma unroll
   for (int k = 0; k < 9; ++k) cgn[k] = a.urcs_n[k * ng + g];
   const Layout L = Layout::make(a.nslip, a.num_hard);
-  const Props<NS> *P = reinterpret_cast<const Props<NS> *>(
-      a.props + (size_t)slot * a.ncrystals * (sizeof(Props<NS>) / sizeof(double)));
+  const Props<NS> *P = staged ? reinterpret_cast<const Props<NS> *>(sProps + (size_t)el * erec)
+                              : reinterpret_cast<const Props<NS> *>(a.props + (size_t)slot * erec);
   const CHist hn{a.hist_n + g, ng};
   const Hist h1{a.hist_n1 + g, ng};
-#ifdef W3D_MM10_SLIP_STORE
-  extern __shared__ double slip_store[];   // [slip_store_doubles<NS>()][TPB], one column per thread
-  double *const sl = slip_store + tid;
-  const int sls = TPB;
-#else
   // no slip store on the device: the core recomputes the rotated Schmid data where needed
-  double *const sl = nullptr;
-  const int sls = 0;
-#endif
   const bool cut = gauss_point_update<NS>(a.step, a.ncrystals, P, L, hn, h1, Rur, uddt, a.dt,
                                           a.iter_0_extrapolate_off != 0, a.asymmetric != 0, cgn, cgn1,
-                                          sl, sls);
+                                          nullptr, 0);
   if (cut) {
     atomicOr(&a.flags[0], 1);
     return;
@@ -79,18 +86,15 @@ void mm10_setup_props_host(const double *ctd, const double *angles, int angle_ty
   std::memcpy(props_out, &P, sizeof P);
 }
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {
-#ifdef W3D_MM10_SLIP_STORE
-  const int smem = slip_store_doubles<12>() * TPB * (int)sizeof(double);
+  const size_t need = sizeof(Props<12>) * (size_t)a.ncrystals * EPC;
+  const int smem = need <= (size_t)MM10_PROPS_SMEM_LIMIT ? (int)need : 0;
   static bool set = false;
   if (!set) {
-    const cudaError_t e =
-        cudaFuncSetAttribute(k_mm10<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const cudaError_t e = cudaFuncSetAttribute(k_mm10<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               MM10_PROPS_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     set = true;
   }
-#else
-  const int smem = 0;
-#endif
   k_mm10<12><<<ncta, TPB, smem, st>>>(a);
   return cudaGetLastError();
 }
