@@ -89,7 +89,9 @@ def mm10_stats(reset=False):
 def mm10_props(model):
     """per (element, crystal) property records = setup_mm10_rknstr (rknstr.f:1568-2027)."""
     L = lib()
-    pd = L.w3do_mm10_props_doubles()
+    nslip_max = int(np.asarray(model.crystal_types)[:, 337].max())
+    L.w3do_mm10_props_doubles_for.restype = C.c_int32
+    pd = L.w3do_mm10_props_doubles_for(C.c_int32(nslip_max))
     n = model.noelem * model.ncrystals
     out = np.zeros((n, pd))
     cn = np.ascontiguousarray(model.elem_cnum.reshape(-1), dtype=np.int32)

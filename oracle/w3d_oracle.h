@@ -7,11 +7,18 @@
  * for hex8 (l3disop, type 2) blocks.  Every function in w3d_oracle.cpp cites the reference
  * file:line it follows (paths relative to the reference tree's src/).
  *
- * PARITY STATUS: "parity unpinned".  The reference ships no function-level golden vectors for
- * this path and cannot be compiled in this environment (no Fortran compiler, needs ifort+MKL), so
- * this oracle is pinned only by (i) literal transcription, (ii) physics invariants in tests/
- * (patch test, rigid rotation, finite-difference tangents, K u = f, symmetry) and (iii) the
- * reference's own end-to-end known answers where a test can reach them.
+ * PARITY STATUS.  The reference ships no function-level golden vectors for this path and cannot
+ * be compiled in this environment (no Fortran compiler, needs ifort+MKL).
+ *   - mm10 (crystal plasticity) together with the hex8 small-strain kinematics, B-bar, internal
+ *     force, tangent and the Newton structure around them: PINNED end to end against numbers the
+ *     Fortran produced -- the 79-point stretch/relaxation curve published with
+ *     example_problems_cp/simple_voce is reproduced to 1.1e-5 at worst, 1e-7 at 80 h
+ *     (tests/test_reference_known_answers.py).
+ *   - everything else (mm01, mm05, the finite-strain kinematics): "parity unpinned" -- pinned only
+ *     by (i) literal transcription and (ii) physics invariants in tests/ (patch test, rigid
+ *     rotation, finite-difference tangents, K u = f, symmetry, closed-form uniaxial response); the
+ *     reference's known answers for those models all need temperature-dependent properties or
+ *     element types outside this path.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load
  * this library.  The CUDA engine (warp3d_b200/) must never include or link it.
@@ -106,6 +113,7 @@ int64_t w3do_block_offset(const w3do_model *m, int32_t blk, int32_t which);
 /* mm10: number of doubles in one property record; fill one record from a crystal-type table
  * entry (w3d_mm10::CrystalType laid out as doubles, see oracle_py.py) and Kocks angles.          */
 int32_t w3do_mm10_props_doubles(void);
+int32_t w3do_mm10_props_doubles_for(int32_t nslip);   /* 12-system record, or 48-system (CPU only) */
 int32_t w3do_mm10_crystal_type_doubles(void);
 void w3do_mm10_setup_props(const double *crystal_type, const double *angles, int32_t angle_type,
                            double *props_out);

@@ -266,13 +266,16 @@ static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
 // drive_10_update (rstgp1.f:4327-4513) -> mm10 (mm10_a.f:29).  The per-Gauss-point crystal update
 // is the single-source core shared with the engine (warp3d_b200/csrc/w3d_mm10_core.h, see its
 // header for why); this wrapper supplies the reference's block-local layouts.
-static void drive_10_update(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int gpn,
-                            int step, int iter, const double *uddt_displ, bool &material_cut_step,
-                            int *fatal) {
+// NS = capacity of the slip-system arrays: 12 (fcc, bcc, ...: what the engine builds) or 48
+// (bcc48: CPU only, used to check the shared core against the reference's published results)
+template <int NS>
+static void drive_10_update_ns(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int gpn,
+                               int step, int iter, const double *uddt_displ, bool &material_cut_step,
+                               int *fatal) {
   using namespace w3d_mm10;
   const int span = bi.span;
   const w3do_cp *cp = (const w3do_cp *)m->cp;
-  if (!cp || cp->nslip > 12 || cp->num_hard != 1) { *fatal = 3; return; }
+  if (!cp || cp->nslip > NS || cp->num_hard != 1) { *fatal = 3; return; }
   const Layout L = Layout::make(cp->nslip, cp->num_hard);
   if (L.size(cp->ncrystals) != bi.hist_size) { *fatal = 5; return; }
   // small displacement analysis: rotations set to identity at the first point (:4408-4421)
@@ -295,24 +298,33 @@ static void drive_10_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
   const double *rot = &lw.rot_blk_n1[(size_t)(gpn - 1) * 9 * mxvl];
   double *hist = &lw.elem_hist[(size_t)(gpn - 1) * bi.hist_size * span];
   double *hist1 = &lw.elem_hist1[(size_t)(gpn - 1) * bi.hist_size * span];
-  const size_t prec = sizeof(Props<12>) / sizeof(double);
+  const size_t prec = sizeof(Props<NS>) / sizeof(double);
   for (int i = 0; i < span; ++i) {
     const int elem = bi.felem + i;
-    const Props<12> *P =
-        (const Props<12> *)(cp->props + (size_t)(elem - 1) * cp->ncrystals * prec);
+    const Props<NS> *P =
+        (const Props<NS> *)(cp->props + (size_t)(elem - 1) * cp->ncrystals * prec);
     double Rur[9], ud[6], cgn[9], cgn1[9];
     for (int k = 0; k < 9; ++k) Rur[k] = rot[(size_t)k * mxvl + i];
     for (int k = 0; k < 6; ++k) ud[k] = uddt_displ[(size_t)k * mxvl + i] + 0.0;
     for (int k = 0; k < 9; ++k) cgn[k] = urcs_n[(size_t)k * mxvl + i];
     const CHist hn{hist + i, span};
     const Hist h1{hist1 + i, span};
-    double slip_store[slip_store_doubles<12>()];
-    const bool cut = gauss_point_update<12>(step, cp->ncrystals, P, L, hn, h1, Rur, ud, m->dt,
+    double slip_store[slip_store_doubles<NS>()];
+    const bool cut = gauss_point_update<NS>(step, cp->ncrystals, P, L, hn, h1, Rur, ud, m->dt,
                                             iter_0_extrapolate_off, cp->asymmetric_assembly != 0,
                                             cgn, cgn1, slip_store, 1);
     if (cut) { material_cut_step = true; return; }
     for (int k = 0; k < 9; ++k) urcs_n1[(size_t)k * mxvl + i] = cgn1[k];
   }
+}
+static void drive_10_update(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int gpn,
+                            int step, int iter, const double *uddt_displ, bool &material_cut_step,
+                            int *fatal) {
+  const w3do_cp *cp = (const w3do_cp *)m->cp;
+  if (cp && cp->nslip > 12)
+    drive_10_update_ns<48>(m, bi, lw, gpn, step, iter, uddt_displ, material_cut_step, fatal);
+  else
+    drive_10_update_ns<12>(m, bi, lw, gpn, step, iter, uddt_displ, material_cut_step, fatal);
 }
 
 // rknstr_finish_cp (rknstr.f:268-296) -> mm10_calc_grads (mm10_a.f:1579): gradient of the elastic
@@ -654,10 +666,23 @@ void w3do_mm10_setup_props(const double *ctd, const double *angles, int32_t angl
   const double *ti = ctd + nd;
   ct.nslip = (int)ti[0]; ct.num_hard = (int)ti[1]; ct.h_type = (int)ti[2]; ct.tang_calc = (int)ti[3];
   ct.miter = (int)ti[4]; ct.solver = (int)ti[5]; ct.alter_mode = (int)ti[6];
+  if (ct.nslip > 12) {
+    static w3d_mm10::Props<48> P48;   // 48-system record (bcc48), see drive_10_update
+#pragma omp critical(w3do_props48)
+    {
+      std::memset(&P48, 0, sizeof P48);
+      w3d_mm10::setup_props<48>(ct, angles, angle_type, P48);
+      std::memcpy(props_out, &P48, sizeof P48);
+    }
+    return;
+  }
   w3d_mm10::Props<12> P;
   std::memset(&P, 0, sizeof P);
   w3d_mm10::setup_props<12>(ct, angles, angle_type, P);
   std::memcpy(props_out, &P, sizeof P);
+}
+int32_t w3do_mm10_props_doubles_for(int32_t nslip) {
+  return (int32_t)((nslip > 12 ? sizeof(w3d_mm10::Props<48>) : sizeof(w3d_mm10::Props<12>)) / sizeof(double));
 }
 
 // n records at once: cnum (1-based into the table of crystal types), angles (3 per record)
@@ -666,7 +691,13 @@ void w3do_mm10_setup_props_batch(const double *ct_table, const int32_t *cnum, co
   const size_t ctd = sizeof(w3d_mm10::CrystalType) / sizeof(double) + 0;
   const size_t rec = 36 + 144 + 144 + 13 + 7;
   (void)ctd;
-  const size_t pd = sizeof(w3d_mm10::Props<12>) / sizeof(double);
+  // all crystal types of a model share one record size (the 48-system one if any type needs it)
+  int nslip_max = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    const int ns = (int)ct_table[(size_t)(cnum[k] - 1) * rec + 337];
+    if (ns > nslip_max) nslip_max = ns;
+  }
+  const size_t pd = (size_t)w3do_mm10_props_doubles_for(nslip_max);
   for (int64_t k = 0; k < n; ++k)
     w3do_mm10_setup_props(ct_table + (size_t)(cnum[k] - 1) * rec, angles + 3 * k, angle_type,
                           props_out + (size_t)k * pd);

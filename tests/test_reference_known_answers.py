@@ -1,0 +1,109 @@
+"""Known answers published with the reference, reproduced with the CPU restatement (oracle/):
+the only place where results of this repository can be laid next to numbers the Fortran itself
+produced (it cannot be built here).
+
+example_problems_cp/simple_voce (rhdodds/warp3d): a unit cube stretched in z for 5 h and then held
+for 75 h while the stress relaxes; crystal plasticity with Voce hardening, bcc48 slip, 25 crystal
+orientations per integration point (Taylor), alter_mode on.  The deck says every integration point
+of every element has the same solution, so one element with the deck's boundary conditions carries
+it.  results_for_plotting gives the axial stress at 79 times with 9 digits.  Data (angles, curve)
+are in tests/golden/simple_voce_reference.json; nothing here reads /root/reference."""
+import json
+import os
+
+import numpy as np
+import scipy.sparse.linalg as spla
+
+from newton_driver import assemble
+from oracle import oracle_py as op
+from warp3d_b200 import Material, attach_crystals, build_structured_hex8, make_crystal_type, new_state
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _run_simple_voce(nsteps, nel=3, out_elem=21):
+    ref = json.load(open(os.path.join(HERE, "golden", "simple_voce_reference.json")))
+    m = build_structured_hex8(nel, nel, nel, materials=[Material(mat_type=10)], geonl=False, bbar=True,
+                              block_size=4)                   # "blocking automatic size = 4"
+    # the deck's coordinates: multiples of 1/3 as printed single-precision numbers
+    grid = {1: [0.0, 1.0], 3: [0.0, 0.333333343, 0.666666687, 1.0]}[nel]
+    idx = np.rint(m.c.reshape(-1, 3)).astype(int)
+    m.c[:] = np.asarray(grid)[idx].reshape(-1)
+    ct = make_crystal_type(e=200000.0, nu=0.3, slip="bcc48", harden_n=5.0, tau_y=205.0, tau_v=5000.0,
+                           voche_m=1.0, theta_o=0.01, eps_dot_o_y=4.0e-05, alter_mode=True)
+    ang = np.broadcast_to(np.array(ref["angles_deg"]), (m.noelem, 25, 3))
+    attach_crystals(m, ct, ncrystals=25, angles=ang, angle_type=1)
+    m.extrapolated_du = 0                                   # "extrapolate off"
+    x = m.c.reshape(-1, 3)
+    fixed, top = [], []
+    for node in range(m.nonode):
+        for k in range(3):
+            if x[node, k] == 0.0:
+                fixed.append(3 * node + k)                  # symmetry planes x = y = z = 0
+        if x[node, 2] == 1.0:
+            top.append(3 * node + 2)                        # plane z = 1: w imposed
+    fixed, top = np.array(fixed), np.array(top)
+    cons = np.concatenate([fixed, top])
+    free = np.setdiff1d(np.arange(m.nodof), cons)
+    o, st = op.Oracle(m, nthreads=4), new_state(m)
+    u = np.zeros(m.nodof)
+    stress, times, t, spread = [], [], 0.0, []
+    for step in range(1, nsteps + 1):
+        dt = 0.5 if step <= 10 else 0.1 if step <= 30 else 0.5 if step <= 40 else 1.0 if step <= 50 else 2.0
+        dw = 0.0003 if step <= 10 else 1.0e-15
+        m.dt = dt
+        o.sync_globals()
+        du = np.zeros(m.nodof)
+        ifv, _ = o.eps_sig_ifv(st, step, 0, u, du)
+        K = assemble(m, o.tanstf(st, step, 0, u, du))
+        for it in range(1, 12):
+            delta = np.zeros(m.nodof)
+            if it == 1:
+                delta[top] = dw
+            rhs = (-ifv)[free] - K[free][:, cons] @ delta[cons]
+            delta[free] = spla.spsolve(K[free][:, free].tocsc(), rhs)
+            du = du + delta
+            ifv, sc = o.eps_sig_ifv(st, step, it, u, du)
+            assert not sc["material_cut_step"], (step, it)
+            rn = np.linalg.norm(ifv[free]); rf = np.linalg.norm(ifv[cons]) or 1.0
+            if it >= 2 and rn <= 1.0e-9 * rf:              # the deck: at least 2 iterations
+                break
+            K = assemble(m, o.tanstf(st, step, it, u, du))
+        u = u + du
+        o.update(st); o.adaptive_save(st)
+        t += dt
+        s = st.urcs_n.reshape(-1, 8, 9)                     # (element, Gauss point, component)
+        spread.append(float(np.ptp(s[:, :, 2]) / abs(s[:, :, 2]).max()))
+        # "output stresses 21" with the elements' `center` option: the element value is the
+        # average over its integration points
+        e = min(out_elem, m.noelem) - 1
+        stress.append(float(s[e, :, 2].mean())); times.append(t)
+    return np.array(times), np.array(stress), ref, max(spread)
+
+
+def test_simple_voce_stretch_and_relaxation_curve():
+    nsteps = 79
+    times, stress, ref, spread = _run_simple_voce(nsteps)
+    tr, sr = np.array(ref["time_h"][1:nsteps + 1]), np.array(ref["stress_cp"][1:nsteps + 1])
+    assert np.allclose(times, tr, rtol=0, atol=1e-9)
+    rel = np.abs(stress - sr) / sr
+    # Measured: 1.1e-5 at the first step, 4e-6 at peak stress (523.26 MPa), 1e-7 at 80 h
+    # (264.364496 here, 264.364523 published).  The reference stops its Newton loops at relative
+    # tolerances of 5e-5 (crystal) and 1e-4 (structure) and its own regression tests accept 1e-4.
+    # The whole difference is a constant -6.7e-4 MPa that enters in step 1 and relaxes away: the
+    # published first point is exactly elastic (E x 0.0003 stored as real*4 = 60.000003) while
+    # backward Euler at 60 MPa relaxes 6.7e-4 MPa in 0.5 h -- the same rate law reproduces the
+    # published relaxation of step 2 (0.021526 MPa) to six digits.
+    assert rel.max() < 2.0e-5, (rel.max(), int(rel.argmax()), stress[int(rel.argmax())], sr[int(rel.argmax())])
+    assert rel[9:].max() < 6.0e-6 and rel[-1] < 3.0e-7
+    assert 0.005 < spread < 0.1          # not homogeneous: element 21 of the 3 x 3 x 3 mesh matters
+
+
+def test_simple_voce_one_element_is_not_the_same_problem():
+    """The deck's remark that all points share one solution holds only approximately (25 crystals
+    are not an isotropic aggregate): a single element reproduces the elastic range but drifts to
+    1e-3 once the crystals yield -- the 27-element mesh above is needed for 1e-5."""
+    times, stress, ref, _ = _run_simple_voce(12, nel=1, out_elem=1)
+    sr = np.array(ref["stress_cp"][1:13])
+    rel = np.abs(stress - sr) / sr
+    assert rel[:3].max() < 2.0e-5 and 5.0e-4 < rel[9:].max() < 3.0e-3

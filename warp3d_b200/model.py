@@ -339,6 +339,32 @@ def fcc_slip_systems():
     return bi, ni
 
 
+def bcc48_slip_systems():
+    """The 48 bcc systems of slip_type 8 (src/mod_crystals.f:815-1210): <111> directions on the
+    {110} (12), {112} (12) and {123} (24) planes, unit vectors.  Generated from the families, so
+    the ORDER and the sign of each (b, n) pair are not the reference's table: the stress response
+    and every sum over systems are invariant to both, only the per-system history columns
+    (slip increments) would be permuted."""
+    import itertools
+    dirs = [np.array(d, dtype=float) for d in ((1, 1, 1), (-1, 1, 1), (1, -1, 1), (1, 1, -1))]
+    out_b, out_n = [], []
+    for fam in ((1, 1, 0), (1, 1, 2), (1, 2, 3)):
+        planes = set()
+        for perm in set(itertools.permutations(fam)):
+            for sg in itertools.product((1, -1), repeat=3):
+                v = tuple(int(s * c) for s, c in zip(sg, perm))
+                if v != (0, 0, 0) and tuple(-x for x in v) not in planes:
+                    planes.add(v)
+        for pl in sorted(planes):
+            nrm = np.array(pl, dtype=float)
+            for d in dirs:
+                if abs(nrm @ d) < 1e-12:
+                    out_b.append(d / np.linalg.norm(d)); out_n.append(nrm / np.linalg.norm(nrm))
+    bi, ni = np.array(out_b), np.array(out_n)
+    assert bi.shape == (48, 3)
+    return bi, ni
+
+
 def make_crystal_type(e=69000.0, nu=0.33, mu=None, elastic="isotropic", slip="fcc", harden_n=20.0,
                       tau_y=0.0, tau_v=0.0, voche_m=1.0, theta_o=100.0, k_o=0.0, b=2.87e-7,
                       iD_v=0.0, eps_dot_o_y=1.0e10, atol=1.0e-5, atol1=1.0e-5, rtol=5.0e-5,
@@ -346,10 +372,13 @@ def make_crystal_type(e=69000.0, nu=0.33, mu=None, elastic="isotropic", slip="fc
     """One crystal definition = c_array(cnum) after finalize_new_crystal
     (src/mod_crystals.f:238-417 defaults, :421-1934 derived data).  Returns a
     (CRYSTAL_TYPE_DOUBLES,) float64 record."""
-    if slip != "fcc":
-        raise NotImplementedError("slip systems other than fcc are not built yet")
-    bi, ni = fcc_slip_systems()
-    nslip = 12
+    if slip == "fcc":
+        bi, ni = fcc_slip_systems()
+    elif slip == "bcc48":          # 48 systems: CPU restatement only (the engine builds <= 12)
+        bi, ni = bcc48_slip_systems()
+    else:
+        raise NotImplementedError("slip tables built: fcc, bcc48")
+    nslip = bi.shape[0]
     if mu is None:
         mu = e / 2.0 / (1.0 + nu)
     flex = np.zeros((6, 6))
