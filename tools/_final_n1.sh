@@ -1,0 +1,7 @@
+# round-end single-GPU measurement set: both arms exactly as the driver launches them, the mm10
+# workload, and the ncu launch list of the same default command
+python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/r01_final_reference_arm.json 2> gpurun_out/r01_final_reference_arm.err
+python bench.py --gpus 1 > gpurun_out/r01_final_bench_n1.json 2> gpurun_out/r01_final_bench_n1.err
+python bench.py --workload hex8_1m_mm10 --steps 5 > gpurun_out/r01_final_bench_mm10_1m.json 2> gpurun_out/r01_final_bench_mm10_1m.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_final_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/r01_final_launches.log 2>&1
+tail -c 600 gpurun_out/r01_final_bench_n1.json; echo; tail -c 300 gpurun_out/r01_final_reference_arm.json

@@ -411,7 +411,7 @@ int create_impl(w3d_engine *h) {
     CUDA_TRY(dalloc(&sg.hist_n, (size_t)sg.hist_size * ng));
     CUDA_TRY(dalloc(&sg.hist_n1, (size_t)sg.hist_size * ng));
     CUDA_TRY(dalloc(&sg.elem_vol, (size_t)sg.nslots));
-    CUDA_TRY(dalloc(&sg.partials, (size_t)sg.ncta * 4));
+    CUDA_TRY(dalloc(&sg.partials, (size_t)(sg.ncta + REDUCE_STAGE1_CTAS) * 4));   // + stage-1 sums
     k_rot_identity<<<148 * 4, 256, 0, h->stream>>>(sg.rot_n, sg.ng);
     k_rot_identity<<<148 * 4, 256, 0, h->stream>>>(sg.rot_n1, sg.ng);
     h->launches += 2;
@@ -477,8 +477,15 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
       launch_stress<1, 0>(sg, a, h->stream);
       h->launches += 1;
     }
-    k_reduce_partials<<<1, 256, 0, h->stream>>>(sg.partials, sg.ncta, h->d_scal, first ? 0 : 1);
-    h->launches += 1;
+    if (sg.ncta > 4096) {   // two fixed-order stages (still deterministic)
+      double *tmp = sg.partials + (size_t)sg.ncta * 4;
+      k_reduce_partials_stage1<<<REDUCE_STAGE1_CTAS, 256, 0, h->stream>>>(sg.partials, sg.ncta, tmp);
+      k_reduce_partials<<<1, 256, 0, h->stream>>>(tmp, REDUCE_STAGE1_CTAS, h->d_scal, first ? 0 : 1);
+      h->launches += 2;
+    } else {
+      k_reduce_partials<<<1, 256, 0, h->stream>>>(sg.partials, sg.ncta, h->d_scal, first ? 0 : 1);
+      h->launches += 1;
+    }
     first = 0;
   }
   CUDA_TRY(cudaGetLastError());

@@ -648,6 +648,34 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
   }
 }
 
+// first stage of the deterministic reduction of the per-CTA partials when there are many of them
+// (125 000 CTAs on the 2 M-element mesh took one CTA 130 us): REDUCE_STAGE1_CTAS CTAs each sum a
+// fixed contiguous chunk in a fixed order into tmp[cta*4 + k]; k_reduce_partials finishes
+constexpr int REDUCE_STAGE1_CTAS = 128;
+static __global__ void __launch_bounds__(256) k_reduce_partials_stage1(const double *partials, int ncta,
+                                                                       double *tmp) {
+  __shared__ double s[3][256];
+  const int chunk = (ncta + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * chunk, hi = min(ncta, lo + chunk);
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    v0 += partials[(size_t)i * 4 + 0];
+    v1 += partials[(size_t)i * 4 + 1];
+    v2 += partials[(size_t)i * 4 + 2];
+  }
+  s[0][threadIdx.x] = v0; s[1][threadIdx.x] = v1; s[2][threadIdx.x] = v2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s[0][threadIdx.x] += s[0][threadIdx.x + o];
+      s[1][threadIdx.x] += s[1][threadIdx.x + o];
+      s[2][threadIdx.x] += s[2][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) tmp[(size_t)blockIdx.x * 4 + threadIdx.x] = s[threadIdx.x][0];
+}
+
 // deterministic final reduction of the per-CTA partials: one CTA, fixed tree
 static __global__ void __launch_bounds__(256) k_reduce_partials(const double *partials, int ncta,
                                                          double *out /*[4]*/, int accumulate) {
