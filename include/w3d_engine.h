@@ -170,6 +170,29 @@ int32_t w3d_engine_synchronize(w3d_engine *h);
 /* number of kernels the engine has launched since create (bench.py: gpu_launches) */
 int64_t w3d_engine_launch_count(const w3d_engine *h);
 
+/* ---- assembled equilibrium equations (SURVEY 8(f) NEXT-1), symmetric case, one domain ---------
+ * Replaces assemble_code.f: dof_map (:561-600), count_profile_symmetric (:20-250),
+ * build_col_sparse_symm (:260-500) and assem_by_row / assem_a_row (:659-935) as
+ * drive_assemble_solve.f calls them, so that the 2 400 B per element of estiff_blocks never
+ * cross to the host.  Format = the reference's upper-triangle "VSS" vectors
+ * (assemble_code.f:603-620): k_ptrs(neqns) terms right of the diagonal per row, k_indexes(ncoeff)
+ * their equation numbers (1-based, ascending in a row), k_coeffs(ncoeff), k_diag(neqns).
+ *
+ * w3d_assemble_setup: once per constraint set.  cstmap(nodof): the reference's cstmap, 0 = dof
+ * without an absolute constraint; edest: the packed per-block (totdof, span) tables of the
+ * configuration.  Returns the number of equations and of off-diagonal terms.                     */
+int32_t w3d_assemble_setup(w3d_engine *h, const int32_t *cstmap, const int32_t *edest,
+                           int32_t *neqns_out, int64_t *ncoeff_out);
+/* the integer structure: dof_eqn_map(nodof), eqn_node_map(neqns), k_ptrs(neqns),
+ * k_indexes(ncoeff); any pointer may be NULL                                                     */
+int32_t w3d_assemble_structure(w3d_engine *h, int32_t *dof_eqn_map, int32_t *eqn_node_map,
+                               int32_t *k_ptrs, int32_t *k_indexes);
+/* assem_by_row on the element stiffnesses of the last w3d_tanstf / w3d_tanstf_resident (call
+ * w3d_tanstf with estiff == NULL to keep them on the device).  Sums are taken in the reference's
+ * order (elements on the node ascending, element columns ascending): bit-reproducible.  k_diag /
+ * k_coeffs: host buffers, or both NULL to leave the result in device memory.                     */
+int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs);
+
 #ifdef __cplusplus
 }
 #endif

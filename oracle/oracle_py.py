@@ -212,3 +212,39 @@ def cp_icp(n):
     icp = np.zeros((2, utsz), dtype=np.int32)   # Fortran (utsz, 2)
     lib().w3do_cp_icp(C.c_int32(n), _ptr(cp), _ptr(dcp), _ptr(icp))
     return cp, dcp, icp
+
+
+# ---- assembled equilibrium equations (assemble_code.f), symmetric ---------------------------------
+def assemble_structure(oracle: "Oracle", cstmap):
+    """dof_map, count_profile_symmetric and build_col_sparse_symm for the constraint map `cstmap`
+    (nodof ints, 0 = free).  Returns dict(neqns, ncoeff, dof_eqn_map, eqn_node_map, k_ptrs, k_indexes)."""
+    L, m = lib(), oracle.model
+    cst = np.ascontiguousarray(cstmap, dtype=np.int32)
+    dmap = np.zeros(m.nodof, dtype=np.int32)
+    emap = np.zeros(m.nodof, dtype=np.int32)
+    L.w3do_dof_map.restype = C.c_int32
+    L.w3do_assemble_structure.restype = C.c_int64
+    neq = L.w3do_dof_map(_ptr(cst), C.c_int32(m.nonode), C.c_int32(3), _ptr(dmap), _ptr(emap))
+    emap = np.ascontiguousarray(emap[:neq])
+    kp = np.zeros(neq, dtype=np.int32)
+    oracle.sync_globals()
+    nco = L.w3do_assemble_structure(C.byref(oracle._cm), C.c_int32(neq), _ptr(emap), _ptr(dmap), _ptr(kp), None)
+    ki = np.zeros(max(nco, 1), dtype=np.int32)
+    nco2 = L.w3do_assemble_structure(C.byref(oracle._cm), C.c_int32(neq), _ptr(emap), _ptr(dmap), _ptr(kp), _ptr(ki))
+    assert nco2 == nco
+    return dict(neqns=int(neq), ncoeff=int(nco), dof_eqn_map=dmap, eqn_node_map=emap, k_ptrs=kp,
+                k_indexes=ki[:nco])
+
+
+def assemble(oracle: "Oracle", estiff, s):
+    """assem_by_row: (k_diag, k_coeffs) from the packed element stiffness blocks and a structure
+    returned by assemble_structure."""
+    L = lib()
+    ek = np.ascontiguousarray(estiff, dtype=np.float64).reshape(-1)
+    kd = np.zeros(s["neqns"])
+    kc = np.zeros(max(s["ncoeff"], 1))
+    ki = np.ascontiguousarray(s["k_indexes"] if s["ncoeff"] else np.zeros(1, dtype=np.int32))
+    oracle.sync_globals()
+    L.w3do_assemble(C.byref(oracle._cm), _ptr(ek), C.c_int32(s["neqns"]), _ptr(s["eqn_node_map"]),
+                    _ptr(s["dof_eqn_map"]), _ptr(s["k_ptrs"]), _ptr(ki), _ptr(kd), _ptr(kc))
+    return kd, kc[:s["ncoeff"]]

@@ -1,0 +1,99 @@
+"""Assembly of the element stiffnesses into the reference's sparse upper-triangle vectors
+(assemble_code.f): the CPU restatement against an independent scipy assembly (CPU), and the
+device assembly against the restatement, bit for bit (GPU)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from common import load_path
+from newton_driver import assemble as scipy_assemble
+from oracle import oracle_py as op
+from warp3d_b200 import build_structured_hex8, new_state
+
+
+def _case(nx=4, ny=3, nz=3, seed=5, block_size=7):
+    m = build_structured_hex8(nx, ny, nz, coord_jitter=0.1, seed=seed, block_size=block_size)
+    rng = np.random.default_rng(seed)
+    cst = np.zeros(m.nodof, dtype=np.int32)
+    x = m.c.reshape(-1, 3)
+    for node in np.nonzero(x[:, 0] < 1e-9)[0]:            # a clamped face ...
+        cst[3 * node:3 * node + 3] = 1
+    cst[rng.choice(m.nodof, size=m.nodof // 9, replace=False)] = 1   # ... and scattered constraints
+    return m, cst
+
+
+def _vss_to_csr(s, kd, kc):
+    n = s["neqns"]
+    rows = np.repeat(np.arange(n), s["k_ptrs"])
+    up = sp.csr_matrix((kc, (rows, s["k_indexes"] - 1)), shape=(n, n))
+    return up + up.T + sp.diags(kd)
+
+
+def test_restatement_matches_an_independent_assembly():
+    m, cst = _case()
+    o, st = op.Oracle(m), new_state(m)
+    (step, iters), = list(load_path(m, nsteps=1, strain=3.0e-3))
+    for itr, u, du in iters:
+        o.eps_sig_ifv(st, step, itr, u, du)
+    ek = o.tanstf(st, step, itr, u, du).copy()
+    s = op.assemble_structure(o, cst)
+    free = np.nonzero(cst == 0)[0]
+    # dof_map: free dofs numbered in dof order, node of each equation
+    assert s["neqns"] == free.size
+    assert np.array_equal(s["dof_eqn_map"][free], np.arange(1, free.size + 1)) and not s["dof_eqn_map"][cst != 0].any()
+    assert np.array_equal(s["eqn_node_map"], free // 3 + 1)
+    K = scipy_assemble(m, ek)[free][:, free].tocsr()
+    K.sort_indices()
+    up = sp.triu(K, k=1).tocsr()
+    up.sort_indices()
+    # the reference keeps every structural non-zero, also where the value happens to vanish
+    assert s["k_ptrs"][-1] == 0 and s["ncoeff"] == int(s["k_ptrs"].sum())
+    rows = np.repeat(np.arange(s["neqns"]), s["k_ptrs"])
+    assert np.all(s["k_indexes"] - 1 > rows)                                   # strictly right of the diagonal
+    starts = np.concatenate([[0], np.cumsum(s["k_ptrs"])])
+    for r in range(s["neqns"]):
+        seg = s["k_indexes"][starts[r]:starts[r + 1]]
+        assert np.all(np.diff(seg) > 0)                                        # ascending, no duplicates
+        assert set(up.indices[up.indptr[r]:up.indptr[r + 1]] + 1) <= set(seg)  # covers every numeric non-zero
+    kd, kc = op.assemble(o, ek, s)
+    A = _vss_to_csr(s, kd, kc)
+    scale = abs(K).max()
+    assert abs(A - K).max() <= 1e-14 * scale
+    # a free structure: no constraints at all
+    s0 = op.assemble_structure(o, np.zeros(m.nodof, dtype=np.int32))
+    kd0, kc0 = op.assemble(o, ek, s0)
+    K0 = scipy_assemble(m, ek)
+    assert s0["neqns"] == m.nodof and abs(_vss_to_csr(s0, kd0, kc0) - K0).max() <= 1e-14 * abs(K0).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("constrained", [True, False])
+def test_device_assembly_matches_the_restatement_bit_for_bit(constrained):
+    from warp3d_b200.engine import Engine
+    m, cst = _case(nx=6, ny=5, nz=4, seed=11, block_size=13)
+    if not constrained:
+        cst[:] = 0
+    e, o, st = Engine(m), op.Oracle(m), new_state(m)
+    (step, iters), = list(load_path(m, nsteps=1, strain=3.0e-3))
+    for itr, u, du in iters:
+        e.drive_eps_sig_internal_forces(step, itr, u, du)
+        o.eps_sig_ifv(st, step, itr, u, du)
+    ek_dev = e.tanstf(step, itr, u, du).copy()         # also leaves the stiffnesses on the device
+    sg, so = e.assemble_setup(cst), op.assemble_structure(o, cst)
+    assert sg["neqns"] == so["neqns"] and sg["ncoeff"] == so["ncoeff"]
+    for k in ("dof_eqn_map", "eqn_node_map", "k_ptrs", "k_indexes"):
+        assert np.array_equal(sg[k], so[k]), k                                  # integers: bit exact
+    kd, kc = e.assemble()
+    # same element stiffnesses in, same order of additions: identical bits out
+    kd_o, kc_o = op.assemble(o, ek_dev, so)
+    assert np.array_equal(kd, kd_o) and np.array_equal(kc, kc_o)
+    # and against the restatement's own element stiffnesses at the parity bar
+    kd_r, kc_r = op.assemble(o, o.tanstf(st, step, itr, u, du), so)
+    scale = max(abs(kd_r).max(), abs(kc_r).max())
+    assert abs(kd - kd_r).max() <= 1e-10 * scale and abs(kc - kc_r).max() <= 1e-10 * scale
+    # a second pass (resident, no host copy) leaves the same result behind
+    e.tanstf(step, itr, u, du, to_host=False)
+    e.assemble(to_host=False)
+    kd2, kc2 = e.assemble()
+    assert np.array_equal(kd2, kd) and np.array_equal(kc2, kc)
+    e.close()

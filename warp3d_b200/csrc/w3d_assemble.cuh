@@ -1,0 +1,229 @@
+// w3d_assemble.cuh -- element stiffnesses -> assembled sparse equilibrium equations on the device.
+// Included at the end of w3d_engine.cu (it needs the engine struct).
+//
+// Replaces, for the symmetric case, reference src/assemble_code.f: dof_map (:561-600),
+// count_profile_symmetric (:20-250), build_col_sparse_symm (:260-500) and assem_by_row /
+// assem_a_row / assem_a_row_24 (:659-935), with the inverse incidences of setup.f:158-190.
+// Output = the reference's "NASA-VSS" upper-triangle format (assemble_code.f:603-620):
+//   k_ptrs(neqns)    number of non-zero terms right of the diagonal on each row (last = 0)
+//   k_indexes(ncoef) their column (equation) numbers, ascending within a row, 1-based
+//   k_coeffs(ncoef)  the terms, k_diag(neqns) the diagonal
+// Equations are the dofs without an absolute constraint, numbered in dof order (dof_map).
+//
+// Why on the device: the element stiffnesses are 2 400 B per element (4.8 GB for the 2 M-element
+// mesh) and the host copy of them is what bounds the end-to-end Newton iteration; assembled, the
+// same information is ~2.0 GB.
+//
+// The structure is built once per constraint set on the host (integer work, seconds); the values
+// are assembled every iteration by one thread per equation, which walks the elements on the
+// equation's node in the reference's order (ascending element number) and the 24 element columns
+// in order, so every sum is taken in the reference's order: no atomics, bit-reproducible.
+#pragma once
+
+namespace {
+
+// assem_a_row + assem_a_row_24 (assemble_code.f:785-935) for every equation at once
+__global__ void __launch_bounds__(128) k_assemble_rows(
+    int neqns, const int32_t *__restrict__ eqn_node, const int8_t *__restrict__ eqn_comp,
+    const int32_t *__restrict__ inv_ptr, const int32_t *__restrict__ inv_epos,
+    const int8_t *__restrict__ inv_lnode, const int32_t *__restrict__ eeqn,
+    const double *__restrict__ estiff, const long long *__restrict__ row_start,
+    const int32_t *__restrict__ kidx, double *__restrict__ kdiag, double *__restrict__ kcoef) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= neqns) return;
+  const int srow = r + 1;
+  const int node = eqn_node[r], comp = eqn_comp[r];
+  const long long rs = row_start[r];
+  const int n = (int)(row_start[r + 1] - rs);
+  double *row = kcoef + rs;
+  const int32_t *cols = kidx + rs;
+  for (int k = 0; k < n; ++k) row[k] = 0.0;
+  double diag = 0.0;
+  for (int j = inv_ptr[node]; j < inv_ptr[node + 1]; ++j) {   // elements on the node, ascending
+    const long long e = inv_epos[j];
+    const int erow = comp * 8 + inv_lnode[j];
+    const int32_t *q = eeqn + e * 24;
+    const double *ek = estiff + e * 300;
+#pragma unroll 4
+    for (int ecol = 0; ecol < 24; ++ecol) {
+      const int scol = q[ecol];
+      if (scol < srow) continue;                              // lower triangle or constrained
+      const int hi = max(ecol, erow), lo = min(ecol, erow);
+      const double v = ek[(hi * (hi + 1)) / 2 + lo];          // dcp(max) - |ecol - erow|
+      if (scol == srow) {
+        diag += v;
+      } else {
+        int a = 0, b = n;                                     // first position with cols[] >= scol
+        while (a < b) {
+          const int m = (a + b) >> 1;
+          if (cols[m] < scol) a = m + 1; else b = m;
+        }
+        row[a] += v;
+      }
+    }
+  }
+  kdiag[r] = diag;
+}
+
+}  // namespace
+
+extern "C" {
+
+// dof_map + inverse incidences + count_profile_symmetric + build_col_sparse_symm.
+// cstmap(nodof): 0 = free dof (as the reference's cstmap); edest: the same packed per-block
+// (totdof, span) tables as in the configuration.
+int32_t w3d_assemble_setup(w3d_engine *h, const int32_t *cstmap, const int32_t *edest,
+                           int32_t *neqns_out, int64_t *ncoeff_out) {
+  if (!h || !cstmap || !edest) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  const w3d_engine_config &c = h->cfg;
+  if (c.numprocs > 1)
+    return h->fail(W3D_ERR_UNSUPPORTED, "device assembly is built for one domain (numprocs = 1)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  AssemblyData &A = h->assembly;
+  A.release();
+  const int nodof = c.nodof, nonode = c.nonode;
+  if (nodof != 3 * nonode) return h->fail(W3D_ERR_CONFIG, "assembly expects 3 dofs per node");
+  // ---- dof_map (assemble_code.f:561-600)
+  A.dof_eqn_map.assign(nodof, 0);
+  A.eqn_node_map.clear();
+  std::vector<int8_t> eqn_comp;
+  int neq = 0;
+  for (int dof = 0; dof < nodof; ++dof) {
+    if (cstmap[dof] != 0) continue;
+    A.dof_eqn_map[dof] = ++neq;
+    A.eqn_node_map.push_back(dof / 3 + 1);
+    eqn_comp.push_back((int8_t)(dof % 3));
+  }
+  A.neqns = neq;
+  if (neq == 0) return h->fail(W3D_ERR_CONFIG, "no free dof");
+  // ---- element tables in d_estiff order, inverse incidences (setup.f:158-190: ascending elements)
+  const long long nel = h->n_owned_elems;
+  std::vector<int32_t> eeqn((size_t)nel * 24);
+  std::vector<int32_t> enode((size_t)nel * 8);
+  std::vector<int32_t> inv_count(nonode + 1, 0);
+  // elements sorted by element number: the blocks hold consecutive elements
+  std::vector<std::pair<int, long long>> order;   // (element number, position)
+  order.reserve(nel);
+  for (const BlockInfo &b : h->blocks) {
+    if (!b.owned) continue;
+    if (b.totdof != 24) return h->fail(W3D_ERR_UNSUPPORTED, "assembly: 24-dof elements only");
+    for (int i = 0; i < b.span; ++i) {
+      const long long pos = b.epos0 + i;
+      const int32_t *ed = edest + b.tab_off + (size_t)i * 24;
+      for (int k = 0; k < 24; ++k) {
+        const int d = ed[k];
+        if (d < 1 || d > nodof) return h->fail(W3D_ERR_CONFIG, "edest entry %d out of range", d);
+        eeqn[(size_t)pos * 24 + k] = A.dof_eqn_map[d - 1];
+      }
+      for (int k = 0; k < 8; ++k) {
+        const int nd = (ed[k] - 1) / 3;   // 0-based node of local node k (u-dof = dstmap(node))
+        if (ed[8 + k] != ed[k] + 1 || ed[16 + k] != ed[k] + 2)
+          return h->fail(W3D_ERR_CONFIG, "edest is not in the u(8), v(8), w(8) order of a node-major dof map");
+        for (int p = 0; p < k; ++p)
+          if (enode[(size_t)pos * 8 + p] == nd)
+            return h->fail(W3D_ERR_UNSUPPORTED, "assembly: repeated nodes in an element (collapsed elements) not built");
+        enode[(size_t)pos * 8 + k] = nd;
+        ++inv_count[nd + 1];
+      }
+      order.emplace_back(b.felem + i, pos);
+    }
+  }
+  std::sort(order.begin(), order.end());
+  std::vector<int32_t> inv_ptr(nonode + 1, 0);
+  for (int nd = 0; nd < nonode; ++nd) inv_ptr[nd + 1] = inv_ptr[nd] + inv_count[nd + 1];
+  std::vector<int32_t> fill(inv_ptr.begin(), inv_ptr.end() - 1);
+  std::vector<int32_t> inv_epos((size_t)inv_ptr[nonode]);
+  std::vector<int8_t> inv_lnode((size_t)inv_ptr[nonode]);
+  for (const auto &eo : order) {
+    const long long pos = eo.second;
+    for (int k = 0; k < 8; ++k) {
+      const int nd = enode[(size_t)pos * 8 + k];
+      inv_epos[fill[nd]] = (int32_t)pos;
+      inv_lnode[fill[nd]] = (int8_t)k;
+      ++fill[nd];
+    }
+  }
+  // ---- sparsity: per equation the distinct columns right of the diagonal, ascending
+  A.k_ptrs.assign(neq, 0);
+  A.k_indexes.clear();
+  A.k_indexes.reserve((size_t)neq * 40);
+  std::vector<long long> row_start(neq + 1, 0);
+  std::vector<int32_t> cand;
+  cand.reserve(27 * 3 * 8);
+  for (int r = 0; r < neq; ++r) {
+    const int srow = r + 1;
+    const int nd = A.eqn_node_map[r] - 1;
+    cand.clear();
+    for (int j = inv_ptr[nd]; j < inv_ptr[nd + 1]; ++j) {
+      const int32_t *q = &eeqn[(size_t)inv_epos[j] * 24];
+      for (int k = 0; k < 24; ++k)
+        if (q[k] > srow) cand.push_back(q[k]);
+    }
+    std::sort(cand.begin(), cand.end());
+    cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+    A.k_ptrs[r] = (int32_t)cand.size();
+    A.k_indexes.insert(A.k_indexes.end(), cand.begin(), cand.end());
+    row_start[r + 1] = row_start[r] + (long long)cand.size();
+  }
+  A.ncoeff = row_start[neq];
+  // ---- upload
+  std::vector<int32_t> eqn_node0(neq);
+  for (int r = 0; r < neq; ++r) eqn_node0[r] = A.eqn_node_map[r] - 1;
+  auto up = [&](auto **dptr, const auto &v) -> cudaError_t {
+    using T = typename std::remove_reference<decltype(v[0])>::type;
+    const size_t bytes = sizeof(T) * (v.size() ? v.size() : 1);
+    cudaError_t e = cudaMalloc((void **)dptr, bytes);
+    if (e != cudaSuccess) return e;
+    return v.size() ? cudaMemcpy(*dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice) : cudaSuccess;
+  };
+  CUDA_TRY(up(&A.d_eqn_node, eqn_node0));
+  CUDA_TRY(up(&A.d_eqn_comp, eqn_comp));
+  CUDA_TRY(up(&A.d_row_start, row_start));
+  CUDA_TRY(up(&A.d_kidx, A.k_indexes));
+  CUDA_TRY(up(&A.d_inv_ptr, inv_ptr));
+  CUDA_TRY(up(&A.d_inv_epos, inv_epos));
+  CUDA_TRY(up(&A.d_inv_lnode, inv_lnode));
+  CUDA_TRY(up(&A.d_eeqn, eeqn));
+  CUDA_TRY(cudaMalloc((void **)&A.d_kdiag, sizeof(double) * (size_t)neq));
+  CUDA_TRY(cudaMalloc((void **)&A.d_kcoef, sizeof(double) * (size_t)(A.ncoeff ? A.ncoeff : 1)));
+  A.ready = true;
+  if (neqns_out) *neqns_out = neq;
+  if (ncoeff_out) *ncoeff_out = A.ncoeff;
+  return W3D_OK;
+}
+
+// the integer structure built by w3d_assemble_setup; any pointer may be NULL
+int32_t w3d_assemble_structure(w3d_engine *h, int32_t *dof_eqn_map, int32_t *eqn_node_map,
+                               int32_t *k_ptrs, int32_t *k_indexes) {
+  if (!h) return W3D_ERR_ARG;
+  const AssemblyData &A = h->assembly;
+  if (!A.ready) return h->fail(W3D_ERR_ARG, "w3d_assemble_setup has not been called");
+  if (dof_eqn_map) std::memcpy(dof_eqn_map, A.dof_eqn_map.data(), sizeof(int32_t) * A.dof_eqn_map.size());
+  if (eqn_node_map) std::memcpy(eqn_node_map, A.eqn_node_map.data(), sizeof(int32_t) * A.eqn_node_map.size());
+  if (k_ptrs) std::memcpy(k_ptrs, A.k_ptrs.data(), sizeof(int32_t) * A.k_ptrs.size());
+  if (k_indexes) std::memcpy(k_indexes, A.k_indexes.data(), sizeof(int32_t) * A.k_indexes.size());
+  return W3D_OK;
+}
+
+// assem_by_row on the element stiffnesses of the last w3d_tanstf / w3d_tanstf_resident.
+// k_diag(neqns), k_coeffs(ncoeff): host buffers, or both NULL to leave the result on the device.
+int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs) {
+  if (!h) return W3D_ERR_ARG;
+  AssemblyData &A = h->assembly;
+  if (!A.ready) return h->fail(W3D_ERR_ARG, "w3d_assemble_setup has not been called");
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int tpb = 128;
+  k_assemble_rows<<<(A.neqns + tpb - 1) / tpb, tpb, 0, h->stream>>>(
+      A.neqns, A.d_eqn_node, A.d_eqn_comp, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn,
+      h->d_estiff, A.d_row_start, A.d_kidx, A.d_kdiag, A.d_kcoef);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  if (k_diag) CUDA_TRY(cudaMemcpyAsync(k_diag, A.d_kdiag, sizeof(double) * (size_t)A.neqns, cudaMemcpyDeviceToHost, h->stream));
+  if (k_coeffs && A.ncoeff) CUDA_TRY(cudaMemcpyAsync(k_coeffs, A.d_kcoef, sizeof(double) * (size_t)A.ncoeff, cudaMemcpyDeviceToHost, h->stream));
+  if (k_diag || k_coeffs) CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return W3D_OK;
+}
+
+}  // extern "C"

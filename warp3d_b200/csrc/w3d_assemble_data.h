@@ -1,0 +1,34 @@
+// w3d_assemble_data.h -- device / host tables of the assembled-equations path (w3d_assemble.cuh)
+#pragma once
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+namespace w3d {
+
+struct AssemblyData {
+  bool ready = false;
+  int neqns = 0;
+  long long ncoeff = 0;
+  // host copies handed back by w3d_assemble_structure
+  std::vector<int32_t> dof_eqn_map, eqn_node_map, k_ptrs, k_indexes;
+  // device
+  int32_t *d_eqn_node = nullptr;     // (neqns)  0-based node of each equation
+  int8_t *d_eqn_comp = nullptr;      // (neqns)  dof component 0..2
+  long long *d_row_start = nullptr;  // (neqns + 1) offsets into k_indexes / k_coeffs
+  int32_t *d_kidx = nullptr;         // (ncoeff)
+  int32_t *d_inv_ptr = nullptr;      // (nonode + 1) into the two lists below
+  int32_t *d_inv_epos = nullptr;     // position of the element in d_estiff / d_eeqn
+  int8_t *d_inv_lnode = nullptr;     // local node number (0..7) of the node in that element
+  int32_t *d_eeqn = nullptr;         // (24, n_owned_elems) equation number of each element dof, 0 = constrained
+  double *d_kdiag = nullptr, *d_kcoef = nullptr;
+  void release() {
+    cudaFree(d_eqn_node); cudaFree(d_eqn_comp); cudaFree(d_row_start); cudaFree(d_kidx);
+    cudaFree(d_inv_ptr); cudaFree(d_inv_epos); cudaFree(d_inv_lnode); cudaFree(d_eeqn);
+    cudaFree(d_kdiag); cudaFree(d_kcoef);
+    *this = AssemblyData();
+  }
+};
+
+
+}  // namespace w3d

@@ -16,6 +16,10 @@
 #include "w3d_stress_kernel.cuh"
 #include "w3d_tanstf_kernel.cuh"
 #include "w3d_cp_kernel.h"
+#include "w3d_assemble_data.h"
+#include <algorithm>
+#include <type_traits>
+#include <utility>
 
 using namespace w3d;
 
@@ -83,6 +87,7 @@ struct w3d_engine {
   double dt = 1.0;
   w3d_scalars last{};
   bool have_vectors = false;
+  AssemblyData assembly;            // assembled-equations path (w3d_assemble.cuh)
 
   int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -212,6 +217,7 @@ void free_all(w3d_engine *h) {
     cudaFree(s.hist_n1); cudaFree(s.elem_vol); cudaFree(s.partials);
     cudaFree(s.d_cprops); cudaFree(s.scratch);
   }
+  h->assembly.release();
   cudaFree(h->d_c); cudaFree(h->d_u); cudaFree(h->d_du); cudaFree(h->d_ifv);
   cudaFree(h->d_estiff); cudaFree(h->d_scal); cudaFree(h->d_flags); cudaFree(h->d_stage);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -769,3 +775,5 @@ int32_t w3d_engine_synchronize(w3d_engine *h) {
 int64_t w3d_engine_launch_count(const w3d_engine *h) { return h ? h->launches : -1; }
 
 }  // extern "C"
+
+#include "w3d_assemble.cuh"   // element stiffnesses -> assembled sparse equations (NEXT-1)

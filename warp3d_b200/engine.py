@@ -34,6 +34,7 @@ EXPORTS = (
     "w3d_tanstf_resident", "w3d_last_scalars", "w3d_engine_stream", "w3d_engine_synchronize",
     "w3d_engine_launch_count", "w3d_upload_displacements", "w3d_download_ifv",
     "w3d_download_estiff", "w3d_set_time_step",
+    "w3d_assemble_setup", "w3d_assemble_structure", "w3d_assemble",
 )
 
 
@@ -241,6 +242,37 @@ class Engine:
                                 _ptr(out) if to_host else None)
         self._check(rc)
         return out
+
+    # ---- assembled equilibrium equations (assemble_code.f), symmetric, one domain
+    def assemble_setup(self, cstmap):
+        """dof_map + sparsity of the upper triangle for the constraint map `cstmap` (nodof ints,
+        0 = free).  Returns dict(neqns, ncoeff, dof_eqn_map, eqn_node_map, k_ptrs, k_indexes)."""
+        cst = np.ascontiguousarray(cstmap, dtype=np.int32)
+        ed = np.ascontiguousarray(self.model.edest, dtype=np.int32)
+        neq, nco = C.c_int32(), C.c_int64()
+        self._check(self._L.w3d_assemble_setup(self._h, _ptr(cst), _ptr(ed), C.byref(neq), C.byref(nco)))
+        self._neqns, self._ncoeff = neq.value, nco.value
+        out = dict(neqns=neq.value, ncoeff=nco.value,
+                   dof_eqn_map=np.empty(self.model.nodof, dtype=np.int32),
+                   eqn_node_map=np.empty(neq.value, dtype=np.int32),
+                   k_ptrs=np.empty(neq.value, dtype=np.int32),
+                   k_indexes=np.empty(max(nco.value, 1), dtype=np.int32))
+        self._check(self._L.w3d_assemble_structure(self._h, _ptr(out["dof_eqn_map"]), _ptr(out["eqn_node_map"]),
+                                                   _ptr(out["k_ptrs"]), _ptr(out["k_indexes"])))
+        out["k_indexes"] = out["k_indexes"][:nco.value]
+        return out
+
+    def assemble(self, k_diag=None, k_coeffs=None, to_host=True):
+        """assem_by_row on the element stiffnesses of the last tanstf pass -> (k_diag, k_coeffs)."""
+        if to_host:
+            if k_diag is None:
+                k_diag = np.empty(self._neqns)
+            if k_coeffs is None:
+                k_coeffs = np.empty(max(self._ncoeff, 1))
+            self._check(self._L.w3d_assemble(self._h, _ptr(k_diag), _ptr(k_coeffs)))
+            return k_diag, k_coeffs[:self._ncoeff]
+        self._check(self._L.w3d_assemble(self._h, None, None))
+        return None, None
 
     def update(self):
         self._check(self._L.w3d_update(self._h))
