@@ -20,11 +20,13 @@ struct AssemblyData {
   int32_t *d_inv_ptr = nullptr;      // (nonode + 1) into the two lists below
   int32_t *d_inv_epos = nullptr;     // position of the element in d_estiff / d_eeqn
   int8_t *d_inv_lnode = nullptr;     // local node number (0..7) of the node in that element
+  int32_t *d_dof_eqn = nullptr;      // (nodof) equation number of each structure dof, 0 = constrained
+  int max_row = 0;                   // longest row (terms right of the diagonal)
   int32_t *d_eeqn = nullptr;         // (24, n_owned_elems) equation number of each element dof, 0 = constrained
   double *d_kdiag = nullptr, *d_kcoef = nullptr;
   void release() {
     cudaFree(d_eqn_node); cudaFree(d_eqn_comp); cudaFree(d_row_start); cudaFree(d_kidx);
-    cudaFree(d_inv_ptr); cudaFree(d_inv_epos); cudaFree(d_inv_lnode); cudaFree(d_eeqn);
+    cudaFree(d_inv_ptr); cudaFree(d_inv_epos); cudaFree(d_inv_lnode); cudaFree(d_eeqn); cudaFree(d_dof_eqn);
     cudaFree(d_kdiag); cudaFree(d_kcoef);
     *this = AssemblyData();
   }
