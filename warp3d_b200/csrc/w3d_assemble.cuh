@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) k_assemble_rows(
 constexpr int ASM_WARPS = 4;       // warps (nodes) per CTA
 constexpr int ASM_MAXROW = 192;    // longest row this kernel takes (81 on a structured hex8 mesh)
 __global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_nodes(
-    int nonode, const int32_t *__restrict__ dof_eqn, const int32_t *__restrict__ inv_ptr,
+    int node0, int nonode, const int32_t *__restrict__ dof_eqn, const int32_t *__restrict__ inv_ptr,
     const int32_t *__restrict__ inv_epos, const int8_t *__restrict__ inv_lnode,
     const int32_t *__restrict__ eeqn, const double *__restrict__ estiff,
     const long long *__restrict__ row_start, const int32_t *__restrict__ kidx,
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_nodes(
   __shared__ int32_t scols[ASM_WARPS][3][ASM_MAXROW];
   __shared__ double sdiag[ASM_WARPS][3];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int node = blockIdx.x * ASM_WARPS + w;
+  const int node = node0 + blockIdx.x * ASM_WARPS + w;   // nodes [node0, nonode)
   if (node >= nonode) return;
   int srow[3], n[3];
   long long rs[3];
@@ -250,6 +250,14 @@ int32_t w3d_assemble_setup(w3d_engine *h, const int32_t *cstmap, const int32_t *
   CUDA_TRY(up(&A.d_inv_lnode, inv_lnode));
   CUDA_TRY(up(&A.d_eeqn, eeqn));
   CUDA_TRY(up(&A.d_dof_eqn, A.dof_eqn_map));
+  A.h_row_start = row_start;
+  A.node_first_eqn.assign(nonode + 1, neq);
+  for (int r = neq - 1; r >= 0; --r) A.node_first_eqn[A.eqn_node_map[r] - 1] = r;
+  for (int nd = nonode - 1; nd >= 0; --nd)          // nodes without a free dof take the next node's
+    if (A.node_first_eqn[nd] > A.node_first_eqn[nd + 1]) A.node_first_eqn[nd] = A.node_first_eqn[nd + 1];
+  CUDA_TRY(cudaStreamCreateWithFlags(&A.copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < AssemblyData::NCHUNK; ++k)
+    CUDA_TRY(cudaEventCreateWithFlags(&A.chunk_done[k], cudaEventDisableTiming));
   A.max_row = 0;
   for (int r = 0; r < neq; ++r) A.max_row = std::max(A.max_row, (int)A.k_ptrs[r]);
   CUDA_TRY(cudaMalloc((void **)&A.d_kdiag, sizeof(double) * (size_t)neq));
@@ -281,10 +289,38 @@ int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs) {
   if (!A.ready) return h->fail(W3D_ERR_ARG, "w3d_assemble_setup has not been called");
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   CUDA_TRY(cudaSetDevice(h->device));
+  if (A.max_row <= ASM_MAXROW && k_diag && k_coeffs && A.copy_stream) {
+    // host output: assemble node ranges one after the other and start the copy of each range's
+    // rows (equations are numbered in node order, so they are contiguous) on a second stream as
+    // soon as its kernel is done -- the assembly hides behind the PCIe transfer
+    const int nonode = h->cfg.nonode;
+    const int nchunk = AssemblyData::NCHUNK;
+    for (int k = 0; k < nchunk; ++k) {
+      const int na = (int)((long long)nonode * k / nchunk), nb = (int)((long long)nonode * (k + 1) / nchunk);
+      if (nb <= na) continue;
+      k_assemble_nodes<<<(nb - na + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
+          na, nb, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn, h->d_estiff,
+          A.d_row_start, A.d_kidx, A.d_kdiag, A.d_kcoef);
+      CUDA_TRY(cudaGetLastError());
+      h->launches += 1;
+      CUDA_TRY(cudaEventRecord(A.chunk_done[k], h->stream));
+      CUDA_TRY(cudaStreamWaitEvent(A.copy_stream, A.chunk_done[k], 0));
+      const int ea = A.node_first_eqn[na], eb = A.node_first_eqn[nb];   // equations [ea, eb)
+      if (eb > ea) {
+        const long long ca = A.h_row_start[ea], cb = A.h_row_start[eb];
+        CUDA_TRY(cudaMemcpyAsync(k_diag + ea, A.d_kdiag + ea, sizeof(double) * (size_t)(eb - ea), cudaMemcpyDeviceToHost, A.copy_stream));
+        if (cb > ca)
+          CUDA_TRY(cudaMemcpyAsync(k_coeffs + ca, A.d_kcoef + ca, sizeof(double) * (size_t)(cb - ca), cudaMemcpyDeviceToHost, A.copy_stream));
+      }
+    }
+    CUDA_TRY(cudaStreamSynchronize(A.copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return W3D_OK;
+  }
   if (A.max_row <= ASM_MAXROW) {
     const int nonode = h->cfg.nonode;
     k_assemble_nodes<<<(nonode + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
-        nonode, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn, h->d_estiff,
+        0, nonode, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn, h->d_estiff,
         A.d_row_start, A.d_kidx, A.d_kdiag, A.d_kcoef);
   } else {   // very long rows (nodes shared by many elements): thread per equation
     const int tpb = 128;

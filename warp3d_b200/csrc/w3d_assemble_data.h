@@ -21,10 +21,18 @@ struct AssemblyData {
   int32_t *d_inv_epos = nullptr;     // position of the element in d_estiff / d_eeqn
   int8_t *d_inv_lnode = nullptr;     // local node number (0..7) of the node in that element
   int32_t *d_dof_eqn = nullptr;      // (nodof) equation number of each structure dof, 0 = constrained
+  static constexpr int NCHUNK = 8;   // node ranges whose copy to the host overlaps the next range's assembly
+  std::vector<long long> h_row_start;   // (neqns + 1) host copy of d_row_start
+  std::vector<int32_t> node_first_eqn;  // (nonode + 1) first equation (0-based) at or after each node
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t chunk_done[NCHUNK] = {};
   int max_row = 0;                   // longest row (terms right of the diagonal)
   int32_t *d_eeqn = nullptr;         // (24, n_owned_elems) equation number of each element dof, 0 = constrained
   double *d_kdiag = nullptr, *d_kcoef = nullptr;
   void release() {
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (int k = 0; k < NCHUNK; ++k)
+      if (chunk_done[k]) cudaEventDestroy(chunk_done[k]);
     cudaFree(d_eqn_node); cudaFree(d_eqn_comp); cudaFree(d_row_start); cudaFree(d_kidx);
     cudaFree(d_inv_ptr); cudaFree(d_inv_epos); cudaFree(d_inv_lnode); cudaFree(d_eeqn); cudaFree(d_dof_eqn);
     cudaFree(d_kdiag); cudaFree(d_kcoef);
