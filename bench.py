@@ -8,7 +8,9 @@ structured 2M-element hex8 mesh with mm01 (geonl, B-bar), state at n prepared by
 load step so that about half of the Gauss points are plastic in the timed iteration.
 
   value   Gauss-point updates/s with u, du and all state resident in HBM (whole job, all ranks)
-  e2e     same metric through the host-buffer C-ABI calls (H2D of u, du; D2H of ifv and estiff)
+  e2e     same metric through the host-buffer C-ABI calls: H2D of u, du; D2H of ifv and of the
+          stiffness ASSEMBLED on the device (w3d_assemble: k_diag, k_coeffs); e2e_element_blocks
+          is the variant that returns the estiff(300,span) blocks instead (the only one at N > 1)
   roofline, cpu_baseline, clocks: as the brief defines them.
 
 `--impl reference` times the CPU restatement of the reference path (oracle/, OpenMP over blocks
@@ -34,6 +36,9 @@ WORKLOADS = {
     "hex8_256k_mm01": ((64, 64, 64), "mm01", (64, 50, 50)),    # smaller variant for quick checks
     "hex8_1m_mm10": ((100, 100, 100), "mm10", (32, 25, 25)),   # BASELINE.json configs[4]: CP polycrystal
     "hex8_64k_mm10": ((40, 40, 40), "mm10", (32, 25, 25)),
+    # mm05 cyclic plasticity, both options (the GP one with the reference's own deck values, ksi)
+    "hex8_256k_mm05_fa": ((64, 64, 64), "mm05_fa", (32, 25, 25)),
+    "hex8_256k_mm05_gp": ((64, 64, 64), "mm05_gp", (32, 25, 25)),
 }
 # mm10 workload: fcc (12 slip systems), Voce hardening with the property values of
 # verification/test82/voche_model/warp3d_voche.inp:6-10, one crystal per element, Kocks angles
@@ -51,6 +56,11 @@ def make_workload(name, dims=None):
     if kind == "mm01":
         m = build_structured_hex8(*dims)
         return m, 0.5 * graded_stretch(m), 1
+    if kind.startswith("mm05"):
+        from warp3d_b200 import cyclic_fa_material, cyclic_gp_material
+        mat = cyclic_fa_material() if kind == "mm05_fa" else cyclic_gp_material()
+        m = build_structured_hex8(*dims, materials=[mat])
+        return m, 0.5 * graded_stretch(m), 1      # yield strain 2e-3 for both, as for mm01
     m = build_structured_hex8(*dims, materials=[Material(mat_type=10)], dt=1.0)
     attach_crystals(m, make_crystal_type(**MM10_CRYSTAL), ncrystals=1)
     return m, 0.25 * graded_stretch(m, eps_lo=3.0e-3, eps_hi=9.0e-3), 2
@@ -58,6 +68,11 @@ def make_workload(name, dims=None):
 
 def workload_description(name):
     kind = WORKLOADS[name][1]
+    if kind.startswith("mm05"):
+        # as mm01 with 14 history words per point instead of 11 (3 x 8 B more each way)
+        return dict(material={"mm05_fa": "mm05 cyclic, nonlinear_hardening (q_u 100e6, b_u 20, h_u 10e9, gamma_u 50)",
+                              "mm05_gp": "mm05 cyclic, generalized_plasticity (verification/test39 values, ksi)"}[kind],
+                    bytes_stress=776.0 + 48.0, bytes_tanstf=708.0)
     if kind == "mm01":
         # FP64 flops per Gauss point: 2 x DFMA + DMUL + DADD executed (predicated-on thread
         # instructions / Gauss points) from the ncu per-instruction counts of the two kernels on the
@@ -368,7 +383,7 @@ def engine_arm(args):
         value = ngp_total / (ms_per_step * 1e-3)
         # dominant kernel = the one with the longer average launch; per-launch units = owned GPs
         ngp_own = nel_own * 8
-        sname = "k_eps_sig_ifv" if WORKLOADS[args.workload][1] == "mm01" else "k_eps_sig_ifv<phase 1,2> + k_mm10"
+        sname = "k_eps_sig_ifv<phase 1,2> + k_mm10" if WORKLOADS[args.workload][1] == "mm10" else "k_eps_sig_ifv"
         k_name, k_ms, k_bytes = (("k_tanstf", t_tan, wd["bytes_tanstf"]) if t_tan >= t_stress
                                  else (sname, t_stress, wd["bytes_stress"]))
         ach = ngp_own * k_bytes / (k_ms * 1e-3) / 1e9
