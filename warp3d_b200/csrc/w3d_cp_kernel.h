@@ -16,6 +16,7 @@ struct CpArgs {
   long long ng;
   double dt;
   int step, iter_0_extrapolate_off, asymmetric, ncrystals, nslip, num_hard;
+  int ncta;                   // number of CTA descriptors (set by launch_mm10)
 };
 
 int mm10_props_doubles();

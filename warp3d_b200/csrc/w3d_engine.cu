@@ -434,13 +434,16 @@ int create_impl(w3d_engine *h) {
 }
 
 template <int MAT, int PHASE>
-void launch_stress(const Segment &sg, const StressArgs &a, cudaStream_t st) {
+void launch_stress(const Segment &sg, const StressArgs &a0, cudaStream_t st) {
+  StressArgs a = a0;
+  a.ncta = sg.ncta;                                                  // 16-element groups
+  const int grid = (sg.ncta + STRESS_GROUPS - 1) / STRESS_GROUPS;    // CTAs of STRESS_GROUPS groups
   if (sg.geonl) {
-    if (sg.bbar) k_eps_sig_ifv<MAT, true, true, PHASE><<<sg.ncta, TPB, 0, st>>>(a);
-    else k_eps_sig_ifv<MAT, true, false, PHASE><<<sg.ncta, TPB, 0, st>>>(a);
+    if (sg.bbar) launch_stress_kernel(k_eps_sig_ifv<MAT, true, true, PHASE>, grid, a, st);
+    else launch_stress_kernel(k_eps_sig_ifv<MAT, true, false, PHASE>, grid, a, st);
   } else {
-    if (sg.bbar) k_eps_sig_ifv<MAT, false, true, PHASE><<<sg.ncta, TPB, 0, st>>>(a);
-    else k_eps_sig_ifv<MAT, false, false, PHASE><<<sg.ncta, TPB, 0, st>>>(a);
+    if (sg.bbar) launch_stress_kernel(k_eps_sig_ifv<MAT, false, true, PHASE>, grid, a, st);
+    else launch_stress_kernel(k_eps_sig_ifv<MAT, false, false, PHASE>, grid, a, st);
   }
 }
 

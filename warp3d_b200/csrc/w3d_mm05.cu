@@ -19,15 +19,16 @@ cudaError_t mm05_set_shape_table(const double *tab3, size_t bytes) {
   return cudaMemcpyToSymbol(c_shape, tab3, bytes);
 }
 
-cudaError_t launch_stress_mm05(bool geonl, bool bbar, int ncta, const StressArgs &a, cudaStream_t st) {
+cudaError_t launch_stress_mm05(bool geonl, bool bbar, int ncta, const StressArgs &a0, cudaStream_t st) {
+  StressArgs a = a0;
+  a.ncta = ncta;
+  const int grid = (ncta + STRESS_GROUPS - 1) / STRESS_GROUPS;
   if (geonl) {
-    if (bbar) k_eps_sig_ifv<5, true, true, 0><<<ncta, TPB, 0, st>>>(a);
-    else k_eps_sig_ifv<5, true, false, 0><<<ncta, TPB, 0, st>>>(a);
-  } else {
-    if (bbar) k_eps_sig_ifv<5, false, true, 0><<<ncta, TPB, 0, st>>>(a);
-    else k_eps_sig_ifv<5, false, false, 0><<<ncta, TPB, 0, st>>>(a);
+    if (bbar) return launch_stress_kernel(k_eps_sig_ifv<5, true, true, 0>, grid, a, st);
+    return launch_stress_kernel(k_eps_sig_ifv<5, true, false, 0>, grid, a, st);
   }
-  return cudaGetLastError();
+  if (bbar) return launch_stress_kernel(k_eps_sig_ifv<5, false, true, 0>, grid, a, st);
+  return launch_stress_kernel(k_eps_sig_ifv<5, false, false, 0>, grid, a, st);
 }
 
 }  // namespace w3d

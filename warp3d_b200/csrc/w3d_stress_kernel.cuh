@@ -42,6 +42,7 @@ struct StressArgs {
   // k_mm10 material update, PHASE 2 internal force + lattice-curvature fit
   double *scratch;                // [16][ng]: R(n+1) 9 (column-major), uddt 6, energy factor 1
   int cp_ncrystals, cp_o_gradfe, cp_o_Rp;   // history offsets (w3d_mm10::Layout)
+  int ncta;                       // number of CTA descriptors of the segment (set by the launcher)
 };
 
 // parent-space shape function derivatives of the 8 Gauss points: [dir][node][gp], filled by the
@@ -53,9 +54,40 @@ static __constant__ double c_shape[3][8][8];
 cudaError_t mm05_set_shape_table(const double *tab3, size_t bytes);
 cudaError_t launch_stress_mm05(bool geonl, bool bbar, int ncta, const struct StressArgs &a, cudaStream_t st);
 
-#ifndef STRESS_MIN_CTAS
-#define STRESS_MIN_CTAS 4   // register cap 128/thread -> 4 CTAs (16 warps) per SM
+// A CTA takes STRESS_GROUPS consecutive 16-element groups (CTA descriptors): the warps of a CTA
+// start together and walk the same ~70 KB of straight-line code, so a larger CTA shares more of
+// the instruction fetch (the kernel's second largest stall), at the same 16 warps per SM.
+// Measured on the 2 M-element mm01 mesh: 1 group (128 threads) 5.01 ms, 2 groups 4.71 ms.
+#ifndef STRESS_GROUPS
+#define STRESS_GROUPS 2
 #endif
+#ifndef STRESS_MIN_CTAS
+#define STRESS_MIN_CTAS (4 / STRESS_GROUPS)   // register cap 128/thread -> 16 warps per SM
+#endif
+constexpr int STPB = TPB * STRESS_GROUPS;   // threads per CTA of the stress kernel
+constexpr int SEPC = EPC * STRESS_GROUPS;   // elements per CTA
+constexpr int NSTATE_IN = 6 + 9 + 14;       // eps_n, urcs_n, hist_n (11 mm01 / 14 mm05) per Gauss point
+// shape table 192, c/u/du 3 x SEPC x 24, per-warp sums (+1 pad), state at n NSTATE_IN x STPB
+constexpr int STRESS_SMEM_BYTES =
+    (int)sizeof(double) * (192 + 3 * SEPC * 24 + (STPB / 32) * 3 + 1 + NSTATE_IN * STPB);
+
+// launches one instantiation with its dynamic shared memory (opt-in above 48 KB, once per kernel)
+inline cudaError_t launch_stress_kernel(void (*k)(const struct StressArgs), int grid,
+                                        const struct StressArgs &a, cudaStream_t st) {
+  if (STRESS_SMEM_BYTES > 48 * 1024) {
+    static const void *done[64];
+    static int ndone = 0;
+    bool seen = false;
+    for (int i = 0; i < ndone; ++i) seen = seen || done[i] == (const void *)k;
+    if (!seen) {
+      const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, STRESS_SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+      if (ndone < 64) done[ndone++] = (const void *)k;
+    }
+  }
+  k<<<grid, STPB, STRESS_SMEM_BYTES, st>>>(a);
+  return cudaGetLastError();
+}
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): state at n streams in while the
 // kinematics run, so no warp waits on HBM latency when the material update starts
@@ -65,8 +97,6 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_s
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-constexpr int NSTATE_IN = 6 + 9 + 14;   // eps_n, urcs_n, hist_n (11 mm01 / 14 mm05) per Gauss point
 
 // Jacobian with the node loop kept rolled: shape derivatives and coordinates are re-read from
 // shared memory each trip, so only the 9 accumulators are live (register pressure, not smem
@@ -170,19 +200,26 @@ __device__ __forceinline__ void jacobian_matrix_exact(const double (*sN)[8][8], 
 }
 
 template <int MAT, bool GEONL, bool BBAR, int PHASE = 0>
-__global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const StressArgs a) {
-  __shared__ double sN[3][8][8];
-  __shared__ double sC[EPC][24], sU[EPC][24], sDU[EPC][24];
-  __shared__ double sRed[TPB / 32][3];
-  __shared__ double sSt[NSTATE_IN][TPB];   // state at n, [component][thread]: conflict free
+__global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const StressArgs a) {
+  // dynamic shared memory (STRESS_SMEM_BYTES; above the 48 KB static limit for STRESS_GROUPS = 2)
+  extern __shared__ double dsm[];
+  double (*sN)[8][8] = reinterpret_cast<double (*)[8][8]>(dsm);                       // [3][8][8]
+  double (*sC)[24] = reinterpret_cast<double (*)[24]>(dsm + 192);                     // [SEPC][24]
+  double (*sU)[24] = sC + SEPC, (*sDU)[24] = sC + 2 * SEPC;
+  double (*sRed)[3] = reinterpret_cast<double (*)[3]>(dsm + 192 + 3 * SEPC * 24);     // [STPB/32][3]
+  // state at n, [component][thread]: conflict free
+  double (*sSt)[STPB] = reinterpret_cast<double (*)[STPB]>(dsm + 192 + 3 * SEPC * 24 + (STPB / 32) * 3 + 1);
 
   const int tid = threadIdx.x;
-  for (int k = tid; k < 192; k += TPB) (&sN[0][0][0])[k] = (&c_shape[0][0][0])[k];
+  for (int k = tid; k < 192; k += STPB) (&sN[0][0][0])[k] = (&c_shape[0][0][0])[k];
 
-  const CtaDesc cd = a.cta[blockIdx.x];
-  const int el = tid >> 3, gp = tid & 7;
-  const bool valid = el < cd.nvalid;
-  const int slot = cd.slot0 + (valid ? el : cd.nvalid - 1);
+  const int idesc = blockIdx.x * STRESS_GROUPS + tid / TPB;   // this thread's 16-element group
+  const bool have = idesc < a.ncta;
+  const CtaDesc cd = a.cta[have ? idesc : a.ncta - 1];
+  const int el = tid >> 3, gp = tid & 7;                       // element within the CTA
+  const int elg = el % EPC;                                    // ... within its group
+  const bool valid = have && elg < cd.nvalid;
+  const int slot = cd.slot0 + (elg < cd.nvalid ? elg : cd.nvalid - 1);
   const long long g = (long long)slot * 8 + gp;
   const long long ng = a.ng;
 
@@ -640,11 +677,12 @@ __global__ void __launch_bounds__(TPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Stre
   en = warp_sum(en); pw = warp_sum(pw); sabs = warp_sum(sabs);
   if ((tid & 31) == 0) { sRed[tid >> 5][0] = en; sRed[tid >> 5][1] = pw; sRed[tid >> 5][2] = sabs; }
   __syncthreads();
-  if (tid < 3) {
+  if (tid % TPB < 3 && have) {     // one partial per 16-element group, as the host reduces them
+    const int q = tid % TPB, w0 = (tid / TPB) * (TPB / 32);
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < TPB / 32; ++w) v += sRed[w][tid];
-    a.partials[(size_t)blockIdx.x * 4 + tid] = v;
+    for (int w = 0; w < TPB / 32; ++w) v += sRed[w0 + w][q];
+    a.partials[(size_t)idesc * 4 + q] = v;
   }
 }
 
