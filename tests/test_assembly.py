@@ -97,3 +97,23 @@ def test_device_assembly_matches_the_restatement_bit_for_bit(constrained):
     kd2, kc2 = e.assemble()
     assert np.array_equal(kd2, kd) and np.array_equal(kc2, kc)
     e.close()
+
+
+@pytest.mark.gpu
+def test_device_assembly_refuses_what_is_not_built():
+    from warp3d_b200 import slab_domains
+    from warp3d_b200.engine import Engine, EngineError
+    m, cst = _case(nx=4, ny=3, nz=3, seed=3, block_size=6)
+    e = Engine(m)
+    with pytest.raises(EngineError) as err:          # assemble before set-up
+        e._neqns, e._ncoeff = 1, 1
+        e.assemble()
+    assert "w3d_assemble_setup" in str(err.value)
+    e.close()
+    # several domains: rows at interface nodes would need the neighbours' elements
+    m.elblks[:, 2] = slab_domains(m, 2)
+    e2 = Engine(m, myid=0, numprocs=2)
+    with pytest.raises(EngineError) as err:
+        e2.assemble_setup(cst)
+    assert "one domain" in str(err.value)
+    e2.close()
