@@ -11,9 +11,9 @@ from warp3d_b200 import (Material, attach_crystals, build_structured_hex8, make_
 pytestmark = pytest.mark.gpu
 
 
-def _model(nx, ny, nz, ncrystals=1, geonl=True, bbar=True, dt=0.5, **kw):
-    ct = make_crystal_type(e=100000.0, nu=0.3, harden_n=20, tau_y=100.0, tau_v=50.0, theta_o=500.0,
-                           voche_m=1.0)
+def _model(nx, ny, nz, ncrystals=1, geonl=True, bbar=True, dt=0.5, crystal=None, **kw):
+    ct = make_crystal_type(**(crystal or dict(e=100000.0, nu=0.3, harden_n=20, tau_y=100.0, tau_v=50.0,
+                                              theta_o=500.0, voche_m=1.0)))
     m = build_structured_hex8(nx, ny, nz, materials=[Material(mat_type=10)], geonl=geonl, bbar=bbar,
                               coord_jitter=0.1, seed=7, dt=dt, **kw)
     return attach_crystals(m, ct, ncrystals=ncrystals)
@@ -74,3 +74,11 @@ def test_single_crystal_small_strain():
 
 def test_polycrystal_three_crystals_per_point():
     assert _run(_model(2, 2, 1, ncrystals=3), nsteps=2, strain=3.0e-3) > 0.0
+
+
+def test_bcc_crystal_with_the_reference_voche_deck_values():
+    # verification/test82/voche_model/warp3d_voche.inp:6-10: slip_type bcc, e 150000 nu 0.28,
+    # harden_n 20 voce_m 5.0 theta_0 400 tau_y 300 tau_v 1200 (m = 5: the non-trivial Voce exponent)
+    ct = dict(e=150000.0, nu=0.28, slip="bcc", harden_n=20.0, voche_m=5.0, theta_o=400.0, tau_y=300.0,
+              tau_v=1200.0)
+    assert _run(_model(2, 2, 2, geonl=False, crystal=ct), nsteps=3, strain=3.0e-3) > 0.0

@@ -374,10 +374,12 @@ def make_crystal_type(e=69000.0, nu=0.33, mu=None, elastic="isotropic", slip="fc
     (CRYSTAL_TYPE_DOUBLES,) float64 record."""
     if slip == "fcc":
         bi, ni = fcc_slip_systems()
+    elif slip == "bcc":            # slip_type 2 (src/mod_crystals.f:519-596): the fcc table with
+        ni, bi = fcc_slip_systems()    # directions and normals exchanged, {110}<111>, 12 systems
     elif slip == "bcc48":          # 48 systems: CPU restatement only (the engine builds <= 12)
         bi, ni = bcc48_slip_systems()
     else:
-        raise NotImplementedError("slip tables built: fcc, bcc48")
+        raise NotImplementedError("slip tables built: fcc, bcc, bcc48")
     nslip = bi.shape[0]
     if mu is None:
         mu = e / 2.0 / (1.0 + nu)
