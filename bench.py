@@ -79,7 +79,11 @@ def workload_description(name):
         # 50 %-plastic workload (profiles/r01_summary.md "mm01 instruction mix"); the hand count of
         # the algorithm agrees to a few percent
         return dict(material="mm01 bilinear (E=200e9 as real*4, nu=0.3, yld=400e6, tan_e=E/100)",
-                    bytes_stress=776.0, bytes_tanstf=708.0, flops_stress=3573.0, flops_tanstf=4540.0)
+                    bytes_stress=776.0, bytes_tanstf=708.0, flops_stress=3573.0, flops_tanstf=4540.0,
+                    # measured DRAM bytes per Gauss point (dram__bytes_read + write of one `ncu --set
+                    # full` launch on hex8_256k_mm01 / 2 097 152 points, profiles/r01_mm01_*_256k_ncu.csv)
+                    dram_stress=(533.111552e6 + 1038.039e6) / 2097152.0,
+                    dram_tanstf=(674.389760e6 + 583.456512e6) / 2097152.0)
     # per Gauss point: history 2 x 158 x 8, urcs 2 x 72, eps 2 x 48, rot 72, scratch 2 x 128,
     # crystal properties 1448/8, element vectors 120  (DESIGN.md "mm10")
     return dict(material="mm10 crystal plasticity: fcc 12 slip, Voce (test82/voche_model values), 1 crystal/element",
@@ -406,7 +410,11 @@ def engine_arm(args):
             stress_pass=dict(ms=t_stress, gp_updates_per_s=ngp_total / (t_stress * 1e-3)),
             stiffness_pass=dict(ms=t_tan, element_stiffnesses_per_s=model.noelem / (t_tan * 1e-3)),
             roofline=dict(bound="hbm", kernel=k_name, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
-                          peak_kind=f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)", traffic=None,
+                          peak_kind=f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)",
+                          traffic=(ngp_own * wd["dram_tanstf" if k_name == "k_tanstf" else "dram_stress"]
+                                   if "dram_stress" in wd else None),
+                          traffic_note="bytes per launch = DRAM bytes per point of one ncu --set full launch "
+                                       "(256k-element mesh) x points of this launch",
                           bytes_per_gp=k_bytes, launch_ms=k_ms,
                           other_kernel=dict(kernel=other[0], launch_ms=other[1],
                                             achieved=ngp_own * other[2] / (other[1] * 1e-3) / 1e9,
