@@ -14,11 +14,16 @@
  *     Fortran produced -- the 79-point stretch/relaxation curve published with
  *     example_problems_cp/simple_voce is reproduced to 1.1e-5 at worst, 1e-7 at 80 h
  *     (tests/test_reference_known_answers.py).
- *   - everything else (mm01, mm05, the finite-strain kinematics): "parity unpinned" -- pinned only
- *     by (i) literal transcription and (ii) physics invariants in tests/ (patch test, rigid
- *     rotation, finite-difference tangents, K u = f, symmetry, closed-form uniaxial response); the
- *     reference's known answers for those models all need temperature-dependent properties or
- *     element types outside this path.
+ *   - mm01 (bilinear Mises) with the finite-strain kinematics (polar decomposition, un-rotated
+ *     rates), B-bar, internal force and tangent: PINNED end to end by the reference's known answer
+ *     for verification/test24 (hollow sphere sector, 21 elastic-plastic load steps, the inner
+ *     radius grows by a quarter, skew constraints): sigma_xx of element 1 = -205.046618 here against
+ *     -205.047360 printed by the Fortran, 3.6e-6 (same test file; the reference's own tolerance for
+ *     this number is 1e-4 and it stops its Newton loop at 1e-5).
+ *   - mm05 (both options): "parity unpinned" -- pinned only by (i) literal transcription and (ii)
+ *     physics invariants in tests/ (yield-surface consistency, finite-difference tangents, cyclic
+ *     saturation); the reference's known answers for mm05 all use temperature-dependent
+ *     properties or meshes of other element types.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load
  * this library.  The CUDA engine (warp3d_b200/) must never include or link it.

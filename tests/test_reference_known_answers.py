@@ -1,6 +1,7 @@
 """Known answers published with the reference, reproduced with the CPU restatement (oracle/):
 the only place where results of this repository can be laid next to numbers the Fortran itself
-produced (it cannot be built here).
+produced (it cannot be built here).  Two of them are within reach of the path: simple_voce (mm10,
+small strain) and verification/test24 (mm01, finite strain), below.
 
 example_problems_cp/simple_voce (rhdodds/warp3d): a unit cube stretched in z for 5 h and then held
 for 75 h while the stress relaxes; crystal plasticity with Voce hardening, bcc48 slip, 25 crystal
@@ -107,3 +108,83 @@ def test_simple_voce_one_element_is_not_the_same_problem():
     sr = np.array(ref["stress_cp"][1:13])
     rel = np.abs(stress - sr) / sr
     assert rel[:3].max() < 2.0e-5 and 5.0e-4 < rel[9:].max() < 3.0e-3
+
+
+# ---- verification/test24: hollow sphere sector, mm01 bilinear, geonl + B-bar, skew constraints -----
+def _run_test24(nsteps=21):
+    ref = json.load(open(os.path.join(HERE, "golden", "test24_reference.json")))
+    mat = Material(e=30000.0, nu=0.3, yld_pt=60.0, tan_e=500.0, beta=1.0)
+    m = build_structured_hex8(3, 3, 5, materials=[mat], geonl=True, bbar=True)   # 45 elements, 96 nodes
+    # the deck's own nodes and incidences replace the box: same counts, different numbering
+    inc = np.array(ref["incid"], dtype=np.int32)
+    m.c[:] = np.array(ref["coords"]).reshape(-1)
+    m.incid[:] = inc
+    base = 3 * (inc.astype(np.int64) - 1) + 1
+    m.edest[:] = np.concatenate([base, base + 1, base + 2], axis=1).astype(np.int32).reshape(-1)
+    m.cdest[:] = m.edest
+    m.extrapolated_du = 0
+    n = m.nodof
+    x = m.c.reshape(-1, 3)
+    # node frames: u_local = T u_global (rows of T = local axes); fixed local dofs
+    Q = np.eye(n)
+    fixed = set()
+    for g in ref["skew"]:
+        T = np.array(g["T"])
+        for node in g["nodes"]:
+            s = 3 * (node - 1)
+            Q[s:s + 3, s:s + 3] = T
+            fixed.update(s + k for k in g["fixed"])
+    for node in range(m.nonode):
+        if x[node, 2] == 0.0:
+            fixed.add(3 * node + 2)        # plane z = 0 symmetry
+        if x[node, 1] == 0.0:
+            fixed.add(3 * node + 1)        # plane y = 0 symmetry
+    fixed = np.array(sorted(fixed))
+    free = np.setdiff1d(np.arange(n), fixed)
+    P1 = np.zeros(n)
+    for node, f in ref["loads"].items():
+        P1[3 * (int(node) - 1):3 * int(node)] = f
+    o, st = op.Oracle(m), new_state(m)
+    u = np.zeros(n)
+    factor = 0.0
+    for step in range(1, nsteps + 1):
+        factor += 1.0 if step == 1 else 0.2
+        P = factor * P1
+        du = np.zeros(n)
+        ifv, _ = o.eps_sig_ifv(st, step, 0, u, du)
+        K = assemble(m, o.tanstf(st, step, 0, u, du)).toarray()
+        for it in range(1, 40):
+            r = Q @ (P - ifv)                                   # residual in the node frames
+            Kl = Q @ K @ Q.T
+            dl = np.zeros(n)
+            dl[free] = np.linalg.solve(Kl[np.ix_(free, free)], r[free])
+            du = du + Q.T @ dl
+            ifv, sc = o.eps_sig_ifv(st, step, it, u, du)
+            assert not sc["material_cut_step"], (step, it)
+            rn = np.linalg.norm((Q @ (P - ifv))[free])
+            # (the reference's polar decomposition leaves ~1e-9 of noise in the forces: DESIGN.md 4)
+            if rn <= 1.0e-7 * np.linalg.norm(P):
+                break
+            K = assemble(m, o.tanstf(st, step, it, u, du)).toarray()
+        else:
+            raise AssertionError(f"step {step} did not converge: {rn}")
+        u = u + du
+        o.update(st); o.adaptive_save(st)
+    # "output stresses 1": Cauchy stress = R t R^T at each point, element-centre value = mean
+    t = st.urcs_n.reshape(-1, 8, 9)[0]
+    R = st.rot_n.reshape(-1, 8, 9)[0]
+    sxx = []
+    for gp in range(8):
+        Rm = R[gp].reshape(3, 3).T                              # stored column-major
+        tm = np.array([[t[gp, 0], t[gp, 3], t[gp, 5]], [t[gp, 3], t[gp, 1], t[gp, 4]], [t[gp, 5], t[gp, 4], t[gp, 2]]])
+        sxx.append((Rm @ tm @ Rm.T)[0, 0])
+    return float(np.mean(sxx)), ref, u, m
+
+
+def test_verification_test24_sphere_with_skew_constraints():
+    """mm01 (bilinear, isotropic hardening) with the finite-strain kinematics and B-bar: the
+    reference's known answer for verification/test24, sigma_xx of element 1 after 21 load steps
+    of internal pressure on a hollow sphere sector (the inner radius grows by half)."""
+    sxx, ref, u, m = _run_test24()
+    want = ref["answer"]["value"]
+    assert abs(sxx - want) <= 1.0e-4 * abs(want), (sxx, want)
