@@ -6,8 +6,9 @@
  * block-local arrays with leading dimension mxvl) and its evaluation order; compile with
  * -ffp-contract=off so no FMA contraction changes the arithmetic.
  *
- * PARITY STATUS: parity unpinned (no function-level golden vectors exist in the reference and the
- * reference cannot be built here).  Citations are reference src/ file:line.
+ * PARITY STATUS: no function-level golden vectors exist in the reference and it cannot be built
+ * here; pinned end to end by two of its known answers (see w3d_oracle.h).  Citations are
+ * reference src/ file:line.
  */
 #include "w3d_oracle.h"
 #include "w3d_oracle_internal.h"

@@ -2,7 +2,8 @@
 
 These are *regression* vectors: the reference (ifort-only Fortran + MKL) cannot be built or run
 in this environment and ships no function-level golden vectors for the path, so the fixtures pin
-the oracle's own output, not the Fortran's ("parity unpinned", see oracle/w3d_oracle.h).
+the oracle's own output, not the Fortran's; what ties the oracle to the Fortran is in
+tests/test_reference_known_answers.py (status per model: oracle/w3d_oracle.h).
 Run:  python tests/golden/make_golden.py
 """
 import os
