@@ -20,10 +20,13 @@
  *     radius grows by a quarter, skew constraints): sigma_xx of element 1 = -205.046618 here against
  *     -205.047360 printed by the Fortran, 3.6e-6 (same test file; the reference's own tolerance for
  *     this number is 1e-4 and it stops its Newton loop at 1e-5).
- *   - mm05 (both options): "parity unpinned" -- pinned only by (i) literal transcription and (ii)
- *     physics invariants in tests/ (yield-surface consistency, finite-difference tangents, cyclic
- *     saturation); the reference's known answers for mm05 all use temperature-dependent
- *     properties or meshes of other element types.
+ *   - mm05 (cyclic plasticity), both options, with the same finite-strain chain: PINNED end to end
+ *     by the reference's known answers for verification/test60 a and b (notched bar, 405 elements,
+ *     420 load steps of cyclic end displacement): total axial reaction 0.0210364867 against
+ *     0.021036833 (nonlinear_hardening, 1.6e-5) and 0.0232109041 against 0.023211111
+ *     (generalized_plasticity, 8.9e-6).
+ *   Nothing is pinned at function granularity or at 1e-10: there the status stays "parity
+ *   unpinned" (literal transcription + the physics invariants in tests/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load
  * this library.  The CUDA engine (warp3d_b200/) must never include or link it.

@@ -7,8 +7,8 @@
  *   rstgp1.f:19-332 (rstgp1), :351-598 (rstgp2), :614-1034 (drive_01_update),
  *   :4983-5005, :5168-5241, :5360-5427, gtmat1.f:17-190 (gtmat1), rplstr.f:15-93,
  *   rknifv.f:15-215, gpifv1.f:16-165, addifv.f:86-113, update.f:75-93, mnralg.f:1258-1420.
- * PARITY STATUS: see w3d_oracle.h (mm01 and mm10 pinned end to end by reference known answers,
- * mm05 unpinned).
+ * PARITY STATUS: see w3d_oracle.h (mm01, mm05 and mm10 pinned end to end by reference known
+ * answers at 1e-5; unpinned at function granularity).
  */
 #include <cmath>
 #include <cstdio>

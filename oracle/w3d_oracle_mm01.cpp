@@ -6,8 +6,8 @@
  *   - wbar reads history(1,11) (first element of the block), not (i,11) (mm01.f:843-845)
  *   - lambda_deltat = min(qroot1,qroot2) re-evaluated after the discr<0 branch (mm01.f:864-877)
  *   - cnst1 uses root2 = 1.414213562d0 (10 digits) (mm01.f:1220-1221)
- * PARITY STATUS: see w3d_oracle.h (mm01 and mm10 pinned end to end by reference known answers,
- * mm05 unpinned).
+ * PARITY STATUS: see w3d_oracle.h (mm01, mm05 and mm10 pinned end to end by reference known
+ * answers at 1e-5; unpinned at function granularity).
  */
 #include <cmath>
 #include <cstdint>

@@ -4,8 +4,8 @@
  * (dptstf_blocks), dptstf.f:16-215, rktstf.f:15-296, gptns1.f:16-342 (gptns1, gptns1_a),
  * :837-878 (drive_01_cnst), :1174-1283 (extract_D_symmetric), :1628-1718 (bdbtgen),
  * :1735-1970 (ctran1, ctran1_qbar), kg1.f:16-160 (kgstiff, symmetric assembly).
- * PARITY STATUS: see w3d_oracle.h (mm01 and mm10 pinned end to end by reference known answers,
- * mm05 unpinned).
+ * PARITY STATUS: see w3d_oracle.h (mm01, mm05 and mm10 pinned end to end by reference known
+ * answers at 1e-5; unpinned at function granularity).
  */
 #include <cmath>
 #include <cstring>

@@ -1,7 +1,8 @@
 """Known answers published with the reference, reproduced with the CPU restatement (oracle/):
 the only place where results of this repository can be laid next to numbers the Fortran itself
-produced (it cannot be built here).  Two of them are within reach of the path: simple_voce (mm10,
-small strain) and verification/test24 (mm01, finite strain), below.
+produced (it cannot be built here).  Four of them are within reach of the path and cover every
+material model it builds: simple_voce (mm10, small strain), verification/test24 (mm01, finite
+strain) and verification/test60 a and b (mm05, both options, finite strain, 420 cyclic steps).
 
 example_problems_cp/simple_voce (rhdodds/warp3d): a unit cube stretched in z for 5 h and then held
 for 75 h while the stress relaxes; crystal plasticity with Voce hardening, bcc48 slip, 25 crystal
@@ -13,6 +14,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 import scipy.sparse.linalg as spla
 
 from newton_driver import assemble
@@ -114,14 +116,8 @@ def test_simple_voce_one_element_is_not_the_same_problem():
 def _run_test24(nsteps=21):
     ref = json.load(open(os.path.join(HERE, "golden", "test24_reference.json")))
     mat = Material(e=30000.0, nu=0.3, yld_pt=60.0, tan_e=500.0, beta=1.0)
-    m = build_structured_hex8(3, 3, 5, materials=[mat], geonl=True, bbar=True)   # 45 elements, 96 nodes
-    # the deck's own nodes and incidences replace the box: same counts, different numbering
-    inc = np.array(ref["incid"], dtype=np.int32)
-    m.c[:] = np.array(ref["coords"]).reshape(-1)
-    m.incid[:] = inc
-    base = 3 * (inc.astype(np.int64) - 1) + 1
-    m.edest[:] = np.concatenate([base, base + 1, base + 2], axis=1).astype(np.int32).reshape(-1)
-    m.cdest[:] = m.edest
+    from warp3d_b200 import build_hex8_model
+    m = build_hex8_model(ref["coords"], ref["incid"], materials=[mat], geonl=True, bbar=True)   # 45 elements
     m.extrapolated_du = 0
     n = m.nodof
     x = m.c.reshape(-1, 3)
@@ -188,3 +184,88 @@ def test_verification_test24_sphere_with_skew_constraints():
     sxx, ref, u, m = _run_test24()
     want = ref["answer"]["value"]
     assert abs(sxx - want) <= 1.0e-4 * abs(want), (sxx, want)
+
+
+# ---- verification/test60: cyclic loading of a notched bar, mm05 (both options), geonl + B-bar -------
+def _run_test60(option, nsteps=420):
+    import scipy.sparse as sp
+    from warp3d_b200 import build_hex8_model, cyclic_fa_material, cyclic_gp_material
+    ref = json.load(open(os.path.join(HERE, "golden", "test60_reference.json")))
+    if option == "a":     # nonlinear_hardening
+        mat = cyclic_fa_material(e=30000.0, nu=0.3, yld_pt=60.0, q_u=0.0, b_u=0.0, h_u=30000.0, gamma_u=735.0,
+                                 sig_tol=0.001)
+    else:                 # generalized_plasticity
+        mat = cyclic_gp_material(e=30000.0, nu=0.3, yld_pt=60.0, gp_h_u=400.0, gp_tau=0.25, gp_beta_u=100.0,
+                                 gp_delta_u=800.0, sig_tol=0.001)
+    m = build_hex8_model(ref["coords"], ref["incid"], materials=[mat], geonl=True, bbar=True)
+    m.extrapolated_du = 0
+    m.adaptive_flag = True                                       # "adaptive on"
+    n = m.nodof
+    T = np.array(ref["skew"]["T"])
+    blocks = {node: T for node in ref["skew"]["nodes"]}
+    Q = sp.csr_matrix(sp.block_diag([blocks.get(node + 1, np.eye(3)) for node in range(m.nonode)]))
+    fixed_val = {}
+    for node, dof, val in ref["constraints"]:
+        fixed_val[3 * (node - 1) + dof] = val
+    fixed = np.array(sorted(fixed_val))
+    dfix = np.array([fixed_val[k] for k in fixed])
+    free = np.setdiff1d(np.arange(n), fixed)
+    mult = np.zeros(nsteps + 1)
+    for a, b, f in ref["steps"]:
+        mult[a:min(b, nsteps) + 1] = f
+    ry = np.array([3 * (node - 1) + 1 for node in ref["reaction_nodes"]])
+    o, st = op.Oracle(m, nthreads=4), new_state(m)
+    u = np.zeros(n)
+    total = None
+    QT = Q.T.tocsr()
+
+    def increment(step, u, frac, depth=0):
+        """One (sub-)increment of the step's imposed displacements; halves itself when a material
+        point asks for a step cut, as the reference's adaptive solution does.  Returns (du, ifv)."""
+        du = np.zeros(n)
+        ifv, _ = o.eps_sig_ifv(st, step, 0, u, du)
+        K = assemble(m, o.tanstf(st, step, 0, u, du))
+        for it in range(1, 40):
+            r = -(Q @ ifv)
+            Kl = (Q @ K @ QT).tocsr()
+            dl = np.zeros(n)
+            if it == 1:
+                dl[fixed] = frac * mult[step] * dfix
+            rhs = r[free] - Kl[free][:, fixed] @ dl[fixed]
+            dl[free] = spla.spsolve(Kl[free][:, free].tocsc(), rhs)
+            du = du + QT @ dl
+            ifv, sc = o.eps_sig_ifv(st, step, it, u, du)
+            if sc["material_cut_step"]:
+                assert depth < 4, (step, it, depth)
+                o.adaptive_reset(st)
+                du1, _ = increment(step, u, 0.5 * frac, depth + 1)
+                o.update(st); o.adaptive_save(st)
+                du2, ifv = increment(step, u + du1, 0.5 * frac, depth + 1)
+                return du1 + du2, ifv
+            fl = Q @ ifv
+            rn = np.linalg.norm(fl[free]); rf = np.linalg.norm(fl[fixed]) or 1.0
+            # the reference's own test: norm res tol 0.0001 (percent); the generalized-plasticity
+            # update carries ~1e-8 of self-noise (DESIGN.md 3.3b), 1e-7 is not always reachable
+            if rn <= 1.0e-6 * rf or (it >= 12 and rn <= 1.0e-5 * rf):
+                return du, ifv
+            K = assemble(m, o.tanstf(st, step, it, u, du))
+        raise AssertionError(f"step {step} did not converge: {rn / rf}")
+
+    for step in range(1, nsteps + 1):
+        du, ifv = increment(step, u, 1.0)
+        u = u + du
+        o.update(st); o.adaptive_save(st)
+        total = float(ifv[ry].sum())
+    return total, ref
+
+
+@pytest.mark.parametrize("option", ["a", "b"])
+def test_verification_test60_cyclic_notched_bar(option):
+    """mm05 with the finite-strain kinematics and B-bar over 420 load steps (2 1/2 cycles between
+    unsymmetric end displacements): the reference's known answers for verification/test60, the total
+    axial reaction on the loaded end.  a = nonlinear_hardening, b = generalized_plasticity.
+    Measured: a 0.0210364867 against 0.021036833 (1.6e-5), b 0.0232109041 against 0.023211111
+    (8.9e-6); the reference accepts 1e-4 and converges its steps to 1e-6 of the force norm."""
+    total, ref = _run_test60(option)
+    want = ref["answers"][option]["value"]
+    assert abs(total - want) <= 5.0e-5 * abs(want), (option, total, want)

@@ -201,8 +201,6 @@ def build_structured_hex8(nx, ny, nz, materials=None, elem_material=None, geonl=
         interior = ((i.ravel() > 0) & (i.ravel() < nx) & (j.ravel() > 0) & (j.ravel() < ny)
                     & (k.ravel() > 0) & (k.ravel() < nz))
         coords[interior] += rng.uniform(-coord_jitter, coord_jitter, (int(interior.sum()), 3)) * h
-    c = coords.reshape(-1).copy()
-
     ek, ej, ei = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
     ei, ej, ek = ei.ravel(), ej.ravel(), ek.ravel()
     incid = np.empty((noelem, 8), dtype=np.int32)
@@ -212,6 +210,21 @@ def build_structured_hex8(nx, ny, nz, materials=None, elem_material=None, geonl=
         nk = ek + (sz > 0)
         incid[:, a] = (nk * nny + nj) * nnx + ni + 1
 
+    return build_hex8_model(coords, incid, materials=materials, elem_material=elem_material, geonl=geonl,
+                            bbar=bbar, block_size=block_size, numprocs=numprocs, grid=(nx, ny, nz),
+                            **globals_)
+
+
+def build_hex8_model(coords, incid, materials=None, elem_material=None, geonl=True, bbar=True,
+                     block_size=MXVL, numprocs=1, grid=None, **globals_) -> Model:
+    """The reference's tables for an arbitrary mesh of l3disop elements: coords (nonode, 3),
+    incid (noelem, 8) 1-based in WARP3D's node order."""
+    materials = materials or [Material()]
+    coords = np.asarray(coords, dtype=np.float64).reshape(-1, 3)
+    incid = np.ascontiguousarray(np.asarray(incid, dtype=np.int32).reshape(-1, 8))
+    nonode, noelem = coords.shape[0], incid.shape[0]
+    nodof = 3 * nonode
+    c = coords.reshape(-1).copy()
     if elem_material is None:
         elem_material = np.ones(noelem, dtype=np.int32)
     elem_material = np.asarray(elem_material, dtype=np.int32)
@@ -276,7 +289,7 @@ def build_structured_hex8(nx, ny, nz, materials=None, elem_material=None, geonl=
             hist_size[b] = mt.extra["hist_size"]
     return Model(nonode=nonode, noelem=noelem, nodof=nodof, nelblk=nelblk, c=c, incid=incid,
                  elblks=elblks, props=props, matprp=matprp, edest=edest, cdest=cdest,
-                 hist_size=hist_size, materials=materials, grid=(nx, ny, nz), **globals_)
+                 hist_size=hist_size, materials=materials, grid=grid, **globals_)
 
 
 def smooth_displacement(model: Model, strain=1.0e-3, seed=1, noise=1.0e-4, axis=0):
