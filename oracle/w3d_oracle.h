@@ -13,7 +13,10 @@
  *     force, tangent and the Newton structure around them: PINNED end to end against numbers the
  *     Fortran produced -- the 79-point stretch/relaxation curve published with
  *     example_problems_cp/simple_voce is reproduced to 1.1e-5 at worst, 1e-7 at 80 h
- *     (tests/test_reference_known_answers.py).
+ *     (tests/test_reference_known_answers.py); and the known answer of
+ *     verification/test82/voche_model (bcc, 12 systems, Voce exponent 5, cube with a void under
+ *     biaxial face pressures): sigma_xx of element 64 = 476.664670 against 476.645594, 4.0e-5
+ *     (the reference stops that analysis at 1e-4 of the force norm and accepts 1e-4).
  *   - mm01 (bilinear Mises) with the finite-strain kinematics (polar decomposition, un-rotated
  *     rates), B-bar, internal force and tangent: PINNED end to end by the reference's known answer
  *     for verification/test24 (hollow sphere sector, 21 elastic-plastic load steps, the inner

@@ -1,8 +1,10 @@
 """Known answers published with the reference, reproduced with the CPU restatement (oracle/):
 the only place where results of this repository can be laid next to numbers the Fortran itself
-produced (it cannot be built here).  Four of them are within reach of the path and cover every
-material model it builds: simple_voce (mm10, small strain), verification/test24 (mm01, finite
-strain) and verification/test60 a and b (mm05, both options, finite strain, 420 cyclic steps).
+produced (it cannot be built here).  Five of them are within reach of the path and cover every
+material model it builds: simple_voce and verification/test82/voche_model (mm10, small strain),
+verification/test24 (mm01, finite strain) and verification/test60 a and b (mm05, both options,
+finite strain, 420 cyclic steps).  All but simple_voce (48 slip systems) also run through the CUDA
+engine (gpu-marked tests at the end).
 
 example_problems_cp/simple_voce (rhdodds/warp3d): a unit cube stretched in z for 5 h and then held
 for 75 h while the stress relaxes; crystal plasticity with Voce hardening, bcc48 slip, 25 crystal
@@ -323,6 +325,70 @@ def test_verification_test60_cyclic_notched_bar(option):
     assert abs(total - want) <= 5.0e-5 * abs(want), (option, total, want)
 
 
+# ---- verification/test82/voche_model: cube with a void, mm10 (bcc, 12 systems), small strain ---------
+def _run_test82_voche(nsteps=8, backend=OracleBackend):
+    from warp3d_b200 import build_hex8_model
+    ref = json.load(open(os.path.join(HERE, "golden", "test82_voche_reference.json")))
+    m = build_hex8_model(ref["coords"], ref["incid"], materials=[Material(mat_type=10)], geonl=False, bbar=True,
+                         block_size=20, dt=1.0e6)                      # "blocking automatic size = 20"
+    ct = make_crystal_type(e=150000.0, nu=0.28, slip="bcc", harden_n=20.0, voche_m=5.0, theta_o=400.0,
+                           tau_y=300.0, tau_v=1200.0)
+    ang = np.broadcast_to(np.array(ref["angles_deg"]), (m.noelem, 1, 3))
+    attach_crystals(m, ct, ncrystals=1, angles=ang, angle_type=1)
+    m.extrapolated_du = 0
+    n = m.nodof
+    x = m.c.reshape(-1, 3)
+    inc = np.array(ref["incid"])
+    # equivalent nodal loads of the face pressures (elem_load_b.f hex_face_nloads): the faces are
+    # plane squares, so each of the 4 face nodes takes p A / 4 along the inward normal
+    P1 = np.zeros(n)
+    for elem, face, p in ref["face_pressures"]:
+        nodes = inc[elem - 1][np.array(ref["hex8_face_nodes"][face - 1]) - 1] - 1
+        xf = x[nodes]
+        nrm = np.cross(xf[1] - xf[0], xf[3] - xf[0])
+        area = np.linalg.norm(nrm)
+        nrm = nrm / area
+        if np.dot(nrm, xf.mean(axis=0) - x[inc[elem - 1] - 1].mean(axis=0)) < 0:
+            nrm = -nrm                                                 # outward
+        for nd in nodes:
+            P1[3 * nd:3 * nd + 3] += -p * area / 4.0 * nrm             # positive pressure pushes inward
+    fixed = np.array(sorted({3 * nd + k for nd in range(m.nonode) for k in range(3) if x[nd, k] == 0.0}))
+    free = np.setdiff1d(np.arange(n), fixed)
+    be = backend(m)
+    be.sync()
+    u = np.zeros(n)
+    for step in range(1, nsteps + 1):
+        P = ref["load_factor_per_step"] * step * P1
+        du = np.zeros(n)
+        ifv, _ = be.eps_sig_ifv(step, 0, u, du)
+        K = assemble(m, be.tanstf(step, 0, u, du))
+        for it in range(1, 40):
+            r = P - ifv
+            delta = np.zeros(n)
+            delta[free] = spla.spsolve(K[free][:, free].tocsc(), r[free])
+            du = du + delta
+            ifv, sc = be.eps_sig_ifv(step, it, u, du)
+            assert not sc["material_cut_step"], (step, it)
+            rn = np.linalg.norm((P - ifv)[free])
+            if it >= 2 and rn <= 1.0e-9 * np.linalg.norm(P):
+                break
+            K = assemble(m, be.tanstf(step, it, u, du))
+        else:
+            raise AssertionError(f"step {step} did not converge: {rn}")
+        u = u + du
+        be.update()
+    s = be.state().urcs_n.reshape(-1, 8, 9)
+    return float(s[63, :, 0].mean()), ref                              # element 64, centre value
+
+
+def test_verification_test82_voche_model():
+    """mm10 with the 12-system bcc table (the size the engine builds) and the non-trivial Voce
+    exponent: the reference's known answer for verification/test82/voche_model."""
+    sxx, ref = _run_test82_voche()
+    want = ref["answer"]["value"]
+    assert abs(sxx - want) <= 1.0e-4 * abs(want), (sxx, want)
+
+
 # ---- the same known answers through the CUDA engine (the product, not its checker) ------------------
 @pytest.mark.gpu
 def test_engine_reproduces_verification_test24():
@@ -337,3 +403,10 @@ def test_engine_reproduces_verification_test60(option):
     total, ref = _run_test60(option, backend=EngineBackend)
     want = ref["answers"][option]["value"]
     assert abs(total - want) <= 5.0e-5 * abs(want), (option, total, want)
+
+
+@pytest.mark.gpu
+def test_engine_reproduces_verification_test82_voche_model():
+    sxx, ref = _run_test82_voche(backend=EngineBackend)
+    want = ref["answer"]["value"]
+    assert abs(sxx - want) <= 1.0e-4 * abs(want), (sxx, want)
