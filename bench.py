@@ -372,6 +372,19 @@ def engine_arm(args):
                    neqns=st_["neqns"], ncoeff=st_["ncoeff"], setup_s=setup_s,
                    d2h=8 * nodof + 8 * (st_["neqns"] + st_["ncoeff"]))
 
+        # structure residual + convergence norms on the device (upres.f, cvtest.f:62-78): the internal
+        # forces stay in HBM, 7 scalars come back.  Not part of the timed step; reported beside it.
+        eng.residual_set_loads(cst, pbar=np.ones(nodof), load=np.ones(nodof))
+        for _ in range(3):
+            eng.residual(1, to_host=False)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(S)
+        for _ in range(20):
+            eng.residual(1, to_host=False)
+        r1.record(S)
+        barrier()
+        asm["residual_ms"] = r0.elapsed_time(r1) / 20
+
     t = torch.tensor([total_ms, t_stress, t_tan, e2e_ms, e2e_wall_ms, float(launches)], dtype=torch.float64,
                      device="cuda")
     if world > 1:
@@ -438,6 +451,12 @@ def engine_arm(args):
                 note="pinned host buffers; u,du in; ifv, k_diag(neqns) and k_coeffs(ncoeff) out: w3d_eps_sig_ifv + "
                      "w3d_tanstf(estiff=NULL) + w3d_assemble (assemble_code.f on the device, x=xmin face clamped); "
                      "sparsity set-up once per constraint set, outside the timed region")
+            rb = 44 * nodof      # cstmap 4 + pbar, load, du, ifv in + res out, 8 each
+            line["residual"] = dict(
+                call_ms=asm["residual_ms"], bytes=rb, achieved=rb / (asm["residual_ms"] * 1e-3) / 1e9, unit="GB/s",
+                frac=rb / (asm["residual_ms"] * 1e-3) / 1e9 / peak,
+                note="w3d_residual (upres + cvtest residual loop), residual left on the device; the call "
+                     "includes the read-back of the 7 scalars (one stream synchronisation)")
         if "flops_stress" in wd and fp64_peak:
             # both mm01 kernels are at the FP64 ridge (4.6 and 6.4 flop/B against 36.4 TFLOP/s /
             # 6.55 TB/s = 5.6 flop/B), and a DMUL or DADD occupies the pipe like a DFMA: with 2 639

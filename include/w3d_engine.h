@@ -193,6 +193,42 @@ int32_t w3d_assemble_structure(w3d_engine *h, int32_t *dof_eqn_map, int32_t *eqn
  * k_coeffs: host buffers, or both NULL to leave the result in device memory.                     */
 int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs);
 
+/* ---- structure residual and its norms (SURVEY 8(f) NEXT-2) ------------------------------------
+ * Replaces upres_iter_0 (upres.f:13-77), upres (upres.f:121-226) and the residual loop of cvtest
+ * (cvtest.f:62-78) as mnralg.f calls them after drive_eps_sig_internal_forces: the internal
+ * forces and du are already on the device, so only res (the next right-hand side) and these
+ * scalars come back.  All vectors are (nodof) in structure-dof order.  NULL = the vector is
+ * identically zero (statics: no mdiag/velocity/accel; no contact; d_lagrange_forces NULL = the
+ * reference's have_mpc_equations false).                                                          */
+typedef struct w3d_residual_loads {
+  const int32_t *cstmap;            /* != 0: dof has an absolute constraint                        */
+  const double  *pbar;              /* applied nodal forces at n+1 as mnralg.f holds them          */
+  const double  *load;              /* `load` of upres: user nodal loads at n+1 (mgload measure)   */
+  const double  *mdiag, *velocity, *accel;
+  const double  *contact_force;
+  const double  *d_lagrange_forces;
+} w3d_residual_loads;
+
+typedef struct w3d_residual_norms {
+  double  norm_res;        /* sqrt(sum res^2): norm_load of upres_iter_0, `sum` of cvtest.f:75      */
+  double  mgload;          /* iter >= 1 only (upres.f:219); 0 at iter 0                            */
+  double  sum_loads;       /* iter >= 1 only                                                       */
+  int64_t num_term_loads;  /* iter >= 1 only                                                       */
+  double  res_max;         /* res(res_max_dof), signed (cvtest.f:77)                               */
+  int32_t res_max_dof;     /* 1-based dof of the largest |res|, the lowest such dof                */
+} w3d_residual_norms;
+
+/* once per load step (or whenever one of the vectors changes); copies them to the device          */
+int32_t w3d_residual_set_loads(w3d_engine *h, const w3d_residual_loads *loads);
+/* iter == 0: upres_iter_0, iter >= 1: upres; then the cvtest residual loop.  Uses the internal
+ * forces of the last stress pass and the du it was given.  res: host (nodof) or NULL to leave it
+ * on the device (w3d_residual_device).  res(i) follows the reference's expression and operation
+ * order; the three sums are fixed-order tree sums (run-to-run reproducible, equal to the
+ * reference's sequential sums to rounding); num_term_loads and res_max_dof are exact.             */
+int32_t w3d_residual(w3d_engine *h, int32_t iter, double dt, double nbeta, double *res,
+                     w3d_residual_norms *out);
+int32_t w3d_residual_device(w3d_engine *h, double **d_res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -248,3 +248,46 @@ def assemble(oracle: "Oracle", estiff, s):
     L.w3do_assemble(C.byref(oracle._cm), _ptr(ek), C.c_int32(s["neqns"]), _ptr(s["eqn_node_map"]),
                     _ptr(s["dof_eqn_map"]), _ptr(s["k_ptrs"]), _ptr(ki), _ptr(kd), _ptr(kc))
     return kd, kc[:s["ncoeff"]]
+
+
+# ---- structure residual and its norms (upres.f, cvtest.f:62-78) -----------------------------------
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def upres_iter_0(cstmap, pbar, ifv, du, dt=1.0, nbeta=0.25, mdiag=None, contact_force=None):
+    """upres_iter_0 (upres.f:13): returns (res, norm_load)."""
+    L = lib()
+    cst = np.ascontiguousarray(cstmap, dtype=np.int32)
+    pbar, ifv, du, mdiag, cf = map(_f64, (pbar, ifv, du, mdiag, contact_force))
+    res = np.zeros(cst.size)
+    L.w3do_upres_iter_0.restype = C.c_double
+    nl = L.w3do_upres_iter_0(C.c_int32(cst.size), C.c_double(dt), C.c_double(nbeta), _ptr(cst), _ptr(pbar),
+                             _ptr(ifv), _ptr(mdiag), _ptr(du), _ptr(cf), _ptr(res))
+    return res, float(nl)
+
+
+def upres(cstmap, pbar, load, ifv, du, dt=1.0, nbeta=0.25, mdiag=None, velocity=None, accel=None,
+          contact_force=None, d_lagrange_forces=None):
+    """upres (upres.f:121): returns (res, dict(mgload, sum_loads, num_term_loads))."""
+    L = lib()
+    cst = np.ascontiguousarray(cstmap, dtype=np.int32)
+    pbar, load, ifv, du, mdiag, vel, acc, cf, dl = map(
+        _f64, (pbar, load, ifv, du, mdiag, velocity, accel, contact_force, d_lagrange_forces))
+    res = np.zeros(cst.size)
+    out2 = np.zeros(2)
+    L.w3do_upres.restype = C.c_int64
+    n = L.w3do_upres(C.c_int32(cst.size), C.c_double(dt), C.c_double(nbeta), _ptr(cst), _ptr(pbar), _ptr(load),
+                     _ptr(ifv), _ptr(mdiag), _ptr(du), _ptr(vel), _ptr(acc), _ptr(cf), _ptr(dl), _ptr(res),
+                     _ptr(out2))
+    return res, dict(mgload=float(out2[0]), sum_loads=float(out2[1]), num_term_loads=int(n))
+
+
+def cvtest_residual(res, d_lagrange_forces=None):
+    """The residual loop of cvtest (cvtest.f:62-78): dict(norm_res, res_max, res_max_dof)."""
+    L = lib()
+    res, dl = _f64(res), _f64(d_lagrange_forces)
+    out2 = np.zeros(2)
+    L.w3do_cvtest_residual.restype = C.c_int32
+    dof = L.w3do_cvtest_residual(C.c_int32(res.size), _ptr(res), _ptr(dl), _ptr(out2))
+    return dict(norm_res=float(out2[0]), res_max=float(out2[1]), res_max_dof=int(dof))

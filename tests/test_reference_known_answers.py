@@ -50,6 +50,15 @@ class OracleBackend:
     def state(self):
         return self.st
 
+    def set_loads(self, cstmap, pbar):
+        self.cst, self.pbar = cstmap, pbar
+
+    def residual(self, it, ifv, du):
+        """upres + the cvtest residual loop (upres.f:121, cvtest.f:62-78)"""
+        res, n = op.upres(self.cst, self.pbar, self.pbar, ifv, du)
+        n.update(op.cvtest_residual(res))
+        return res, n
+
 
 class EngineBackend:
     """The CUDA engine through the C ABI: the same drivers, the product instead of the oracle."""
@@ -75,6 +84,13 @@ class EngineBackend:
 
     def state(self):
         return self.e.pull_state(new_state(self.m))
+
+    def set_loads(self, cstmap, pbar):
+        self.e.residual_set_loads(cstmap, pbar, load=pbar)
+
+    def residual(self, it, ifv, du):
+        """the same on the device, from the internal forces the stress pass left there"""
+        return self.e.residual(it)
 
 
 def _run_simple_voce(nsteps, nel=3, out_elem=21):
@@ -354,22 +370,27 @@ def _run_test82_voche(nsteps=8, backend=OracleBackend):
             P1[3 * nd:3 * nd + 3] += -p * area / 4.0 * nrm             # positive pressure pushes inward
     fixed = np.array(sorted({3 * nd + k for nd in range(m.nonode) for k in range(3) if x[nd, k] == 0.0}))
     free = np.setdiff1d(np.arange(n), fixed)
+    cst = np.zeros(n, dtype=np.int32)
+    cst[fixed] = 1
     be = backend(m)
     be.sync()
     u = np.zeros(n)
     for step in range(1, nsteps + 1):
         P = ref["load_factor_per_step"] * step * P1
+        be.set_loads(cst, P)
         du = np.zeros(n)
         ifv, _ = be.eps_sig_ifv(step, 0, u, du)
         K = assemble(m, be.tanstf(step, 0, u, du))
+        r = np.where(cst == 0, P - ifv, 0.0)
         for it in range(1, 40):
-            r = P - ifv
             delta = np.zeros(n)
             delta[free] = spla.spsolve(K[free][:, free].tocsc(), r[free])
             du = du + delta
             ifv, sc = be.eps_sig_ifv(step, it, u, du)
             assert not sc["material_cut_step"], (step, it)
-            rn = np.linalg.norm((P - ifv)[free])
+            r, norms = be.residual(it, ifv, du)                        # upres + cvtest norms
+            rn = norms["norm_res"]
+            assert abs(rn - np.linalg.norm((P - ifv)[free])) <= 1e-12 * np.linalg.norm(P)
             if it >= 2 and rn <= 1.0e-9 * np.linalg.norm(P):
                 break
             K = assemble(m, be.tanstf(step, it, u, du))

@@ -17,6 +17,8 @@
 #include "w3d_tanstf_kernel.cuh"
 #include "w3d_cp_kernel.h"
 #include "w3d_assemble_data.h"
+#include "w3d_residual_data.h"
+#include <cmath>
 #include <algorithm>
 #include <type_traits>
 #include <utility>
@@ -88,6 +90,7 @@ struct w3d_engine {
   w3d_scalars last{};
   bool have_vectors = false;
   AssemblyData assembly;            // assembled-equations path (w3d_assemble.cuh)
+  ResidualData residual;            // structure residual and norms (w3d_residual.cuh)
 
   int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -218,6 +221,7 @@ void free_all(w3d_engine *h) {
     cudaFree(s.d_cprops); cudaFree(s.scratch);
   }
   h->assembly.release();
+  h->residual.release();
   cudaFree(h->d_c); cudaFree(h->d_u); cudaFree(h->d_du); cudaFree(h->d_ifv);
   cudaFree(h->d_estiff); cudaFree(h->d_scal); cudaFree(h->d_flags); cudaFree(h->d_stage);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -780,3 +784,4 @@ int64_t w3d_engine_launch_count(const w3d_engine *h) { return h ? h->launches : 
 }  // extern "C"
 
 #include "w3d_assemble.cuh"   // element stiffnesses -> assembled sparse equations (NEXT-1)
+#include "w3d_residual.cuh"   // structure residual and convergence norms (NEXT-2)

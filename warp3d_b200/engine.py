@@ -35,7 +35,20 @@ EXPORTS = (
     "w3d_engine_launch_count", "w3d_upload_displacements", "w3d_download_ifv",
     "w3d_download_estiff", "w3d_set_time_step",
     "w3d_assemble_setup", "w3d_assemble_structure", "w3d_assemble",
+    "w3d_residual_set_loads", "w3d_residual", "w3d_residual_device",
 )
+
+
+class _ResidualLoads(C.Structure):
+    """w3d_residual_loads (include/w3d_engine.h)"""
+    _fields_ = [(n, C.c_void_p) for n in ("cstmap", "pbar", "load", "mdiag", "velocity", "accel",
+                                           "contact_force", "d_lagrange_forces")]
+
+
+class _ResidualNorms(C.Structure):
+    """w3d_residual_norms (include/w3d_engine.h)"""
+    _fields_ = [("norm_res", C.c_double), ("mgload", C.c_double), ("sum_loads", C.c_double),
+                ("num_term_loads", C.c_int64), ("res_max", C.c_double), ("res_max_dof", C.c_int32)]
 
 
 class EngineError(RuntimeError):
@@ -273,6 +286,30 @@ class Engine:
             return k_diag, k_coeffs[:self._ncoeff]
         self._check(self._L.w3d_assemble(self._h, None, None))
         return None, None
+
+    # ---- structure residual and its norms (upres.f, cvtest.f:62-78)
+    def residual_set_loads(self, cstmap, pbar, load=None, mdiag=None, velocity=None, accel=None,
+                           contact_force=None, d_lagrange_forces=None):
+        """Copies the step's load vectors to the device (None = identically zero)."""
+        keep = [np.ascontiguousarray(cstmap, dtype=np.int32)]
+        keep += [None if v is None else _f64(v)
+                 for v in (pbar, load, mdiag, velocity, accel, contact_force, d_lagrange_forces)]
+        for v in keep:
+            if v is not None and v.size != self.model.nodof:
+                raise ValueError("residual vectors must have nodof entries")
+        arg = _ResidualLoads(*[None if v is None else v.ctypes.data for v in keep])
+        self._check(self._L.w3d_residual_set_loads(self._h, C.byref(arg)))
+
+    def residual(self, iter, dt=1.0, nbeta=0.25, to_host=True):
+        """upres_iter_0 (iter 0) or upres (iter >= 1) + the cvtest residual loop on the internal
+        forces of the last stress pass.  Returns (res or None, dict of norms)."""
+        res = np.empty(self.model.nodof) if to_host else None
+        out = _ResidualNorms()
+        self._check(self._L.w3d_residual(self._h, C.c_int32(iter), C.c_double(dt), C.c_double(nbeta),
+                                         _ptr(res) if to_host else None, C.byref(out)))
+        return res, dict(norm_res=out.norm_res, mgload=out.mgload, sum_loads=out.sum_loads,
+                         num_term_loads=out.num_term_loads, res_max=out.res_max,
+                         res_max_dof=out.res_max_dof)
 
     def update(self):
         self._check(self._L.w3d_update(self._h))
