@@ -378,6 +378,13 @@ class Engine:
                     self._check(self._L.w3d_push_state(self._h, _STATE_WHICH[name], int(blk) + 1,
                                                        _ptr(seg)))
 
+    def pull_block(self, name, blk):
+        """One block (0-based) of the state array `name` in the reference's layout, flattened."""
+        off = self._owned_offsets(name)
+        out = np.empty(int(off[blk + 1] - off[blk]))
+        self._check(self._L.w3d_pull_state(self._h, _STATE_WHICH[name], int(blk) + 1, _ptr(out)))
+        return out
+
     def pull_state(self, state: State, names=None):
         for name in names or State.NAMES:
             a = getattr(state, name)
