@@ -34,6 +34,16 @@ struct CtaDesc {
 __device__ __forceinline__ double xm(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double xa(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double xs(double a, double b) { return __dsub_rn(a, b); }
+// a / b, correctly rounded like __ddiv_rn, without the division's ~65-instruction subroutine for
+// a == 0.  That subroutine runs whenever the quotient is zero or subnormal, and zero numerators
+// are the rule, not the exception, on this path: the off-diagonal cofactors of an axis-aligned
+// element, every back-stress term of an isotropically hardening material.  +-0 / b = +-0 * (1 / b)
+// in every IEEE case (b = 0 and NaN give NaN, b = inf gives the signed zero) except |b| subnormal.
+__device__ __forceinline__ double xdiv(double a, double b) {
+  const bool z = (a == 0.0);
+  const double q = __ddiv_rn(z ? 1.0 : a, b);
+  return z ? __dmul_rn(a, q) : q;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Jacobian at one Gauss point.  jacob1 (gtmat1.f:300-507), 3-D branch.  X,Y,Z: the element's 8
@@ -68,15 +78,15 @@ __device__ __forceinline__ void jacobian(const double (&nx)[8], const double (&n
     const double j2 = xs(xm(J[1][0], J[2][2]), xm(J[1][2], J[2][0]));
     const double j3 = xs(xm(J[1][0], J[2][1]), xm(J[1][1], J[2][0]));
     dj = xa(xs(xm(J[0][0], j1), xm(J[0][1], j2)), xm(J[0][2], j3));
-    G[0][0] = __ddiv_rn(j1, dj);
-    G[1][0] = __ddiv_rn(-j2, dj);
-    G[2][0] = __ddiv_rn(j3, dj);
-    G[0][1] = __ddiv_rn(xs(xm(J[2][1], J[0][2]), xm(J[0][1], J[2][2])), dj);
-    G[1][1] = __ddiv_rn(xs(xm(J[0][0], J[2][2]), xm(J[2][0], J[0][2])), dj);
-    G[2][1] = __ddiv_rn(xs(xm(J[0][1], J[2][0]), xm(J[0][0], J[2][1])), dj);
-    G[0][2] = __ddiv_rn(xs(xm(J[0][1], J[1][2]), xm(J[0][2], J[1][1])), dj);
-    G[1][2] = __ddiv_rn(xs(xm(J[0][2], J[1][0]), xm(J[0][0], J[1][2])), dj);
-    G[2][2] = __ddiv_rn(xs(xm(J[0][0], J[1][1]), xm(J[0][1], J[1][0])), dj);
+    G[0][0] = xdiv(j1, dj);
+    G[1][0] = xdiv(-j2, dj);
+    G[2][0] = xdiv(j3, dj);
+    G[0][1] = xdiv(xs(xm(J[2][1], J[0][2]), xm(J[0][1], J[2][2])), dj);
+    G[1][1] = xdiv(xs(xm(J[0][0], J[2][2]), xm(J[2][0], J[0][2])), dj);
+    G[2][1] = xdiv(xs(xm(J[0][1], J[2][0]), xm(J[0][0], J[2][1])), dj);
+    G[0][2] = xdiv(xs(xm(J[0][1], J[1][2]), xm(J[0][2], J[1][1])), dj);
+    G[1][2] = xdiv(xs(xm(J[0][2], J[1][0]), xm(J[0][0], J[1][2])), dj);
+    G[2][2] = xdiv(xs(xm(J[0][0], J[1][1]), xm(J[0][1], J[1][0])), dj);
   } else {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -145,7 +155,13 @@ __device__ __forceinline__ void polar_rotation(const double (&F)[3][3], double (
   const double sqrtp = sqrt(fabs(p));
   double phi = xm(twentyseven, xa(xm(xm(xm(quarter, cc1e), cc1e), xs(p, cc1e)),
                                   xm(c0, xa(q, xm(sixpt75, c0)))));
-  phi = xm(third, atan2(sqrt(fabs(phi)), q));
+  // the argument is a difference of nearly equal numbers and comes out exactly zero at a good
+  // share of the points: atan2(+0, q) is 0 or pi by the sign of q -- the same bits without the
+  // slow paths of sqrt(0) and of the zero quotient inside atan2
+  if (phi == 0.0 && q == q)
+    phi = (q > 0.0 || (q == 0.0 && !signbit(q))) ? 0.0 : xm(third, 3.141592653589793116);
+  else
+    phi = xm(third, atan2(sqrt(fabs(phi)), q));
   double sn, cs;
   sincos(phi, &sn, &cs);
   const double cphi = xm(sqrtp, cs);

@@ -76,7 +76,9 @@ __device__ __forceinline__ int mm01_update(int step, const Mm01Props &pr, double
     const double hbark_n = (one - beta) * h[4];
     kbar = (yld_n1 + hbari_np1 * h[2]) / root3;
     lk = one;
-    if (fabs(hbark_n) > htol) lk = hbark_np1 / hbark_n;
+    const bool hk = fabs(hbark_n) > htol;            // operands kept off the division's slow path
+    const double lkq = xdiv(hbark_np1, hk ? hbark_n : one);
+    if (hk) lk = lkq;
 #pragma unroll
     for (int k = 0; k < 6; ++k) rtse[k] = dse[k] - alpha_n[k] * lk;
     mrts = sqrt(rtse[0] * rtse[0] + rtse[1] * rtse[1] + rtse[2] * rtse[2] +
@@ -123,7 +125,7 @@ __device__ __forceinline__ int mm01_update(int step, const Mm01Props &pr, double
     h1[1] = kbar + (root2 / three) * hbari_np1 * lambda_deltat;
     h1[2] = h[2] + lambda_deltat * root23;
     h1[4] = hprime_n1;
-    const double const1 = twthrd * hbark_np1 * lambda_deltat / mrts;
+    const double const1 = xdiv(twthrd * hbark_np1 * lambda_deltat, mrts);
     const double const2 = one - lambda_deltat * (twthrd * hbark_np1 + two * shear_mod_n1) / mrts;
     b = one - lk;
 #pragma unroll

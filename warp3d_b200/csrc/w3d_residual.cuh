@@ -48,6 +48,7 @@ __device__ __forceinline__ ResidualPartial shfl_down(const ResidualPartial &p, i
   q.num_term_loads = __shfl_down_sync(0xffffffffu, p.num_term_loads, d);
   q.max_dof = __shfl_down_sync(0xffffffffu, p.max_dof, d);
   q.pad = 0;
+  q.res_at_max = 0.0;
   return q;
 }
 
@@ -69,7 +70,7 @@ __device__ __forceinline__ void cta_reduce(ResidualPartial &p, ResidualPartial *
 
 // upres_iter_0 / upres + the residual loop of cvtest, one thread per dof (grid-stride)
 __global__ void __launch_bounds__(RES_TPB) k_residual(const ResidualArgs a) {
-  ResidualPartial p{0.0, 0.0, 0.0, 0.0, 0, 0, 0};
+  ResidualPartial p{0.0, 0.0, 0.0, 0.0, 0, 0, 0, 0.0};
   for (int i = blockIdx.x * RES_TPB + threadIdx.x; i < a.nodof; i += gridDim.x * RES_TPB) {
     const bool constrained = a.cstmap[i] != 0;
     const double du = a.du[i], ifv = a.ifv[i], md = ld0(a.mdiag, i), cf = ld0(a.cf, i);
@@ -114,10 +115,14 @@ __global__ void __launch_bounds__(RES_TPB) k_residual(const ResidualArgs a) {
   cta_reduce(p, a.part + blockIdx.x);
 }
 
-__global__ void __launch_bounds__(RES_TPB) k_residual_finish(ResidualPartial *part, int n) {
-  ResidualPartial p{0.0, 0.0, 0.0, 0.0, 0, 0, 0};
+__global__ void __launch_bounds__(RES_TPB) k_residual_finish(ResidualPartial *part, int n, const double *res) {
+  ResidualPartial p{0.0, 0.0, 0.0, 0.0, 0, 0, 0, 0.0};
   for (int k = threadIdx.x; k < n; k += RES_TPB) combine(p, part[k]);
   cta_reduce(p, part + RES_MAX_CTAS);
+  if (threadIdx.x == 0) {   // cvtest.f:77: the signed residual at that dof
+    ResidualPartial &t = part[RES_MAX_CTAS];
+    t.res_at_max = t.max_dof >= 1 ? res[t.max_dof - 1] : 0.0;
+  }
 }
 
 template <typename T>
@@ -186,7 +191,7 @@ int32_t w3d_residual(w3d_engine *h, int32_t iter, double dt, double nbeta, doubl
   a.part = R.d_part;
   const int ncta = std::min((a.nodof + RES_TPB - 1) / RES_TPB, RES_MAX_CTAS);
   k_residual<<<ncta, RES_TPB, 0, h->stream>>>(a);
-  k_residual_finish<<<1, RES_TPB, 0, h->stream>>>(R.d_part, ncta);
+  k_residual_finish<<<1, RES_TPB, 0, h->stream>>>(R.d_part, ncta, R.d_res);
   h->launches += 2;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(R.h_part, R.d_part + RES_MAX_CTAS, sizeof(ResidualPartial), cudaMemcpyDeviceToHost, h->stream));
@@ -198,9 +203,7 @@ int32_t w3d_residual(w3d_engine *h, int32_t iter, double dt, double nbeta, doubl
   out->sum_loads = p.sum_loads;
   out->num_term_loads = p.num_term_loads;
   out->res_max_dof = p.max_dof;
-  out->res_max = 0.0;
-  if (p.max_dof >= 1)   // cvtest.f:77: the signed residual at that dof
-    CUDA_TRY(cudaMemcpy(&out->res_max, R.d_res + (p.max_dof - 1), sizeof(double), cudaMemcpyDeviceToHost));
+  out->res_max = p.res_at_max;
   return W3D_OK;
 }
 

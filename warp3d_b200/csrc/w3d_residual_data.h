@@ -13,6 +13,7 @@ struct ResidualPartial {            // one per CTA of k_residual, then one for t
   long long num_term_loads;
   int max_dof;                      // 1-based dof of max_abs (lowest such dof), 0 = none
   int pad;
+  double res_at_max;                // res(max_dof), signed: filled by k_residual_finish only
 };
 
 struct ResidualData {

@@ -134,15 +134,15 @@ __device__ __forceinline__ void jacobian_smem(const double (*sN)[8][8], int gp, 
     const double j2 = xs(xm(J[1][0], J[2][2]), xm(J[1][2], J[2][0]));
     const double j3 = xs(xm(J[1][0], J[2][1]), xm(J[1][1], J[2][0]));
     dj = xa(xs(xm(J[0][0], j1), xm(J[0][1], j2)), xm(J[0][2], j3));
-    G[0][0] = __ddiv_rn(j1, dj);
-    G[1][0] = __ddiv_rn(-j2, dj);
-    G[2][0] = __ddiv_rn(j3, dj);
-    G[0][1] = __ddiv_rn(xs(xm(J[2][1], J[0][2]), xm(J[0][1], J[2][2])), dj);
-    G[1][1] = __ddiv_rn(xs(xm(J[0][0], J[2][2]), xm(J[2][0], J[0][2])), dj);
-    G[2][1] = __ddiv_rn(xs(xm(J[0][1], J[2][0]), xm(J[0][0], J[2][1])), dj);
-    G[0][2] = __ddiv_rn(xs(xm(J[0][1], J[1][2]), xm(J[0][2], J[1][1])), dj);
-    G[1][2] = __ddiv_rn(xs(xm(J[0][2], J[1][0]), xm(J[0][0], J[1][2])), dj);
-    G[2][2] = __ddiv_rn(xs(xm(J[0][0], J[1][1]), xm(J[0][1], J[1][0])), dj);
+    G[0][0] = xdiv(j1, dj);
+    G[1][0] = xdiv(-j2, dj);
+    G[2][0] = xdiv(j3, dj);
+    G[0][1] = xdiv(xs(xm(J[2][1], J[0][2]), xm(J[0][1], J[2][2])), dj);
+    G[1][1] = xdiv(xs(xm(J[0][0], J[2][2]), xm(J[2][0], J[0][2])), dj);
+    G[2][1] = xdiv(xs(xm(J[0][1], J[2][0]), xm(J[0][0], J[2][1])), dj);
+    G[0][2] = xdiv(xs(xm(J[0][1], J[1][2]), xm(J[0][2], J[1][1])), dj);
+    G[1][2] = xdiv(xs(xm(J[0][2], J[1][0]), xm(J[0][0], J[1][2])), dj);
+    G[2][2] = xdiv(xs(xm(J[0][0], J[1][1]), xm(J[0][1], J[1][0])), dj);
   } else {
     const double j1 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
     const double j2 = J[1][0] * J[2][2] - J[1][2] * J[2][0];
