@@ -67,9 +67,10 @@ cudaError_t launch_stress_mm05(bool geonl, bool bbar, int ncta, const struct Str
 constexpr int STPB = TPB * STRESS_GROUPS;   // threads per CTA of the stress kernel
 constexpr int SEPC = EPC * STRESS_GROUPS;   // elements per CTA
 constexpr int NSTATE_IN = 6 + 9 + 14;       // eps_n, urcs_n, hist_n (11 mm01 / 14 mm05) per Gauss point
-// shape table 192, c/u/du 3 x SEPC x 24, per-warp sums (+1 pad), state at n NSTATE_IN x STPB
+// shape table 192, c/u/du 3 x SEPC x 24, per-warp sums (+1 pad), state at n NSTATE_IN x STPB,
+// element property records SEPC x EPROP floats
 constexpr int STRESS_SMEM_BYTES =
-    (int)sizeof(double) * (192 + 3 * SEPC * 24 + (STPB / 32) * 3 + 1 + NSTATE_IN * STPB);
+    (int)sizeof(double) * (192 + 3 * SEPC * 24 + (STPB / 32) * 3 + 1 + NSTATE_IN * STPB + SEPC * (EPROP / 2));
 
 // launches one instantiation with its dynamic shared memory (opt-in above 48 KB, once per kernel)
 inline cudaError_t launch_stress_kernel(void (*k)(const struct StressArgs), int grid,
@@ -209,6 +210,8 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
   double (*sRed)[3] = reinterpret_cast<double (*)[3]>(dsm + 192 + 3 * SEPC * 24);     // [STPB/32][3]
   // state at n, [component][thread]: conflict free
   double (*sSt)[STPB] = reinterpret_cast<double (*)[STPB]>(dsm + 192 + 3 * SEPC * 24 + (STPB / 32) * 3 + 1);
+  // the element's property record (EPROP floats), streamed with the state: 8 bytes per lane
+  double (*sEp)[EPROP / 2] = reinterpret_cast<double (*)[EPROP / 2]>(&sSt[NSTATE_IN][0]);
 
   const int tid = threadIdx.x;
   for (int k = tid; k < 192; k += STPB) (&sN[0][0][0])[k] = (&c_shape[0][0][0])[k];
@@ -247,6 +250,8 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
     for (int k = 0; k < 9; ++k) cp_async8(&sSt[6 + k][tid], a.urcs_n + k * ng + g);
 #pragma unroll
     for (int k = 0; k < (MAT == 1 ? 11 : 14); ++k) cp_async8(&sSt[15 + k][tid], a.hist_n + k * ng + g);
+    static_assert(EPROP == 16, "one 8-byte piece of the property record per Gauss-point lane");
+    cp_async8(&sEp[el][gp], reinterpret_cast<const double *>(a.eprops + (size_t)slot * EPROP) + gp);
   }
   cp_async_commit();
 
@@ -394,7 +399,8 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
   }
 
   // ---- rstgp1_update_strains (rstgp1.f:4983-5005): total strain at n+1, stored at once
-  cp_async_wait_all();   // each thread reads back only what it copied itself
+  cp_async_wait_all();   // each thread reads back only what it copied itself ...
+  if (MAT == 1 || MAT == 5) __syncwarp();   // ... except the property record, shared by the 8 lanes of an element
   if (PHASE != 2) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
     double cgn[9], cep[21];
 #pragma unroll
     for (int k = 0; k < 9; ++k) cgn[k] = sSt[6 + k][tid];
-    const float *ep = a.eprops + (size_t)slot * EPROP;
+    const float *ep = reinterpret_cast<const float *>(&sEp[el][0]);
     Mm01Props pr;
     pr.e = (double)ep[0]; pr.nu = (double)ep[1]; pr.beta = (double)ep[2];
     pr.hprime = (double)ep[3]; pr.yld = (double)ep[4]; pr.lnelas = ep[5] != 0.0f;
@@ -471,7 +477,7 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
     double cgn[9], D[6][6];
 #pragma unroll
     for (int k = 0; k < 9; ++k) cgn[k] = sSt[6 + k][tid];
-    const float *ep = a.eprops + (size_t)slot * EPROP;
+    const float *ep = reinterpret_cast<const float *>(&sEp[el][0]);
     w3d_mm05::Props pr;
     pr.e = (double)ep[0]; pr.nu = (double)ep[1]; pr.sigyld = (double)ep[4];
 #pragma unroll
