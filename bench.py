@@ -81,9 +81,10 @@ def workload_description(name):
         return dict(material="mm01 bilinear (E=200e9 as real*4, nu=0.3, yld=400e6, tan_e=E/100)",
                     bytes_stress=776.0, bytes_tanstf=708.0, flops_stress=3573.0, flops_tanstf=4540.0,
                     # measured DRAM bytes per Gauss point (dram__bytes_read + write of one `ncu --set
-                    # full` launch on hex8_256k_mm01 / 2 097 152 points, profiles/r01_mm01_*_256k_ncu.csv)
-                    dram_stress=(533.111552e6 + 1038.039e6) / 2097152.0,
-                    dram_tanstf=(674.389760e6 + 583.456512e6) / 2097152.0)
+                    # full` launch on hex8_256k_mm01 / 2 097 152 points,
+                    # profiles/r01_final_mm01_*_256k_ncu.csv)
+                    dram_stress=(532.444928e6 + 1046.123e6) / 2097152.0,
+                    dram_tanstf=(674.460672e6 + 582.819328e6) / 2097152.0)
     # per Gauss point: history 2 x 158 x 8, urcs 2 x 72, eps 2 x 48, rot 72, scratch 2 x 128,
     # crystal properties 1448/8, element vectors 120  (DESIGN.md "mm10")
     return dict(material="mm10 crystal plasticity: fcc 12 slip, Voce (test82/voche_model values), 1 crystal/element",
@@ -344,16 +345,17 @@ def engine_arm(args):
 
     # ---- the same iteration with the stiffnesses assembled on the device (assemble_code.f): what
     #      crosses to the host is the sparse upper triangle the solver consumes, not the element
-    #      blocks.  One domain only; x = xmin face clamped.
+    #      blocks.  x = xmin face clamped.  With several domains every rank returns the rows of the
+    #      nodes its own elements touch (interface rows come from two ranks and add on the host).
     asm = None
-    if world == 1:
+    if True:
         cst = np.zeros(nodof, dtype=np.int32)
         xs = model.c.reshape(-1, 3)[:, 0]
         cst.reshape(-1, 3)[xs <= xs.min() + 1e-9] = 1
         ts0 = time.perf_counter()
         st_ = eng.assemble_setup(cst)
         setup_s = time.perf_counter() - ts0
-        kd_h, kc_h = pinned(st_["neqns"]), pinned(max(st_["ncoeff"], 1))
+        kd_h, kc_h = pinned(st_["n_eqns"]), pinned(max(st_["ncoeff"], 1))
         for _ in range(2):
             de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
             eng.tanstf_resident(TS, 1); eng.assemble(kd_h, kc_h)
@@ -370,7 +372,7 @@ def engine_arm(args):
         barrier()
         asm = dict(ms=a0.elapsed_time(a1) / nrep_e2e, kernel_ms=a1.elapsed_time(a2) / nrep_e2e,
                    neqns=st_["neqns"], ncoeff=st_["ncoeff"], setup_s=setup_s,
-                   d2h=8 * nodof + 8 * (st_["neqns"] + st_["ncoeff"]))
+                   d2h=8 * nodof + 8 * (st_["n_eqns"] + st_["ncoeff"]))
 
         # structure residual + convergence norms on the device (upres.f, cvtest.f:62-78): the internal
         # forces stay in HBM, 7 scalars come back.  Not part of the timed step; reported beside it.
@@ -385,14 +387,16 @@ def engine_arm(args):
         barrier()
         asm["residual_ms"] = r0.elapsed_time(r1) / 20
 
-    t = torch.tensor([total_ms, t_stress, t_tan, e2e_ms, e2e_wall_ms, float(launches)], dtype=torch.float64,
-                     device="cuda")
+    t = torch.tensor([total_ms, t_stress, t_tan, e2e_ms, e2e_wall_ms, float(launches), asm["ms"], asm["kernel_ms"],
+                      float(asm["d2h"]), float(asm["ncoeff"])], dtype=torch.float64, device="cuda")
     if world > 1:
         tl = t.clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
         launches = int(tl[5].item())
+        asm["d2h"], asm["ncoeff"] = int(tl[8].item()), int(tl[9].item())     # bytes / terms over all ranks
     total_ms, t_stress, t_tan, e2e_ms, e2e_wall_ms = [float(x) for x in t[:5].tolist()]
+    asm["ms"], asm["kernel_ms"] = float(t[6].item()), float(t[7].item())     # max over ranks
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
@@ -445,12 +449,14 @@ def engine_arm(args):
             line["e2e_element_blocks"] = line["e2e"]
             line["e2e"] = dict(
                 value=ngp_total / (asm["ms"] * 1e-3), unit=UNIT, ms_per_step=asm["ms"],
-                h2d_bytes_per_step=2 * 8 * nodof, d2h_bytes_per_step=asm["d2h"],
+                h2d_bytes_per_step=2 * 8 * nodof * world, d2h_bytes_per_step=asm["d2h"],
                 assemble_kernel_ms=asm["kernel_ms"], neqns=asm["neqns"], ncoeff=asm["ncoeff"],
                 structure_setup_s=asm["setup_s"],
                 note="pinned host buffers; u,du in; ifv, k_diag(neqns) and k_coeffs(ncoeff) out: w3d_eps_sig_ifv + "
                      "w3d_tanstf(estiff=NULL) + w3d_assemble (assemble_code.f on the device, x=xmin face clamped); "
-                     "sparsity set-up once per constraint set, outside the timed region")
+                     "sparsity set-up once per constraint set, outside the timed region"
+                     + ("; every rank returns the rows of its own nodes (interface rows from two ranks add on "
+                        "the host), ncoeff = terms over all ranks" if world > 1 else ""))
             rb = 44 * nodof      # cstmap 4 + pbar, load, du, ifv in + res out, 8 each
             line["residual"] = dict(
                 call_ms=asm["residual_ms"], bytes=rb, achieved=rb / (asm["residual_ms"] * 1e-3) / 1e9, unit="GB/s",

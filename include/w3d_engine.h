@@ -170,7 +170,7 @@ int32_t w3d_engine_synchronize(w3d_engine *h);
 /* number of kernels the engine has launched since create (bench.py: gpu_launches) */
 int64_t w3d_engine_launch_count(const w3d_engine *h);
 
-/* ---- assembled equilibrium equations (SURVEY 8(f) NEXT-1), symmetric case, one domain ---------
+/* ---- assembled equilibrium equations (SURVEY 8(f) NEXT-1), symmetric case -------------------
  * Replaces assemble_code.f: dof_map (:561-600), count_profile_symmetric (:20-250),
  * build_col_sparse_symm (:260-500) and assem_by_row / assem_a_row (:659-935) as
  * drive_assemble_solve.f calls them, so that the 2 400 B per element of estiff_blocks never
@@ -180,17 +180,29 @@ int64_t w3d_engine_launch_count(const w3d_engine *h);
  *
  * w3d_assemble_setup: once per constraint set.  cstmap(nodof): the reference's cstmap, 0 = dof
  * without an absolute constraint; edest: the packed per-block (totdof, span) tables of the
- * configuration.  Returns the number of equations and of off-diagonal terms.                     */
+ * configuration.  Returns the number of equations of the structure and the number of
+ * off-diagonal terms in the rows this domain holds.
+ *
+ * Several domains (numprocs > 1): every engine holds the rows of the nodes its own elements touch
+ * -- a contiguous range of equations, w3d_assemble_rows -- in the layout of the WHOLE structure
+ * (a row lists every column the structure has there, whichever domain's elements contribute),
+ * with the values summed over its own elements.  Ranges of neighbouring domains overlap on the
+ * interface nodes; there the rows have identical structure and the caller adds the values
+ * (what wmpi_combine_stf + the root assembly do in the reference, mpi_code_real.f:2551).
+ * One domain: the range is all equations and nothing below changes meaning.                      */
 int32_t w3d_assemble_setup(w3d_engine *h, const int32_t *cstmap, const int32_t *edest,
                            int32_t *neqns_out, int64_t *ncoeff_out);
-/* the integer structure: dof_eqn_map(nodof), eqn_node_map(neqns), k_ptrs(neqns),
- * k_indexes(ncoeff); any pointer may be NULL                                                     */
+/* the rows of this domain: equations first_eqn .. first_eqn + n_eqns - 1 (1-based)              */
+int32_t w3d_assemble_rows(w3d_engine *h, int32_t *first_eqn, int32_t *n_eqns);
+/* the integer structure: dof_eqn_map(nodof), eqn_node_map(neqns) for the whole structure;
+ * k_ptrs(n_eqns), k_indexes(ncoeff) for this domain's rows; any pointer may be NULL              */
 int32_t w3d_assemble_structure(w3d_engine *h, int32_t *dof_eqn_map, int32_t *eqn_node_map,
                                int32_t *k_ptrs, int32_t *k_indexes);
 /* assem_by_row on the element stiffnesses of the last w3d_tanstf / w3d_tanstf_resident (call
  * w3d_tanstf with estiff == NULL to keep them on the device).  Sums are taken in the reference's
- * order (elements on the node ascending, element columns ascending): bit-reproducible.  k_diag /
- * k_coeffs: host buffers, or both NULL to leave the result in device memory.                     */
+ * order (elements on the node ascending, element columns ascending): bit-reproducible.  k_diag
+ * (n_eqns) / k_coeffs (ncoeff): host buffers for this domain's rows, or both NULL to leave the
+ * result in device memory.                                                                       */
 int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs);
 
 /* ---- structure residual and its norms (SURVEY 8(f) NEXT-2) ------------------------------------

@@ -101,7 +101,6 @@ def test_device_assembly_matches_the_restatement_bit_for_bit(constrained):
 
 @pytest.mark.gpu
 def test_device_assembly_refuses_what_is_not_built():
-    from warp3d_b200 import slab_domains
     from warp3d_b200.engine import Engine, EngineError
     m, cst = _case(nx=4, ny=3, nz=3, seed=3, block_size=6)
     e = Engine(m)
@@ -110,10 +109,55 @@ def test_device_assembly_refuses_what_is_not_built():
         e.assemble()
     assert "w3d_assemble_setup" in str(err.value)
     e.close()
-    # several domains: rows at interface nodes would need the neighbours' elements
-    m.elblks[:, 2] = slab_domains(m, 2)
-    e2 = Engine(m, myid=0, numprocs=2)
-    with pytest.raises(EngineError) as err:
-        e2.assemble_setup(cst)
-    assert "one domain" in str(err.value)
-    e2.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndom", [2, 3])
+def test_device_assembly_by_domains_adds_up_to_the_one_domain_result(ndom):
+    """numprocs > 1: every engine returns the rows of the nodes its elements touch, in the layout of
+    the whole structure; rows of interface nodes come from two domains and add."""
+    from warp3d_b200 import slab_domains
+    from warp3d_b200.engine import Engine
+    m, cst = _case(nx=5, ny=4, nz=6, seed=13, block_size=10)
+    (step, iters), = list(load_path(m, nsteps=1, strain=3.0e-3))
+    itr, u, du = iters[-1]
+
+    def run(e):
+        for it, uu, dd in iters:
+            e.drive_eps_sig_internal_forces(step, it, uu, dd)
+        e.tanstf(step, itr, u, du, to_host=False)
+
+    e1 = Engine(m)
+    run(e1)
+    s1 = e1.assemble_setup(cst)
+    kd1, kc1 = e1.assemble()
+    assert s1["first_eqn"] == 1 and s1["n_eqns"] == s1["neqns"]
+    start1 = np.concatenate([[0], np.cumsum(s1["k_ptrs"])])
+    e1.close()
+
+    m.elblks[:, 2] = slab_domains(m, ndom)
+    kd_sum, kc_sum = np.zeros_like(kd1), np.zeros_like(kc1)
+    covered = np.zeros(s1["neqns"], dtype=np.int32)
+    for rank in range(ndom):
+        e = Engine(m, myid=rank, numprocs=ndom)
+        run(e)
+        s = e.assemble_setup(cst)
+        kd, kc = e.assemble()
+        lo, n = s["first_eqn"] - 1, s["n_eqns"]
+        assert 0 < n < s1["neqns"] and s["neqns"] == s1["neqns"]
+        assert np.array_equal(s["dof_eqn_map"], s1["dof_eqn_map"]) and np.array_equal(s["eqn_node_map"], s1["eqn_node_map"])
+        # the rows carry the structure of the whole model, bit for bit
+        assert np.array_equal(s["k_ptrs"], s1["k_ptrs"][lo:lo + n])
+        assert np.array_equal(s["k_indexes"], s1["k_indexes"][start1[lo]:start1[lo + n]])
+        assert kd.size == n and kc.size == s["ncoeff"] == start1[lo + n] - start1[lo]
+        kd_sum[lo:lo + n] += kd
+        kc_sum[start1[lo]:start1[lo + n]] += kc
+        covered[lo:lo + n] += 1
+        e.close()
+    assert covered.min() == 1 and covered.max() == 2            # interface rows come twice
+    once = covered == 1
+    assert np.array_equal(kd_sum[once], kd1[once])              # rows of one domain: the same bits
+    rows = np.repeat(np.arange(s1["neqns"]), s1["k_ptrs"])
+    assert np.array_equal(kc_sum[once[rows]], kc1[once[rows]])
+    scale = max(abs(kd1).max(), abs(kc1).max())                 # interface rows: one more rounding
+    assert abs(kd_sum - kd1).max() <= 1e-14 * scale and abs(kc_sum - kc1).max() <= 1e-14 * scale

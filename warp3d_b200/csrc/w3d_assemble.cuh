@@ -24,15 +24,15 @@ namespace {
 
 // assem_a_row + assem_a_row_24 (assemble_code.f:785-935) for every equation at once
 __global__ void __launch_bounds__(128) k_assemble_rows(
-    int neqns, const int32_t *__restrict__ eqn_node, const int8_t *__restrict__ eqn_comp,
+    int neqns, int eq0, const int32_t *__restrict__ eqn_node, const int8_t *__restrict__ eqn_comp,
     const int32_t *__restrict__ inv_ptr, const int32_t *__restrict__ inv_epos,
     const int8_t *__restrict__ inv_lnode, const int32_t *__restrict__ eeqn,
     const double *__restrict__ estiff, const long long *__restrict__ row_start,
     const int32_t *__restrict__ kidx, double *__restrict__ kdiag, double *__restrict__ kcoef) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;   // row of this domain; equation eq0 + r + 1
   if (r >= neqns) return;
-  const int srow = r + 1;
-  const int node = eqn_node[r], comp = eqn_comp[r];
+  const int srow = eq0 + r + 1;
+  const int node = eqn_node[eq0 + r], comp = eqn_comp[eq0 + r];
   const long long rs = row_start[r];
   const int n = (int)(row_start[r + 1] - rs);
   double *row = kcoef + rs;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) k_assemble_rows(
 constexpr int ASM_WARPS = 4;       // warps (nodes) per CTA
 constexpr int ASM_MAXROW = 192;    // longest row this kernel takes (81 on a structured hex8 mesh)
 __global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_nodes(
-    int node0, int nonode, const int32_t *__restrict__ dof_eqn, const int32_t *__restrict__ inv_ptr,
+    int node0, int nonode, int eq0, const int32_t *__restrict__ dof_eqn, const int32_t *__restrict__ inv_ptr,
     const int32_t *__restrict__ inv_epos, const int8_t *__restrict__ inv_lnode,
     const int32_t *__restrict__ eeqn, const double *__restrict__ estiff,
     const long long *__restrict__ row_start, const int32_t *__restrict__ kidx,
@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_nodes(
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     srow[c] = dof_eqn[3 * node + c];
-    rs[c] = srow[c] ? row_start[srow[c] - 1] : 0;
-    n[c] = srow[c] ? (int)(row_start[srow[c]] - rs[c]) : 0;
+    rs[c] = srow[c] ? row_start[srow[c] - 1 - eq0] : 0;              // rows are stored from eq0 on
+    n[c] = srow[c] ? (int)(row_start[srow[c] - eq0] - rs[c]) : 0;
     for (int k = lane; k < n[c]; k += 32) { scols[w][c][k] = kidx[rs[c] + k]; sval[w][c][k] = 0.0; }
     if (lane == 0) sdiag[w][c] = 0.0;
   }
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_nodes(
   for (int c = 0; c < 3; ++c) {
     if (srow[c] == 0) continue;
     for (int k = lane; k < n[c]; k += 32) kcoef[rs[c] + k] = sval[w][c][k];
-    if (lane == 0) kdiag[srow[c] - 1] = sdiag[w][c];
+    if (lane == 0) kdiag[srow[c] - 1 - eq0] = sdiag[w][c];
   }
 }
 
@@ -141,8 +141,6 @@ int32_t w3d_assemble_setup(w3d_engine *h, const int32_t *cstmap, const int32_t *
   if (!h || !cstmap || !edest) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   const w3d_engine_config &c = h->cfg;
-  if (c.numprocs > 1)
-    return h->fail(W3D_ERR_UNSUPPORTED, "device assembly is built for one domain (numprocs = 1)");
   CUDA_TRY(cudaSetDevice(h->device));
   AssemblyData &A = h->assembly;
   A.release();
@@ -161,66 +159,98 @@ int32_t w3d_assemble_setup(w3d_engine *h, const int32_t *cstmap, const int32_t *
   }
   A.neqns = neq;
   if (neq == 0) return h->fail(W3D_ERR_CONFIG, "no free dof");
-  // ---- element tables in d_estiff order, inverse incidences (setup.f:158-190: ascending elements)
+  // ---- element tables, inverse incidences (setup.f:158-190: ascending elements).  Two sets:
+  //      every element of the model for the sparsity (the rows are those of the whole structure,
+  //      whichever domain holds the contributing elements), this domain's elements in d_estiff
+  //      order for the values.
   const long long nel = h->n_owned_elems;
-  std::vector<int32_t> eeqn((size_t)nel * 24);
-  std::vector<int32_t> enode((size_t)nel * 8);
-  std::vector<int32_t> inv_count(nonode + 1, 0);
-  // elements sorted by element number: the blocks hold consecutive elements
-  std::vector<std::pair<int, long long>> order;   // (element number, position)
-  order.reserve(nel);
+  const int noelem = c.noelem;
+  std::vector<int32_t> eeqn((size_t)nel * 24);          // owned, by position in d_estiff
+  std::vector<int32_t> eeqn_all((size_t)noelem * 24);   // all, by element number
+  std::vector<int32_t> enode_all((size_t)noelem * 8);
+  std::vector<int32_t> cnt_all(nonode + 1, 0), cnt_own(nonode + 1, 0);
+  std::vector<long long> pos_of((size_t)noelem, -1);     // element number - 1 -> position, -1 = not owned
+  int node_lo = nonode, node_hi = 0;
   for (const BlockInfo &b : h->blocks) {
-    if (!b.owned) continue;
     if (b.totdof != 24) return h->fail(W3D_ERR_UNSUPPORTED, "assembly: 24-dof elements only");
     for (int i = 0; i < b.span; ++i) {
-      const long long pos = b.epos0 + i;
+      const int elem0 = b.felem - 1 + i;
+      if (elem0 < 0 || elem0 >= noelem) return h->fail(W3D_ERR_CONFIG, "element number out of range in block table");
       const int32_t *ed = edest + b.tab_off + (size_t)i * 24;
+      int32_t *q = &eeqn_all[(size_t)elem0 * 24];
+      int32_t *en = &enode_all[(size_t)elem0 * 8];
       for (int k = 0; k < 24; ++k) {
         const int d = ed[k];
         if (d < 1 || d > nodof) return h->fail(W3D_ERR_CONFIG, "edest entry %d out of range", d);
-        eeqn[(size_t)pos * 24 + k] = A.dof_eqn_map[d - 1];
+        q[k] = A.dof_eqn_map[d - 1];
       }
       for (int k = 0; k < 8; ++k) {
         const int nd = (ed[k] - 1) / 3;   // 0-based node of local node k (u-dof = dstmap(node))
         if (ed[8 + k] != ed[k] + 1 || ed[16 + k] != ed[k] + 2)
           return h->fail(W3D_ERR_CONFIG, "edest is not in the u(8), v(8), w(8) order of a node-major dof map");
         for (int p = 0; p < k; ++p)
-          if (enode[(size_t)pos * 8 + p] == nd)
+          if (en[p] == nd)
             return h->fail(W3D_ERR_UNSUPPORTED, "assembly: repeated nodes in an element (collapsed elements) not built");
-        enode[(size_t)pos * 8 + k] = nd;
-        ++inv_count[nd + 1];
+        en[k] = nd;
+        ++cnt_all[nd + 1];
+        if (b.owned) {
+          ++cnt_own[nd + 1];
+          node_lo = std::min(node_lo, nd);
+          node_hi = std::max(node_hi, nd + 1);
+        }
       }
-      order.emplace_back(b.felem + i, pos);
+      if (b.owned) {
+        pos_of[elem0] = b.epos0 + i;
+        std::memcpy(&eeqn[(size_t)(b.epos0 + i) * 24], q, sizeof(int32_t) * 24);
+      }
     }
   }
-  std::sort(order.begin(), order.end());
-  std::vector<int32_t> inv_ptr(nonode + 1, 0);
-  for (int nd = 0; nd < nonode; ++nd) inv_ptr[nd + 1] = inv_ptr[nd] + inv_count[nd + 1];
-  std::vector<int32_t> fill(inv_ptr.begin(), inv_ptr.end() - 1);
+  if (node_hi <= node_lo) return h->fail(W3D_ERR_CONFIG, "assembly: this domain owns no element");
+  // inverse incidences by ascending element number
+  std::vector<int32_t> ptr_all(nonode + 1, 0), inv_ptr(nonode + 1, 0);
+  for (int nd = 0; nd < nonode; ++nd) {
+    ptr_all[nd + 1] = ptr_all[nd] + cnt_all[nd + 1];
+    inv_ptr[nd + 1] = inv_ptr[nd] + cnt_own[nd + 1];
+  }
+  std::vector<int32_t> fill_all(ptr_all.begin(), ptr_all.end() - 1), fill(inv_ptr.begin(), inv_ptr.end() - 1);
+  std::vector<int32_t> inv_all((size_t)ptr_all[nonode]);      // element numbers - 1
   std::vector<int32_t> inv_epos((size_t)inv_ptr[nonode]);
   std::vector<int8_t> inv_lnode((size_t)inv_ptr[nonode]);
-  for (const auto &eo : order) {
-    const long long pos = eo.second;
+  for (int elem0 = 0; elem0 < noelem; ++elem0) {
+    const long long pos = pos_of[elem0];
     for (int k = 0; k < 8; ++k) {
-      const int nd = enode[(size_t)pos * 8 + k];
-      inv_epos[fill[nd]] = (int32_t)pos;
-      inv_lnode[fill[nd]] = (int8_t)k;
-      ++fill[nd];
+      const int nd = enode_all[(size_t)elem0 * 8 + k];
+      inv_all[fill_all[nd]++] = elem0;
+      if (pos >= 0) {
+        inv_epos[fill[nd]] = (int32_t)pos;
+        inv_lnode[fill[nd]] = (int8_t)k;
+        ++fill[nd];
+      }
     }
   }
+  // ---- the rows of this domain: equations of the nodes [node_lo, node_hi)
+  A.node_first_eqn.assign(nonode + 1, neq);
+  for (int r = neq - 1; r >= 0; --r) A.node_first_eqn[A.eqn_node_map[r] - 1] = r;
+  for (int nd = nonode - 1; nd >= 0; --nd)          // nodes without a free dof take the next node's
+    if (A.node_first_eqn[nd] > A.node_first_eqn[nd + 1]) A.node_first_eqn[nd] = A.node_first_eqn[nd + 1];
+  A.node_lo = node_lo; A.node_hi = node_hi;
+  A.eq0 = A.node_first_eqn[node_lo];
+  A.neq_local = A.node_first_eqn[node_hi] - A.eq0;
+  if (A.neq_local <= 0) return h->fail(W3D_ERR_CONFIG, "assembly: no free dof on this domain's nodes");
+  const int nloc = A.neq_local;
   // ---- sparsity: per equation the distinct columns right of the diagonal, ascending
-  A.k_ptrs.assign(neq, 0);
+  A.k_ptrs.assign(nloc, 0);
   A.k_indexes.clear();
-  A.k_indexes.reserve((size_t)neq * 40);
-  std::vector<long long> row_start(neq + 1, 0);
+  A.k_indexes.reserve((size_t)nloc * 40);
+  std::vector<long long> row_start(nloc + 1, 0);
   std::vector<int32_t> cand;
   cand.reserve(27 * 3 * 8);
-  for (int r = 0; r < neq; ++r) {
-    const int srow = r + 1;
-    const int nd = A.eqn_node_map[r] - 1;
+  for (int r = 0; r < nloc; ++r) {
+    const int srow = A.eq0 + r + 1;
+    const int nd = A.eqn_node_map[A.eq0 + r] - 1;
     cand.clear();
-    for (int j = inv_ptr[nd]; j < inv_ptr[nd + 1]; ++j) {
-      const int32_t *q = &eeqn[(size_t)inv_epos[j] * 24];
+    for (int j = ptr_all[nd]; j < ptr_all[nd + 1]; ++j) {
+      const int32_t *q = &eeqn_all[(size_t)inv_all[j] * 24];
       for (int k = 0; k < 24; ++k)
         if (q[k] > srow) cand.push_back(q[k]);
     }
@@ -230,7 +260,7 @@ int32_t w3d_assemble_setup(w3d_engine *h, const int32_t *cstmap, const int32_t *
     A.k_indexes.insert(A.k_indexes.end(), cand.begin(), cand.end());
     row_start[r + 1] = row_start[r] + (long long)cand.size();
   }
-  A.ncoeff = row_start[neq];
+  A.ncoeff = row_start[nloc];
   // ---- upload
   std::vector<int32_t> eqn_node0(neq);
   for (int r = 0; r < neq; ++r) eqn_node0[r] = A.eqn_node_map[r] - 1;
@@ -251,20 +281,26 @@ int32_t w3d_assemble_setup(w3d_engine *h, const int32_t *cstmap, const int32_t *
   CUDA_TRY(up(&A.d_eeqn, eeqn));
   CUDA_TRY(up(&A.d_dof_eqn, A.dof_eqn_map));
   A.h_row_start = row_start;
-  A.node_first_eqn.assign(nonode + 1, neq);
-  for (int r = neq - 1; r >= 0; --r) A.node_first_eqn[A.eqn_node_map[r] - 1] = r;
-  for (int nd = nonode - 1; nd >= 0; --nd)          // nodes without a free dof take the next node's
-    if (A.node_first_eqn[nd] > A.node_first_eqn[nd + 1]) A.node_first_eqn[nd] = A.node_first_eqn[nd + 1];
   CUDA_TRY(cudaStreamCreateWithFlags(&A.copy_stream, cudaStreamNonBlocking));
   for (int k = 0; k < AssemblyData::NCHUNK; ++k)
     CUDA_TRY(cudaEventCreateWithFlags(&A.chunk_done[k], cudaEventDisableTiming));
   A.max_row = 0;
-  for (int r = 0; r < neq; ++r) A.max_row = std::max(A.max_row, (int)A.k_ptrs[r]);
-  CUDA_TRY(cudaMalloc((void **)&A.d_kdiag, sizeof(double) * (size_t)neq));
+  for (int r = 0; r < nloc; ++r) A.max_row = std::max(A.max_row, (int)A.k_ptrs[r]);
+  CUDA_TRY(cudaMalloc((void **)&A.d_kdiag, sizeof(double) * (size_t)nloc));
   CUDA_TRY(cudaMalloc((void **)&A.d_kcoef, sizeof(double) * (size_t)(A.ncoeff ? A.ncoeff : 1)));
   A.ready = true;
   if (neqns_out) *neqns_out = neq;
   if (ncoeff_out) *ncoeff_out = A.ncoeff;
+  return W3D_OK;
+}
+
+// the rows this domain assembles: equations first_eqn .. first_eqn + n_eqns - 1 (1-based)
+int32_t w3d_assemble_rows(w3d_engine *h, int32_t *first_eqn, int32_t *n_eqns) {
+  if (!h) return W3D_ERR_ARG;
+  const AssemblyData &A = h->assembly;
+  if (!A.ready) return h->fail(W3D_ERR_ARG, "w3d_assemble_setup has not been called");
+  if (first_eqn) *first_eqn = A.eq0 + 1;
+  if (n_eqns) *n_eqns = A.neq_local;
   return W3D_OK;
 }
 
@@ -293,19 +329,19 @@ int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs) {
     // host output: assemble node ranges one after the other and start the copy of each range's
     // rows (equations are numbered in node order, so they are contiguous) on a second stream as
     // soon as its kernel is done -- the assembly hides behind the PCIe transfer
-    const int nonode = h->cfg.nonode;
+    const int nnode = A.node_hi - A.node_lo;
     const int nchunk = AssemblyData::NCHUNK;
     for (int k = 0; k < nchunk; ++k) {
-      const int na = (int)((long long)nonode * k / nchunk), nb = (int)((long long)nonode * (k + 1) / nchunk);
+      const int na = A.node_lo + (int)((long long)nnode * k / nchunk), nb = A.node_lo + (int)((long long)nnode * (k + 1) / nchunk);
       if (nb <= na) continue;
       k_assemble_nodes<<<(nb - na + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
-          na, nb, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn, h->d_estiff,
+          na, nb, A.eq0, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn, h->d_estiff,
           A.d_row_start, A.d_kidx, A.d_kdiag, A.d_kcoef);
       CUDA_TRY(cudaGetLastError());
       h->launches += 1;
       CUDA_TRY(cudaEventRecord(A.chunk_done[k], h->stream));
       CUDA_TRY(cudaStreamWaitEvent(A.copy_stream, A.chunk_done[k], 0));
-      const int ea = A.node_first_eqn[na], eb = A.node_first_eqn[nb];   // equations [ea, eb)
+      const int ea = A.node_first_eqn[na] - A.eq0, eb = A.node_first_eqn[nb] - A.eq0;   // local rows [ea, eb)
       if (eb > ea) {
         const long long ca = A.h_row_start[ea], cb = A.h_row_start[eb];
         CUDA_TRY(cudaMemcpyAsync(k_diag + ea, A.d_kdiag + ea, sizeof(double) * (size_t)(eb - ea), cudaMemcpyDeviceToHost, A.copy_stream));
@@ -318,19 +354,18 @@ int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs) {
     return W3D_OK;
   }
   if (A.max_row <= ASM_MAXROW) {
-    const int nonode = h->cfg.nonode;
-    k_assemble_nodes<<<(nonode + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
-        0, nonode, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn, h->d_estiff,
+    k_assemble_nodes<<<(A.node_hi - A.node_lo + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
+        A.node_lo, A.node_hi, A.eq0, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn, h->d_estiff,
         A.d_row_start, A.d_kidx, A.d_kdiag, A.d_kcoef);
   } else {   // very long rows (nodes shared by many elements): thread per equation
     const int tpb = 128;
-    k_assemble_rows<<<(A.neqns + tpb - 1) / tpb, tpb, 0, h->stream>>>(
-        A.neqns, A.d_eqn_node, A.d_eqn_comp, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn,
+    k_assemble_rows<<<(A.neq_local + tpb - 1) / tpb, tpb, 0, h->stream>>>(
+        A.neq_local, A.eq0, A.d_eqn_node, A.d_eqn_comp, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn,
         h->d_estiff, A.d_row_start, A.d_kidx, A.d_kdiag, A.d_kcoef);
   }
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
-  if (k_diag) CUDA_TRY(cudaMemcpyAsync(k_diag, A.d_kdiag, sizeof(double) * (size_t)A.neqns, cudaMemcpyDeviceToHost, h->stream));
+  if (k_diag) CUDA_TRY(cudaMemcpyAsync(k_diag, A.d_kdiag, sizeof(double) * (size_t)A.neq_local, cudaMemcpyDeviceToHost, h->stream));
   if (k_coeffs && A.ncoeff) CUDA_TRY(cudaMemcpyAsync(k_coeffs, A.d_kcoef, sizeof(double) * (size_t)A.ncoeff, cudaMemcpyDeviceToHost, h->stream));
   if (k_diag || k_coeffs) CUDA_TRY(cudaStreamSynchronize(h->stream));
   return W3D_OK;

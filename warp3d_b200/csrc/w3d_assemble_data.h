@@ -8,21 +8,25 @@ namespace w3d {
 
 struct AssemblyData {
   bool ready = false;
-  int neqns = 0;
-  long long ncoeff = 0;
+  int neqns = 0;                     // equations of the whole structure (dof_map)
+  // rows held by this domain: the equations of the nodes its elements touch, a contiguous range
+  // (equations are numbered in node order).  One domain: all of them.
+  int eq0 = 0, neq_local = 0;        // first equation (0-based) and count
+  int node_lo = 0, node_hi = 0;      // node range [node_lo, node_hi)
+  long long ncoeff = 0;              // off-diagonal terms in those rows
   // host copies handed back by w3d_assemble_structure
   std::vector<int32_t> dof_eqn_map, eqn_node_map, k_ptrs, k_indexes;
   // device
   int32_t *d_eqn_node = nullptr;     // (neqns)  0-based node of each equation
   int8_t *d_eqn_comp = nullptr;      // (neqns)  dof component 0..2
-  long long *d_row_start = nullptr;  // (neqns + 1) offsets into k_indexes / k_coeffs
+  long long *d_row_start = nullptr;  // (neq_local + 1) offsets into k_indexes / k_coeffs, local rows
   int32_t *d_kidx = nullptr;         // (ncoeff)
   int32_t *d_inv_ptr = nullptr;      // (nonode + 1) into the two lists below
   int32_t *d_inv_epos = nullptr;     // position of the element in d_estiff / d_eeqn
   int8_t *d_inv_lnode = nullptr;     // local node number (0..7) of the node in that element
   int32_t *d_dof_eqn = nullptr;      // (nodof) equation number of each structure dof, 0 = constrained
   static constexpr int NCHUNK = 8;   // node ranges whose copy to the host overlaps the next range's assembly
-  std::vector<long long> h_row_start;   // (neqns + 1) host copy of d_row_start
+  std::vector<long long> h_row_start;   // (neq_local + 1) host copy of d_row_start
   std::vector<int32_t> node_first_eqn;  // (nonode + 1) first equation (0-based) at or after each node
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t chunk_done[NCHUNK] = {};

@@ -34,7 +34,7 @@ EXPORTS = (
     "w3d_tanstf_resident", "w3d_last_scalars", "w3d_engine_stream", "w3d_engine_synchronize",
     "w3d_engine_launch_count", "w3d_upload_displacements", "w3d_download_ifv",
     "w3d_download_estiff", "w3d_set_time_step",
-    "w3d_assemble_setup", "w3d_assemble_structure", "w3d_assemble",
+    "w3d_assemble_setup", "w3d_assemble_structure", "w3d_assemble", "w3d_assemble_rows",
     "w3d_residual_set_loads", "w3d_residual", "w3d_residual_device",
 )
 
@@ -264,11 +264,14 @@ class Engine:
         ed = np.ascontiguousarray(self.model.edest, dtype=np.int32)
         neq, nco = C.c_int32(), C.c_int64()
         self._check(self._L.w3d_assemble_setup(self._h, _ptr(cst), _ptr(ed), C.byref(neq), C.byref(nco)))
-        self._neqns, self._ncoeff = neq.value, nco.value
-        out = dict(neqns=neq.value, ncoeff=nco.value,
+        first, nloc = C.c_int32(), C.c_int32()
+        self._check(self._L.w3d_assemble_rows(self._h, C.byref(first), C.byref(nloc)))
+        # one domain: first_eqn = 1 and n_eqns = neqns; several: this domain's row range
+        self._neqns, self._ncoeff = nloc.value, nco.value
+        out = dict(neqns=neq.value, ncoeff=nco.value, first_eqn=first.value, n_eqns=nloc.value,
                    dof_eqn_map=np.empty(self.model.nodof, dtype=np.int32),
                    eqn_node_map=np.empty(neq.value, dtype=np.int32),
-                   k_ptrs=np.empty(neq.value, dtype=np.int32),
+                   k_ptrs=np.empty(nloc.value, dtype=np.int32),
                    k_indexes=np.empty(max(nco.value, 1), dtype=np.int32))
         self._check(self._L.w3d_assemble_structure(self._h, _ptr(out["dof_eqn_map"]), _ptr(out["eqn_node_map"]),
                                                    _ptr(out["k_ptrs"]), _ptr(out["k_indexes"])))
