@@ -10,7 +10,9 @@ load step so that about half of the Gauss points are plastic in the timed iterat
   value   Gauss-point updates/s with u, du and all state resident in HBM (whole job, all ranks)
   e2e     same metric through the host-buffer C-ABI calls: H2D of u, du; D2H of ifv and of the
           stiffness ASSEMBLED on the device (w3d_assemble: k_diag, k_coeffs); e2e_element_blocks
-          is the variant that returns the estiff(300,span) blocks instead (the only one at N > 1)
+          is the variant that returns the estiff(300,span) blocks instead.  At N > 1 every rank
+          returns the assembled rows of its own domain (w3d_assemble_rows)
+  residual  one w3d_residual call (upres + cvtest residual loop on the device), beside the step
   roofline, cpu_baseline, clocks: as the brief defines them.
 
 `--impl reference` times the CPU restatement of the reference path (oracle/, OpenMP over blocks
