@@ -349,45 +349,43 @@ def engine_arm(args):
     #      crosses to the host is the sparse upper triangle the solver consumes, not the element
     #      blocks.  x = xmin face clamped.  With several domains every rank returns the rows of the
     #      nodes its own elements touch (interface rows come from two ranks and add on the host).
-    asm = None
-    if True:
-        cst = np.zeros(nodof, dtype=np.int32)
-        xs = model.c.reshape(-1, 3)[:, 0]
-        cst.reshape(-1, 3)[xs <= xs.min() + 1e-9] = 1
-        ts0 = time.perf_counter()
-        st_ = eng.assemble_setup(cst)
-        setup_s = time.perf_counter() - ts0
-        kd_h, kc_h = pinned(st_["n_eqns"]), pinned(max(st_["ncoeff"], 1))
-        for _ in range(2):
-            de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
-            eng.tanstf_resident(TS, 1); eng.assemble(kd_h, kc_h)
-        barrier()
-        a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a0.record(S)
-        for _ in range(nrep_e2e):
-            de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
-            eng.tanstf_resident(TS, 1); eng.assemble(kd_h, kc_h)
-        a1.record(S)
-        for _ in range(nrep_e2e):
-            eng.assemble(to_host=False)
-        a2.record(S)
-        barrier()
-        asm = dict(ms=a0.elapsed_time(a1) / nrep_e2e, kernel_ms=a1.elapsed_time(a2) / nrep_e2e,
-                   neqns=st_["neqns"], ncoeff=st_["ncoeff"], setup_s=setup_s,
-                   d2h=8 * nodof + 8 * (st_["n_eqns"] + st_["ncoeff"]))
+    cst = np.zeros(nodof, dtype=np.int32)
+    xs = model.c.reshape(-1, 3)[:, 0]
+    cst.reshape(-1, 3)[xs <= xs.min() + 1e-9] = 1
+    ts0 = time.perf_counter()
+    st_ = eng.assemble_setup(cst)
+    setup_s = time.perf_counter() - ts0
+    kd_h, kc_h = pinned(st_["n_eqns"]), pinned(max(st_["ncoeff"], 1))
+    for _ in range(2):
+        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
+        eng.tanstf_resident(TS, 1); eng.assemble(kd_h, kc_h)
+    barrier()
+    a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    a0.record(S)
+    for _ in range(nrep_e2e):
+        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
+        eng.tanstf_resident(TS, 1); eng.assemble(kd_h, kc_h)
+    a1.record(S)
+    for _ in range(nrep_e2e):
+        eng.assemble(to_host=False)
+    a2.record(S)
+    barrier()
+    asm = dict(ms=a0.elapsed_time(a1) / nrep_e2e, kernel_ms=a1.elapsed_time(a2) / nrep_e2e,
+               neqns=st_["neqns"], ncoeff=st_["ncoeff"], setup_s=setup_s,
+               d2h=8 * nodof + 8 * (st_["n_eqns"] + st_["ncoeff"]))
 
-        # structure residual + convergence norms on the device (upres.f, cvtest.f:62-78): the internal
-        # forces stay in HBM, 7 scalars come back.  Not part of the timed step; reported beside it.
-        eng.residual_set_loads(cst, pbar=np.ones(nodof), load=np.ones(nodof))
-        for _ in range(3):
-            eng.residual(1, to_host=False)
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record(S)
-        for _ in range(20):
-            eng.residual(1, to_host=False)
-        r1.record(S)
-        barrier()
-        asm["residual_ms"] = r0.elapsed_time(r1) / 20
+    # structure residual + convergence norms on the device (upres.f, cvtest.f:62-78): the internal
+    # forces stay in HBM, 7 scalars come back.  Not part of the timed step; reported beside it.
+    eng.residual_set_loads(cst, pbar=np.ones(nodof), load=np.ones(nodof))
+    for _ in range(3):
+        eng.residual(1, to_host=False)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(S)
+    for _ in range(20):
+        eng.residual(1, to_host=False)
+    r1.record(S)
+    barrier()
+    asm["residual_ms"] = r0.elapsed_time(r1) / 20
 
     t = torch.tensor([total_ms, t_stress, t_tan, e2e_ms, e2e_wall_ms, float(launches), asm["ms"], asm["kernel_ms"],
                       float(asm["d2h"]), float(asm["ncoeff"])], dtype=torch.float64, device="cuda")
