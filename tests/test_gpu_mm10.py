@@ -82,3 +82,11 @@ def test_bcc_crystal_with_the_reference_voche_deck_values():
     ct = dict(e=150000.0, nu=0.28, slip="bcc", harden_n=20.0, voche_m=5.0, theta_o=400.0, tau_y=300.0,
               tau_v=1200.0)
     assert _run(_model(2, 2, 2, geonl=False, crystal=ct), nsteps=3, strain=3.0e-3) > 0.0
+
+
+def test_bcc48_two_crystals_per_point():
+    # the 48-system table (mod_crystals.f bcc48) goes through the second instantiation, k_mm10<48>;
+    # property values of example_problems_cp/simple_voce
+    ct = dict(e=200000.0, nu=0.3, slip="bcc48", harden_n=5.0, tau_y=205.0, tau_v=5000.0, voche_m=1.0,
+              theta_o=0.01, eps_dot_o_y=4.0e-05, alter_mode=True)
+    assert _run(_model(2, 2, 2, ncrystals=2, crystal=ct), nsteps=3, strain=3.0e-3) > 0.0

@@ -93,7 +93,7 @@ class EngineBackend:
         return self.e.residual(it)
 
 
-def _run_simple_voce(nsteps, nel=3, out_elem=21):
+def _run_simple_voce(nsteps, nel=3, out_elem=21, backend=None):
     ref = json.load(open(os.path.join(HERE, "golden", "simple_voce_reference.json")))
     m = build_structured_hex8(nel, nel, nel, materials=[Material(mat_type=10)], geonl=False, bbar=True,
                               block_size=4)                   # "blocking automatic size = 4"
@@ -117,17 +117,17 @@ def _run_simple_voce(nsteps, nel=3, out_elem=21):
     fixed, top = np.array(fixed), np.array(top)
     cons = np.concatenate([fixed, top])
     free = np.setdiff1d(np.arange(m.nodof), cons)
-    o, st = op.Oracle(m, nthreads=4), new_state(m)
+    be = (backend or OracleBackend)(m)
     u = np.zeros(m.nodof)
     stress, times, t, spread = [], [], 0.0, []
     for step in range(1, nsteps + 1):
         dt = 0.5 if step <= 10 else 0.1 if step <= 30 else 0.5 if step <= 40 else 1.0 if step <= 50 else 2.0
         dw = 0.0003 if step <= 10 else 1.0e-15
         m.dt = dt
-        o.sync_globals()
+        be.sync()
         du = np.zeros(m.nodof)
-        ifv, _ = o.eps_sig_ifv(st, step, 0, u, du)
-        K = assemble(m, o.tanstf(st, step, 0, u, du))
+        ifv, _ = be.eps_sig_ifv(step, 0, u, du)
+        K = assemble(m, be.tanstf(step, 0, u, du))
         for it in range(1, 12):
             delta = np.zeros(m.nodof)
             if it == 1:
@@ -135,16 +135,16 @@ def _run_simple_voce(nsteps, nel=3, out_elem=21):
             rhs = (-ifv)[free] - K[free][:, cons] @ delta[cons]
             delta[free] = spla.spsolve(K[free][:, free].tocsc(), rhs)
             du = du + delta
-            ifv, sc = o.eps_sig_ifv(st, step, it, u, du)
+            ifv, sc = be.eps_sig_ifv(step, it, u, du)
             assert not sc["material_cut_step"], (step, it)
             rn = np.linalg.norm(ifv[free]); rf = np.linalg.norm(ifv[cons]) or 1.0
             if it >= 2 and rn <= 1.0e-9 * rf:              # the deck: at least 2 iterations
                 break
-            K = assemble(m, o.tanstf(st, step, it, u, du))
+            K = assemble(m, be.tanstf(step, it, u, du))
         u = u + du
-        o.update(st); o.adaptive_save(st)
+        be.update()
         t += dt
-        s = st.urcs_n.reshape(-1, 8, 9)                     # (element, Gauss point, component)
+        s = be.state().urcs_n.reshape(-1, 8, 9)             # (element, Gauss point, component)
         spread.append(float(np.ptp(s[:, :, 2]) / abs(s[:, :, 2]).max()))
         # "output stresses 21" with the elements' `center` option: the element value is the
         # average over its integration points
@@ -411,6 +411,16 @@ def test_verification_test82_voche_model():
 
 
 # ---- the same known answers through the CUDA engine (the product, not its checker) ------------------
+@pytest.mark.gpu
+def test_engine_reproduces_the_simple_voce_curve():
+    """25 crystals per point with the 48-system bcc table (k_mm10<48>): the whole published curve."""
+    nsteps = 79
+    times, stress, ref, spread = _run_simple_voce(nsteps, backend=EngineBackend)
+    sr = np.array(ref["stress_cp"][1:nsteps + 1])
+    rel = np.abs(stress - sr) / sr
+    assert rel.max() < 2.0e-5 and rel[9:].max() < 6.0e-6 and rel[-1] < 3.0e-7, (rel.max(), rel[-1])
+
+
 @pytest.mark.gpu
 def test_engine_reproduces_verification_test24():
     sxx, ref, u, m = _run_test24(backend=EngineBackend)

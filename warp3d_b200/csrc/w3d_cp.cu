@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(TPB * MM10_GROUPS, MM10_MIN_CTAS) k_mm10(const
   for (int k = 0; k < 9; ++k) a.urcs_n1[k * ng + g] = cgn1[k];
 }
 
-int mm10_props_doubles() { return (int)(sizeof(Props<12>) / sizeof(double)); }
+int mm10_props_doubles(int nslip) {
+  return (int)((nslip <= 12 ? sizeof(Props<12>) : sizeof(Props<48>)) / sizeof(double));
+}
 int mm10_hist_size(int nslip, int num_hard, int ncrystals) { return Layout::make(nslip, num_hard).size(ncrystals); }
 void mm10_layout_offsets(int nslip, int num_hard, int *o_gradfe, int *o_Rp0) {
   const Layout L = Layout::make(nslip, num_hard);
@@ -91,25 +93,36 @@ void mm10_setup_props_host(const double *ctd, const double *angles, int angle_ty
   const double *ti = ctd + nd;
   ct.nslip = (int)ti[0]; ct.num_hard = (int)ti[1]; ct.h_type = (int)ti[2]; ct.tang_calc = (int)ti[3];
   ct.miter = (int)ti[4]; ct.solver = (int)ti[5]; ct.alter_mode = (int)ti[6];
-  Props<12> P;
-  std::memset(&P, 0, sizeof P);
-  setup_props<12>(ct, angles, angle_type, P);
-  std::memcpy(props_out, &P, sizeof P);
+  if (ct.nslip <= 12) {
+    Props<12> P;
+    std::memset(&P, 0, sizeof P);
+    setup_props<12>(ct, angles, angle_type, P);
+    std::memcpy(props_out, &P, sizeof P);
+  } else {
+    Props<48> P;
+    std::memset(&P, 0, sizeof P);
+    setup_props<48>(ct, angles, angle_type, P);
+    std::memcpy(props_out, &P, sizeof P);
+  }
 }
-cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {
-  const size_t need = sizeof(Props<12>) * (size_t)a.ncrystals * EPC * MM10_GROUPS;
+template <int NS>
+static cudaError_t launch_mm10_ns(const CpArgs &a, int ncta, cudaStream_t st) {
+  const size_t need = sizeof(Props<NS>) * (size_t)a.ncrystals * EPC * MM10_GROUPS;
   const int smem = need <= (size_t)MM10_PROPS_SMEM_LIMIT ? (int)need : 0;
   static bool set = false;
   if (!set) {
-    const cudaError_t e = cudaFuncSetAttribute(k_mm10<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const cudaError_t e = cudaFuncSetAttribute(k_mm10<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                MM10_PROPS_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     set = true;
   }
   CpArgs b = a;
   b.ncta = ncta;
-  k_mm10<12><<<(ncta + MM10_GROUPS - 1) / MM10_GROUPS, TPB * MM10_GROUPS, smem, st>>>(b);
+  k_mm10<NS><<<(ncta + MM10_GROUPS - 1) / MM10_GROUPS, TPB * MM10_GROUPS, smem, st>>>(b);
   return cudaGetLastError();
+}
+cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {
+  return a.nslip <= 12 ? launch_mm10_ns<12>(a, ncta, st) : launch_mm10_ns<48>(a, ncta, st);
 }
 
 }  // namespace w3d

@@ -9,7 +9,7 @@ namespace w3d {
 
 struct CpArgs {
   const CtaDesc *cta;
-  const double *props;        // [slot][ncrystals][props_doubles]  (w3d_mm10::Props<12>)
+  const double *props;        // [slot][ncrystals][props_doubles]  (w3d_mm10::Props<12> or <48>)
   const double *hist_n, *urcs_n, *scratch;
   double *hist_n1, *urcs_n1;
   int *flags;
@@ -19,7 +19,10 @@ struct CpArgs {
   int ncta;                   // number of CTA descriptors (set by launch_mm10)
 };
 
-int mm10_props_doubles();
+// Two instantiations of the shared core: up to 12 slip systems (fcc, bcc: the fast path, property
+// records staged in shared memory) and up to 48 (bcc48 and the other long tables of
+// mod_crystals.f; records read from global memory).
+int mm10_props_doubles(int nslip);
 // host: one property record from a crystal-type record (setup_mm10_rknstr, rknstr.f:1568-2027)
 void mm10_setup_props_host(const double *crystal_type_rec, const double *angles, int angle_type,
                            double *props_out);

@@ -289,8 +289,11 @@ int create_impl(w3d_engine *h) {
         return fail(W3D_ERR_CONFIG, "block %d uses mm10 but no crystal tables were given", blk + 1);
       const double *ct0 = c.crystal_types;
       const int nslip = (int)ct0[337], num_hard = (int)ct0[338], h_type = (int)ct0[339];
-      if (nslip > 12 || num_hard != 1 || h_type != 1)
-        return fail(W3D_ERR_UNSUPPORTED, "block %d: mm10 with nslip %d, num_hard %d, hardening %d (built: <=12 systems, Voce)", blk + 1, nslip, num_hard, h_type);
+      if (nslip < 1 || nslip > 48 || num_hard != 1 || h_type != 1)
+        return fail(W3D_ERR_UNSUPPORTED, "block %d: mm10 with nslip %d, num_hard %d, hardening %d (built: <=48 systems, Voce)", blk + 1, nslip, num_hard, h_type);
+      for (int t = 1; t < c.n_crystal_types; ++t)      // one kernel instantiation per segment
+        if (((int)c.crystal_types[(size_t)t * W3D_CRYSTAL_TYPE_DOUBLES + 337] <= 12) != (nslip <= 12))
+          return fail(W3D_ERR_UNSUPPORTED, "mm10: crystal types with <=12 and with >12 slip systems in one model");
       if (b.hist_size != mm10_hist_size(nslip, num_hard, c.cp_ncrystals))
         return fail(W3D_ERR_CONFIG, "block %d: mm10 history size %d != %d", blk + 1, b.hist_size, mm10_hist_size(nslip, num_hard, c.cp_ncrystals));
     }
@@ -378,9 +381,9 @@ int create_impl(w3d_engine *h) {
     if (sg.mat_type == 10) {
       // setup_mm10_rknstr (rknstr.f:1568-2027) once per (element, crystal): rotation from the
       // Kocks angles, Schmid tensors and elastic stiffness in the reference frame
-      const int pd = mm10_props_doubles();
       sg.ncrystals = c.cp_ncrystals;
       sg.nslip = (int)c.crystal_types[337];
+      const int pd = mm10_props_doubles(sg.nslip);
       sg.num_hard = (int)c.crystal_types[338];
       mm10_layout_offsets(sg.nslip, sg.num_hard, &sg.o_gradfe, &sg.o_Rp0);
       std::vector<double> cp((size_t)sg.nslots * sg.ncrystals * pd, 0.0);

@@ -6,7 +6,7 @@
 namespace w3d {
 
 constexpr int RES_TPB = 256;
-constexpr int RES_MAX_CTAS = 592;   // 148 SMs x 4: partials of the two-stage, fixed-order reduction
+constexpr int RES_MAX_CTAS = 1184;  // 148 SMs x 8 (all 64 warps of an SM): partials of the two-stage, fixed-order reduction
 
 struct ResidualPartial {            // one per CTA of k_residual, then one for the whole vector
   double sum_res2, mgload2, sum_loads, max_abs;
