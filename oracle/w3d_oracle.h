@@ -124,7 +124,7 @@ int64_t w3do_block_offset(const w3do_model *m, int32_t blk, int32_t which);
 /* mm10: number of doubles in one property record; fill one record from a crystal-type table
  * entry (w3d_mm10::CrystalType laid out as doubles, see oracle_py.py) and Kocks angles.          */
 int32_t w3do_mm10_props_doubles(void);
-int32_t w3do_mm10_props_doubles_for(int32_t nslip);   /* 12-system record, or 48-system (CPU only) */
+int32_t w3do_mm10_props_doubles_for(int32_t nslip);   /* 12-system record, or 48-system */
 int32_t w3do_mm10_crystal_type_doubles(void);
 void w3do_mm10_setup_props(const double *crystal_type, const double *angles, int32_t angle_type,
                            double *props_out);
