@@ -36,6 +36,9 @@ WORKLOADS = {
     # name: (dims, material kind, CPU sample dims)
     "hex8_2m_mm01": ((200, 100, 100), "mm01", (64, 50, 50)),   # BASELINE.json configs[3]
     "hex8_256k_mm01": ((64, 64, 64), "mm01", (64, 50, 50)),    # smaller variant for quick checks
+    # SURVEY 8(d) variants of the headline workload: every point elastic; mixed hardening (beta 0.5)
+    "hex8_2m_mm01_elastic": ((200, 100, 100), "mm01", (64, 50, 50)),
+    "hex8_2m_mm01_beta05": ((200, 100, 100), "mm01", (64, 50, 50)),
     "hex8_1m_mm10": ((100, 100, 100), "mm10", (32, 25, 25)),   # BASELINE.json configs[4]: CP polycrystal
     "hex8_64k_mm10": ((40, 40, 40), "mm10", (32, 25, 25)),
     # mm05 cyclic plasticity, both options (the GP one with the reference's own deck values, ksi)
@@ -56,8 +59,13 @@ def make_workload(name, dims=None):
     wdims, kind, _ = WORKLOADS[name]
     dims = dims or wdims
     if kind == "mm01":
-        m = build_structured_hex8(*dims)
-        return m, 0.5 * graded_stretch(m), 1
+        if name.endswith("_beta05"):
+            m = build_structured_hex8(*dims, materials=[Material(beta=0.5)])
+        else:
+            m = build_structured_hex8(*dims)
+        # elastic variant: 0.2 x the stretch keeps the largest strain (1.2e-3 after two steps)
+        # under the yield strain 2e-3
+        return m, (0.2 if name.endswith("_elastic") else 0.5) * graded_stretch(m), 1
     if kind.startswith("mm05"):
         from warp3d_b200 import cyclic_fa_material, cyclic_gp_material
         mat = cyclic_fa_material() if kind == "mm05_fa" else cyclic_gp_material()
@@ -80,7 +88,9 @@ def workload_description(name):
         # instructions / Gauss points) from the ncu per-instruction counts of the two kernels on the
         # 50 %-plastic workload (profiles/r01_summary.md "mm01 instruction mix"); the hand count of
         # the algorithm agrees to a few percent
-        return dict(material="mm01 bilinear (E=200e9 as real*4, nu=0.3, yld=400e6, tan_e=E/100)",
+        return dict(material="mm01 bilinear (E=200e9 as real*4, nu=0.3, yld=400e6, tan_e=E/100)"
+                             + (", beta 0.5 (mixed hardening)" if name.endswith("_beta05") else "")
+                             + (", stretch scaled to stay elastic" if name.endswith("_elastic") else ""),
                     bytes_stress=776.0, bytes_tanstf=708.0, flops_stress=3573.0, flops_tanstf=4540.0,
                     # measured DRAM bytes per Gauss point (dram__bytes_read + write of one `ncu --set
                     # full` launch on hex8_256k_mm01 / 2 097 152 points,
