@@ -68,9 +68,10 @@ constexpr int STPB = TPB * STRESS_GROUPS;   // threads per CTA of the stress ker
 constexpr int SEPC = EPC * STRESS_GROUPS;   // elements per CTA
 constexpr int NSTATE_IN = 6 + 9 + 14;       // eps_n, urcs_n, hist_n (11 mm01 / 14 mm05) per Gauss point
 // shape table 192, c/u/du 3 x SEPC x 24, per-warp sums (+1 pad), state at n NSTATE_IN x STPB,
-// element property records SEPC x EPROP floats
+// element property records SEPC x EPROP floats, mid-step and n+1 coordinates 2 x SEPC x 24
 constexpr int STRESS_SMEM_BYTES =
-    (int)sizeof(double) * (192 + 3 * SEPC * 24 + (STPB / 32) * 3 + 1 + NSTATE_IN * STPB + SEPC * (EPROP / 2));
+    (int)sizeof(double) * (192 + 3 * SEPC * 24 + (STPB / 32) * 3 + 1 + NSTATE_IN * STPB + SEPC * (EPROP / 2) +
+                           2 * SEPC * 24);
 
 // launches one instantiation with its dynamic shared memory (opt-in above 48 KB, once per kernel)
 inline cudaError_t launch_stress_kernel(void (*k)(const struct StressArgs), int grid,
@@ -212,6 +213,10 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
   double (*sSt)[STPB] = reinterpret_cast<double (*)[STPB]>(dsm + 192 + 3 * SEPC * 24 + (STPB / 32) * 3 + 1);
   // the element's property record (EPROP floats), streamed with the state: 8 bytes per lane
   double (*sEp)[EPROP / 2] = reinterpret_cast<double (*)[EPROP / 2]>(&sSt[NSTATE_IN][0]);
+  // nodal coordinates on the mid-step and n+1 configurations, formed once per element by the
+  // gathering lanes instead of by each of its 8 Gauss points inside the Jacobian loops
+  double (*sXm)[24] = reinterpret_cast<double (*)[24]>(&sEp[SEPC][0]);
+  double (*sX1)[24] = sXm + SEPC;
 
   const int tid = threadIdx.x;
   for (int k = tid; k < 192; k += STPB) (&sN[0][0][0])[k] = (&c_shape[0][0][0])[k];
@@ -269,6 +274,11 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
       sU[el][k * 8 + gp] = vu[k];
       sDU[el][k * 8 + gp] = vdu[k];
       sC[el][k * 8 + gp] = vc[k];
+      if (GEONL) {
+        const double cu = vc[k] + vu[k];
+        sXm[el][k * 8 + gp] = fma(0.5, vdu[k], cu);
+        sX1[el][k * 8 + gp] = cu + vdu[k];
+      }
     }
   }
   __syncthreads();
@@ -361,8 +371,7 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
     double ddt[6];
     {
       double Gm[3][3], djm;
-      if (a.update_coords) jacobian_smem<false, 1>(sN, gp, C, U, DU, Gm, djm);
-      else jacobian_smem<false, 0>(sN, gp, C, U, DU, Gm, djm);
+      jacobian_smem<false, 0>(sN, gp, a.update_coords ? sXm[el] : C, U, DU, Gm, djm);
       strain_increment(sN, gp, Gm, DU, ddt);
       if (BBAR) {
         // mean-dilatation B-bar (vol_terms / vol_avg / bmod): eps_kk -> eps_kk + beta (thbar - th)
@@ -617,8 +626,7 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
       for (int k = 0; k < 6; ++k) sig[k] = 0.0;
     }
     double dj1;
-    if (GEONL && a.update_coords) jacobian_smem<false, 2>(sN, gp, C, U, DU, G1, dj1);
-    else jacobian_smem<false, 0>(sN, gp, C, U, DU, G1, dj1);
+    jacobian_smem<false, 0>(sN, gp, (GEONL && a.update_coords) ? sX1[el] : C, U, DU, G1, dj1);
     const double wdj = weight * dj1;
     evol = sum8(wdj);
     double add = 0.0;
