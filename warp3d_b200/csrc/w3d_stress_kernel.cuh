@@ -112,7 +112,7 @@ __device__ __forceinline__ void jacobian_smem(const double (*sN)[8][8], int gp, 
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) J[r][c] = 0.0;
-#pragma unroll 1
+#pragma unroll 4
   for (int j = 0; j < 8; ++j) {
     const double nx = sN[0][j][gp], ne = sN[1][j][gp], nz = sN[2][j][gp];
     double x = C[j], y = C[8 + j], z = C[16 + j];
@@ -167,7 +167,7 @@ __device__ __forceinline__ void strain_increment(const double (*sN)[8][8], int g
                                                  double (&d)[6]) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) d[k] = 0.0;
-#pragma unroll 1
+#pragma unroll 4
   for (int j = 0; j < 8; ++j) {
     const double nx = sN[0][j][gp], ne = sN[1][j][gp], nz = sN[2][j][gp];
     const double bx = G[0][0] * nx + G[0][1] * ne + G[0][2] * nz;
