@@ -57,3 +57,22 @@ def test_slab_domains_are_contiguous_and_balanced():
         assert np.all(np.diff(d) >= 0) and d[0] == 0 and d[-1] == nproc - 1
         counts = np.bincount(d, weights=m.elblks[:, 0], minlength=nproc)
         assert counts.max() - counts.min() <= 2 * 128
+
+
+def test_every_bench_workload_builds_and_states_its_algorithmic_bytes():
+    """bench.py's workloads on a small box: the tables build, the load increment has the model's
+    size, and the description carries what the roofline needs."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    for name, (dims, kind, cpu_dims) in bench.WORKLOADS.items():
+        m, du, nprep = bench.make_workload(name, (6, 4, 4))
+        assert m.noelem == 96 and du.shape == (m.nodof,) and nprep in (1, 2), name
+        wd = bench.workload_description(name)
+        assert wd["bytes_stress"] >= 776.0 and wd["bytes_tanstf"] >= 708.0 and wd["material"], name
+        assert np.prod(dims) >= np.prod(cpu_dims), name          # the CPU sample is a sub-box
+    beta = bench.make_workload("hex8_2m_mm01_beta05", (2, 2, 2))[0].matprp[0, 2]
+    assert beta == np.float32(0.5)
+    e, p = (abs(bench.make_workload(w, (2, 2, 2))[1]).max() for w in ("hex8_2m_mm01_elastic", "hex8_2m_mm01"))
+    assert e < 0.5 * p                                           # the elastic variant stays under yield

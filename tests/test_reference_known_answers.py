@@ -273,7 +273,7 @@ def _run_test60(option, nsteps=420, backend=OracleBackend):
     n = m.nodof
     T = np.array(ref["skew"]["T"])
     blocks = {node: T for node in ref["skew"]["nodes"]}
-    Q = sp.csr_matrix(sp.block_diag([blocks.get(node + 1, np.eye(3)) for node in range(m.nonode)]))
+    Q = sp.csr_matrix(sp.block_diag([sp.coo_matrix(blocks.get(node + 1, np.eye(3))) for node in range(m.nonode)]))
     fixed_val = {}
     for node, dof, val in ref["constraints"]:
         fixed_val[3 * (node - 1) + dof] = val
