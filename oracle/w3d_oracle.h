@@ -28,6 +28,12 @@
  *     420 load steps of cyclic end displacement): total axial reaction 0.0210364867 against
  *     0.021036833 (nonlinear_hardening, 1.6e-5) and 0.0232109041 against 0.023211111
  *     (generalized_plasticity, 8.9e-6).
+ *   - the assembly (w3d_oracle_assemble.cpp: dof_map, count_profile_symmetric,
+ *     build_col_sparse_symm, assem_by_row) and the structure residual with its norms
+ *     (w3d_oracle_residual.cpp: upres_iter_0, upres, the cvtest residual loop): literal sequential
+ *     restatements, checked against independent scipy / numpy formulations of the same
+ *     definitions (tests/test_assembly.py, tests/test_residual.py); the reference holds no
+ *     vectors for them: "parity unpinned".
  *   Nothing is pinned at function granularity or at 1e-10: there the status stays "parity
  *   unpinned" (literal transcription + the physics invariants in tests/).
  *
