@@ -159,3 +159,17 @@ def test_device_residual_edge_cases_and_refusals():
     with pytest.raises(ValueError):
         e.residual_set_loads(np.zeros(3, dtype=np.int32), z)
     e.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 257, 1025])
+def test_restatement_on_ragged_sizes(n):
+    """sizes around the reduction widths of the device kernel (warp, CTA), one dof included"""
+    for seed, (dyn, mpc, con) in enumerate([(False, False, False), (True, True, True)]):
+        v = _vectors(n, 100 + seed, dyn, mpc, con)
+        res, n1 = _oracle_upres(v, 0.1, 0.25)
+        res_np, n_np = _numpy_upres(v, 0.1, 0.25)
+        assert np.array_equal(res, res_np)
+        assert n1["num_term_loads"] == n_np["num_term_loads"] and n1["res_max_dof"] == n_np["res_max_dof"]
+        assert n1["res_max"] == n_np["res_max"]
+        for k in ("mgload", "sum_loads", "norm_res"):
+            assert _close(n1[k], n_np[k]), (n, k)
