@@ -282,7 +282,9 @@ def engine_arm(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line)
+        # stdout carries exactly one JSON line: NCCL's own log (whatever NCCL_DEBUG the harness set,
+        # e.g. INFO for its communicator check) goes to stderr unless the harness routed it itself
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     model, du_step, nprep = make_workload(args.workload)

@@ -14,7 +14,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # W3D_ORACLE_STATS=1 selects the build with mm10 operation counters (w3d_mm10_core.h, W3D_STAT)
 _STATS = bool(os.environ.get("W3D_ORACLE_STATS"))
-_LIB = os.path.join(_HERE, "libw3d_oracle_stats.so" if _STATS else "libw3d_oracle.so")
+# W3D_ORACLE_FAST=1 selects the -O3 / FMA build used ONLY as the timed CPU baseline (bench.py)
+_FAST = bool(os.environ.get("W3D_ORACLE_FAST")) and not _STATS
+_LIB = os.path.join(_HERE, "libw3d_oracle_stats.so" if _STATS else
+                    "libw3d_oracle_fast.so" if _FAST else "libw3d_oracle.so")
 
 
 class _Model(C.Structure):

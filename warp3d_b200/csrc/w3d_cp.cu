@@ -109,17 +109,16 @@ template <int NS>
 static cudaError_t launch_mm10_ns(const CpArgs &a, int ncta, cudaStream_t st) {
   const size_t need = sizeof(Props<NS>) * (size_t)a.ncrystals * EPC * MM10_GROUPS;
   const int smem = need <= (size_t)MM10_PROPS_SMEM_LIMIT ? (int)need : 0;
-  static bool set = false;
-  if (!set) {
-    const cudaError_t e = cudaFuncSetAttribute(k_mm10<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               MM10_PROPS_SMEM_LIMIT);
-    if (e != cudaSuccess) return e;
-    set = true;
-  }
   CpArgs b = a;
   b.ncta = ncta;
   k_mm10<NS><<<(ncta + MM10_GROUPS - 1) / MM10_GROUPS, TPB * MM10_GROUPS, smem, st>>>(b);
   return cudaGetLastError();
+}
+cudaError_t mm10_prepare_device() {
+  cudaError_t e = cudaFuncSetAttribute(k_mm10<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM10_PROPS_SMEM_LIMIT);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_mm10<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM10_PROPS_SMEM_LIMIT);
+  return e;
 }
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {
   return a.nslip <= 12 ? launch_mm10_ns<12>(a, ncta, st) : launch_mm10_ns<48>(a, ncta, st);

@@ -28,6 +28,8 @@ void mm10_setup_props_host(const double *crystal_type_rec, const double *angles,
                            double *props_out);
 int mm10_hist_size(int nslip, int num_hard, int ncrystals);
 void mm10_layout_offsets(int nslip, int num_hard, int *o_gradfe, int *o_Rp0);
+// shared-memory opt-in of both instantiations on the current device (w3d_engine_create)
+cudaError_t mm10_prepare_device();
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st);
 
 }  // namespace w3d

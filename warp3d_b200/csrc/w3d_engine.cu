@@ -228,6 +228,27 @@ void free_all(w3d_engine *h) {
   if (h->stream) cudaStreamDestroy(h->stream);
 }
 
+template <int MAT, int PHASE>
+cudaError_t launch_stress(const Segment &sg, const StressArgs &a0, cudaStream_t st) {
+  StressArgs a = a0;
+  a.ncta = sg.ncta;                                                  // 16-element groups
+  const int grid = (sg.ncta + STRESS_GROUPS - 1) / STRESS_GROUPS;    // CTAs of STRESS_GROUPS groups
+  if (sg.geonl) {
+    if (sg.bbar) return launch_stress_kernel(k_eps_sig_ifv<MAT, true, true, PHASE>, grid, a, st);
+    return launch_stress_kernel(k_eps_sig_ifv<MAT, true, false, PHASE>, grid, a, st);
+  }
+  if (sg.bbar) return launch_stress_kernel(k_eps_sig_ifv<MAT, false, true, PHASE>, grid, a, st);
+  return launch_stress_kernel(k_eps_sig_ifv<MAT, false, false, PHASE>, grid, a, st);
+}
+template <int MAT, int PHASE>
+cudaError_t stress_prepare_device() {
+  cudaError_t e = stress_opt_in(k_eps_sig_ifv<MAT, true, true, PHASE>);
+  if (e == cudaSuccess) e = stress_opt_in(k_eps_sig_ifv<MAT, true, false, PHASE>);
+  if (e == cudaSuccess) e = stress_opt_in(k_eps_sig_ifv<MAT, false, true, PHASE>);
+  if (e == cudaSuccess) e = stress_opt_in(k_eps_sig_ifv<MAT, false, false, PHASE>);
+  return e;
+}
+
 int create_impl(w3d_engine *h) {
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   const w3d_engine_config &c = h->cfg;
@@ -435,23 +456,15 @@ int create_impl(w3d_engine *h) {
   CUDA_TRY(cudaFuncSetAttribute(k_tanstf<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPC * ELREC * 8));
   CUDA_TRY(cudaFuncSetAttribute(k_tanstf<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPC * ELREC * 8));
   CUDA_TRY(cudaFuncSetAttribute(k_tanstf<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPC * ELREC * 8));
+  // opt-in of every kernel that needs more than 48 KB of dynamic shared memory, on THIS device
+  CUDA_TRY((stress_prepare_device<1, 0>()));
+  CUDA_TRY((stress_prepare_device<10, 1>()));
+  CUDA_TRY((stress_prepare_device<10, 2>()));
+  CUDA_TRY(mm05_prepare_device());
+  CUDA_TRY(mm10_prepare_device());
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaGetLastError());
   return W3D_OK;
-}
-
-template <int MAT, int PHASE>
-void launch_stress(const Segment &sg, const StressArgs &a0, cudaStream_t st) {
-  StressArgs a = a0;
-  a.ncta = sg.ncta;                                                  // 16-element groups
-  const int grid = (sg.ncta + STRESS_GROUPS - 1) / STRESS_GROUPS;    // CTAs of STRESS_GROUPS groups
-  if (sg.geonl) {
-    if (sg.bbar) launch_stress_kernel(k_eps_sig_ifv<MAT, true, true, PHASE>, grid, a, st);
-    else launch_stress_kernel(k_eps_sig_ifv<MAT, true, false, PHASE>, grid, a, st);
-  } else {
-    if (sg.bbar) launch_stress_kernel(k_eps_sig_ifv<MAT, false, true, PHASE>, grid, a, st);
-    else launch_stress_kernel(k_eps_sig_ifv<MAT, false, false, PHASE>, grid, a, st);
-  }
 }
 
 int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
@@ -475,7 +488,7 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
     a.hist_size = sg.hist_size;
     if (sg.mat_type == 10) {
       a.scratch = sg.scratch; a.cp_ncrystals = sg.ncrystals; a.cp_o_gradfe = sg.o_gradfe; a.cp_o_Rp = sg.o_Rp0;
-      launch_stress<10, 1>(sg, a, h->stream);
+      CUDA_TRY((launch_stress<10, 1>(sg, a, h->stream)));
       CpArgs ca{};
       ca.cta = sg.d_cta; ca.props = sg.d_cprops; ca.hist_n = sg.hist_n; ca.urcs_n = sg.urcs_n;
       ca.scratch = sg.scratch; ca.hist_n1 = sg.hist_n1; ca.urcs_n1 = sg.urcs_n1; ca.flags = h->d_flags;
@@ -484,13 +497,13 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
       ca.asymmetric = c.asymmetric_assembly ? 1 : 0;
       ca.ncrystals = sg.ncrystals; ca.nslip = sg.nslip; ca.num_hard = sg.num_hard;
       CUDA_TRY(launch_mm10(ca, sg.ncta, h->stream));
-      launch_stress<10, 2>(sg, a, h->stream);
+      CUDA_TRY((launch_stress<10, 2>(sg, a, h->stream)));
       h->launches += 3;
     } else if (sg.mat_type == 5) {
       CUDA_TRY(launch_stress_mm05(sg.geonl, sg.bbar, sg.ncta, a, h->stream));
       h->launches += 1;
     } else {
-      launch_stress<1, 0>(sg, a, h->stream);
+      CUDA_TRY((launch_stress<1, 0>(sg, a, h->stream)));
       h->launches += 1;
     }
     if (sg.ncta > 4096) {   // two fixed-order stages (still deterministic)

@@ -19,6 +19,14 @@ cudaError_t mm05_set_shape_table(const double *tab3, size_t bytes) {
   return cudaMemcpyToSymbol(c_shape, tab3, bytes);
 }
 
+cudaError_t mm05_prepare_device() {
+  cudaError_t e = stress_opt_in(k_eps_sig_ifv<5, true, true, 0>);
+  if (e == cudaSuccess) e = stress_opt_in(k_eps_sig_ifv<5, true, false, 0>);
+  if (e == cudaSuccess) e = stress_opt_in(k_eps_sig_ifv<5, false, true, 0>);
+  if (e == cudaSuccess) e = stress_opt_in(k_eps_sig_ifv<5, false, false, 0>);
+  return e;
+}
+
 cudaError_t launch_stress_mm05(bool geonl, bool bbar, int ncta, const StressArgs &a0, cudaStream_t st) {
   StressArgs a = a0;
   a.ncta = ncta;

@@ -52,6 +52,7 @@ static __constant__ double c_shape[3][8][8];
 
 // MAT = 5 instantiations live in w3d_mm05.cu
 cudaError_t mm05_set_shape_table(const double *tab3, size_t bytes);
+cudaError_t mm05_prepare_device();   // shared-memory opt-in of the MAT = 5 instantiations on the current device
 cudaError_t launch_stress_mm05(bool geonl, bool bbar, int ncta, const struct StressArgs &a, cudaStream_t st);
 
 // A CTA takes STRESS_GROUPS consecutive 16-element groups (CTA descriptors): the warps of a CTA
@@ -73,20 +74,15 @@ constexpr int STRESS_SMEM_BYTES =
     (int)sizeof(double) * (192 + 3 * SEPC * 24 + (STPB / 32) * 3 + 1 + NSTATE_IN * STPB + SEPC * (EPROP / 2) +
                            2 * SEPC * 24);
 
-// launches one instantiation with its dynamic shared memory (opt-in above 48 KB, once per kernel)
+// Dynamic shared memory above 48 KB is an opt-in per kernel AND per device: every instantiation is
+// opted in by w3d_engine_create after cudaSetDevice (stress_prepare_device below), so a second
+// engine on another device of the same process is covered and no process-wide cache is needed.
+inline cudaError_t stress_opt_in(void (*k)(const struct StressArgs)) {
+  if (STRESS_SMEM_BYTES <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, STRESS_SMEM_BYTES);
+}
 inline cudaError_t launch_stress_kernel(void (*k)(const struct StressArgs), int grid,
                                         const struct StressArgs &a, cudaStream_t st) {
-  if (STRESS_SMEM_BYTES > 48 * 1024) {
-    static const void *done[64];
-    static int ndone = 0;
-    bool seen = false;
-    for (int i = 0; i < ndone; ++i) seen = seen || done[i] == (const void *)k;
-    if (!seen) {
-      const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, STRESS_SMEM_BYTES);
-      if (e != cudaSuccess) return e;
-      if (ndone < 64) done[ndone++] = (const void *)k;
-    }
-  }
   k<<<grid, STPB, STRESS_SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }

@@ -81,7 +81,7 @@ class _Scalars(C.Structure):
 
 def build(force=False, verbose=False):
     """Compile libw3d_engine.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", "Makefile"))]
     srcs.append(os.path.join(_HERE, "..", "include", "w3d_engine.h"))
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
