@@ -170,8 +170,15 @@ class ClockSampler:
         return out
 
 
+CPU_BUILD = "g++ -O3 -march=x86-64-v3 -ffp-contract=fast (oracle/Makefile: libw3d_oracle_fast.so)"
+
+
 def prepare_cpu_case(workload, nthreads):
-    """Same mesh family, material and load path as the GPU workload, on the oracle."""
+    """Same mesh family, material and load path as the GPU workload, on the oracle.  The timed
+    CPU legs use the -O3 / FMA build of the restatement (the reference's own build is ifort -O3);
+    the parity tests never do."""
+    if not os.environ.get("W3D_ORACLE_STATS"):
+        os.environ["W3D_ORACLE_FAST"] = "1"
     from oracle.oracle_py import Oracle
     from warp3d_b200 import new_state
     m, du, nprep = make_workload(workload, WORKLOADS[workload][2])
@@ -204,7 +211,7 @@ def cpu_baseline(workload, nrep=3):
     ts = [cpu_pass(m, orc, st, u, du, step) for _ in range(nrep)]
     t_s = float(np.mean([a for a, _ in ts])); t_k = float(np.mean([b for _, b in ts]))
     ngp = m.noelem * 8
-    return dict(value=ngp / (t_s + t_k), unit=UNIT, cores=cores, kind="port",
+    return dict(value=ngp / (t_s + t_k), unit=UNIT, cores=cores, kind="port", build=CPU_BUILD,
                 sample=f"{m.noelem} elements ({CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} sub-box of the same "
                        f"mesh, material and load path), {nrep} passes, oracle/ C++ restatement with OpenMP over blocks",
                 stress_gp_per_s=ngp / t_s, stiffness_elem_per_s=m.noelem / t_k)
@@ -263,7 +270,7 @@ def reference_arm(args):
                 scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=args.workload, cpu_sample_elements=m.noelem,
                             material=workload_description(args.workload)["material"], formulation="geonl+bbar"),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", build=CPU_BUILD, sample=sample,
                                   stress_gp_per_s=ngp / t_s, stiffness_elem_per_s=m.noelem / t_k),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
