@@ -1,0 +1,43 @@
+"""Models of the reference's own decks that BASELINE.json names, rebuilt from fixtures.
+
+``seb_model`` = fracture_models/seb (BASELINE.json configs[1]): a 3-D SE(B) fracture specimen,
+17 318 hex8 (l3disop, geonl, 2x2x2, B-bar), 19 935 nodes, the deck's USER blocking table (137
+blocks, 133 x 128 + 77, 60, 58, 99) with its 4th column as MPI domains 0 / 1, `consistent q off`, `bbar
+stabilization factor 0.0`, `adaptive on`, `extrapolate on` (warp3d.inp:47-72).  The fixture
+(tests/golden/seb_deck.npz) is written by tests/golden/make_seb_fixture.py from the deck files.
+
+The deck ships with material `mises` (mm03); BASELINE's config runs it with mm01, i.e. with the
+card `properties bilinear e 200.0e9 nu 0.3 yld_pt 400.0e6 tan_e 2.0e9` (src/inmat.f:793-796
+sets matprp(9) = 1 for `bilinear`).  `material="mises"` keeps the shipped card (mm03, n_power 10).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .model import Material, build_hex8_model
+
+SEB_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden",
+                           "seb_deck.npz")
+
+
+def seb_model(material="bilinear", fixture=None, domains=True):
+    """Returns (model, constraints) with constraints = dict(dofs (0-based structure dofs),
+    values (imposed displacement per load step, `step 1-160 constraints 1.0`))."""
+    d = np.load(fixture or SEB_FIXTURE)
+    if material == "bilinear":
+        mat = Material(mat_type=1, e=200.0e9, nu=0.3, yld_pt=400.0e6, tan_e=2.0e9, beta=1.0)
+    elif material == "mises":
+        mat = Material(mat_type=3, e=200.0e9, nu=0.3, yld_pt=400.0e6, tan_e=0.0, beta=1.0,
+                       extra={"n_power": 10.0})
+    else:
+        raise ValueError("material: 'bilinear' (mm01, BASELINE config) or 'mises' (mm03, as shipped)")
+    blocking = d["blocking"].copy()
+    if not domains:
+        blocking[:, 2] = 0
+    m = build_hex8_model(d["coords"], d["incid"], materials=[mat], geonl=True, bbar=True,
+                         blocking=blocking, eps_bbar=0.0, qbar_flag=False, adaptive_flag=True,
+                         extrapolated_du=False, dt=1.0e6)   # extrapolate on acts from step 2; callers set it
+    dofs = 3 * (d["cons_node"].astype(np.int64) - 1) + d["cons_dof"].astype(np.int64)
+    return m, dict(dofs=dofs, values=d["cons_val"].copy())

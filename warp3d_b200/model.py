@@ -216,9 +216,11 @@ def build_structured_hex8(nx, ny, nz, materials=None, elem_material=None, geonl=
 
 
 def build_hex8_model(coords, incid, materials=None, elem_material=None, geonl=True, bbar=True,
-                     block_size=MXVL, numprocs=1, grid=None, **globals_) -> Model:
+                     block_size=MXVL, numprocs=1, grid=None, blocking=None, **globals_) -> Model:
     """The reference's tables for an arbitrary mesh of l3disop elements: coords (nonode, 3),
-    incid (noelem, 8) 1-based in WARP3D's node order."""
+    incid (noelem, 8) 1-based in WARP3D's node order.  blocking: a user blocking table
+    (nelblk, 3) = span, felem, domain as the `blocking` input command gives it
+    (src/inelbk.f:60-250: user-defined blocks, 4th column = MPI domain); None = automatic."""
     materials = materials or [Material()]
     coords = np.asarray(coords, dtype=np.float64).reshape(-1, 3)
     incid = np.ascontiguousarray(np.asarray(incid, dtype=np.int32).reshape(-1, 8))
@@ -267,13 +269,30 @@ def build_hex8_model(coords, incid, materials=None, elem_material=None, geonl=Tr
 
     keys = np.stack([props[:, 0], props[:, 37], props[:, 17], props[:, 4], props[:, 5],
                      props[:, 18]], axis=1)
-    blocks = simple_blocking(noelem, keys, block_size)
+    if blocking is not None:
+        blocking = np.asarray(blocking, dtype=np.int32).reshape(-1, 3)
+        blocks = [(int(sp), int(fe)) for sp, fe, _ in blocking]
+        # the checks of inelbk (src/inelbk.f:170-250): blocks cover 1..noelem in order, span <= mxvl,
+        # and every element of a block shares the block keys of its first element
+        nxt = 1
+        for sp, fe in blocks:
+            if fe != nxt or sp < 1 or sp > MXVL:
+                raise ValueError(f"user blocking: block at element {fe} (span {sp}) breaks the 1..noelem cover")
+            if (keys[fe - 1:fe - 1 + sp] != keys[fe - 1]).any():
+                raise ValueError(f"user blocking: block at element {fe} mixes element kinds")
+            nxt = fe + sp
+        if nxt != noelem + 1:
+            raise ValueError("user blocking does not cover every element")
+    else:
+        blocks = simple_blocking(noelem, keys, block_size)
     nelblk = len(blocks)
     elblks = np.zeros((nelblk, 4), dtype=np.int32)
     for b, (span, felem) in enumerate(blocks):
         elblks[b, 0] = span
         elblks[b, 1] = felem
-    if numprocs > 1:                     # round-robin, src/inelbk.f:368-378
+    if blocking is not None:
+        elblks[:, 2] = blocking[:, 2]
+    elif numprocs > 1:                   # round-robin, src/inelbk.f:368-378
         elblks[:, 2] = np.arange(nelblk) % numprocs
 
     # edest / cdest: dstmap(node) = 3*(node-1)+1 ; ordering all u, all v, all w
