@@ -44,6 +44,9 @@ WORKLOADS = {
     # mm05 cyclic plasticity, both options (the GP one with the reference's own deck values, ksi)
     "hex8_256k_mm05_fa": ((64, 64, 64), "mm05_fa", (32, 25, 25)),
     "hex8_256k_mm05_gp": ((64, 64, 64), "mm05_gp", (32, 25, 25)),
+    # BASELINE.json configs[1]: the reference's fracture_models/seb deck with mm01 (17 318 hex8, the
+    # deck's 137 user blocks and 2 domains, consistent q off); mesh from tests/golden/seb_deck.npz
+    "seb_mm01": (None, "seb", None),
 }
 # mm10 workload: fcc (12 slip systems), Voce hardening with the property values of
 # verification/test82/voche_model/warp3d_voche.inp:6-10, one crystal per element, Kocks angles
@@ -58,6 +61,13 @@ def make_workload(name, dims=None):
                              make_crystal_type)
     wdims, kind, _ = WORKLOADS[name]
     dims = dims or wdims
+    if kind == "seb":
+        from warp3d_b200 import seb_bend_field, seb_model
+        m, cons = seb_model()
+        m.deck_constraints = cons
+        # one converged step of the bending field at 0.75 of the first-yield scale, then the timed
+        # iteration adds the same again: ~90 % of the points are plastic in it
+        return m, seb_bend_field(m, 0.6), 1
     if kind == "mm01":
         if name.endswith("_beta05"):
             m = build_structured_hex8(*dims, materials=[Material(beta=0.5)])
@@ -78,6 +88,10 @@ def make_workload(name, dims=None):
 
 def workload_description(name):
     kind = WORKLOADS[name][1]
+    if kind == "seb":
+        return dict(material="mm01 bilinear (deck card switched from mises: e 200e9 nu 0.3 yld_pt 400e6 tan_e 2e9), "
+                             "fracture_models/seb mesh and blocking, consistent q off",
+                    bytes_stress=776.0, bytes_tanstf=708.0, flops_stress=3573.0, flops_tanstf=4540.0)
     if kind.startswith("mm05"):
         # as mm01 with 14 history words per point instead of 11 (3 x 8 B more each way)
         return dict(material={"mm05_fa": "mm05 cyclic, nonlinear_hardening (q_u 100e6, b_u 20, h_u 10e9, gamma_u 50)",
@@ -181,7 +195,7 @@ def prepare_cpu_case(workload, nthreads):
         os.environ["W3D_ORACLE_FAST"] = "1"
     from oracle.oracle_py import Oracle
     from warp3d_b200 import new_state
-    m, du, nprep = make_workload(workload, WORKLOADS[workload][2])
+    m, du, nprep = make_workload(workload, WORKLOADS[workload][2])   # seb: the whole deck
     orc = Oracle(m, nthreads=nthreads)
     st = new_state(m)
     u = np.zeros(m.nodof)
@@ -211,9 +225,10 @@ def cpu_baseline(workload, nrep=3):
     ts = [cpu_pass(m, orc, st, u, du, step) for _ in range(nrep)]
     t_s = float(np.mean([a for a, _ in ts])); t_k = float(np.mean([b for _, b in ts]))
     ngp = m.noelem * 8
+    what = (f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} sub-box of the same mesh, material and load path"
+            if CPU_SAMPLE else "the whole deck")
     return dict(value=ngp / (t_s + t_k), unit=UNIT, cores=cores, kind="port", build=CPU_BUILD,
-                sample=f"{m.noelem} elements ({CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} sub-box of the same "
-                       f"mesh, material and load path), {nrep} passes, oracle/ C++ restatement with OpenMP over blocks",
+                sample=f"{m.noelem} elements ({what}), {nrep} passes, oracle/ C++ restatement with OpenMP over blocks",
                 stress_gp_per_s=ngp / t_s, stiffness_elem_per_s=m.noelem / t_k)
 
 
@@ -263,8 +278,9 @@ def reference_arm(args):
     ngp = m.noelem * 8
     value = ngp * args.steps / total
     t_s = float(np.mean([a for a, _ in ts])); t_k = float(np.mean([b for _, b in ts]))
-    sample = (f"{m.noelem} elements per step ({CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} sub-box of the "
-              f"{args.workload} workload), oracle/ port of the reference path, OpenMP over blocks")
+    what = (f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} sub-box of the {args.workload} workload"
+            if CPU_SAMPLE else f"the whole {args.workload} deck")
+    sample = f"{m.noelem} elements per step ({what}), oracle/ port of the reference path, OpenMP over blocks"
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * total / args.steps, higher_is_better=True,
                 scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
@@ -297,7 +313,9 @@ def engine_arm(args):
     model, du_step, nprep = make_workload(args.workload)
     wd = workload_description(args.workload)
     TS = nprep + 1                      # the timed load step
-    de = DomainEngine(model, rank, world, device=local)
+    # seb: the deck's own domain column (2 domains) when run on 2 GPUs, slabs of blocks otherwise
+    de = DomainEngine(model, rank, world, device=local,
+                      assign_slabs=not (WORKLOADS[args.workload][1] == "seb" and world == 2))
     eng = de.engine
     nodof, nel_own = model.nodof, eng.n_owned_elems
     ngp_total = model.noelem * 8
@@ -369,8 +387,11 @@ def engine_arm(args):
     #      blocks.  x = xmin face clamped.  With several domains every rank returns the rows of the
     #      nodes its own elements touch (interface rows come from two ranks and add on the host).
     cst = np.zeros(nodof, dtype=np.int32)
-    xs = model.c.reshape(-1, 3)[:, 0]
-    cst.reshape(-1, 3)[xs <= xs.min() + 1e-9] = 1
+    if getattr(model, "deck_constraints", None):
+        cst[model.deck_constraints["dofs"]] = 1        # the deck's own constraints
+    else:
+        xs = model.c.reshape(-1, 3)[:, 0]
+        cst.reshape(-1, 3)[xs <= xs.min() + 1e-9] = 1
     ts0 = time.perf_counter()
     st_ = eng.assemble_setup(cst)
     setup_s = time.perf_counter() - ts0
@@ -439,7 +460,9 @@ def engine_arm(args):
             data="synthetic",
             config=dict(workload=args.workload, elements=model.noelem, gauss_points=ngp_total, blocks=model.nelblk,
                         nodof=nodof, material=wd["material"],
-                        formulation="hex8 l3disop 2x2x2, geonl, bbar", l2="inputs_exceed_l2 (state >> 126 MB)",
+                        formulation="hex8 l3disop 2x2x2, geonl, bbar",
+                        l2=("inputs_exceed_l2 (state >> 126 MB)" if model.noelem > 100000 else
+                            "state fits L2 (small deck): launch-latency bound, not a roofline case"),
                         partition=(f"{world} contiguous block slabs; resident pass: NCCL sum of ifv ({args.exchange}), "
                                    f"e2e pass: full all-reduce") if world > 1 else "single GPU",
                         step="w3d_eps_sig_ifv + w3d_tanstf (one Newton iteration)"),

@@ -41,3 +41,19 @@ def seb_model(material="bilinear", fixture=None, domains=True):
                          extrapolated_du=False, dt=1.0e6)   # extrapolate on acts from step 2; callers set it
     dofs = 3 * (d["cons_node"].astype(np.int64) - 1) + d["cons_dof"].astype(np.int64)
     return m, dict(dofs=dofs, values=d["cons_val"].copy())
+
+
+def seb_bend_field(m, scale=1.0):
+    """A smooth bending-like displacement field over the specimen (x: width direction, -W/2..W/2;
+    y: along the span, 0 = crack plane; z: thickness): strains up to ~2.6e-3 at scale 1, i.e. part
+    of the points beyond the yield strain 2e-3 of the deck's steel.  Synthetic load for parity
+    tests and for the bench workload `seb_mm01` (the deck's own load needs the global solve)."""
+    x = m.c.reshape(-1, 3)
+    L = x[:, 0].max() - x[:, 0].min()
+    xi = (x[:, 0] - x[:, 0].min()) / L
+    yi = (x[:, 1] - x[:, 1].min()) / (x[:, 1].max() - x[:, 1].min())
+    u = np.zeros_like(x)
+    u[:, 1] = -7.0e-4 * scale * (1.0 - xi) ** 2 * L
+    u[:, 0] = 5.25e-3 * scale * (yi - 0.5) * xi * L
+    u[:, 2] = -0.3 * 3.5e-3 * scale * x[:, 2] * (yi - 0.5)
+    return u.reshape(-1).copy()
