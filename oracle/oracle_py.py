@@ -1,7 +1,7 @@
 """ctypes binding for the CPU ORACLE (test infrastructure only).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
-this module.  The product package (warp3d_b200/) never does.
+this module.  The product package never does.
 """
 from __future__ import annotations
 
@@ -110,7 +110,7 @@ def _ptr(a):
 
 
 class Oracle:
-    """Runs the oracle on a warp3d_b200.model.Model + State (arrays are used in place)."""
+    """Runs the oracle on the engine package's Model + State tables (arrays are used in place)."""
 
     def __init__(self, model, nthreads=1):
         self.model = model

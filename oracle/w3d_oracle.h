@@ -38,7 +38,7 @@
  *   unpinned" (literal transcription + the physics invariants in tests/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load
- * this library.  The CUDA engine (warp3d_b200/) must never include or link it.
+ * this library.  The CUDA engine package must never include or link it.
  *
  * Array conventions: all arrays are in the reference's (Fortran, column-major) layouts, indices
  * inside index tables are 1-based exactly as the reference stores them.
@@ -79,7 +79,7 @@ typedef struct w3do_model {
 
 /* crystal-plasticity data (mm10): per (element, crystal) property records produced by
  * w3do_mm10_setup_props == setup_mm10_rknstr (rknstr.f:1568-2027).  One record is
- * W3DO_MM10_PROPS_DOUBLES doubles (w3d_mm10::Props<12>); all elements carry `ncrystals`.        */
+ * W3DO_MM10_PROPS_DOUBLES doubles (w3do_mm10::Props<12>); all elements carry `ncrystals`.        */
 typedef struct w3do_cp {
   int32_t ncrystals, nslip, num_hard, asymmetric_assembly;
   const double *props;     /* (noelem, ncrystals, W3DO_MM10_PROPS_DOUBLES) */
@@ -128,7 +128,7 @@ void w3do_adaptive_reset(const w3do_model *m, w3do_state *s);
 int64_t w3do_block_offset(const w3do_model *m, int32_t blk, int32_t which);
 
 /* mm10: number of doubles in one property record; fill one record from a crystal-type table
- * entry (w3d_mm10::CrystalType laid out as doubles, see oracle_py.py) and Kocks angles.          */
+ * entry (w3do_mm10::CrystalType laid out as doubles, see oracle_py.py) and Kocks angles.          */
 int32_t w3do_mm10_props_doubles(void);
 int32_t w3do_mm10_props_doubles_for(int32_t nslip);   /* 12-system record, or 48-system */
 int32_t w3do_mm10_crystal_type_doubles(void);

@@ -18,11 +18,11 @@
 #include <omp.h>
 #endif
 #include "w3d_oracle_internal.h"
-#include "../warp3d_b200/csrc/w3d_mm10_core.h"   // single-source mm10 core (see its header)
+#include "w3d_oracle_mm10.h"   // statement-for-statement mm10 restatement (independent of the product)
 #ifdef W3D_MM10_STATS
 extern "C" { long long w3d_mm10_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }
 #endif
-#include "../warp3d_b200/csrc/w3d_mm05_core.h"   // single-source mm05 core (see its header)
+#include "w3d_oracle_mm05.h"   // per-point mm05 restatement (independent of the product)
 
 namespace w3do {
 
@@ -214,11 +214,11 @@ static void drive_01_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
 }
 
 // drive_05_update (rstgp1.f:2373-2700) -> mm05 (mm05.f:9) + cnst5 (:1566), nonlinear_hardening
-// or generalized_plasticity option by the sign of matprp(58).  Per-point arithmetic = single-source core warp3d_b200/csrc/w3d_mm05_core.h.
+// or generalized_plasticity option by the sign of matprp(58).  Per-point arithmetic = w3d_oracle_mm05.h.
 static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int gpn,
                             int step, int iter, const double *uddt_displ, double *gbl_cep,
                             bool &material_cut_step, int *fatal) {
-  using namespace w3d_mm05;
+  using namespace w3do_mm05;
   const int span = bi.span;
   std::vector<double> cep(mxvl * 36, 0.0);
   double *urcs_n = &lw.urcs_blk_n[(size_t)(gpn - 1) * nstrs * mxvl];
@@ -265,15 +265,15 @@ static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
 }
 
 // drive_10_update (rstgp1.f:4327-4513) -> mm10 (mm10_a.f:29).  The per-Gauss-point crystal update
-// is the single-source core shared with the engine (warp3d_b200/csrc/w3d_mm10_core.h, see its
-// header for why); this wrapper supplies the reference's block-local layouts.
+// is the statement-for-statement restatement in w3d_oracle_mm10.h; this wrapper supplies the
+// reference's block-local layouts.
 // NS = capacity of the slip-system arrays: 12 (fcc, bcc, ...: what the engine builds) or 48
 // (bcc48: CPU only, used to check the shared core against the reference's published results)
 template <int NS>
 static void drive_10_update_ns(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int gpn,
                                int step, int iter, const double *uddt_displ, bool &material_cut_step,
                                int *fatal) {
-  using namespace w3d_mm10;
+  using namespace w3do_mm10;
   const int span = bi.span;
   const w3do_cp *cp = (const w3do_cp *)m->cp;
   if (!cp || cp->nslip > NS || cp->num_hard != 1) { *fatal = 3; return; }
@@ -310,10 +310,9 @@ static void drive_10_update_ns(const w3do_model *m, const BlockInfo &bi, LocalWo
     for (int k = 0; k < 9; ++k) cgn[k] = urcs_n[(size_t)k * mxvl + i];
     const CHist hn{hist + i, span};
     const Hist h1{hist1 + i, span};
-    double slip_store[slip_store_doubles<NS>()];
     const bool cut = gauss_point_update<NS>(step, cp->ncrystals, P, L, hn, h1, Rur, ud, m->dt,
                                             iter_0_extrapolate_off, cp->asymmetric_assembly != 0,
-                                            cgn, cgn1, slip_store, 1);
+                                            cgn, cgn1);
     if (cut) { material_cut_step = true; return; }
     for (int k = 0; k < 9; ++k) urcs_n1[(size_t)k * mxvl + i] = cgn1[k];
   }
@@ -331,7 +330,7 @@ static void drive_10_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
 // rknstr_finish_cp (rknstr.f:268-296) -> mm10_calc_grads (mm10_a.f:1579): gradient of the elastic
 // rotation by a linear fit over the Gauss points, stored in history at n+1 for every point.
 static void finish_cp(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int step) {
-  using namespace w3d_mm10;
+  using namespace w3do_mm10;
   const w3do_cp *cp = (const w3do_cp *)m->cp;
   const int span = bi.span, ngp = bi.ngp, H = bi.hist_size;
   const Layout L = Layout::make(cp->nslip, cp->num_hard);
@@ -354,8 +353,23 @@ static void finish_cp(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, i
             for (int b = 0; b < 3; ++b)
               rt[gp][b * 3 + a] = Rp[0 * 3 + a] * rot[0 * 3 + b] + Rp[1 * 3 + a] * rot[1 * 3 + b] +
                                   Rp[2 * 3 + a] * rot[2 * 3 + b];
-        } else {
-          for (int k = 0; k < 9; ++k) rt[gp][k] = Rp[k];
+        }
+      }
+      if (!bi.geonl) {
+        // mm10_a_copy_vector(Rt3d, Rps, ngp*9) (mm10_a.f:1622): the FIRST ngp*9 contiguous words
+        // of the block-local array starting at elem_hist(1, rs, 1) -- i.e. word rs + k / span of
+        // element 1 + mod(k, span) at Gauss point 1 -- whatever now_elem is.  Every element of a
+        // small-strain block therefore fits the same 72 numbers (for span >= 72: Rp(1,1) of the
+        // block's first 72 elements).  Reproduced literally: the bar is the reference's result.
+        double *flat = &rt[0][0];
+        for (int k = 0; k < ngp * 9; ++k) {
+          const int word = L.c_Rp(0) + k / span, el = k % span;   // word >= H: next Gauss-point plane
+          if (step == 1) {
+            const int q = word % H - L.c_Rp(0);   // block-local history at n initialised at step 1:
+            flat[k] = (q == 0 || q == 4 || q == 8) ? 1.0 : 0.0;   // Rp = I (other words taken as 0)
+          } else {
+            flat[k] = lw.elem_hist[(size_t)word * span + el];
+          }
         }
       }
       if (bi.geonl) {
@@ -653,43 +667,43 @@ void w3do_deriv2(double xi, double eta, double zeta, double *nxi, double *neta, 
 }
 void w3do_cp_icp(int32_t n, int32_t *cp, int32_t *dcp, int32_t *icp) { make_cp_icp(n, cp, dcp, icp); }
 
-int32_t w3do_mm10_props_doubles(void) { return (int32_t)(sizeof(w3d_mm10::Props<12>) / sizeof(double)); }
-int32_t w3do_mm10_crystal_type_doubles(void) { return (int32_t)(sizeof(w3d_mm10::CrystalType) / sizeof(double)); }
+int32_t w3do_mm10_props_doubles(void) { return (int32_t)(sizeof(w3do_mm10::Props<12>) / sizeof(double)); }
+int32_t w3do_mm10_crystal_type_doubles(void) { return (int32_t)(sizeof(w3do_mm10::CrystalType) / sizeof(double)); }
 int32_t w3do_mm10_hist_size(int32_t nslip, int32_t num_hard, int32_t ncrystals) {
-  return w3d_mm10::Layout::make(nslip, num_hard).size(ncrystals);
+  return w3do_mm10::Layout::make(nslip, num_hard).size(ncrystals);
 }
-// crystal_type: w3d_mm10::CrystalType with the trailing ints widened to doubles (oracle_py.py)
+// crystal_type: w3do_mm10::CrystalType with the trailing ints widened to doubles (oracle_py.py)
 void w3do_mm10_setup_props(const double *ctd, const double *angles, int32_t angle_type,
                            double *props_out) {
-  w3d_mm10::CrystalType ct;
+  w3do_mm10::CrystalType ct;
   const size_t nd = 36 + 144 + 144 + 13;
   std::memcpy(&ct, ctd, nd * sizeof(double));
   const double *ti = ctd + nd;
   ct.nslip = (int)ti[0]; ct.num_hard = (int)ti[1]; ct.h_type = (int)ti[2]; ct.tang_calc = (int)ti[3];
   ct.miter = (int)ti[4]; ct.solver = (int)ti[5]; ct.alter_mode = (int)ti[6];
   if (ct.nslip > 12) {
-    static w3d_mm10::Props<48> P48;   // 48-system record (bcc48), see drive_10_update
+    static w3do_mm10::Props<48> P48;   // 48-system record (bcc48), see drive_10_update
 #pragma omp critical(w3do_props48)
     {
       std::memset(&P48, 0, sizeof P48);
-      w3d_mm10::setup_props<48>(ct, angles, angle_type, P48);
+      w3do_mm10::setup_props<48>(ct, angles, angle_type, P48);
       std::memcpy(props_out, &P48, sizeof P48);
     }
     return;
   }
-  w3d_mm10::Props<12> P;
+  w3do_mm10::Props<12> P;
   std::memset(&P, 0, sizeof P);
-  w3d_mm10::setup_props<12>(ct, angles, angle_type, P);
+  w3do_mm10::setup_props<12>(ct, angles, angle_type, P);
   std::memcpy(props_out, &P, sizeof P);
 }
 int32_t w3do_mm10_props_doubles_for(int32_t nslip) {
-  return (int32_t)((nslip > 12 ? sizeof(w3d_mm10::Props<48>) : sizeof(w3d_mm10::Props<12>)) / sizeof(double));
+  return (int32_t)((nslip > 12 ? sizeof(w3do_mm10::Props<48>) : sizeof(w3do_mm10::Props<12>)) / sizeof(double));
 }
 
 // n records at once: cnum (1-based into the table of crystal types), angles (3 per record)
 void w3do_mm10_setup_props_batch(const double *ct_table, const int32_t *cnum, const double *angles,
                                  int64_t n, int32_t angle_type, double *props_out) {
-  const size_t ctd = sizeof(w3d_mm10::CrystalType) / sizeof(double) + 0;
+  const size_t ctd = sizeof(w3do_mm10::CrystalType) / sizeof(double) + 0;
   const size_t rec = 36 + 144 + 144 + 13 + 7;
   (void)ctd;
   // all crystal types of a model share one record size (the 48-system one if any type needs it)

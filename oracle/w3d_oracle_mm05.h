@@ -1,33 +1,35 @@
-// w3d_mm05_core.h -- cyclic plasticity model mm05, "nonlinear_hardening" (Frederick-Armstrong)
-// and "generalized_plasticity" options, for ONE Gauss point: the engine's device core.  The
-// parity tests check it against an independent per-point CPU restatement of mm05.f kept with the
-// test infrastructure; no file is shared with it (the scalar Newton solve for the plastic
-// multiplier and the Richardson sub-increment count are tolerance / threshold driven, so both
-// must make the same decisions -- asserted by the 1e-10 parity and integer-state tests).
+// w3d_oracle_mm05.h -- ORACLE (test infrastructure): per-point CPU restatement of the cyclic
+// plasticity model mm05, "nonlinear_hardening" (Frederick-Armstrong) and "generalized_plasticity"
+// options.  Independent of the product: nothing of the engine package is included here and the
+// engine package includes nothing of oracle/; the engine carries its own device core
+// (csrc/w3d_mm05_core.h of the engine package), which is free to re-order arithmetic for the GPU while this
+// file stays statement for statement with the Fortran (the reference's span-vector loops written
+// for one point, every assignment in the reference's order).
 //
 // Follows reference src/mm05.f: mm05 :9, mm05_fa :288, mm05_fa_step1_set :424, mm05_fa_init :490,
 // mm05_fa_compute :648, mm05_fa_nsteps :883, mm05_fa_lambda_solve :981, mm05_find_pos_lambda
 // :1120, mm05_compute_residual :1269, mm05_update_lambda :1323, mm05_fa_elastic_fraction :1367,
-// cnst5 :1566, mm05_final :3879, mm05_plastic_work :3949; properties src/rknstr.f:1234-1317,
-// src/inmat.f:2003-2040.  The generalized_plasticity option (mm05_gp :1882 ... cnst5_gp :3584)
-// follows the nonlinear_hardening one below.
+// cnst5 :1566, mm05_gp :1882, mm05_gp_init :2128, mm05_gp_compute :2372, mm05_gp_nsteps :2651,
+// mm05_gp_lambda_solve :2859, mm05_gp_elastic_fraction :3002, mm05_gp_felas_eta :3429, cnst5_gp
+// :3584, mm05_final :3879, mm05_plastic_work :3949; properties src/rknstr.f:1234-1317,
+// src/inmat.f:2003-2040.  Checked line by line against the Fortran when this file was split off
+// (round 2): mm05_fa_lambda_solve, mm05_fa_nsteps, mm05_fa_elastic_fraction, mm05_compute_residual,
+// mm05_update_lambda.
 //
 // Parity quirks kept: the 8-digit DATA constants 0.81649658 / 0.66666666 / 0.33333333, the typo
 // 0.8164956809 (for sqrt(2/3) = 0.8164965809) in the local solve, tol = 1e-6 if iter > 1 else
 // 1e-3, max 15 Newton passes, integer state in the low word of history(4).  The reference is
 // built with -fpconstant, so DATA literals without a d-exponent are taken as evaluated in double
 // (define W3D_MM05_DATA_SINGLE to evaluate them in single instead).
+// Parity status: pinned end to end by verification/test60 a and b (tests/
+// test_reference_known_answers.py); function level at 1e-10 unpinned (no Fortran compiler here).
 #pragma once
 #include <math.h>
 #include <string.h>
 
-#if defined(__CUDACC__)
-#define W3D5_HD __host__ __device__
-#else
-#define W3D5_HD
-#endif
+#define W3D5_HD   /* host only */
 
-namespace w3d_mm05 {
+namespace w3do_mm05 {
 
 #ifdef W3D_MM05_DATA_SINGLE
 #define W3D5_K(x) ((double)(x##f))
@@ -36,23 +38,15 @@ namespace w3d_mm05 {
 #endif
 
 W3D5_HD inline double state_dword(int st) {
-#if defined(__CUDA_ARCH__)
-  return __hiloint2double(0, st);
-#else
-  int iw[2] = {st, 0};
+  int iw[2] = {st, 0};      // EQUIVALENCE of an integer with the low word of a double
   double d;
   memcpy(&d, iw, 8);
   return d;
-#endif
 }
 W3D5_HD inline int dword_state(double d) {
-#if defined(__CUDA_ARCH__)
-  return __double2loint(d);
-#else
   int iw[2];
   memcpy(iw, &d, 8);
   return iw[0];
-#endif
 }
 
 struct Props {
@@ -922,4 +916,4 @@ W3D5_HD inline void cnst5(const Props &P, const double *sig_trial, const double 
   else cnst5_fa(P, sig_trial, h1, stress_np1, D);
 }
 
-}  // namespace w3d_mm05
+}  // namespace w3do_mm05

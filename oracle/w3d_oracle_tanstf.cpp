@@ -14,7 +14,7 @@
 #include <omp.h>
 #endif
 #include "w3d_oracle_internal.h"
-#include "../warp3d_b200/csrc/w3d_mm10_core.h"
+#include "w3d_oracle_mm10.h"
 
 namespace w3do {
 

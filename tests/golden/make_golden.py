@@ -1,4 +1,6 @@
-"""Generates tests/golden/*.npz from the CPU oracle (oracle/, gcc -O2 -ffp-contract=off).
+"""Generates tests/golden/*.npz from the CPU oracle (oracle/, gcc -O2 -ffp-contract=off; for mm10
+and mm05 that is the statement-for-statement restatement in oracle/w3d_oracle_mm10.h / _mm05.h,
+not the engine's re-ordered cores).
 
 These are *regression* vectors: the reference (ifort-only Fortran + MKL) cannot be built or run
 in this environment and ships no function-level golden vectors for the path, so the fixtures pin

@@ -45,3 +45,13 @@ def test_product_package_never_touches_the_oracle():
                 src = open(os.path.join(dp, f)).read()
                 hit = re.search(r"(import\s+oracle|from\s+oracle|oracle_py|libw3d_oracle|w3do_|w3d_oracle)", src)
                 assert not hit, f"{f} reaches into oracle/: {hit.group(0)}"
+
+
+def test_oracle_never_includes_product_source():
+    """The checker is independent of what it checks: no file under oracle/ includes, imports or
+    names anything of the engine package (mm05 and mm10 have their own statement-for-statement
+    restatements, oracle/w3d_oracle_mm05.h and w3d_oracle_mm10.h)."""
+    for f in os.listdir(os.path.join(ROOT, "oracle")):
+        if f.endswith((".py", ".cpp", ".h", ".c")) or f == "Makefile":
+            src = open(os.path.join(ROOT, "oracle", f)).read()
+            assert "warp3d_b200" not in src and "csrc/" not in src.replace("(csrc/", "("), f

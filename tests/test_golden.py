@@ -66,12 +66,3 @@ class EngineRun:
 @pytest.mark.parametrize("name", sorted(mg.CASES))
 def test_engine_matches_golden(name):
     _check(name, mg.run(name, EngineRun), RTOL)
-
-
-def test_oracle_matches_literal_order_mm10_fixture():
-    """hex8_geonl_mm10_voce_literal.npz was written by the statement-for-statement transcription
-    of mm10 (every pow() and every sum in the reference's order, commit 'mm05 cyclic plasticity').
-    The shared mm10 core has since been re-associated for speed (one pow per slip system per
-    state, grouped Jacobian sums); it must stay within the parity bar of the literal version."""
-    name = "hex8_geonl_mm10_voce"
-    _check(name, mg.run(name, mg.OracleRun), RTOL, fixture=name + "_literal")

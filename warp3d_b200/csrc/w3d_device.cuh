@@ -28,6 +28,7 @@ struct CtaDesc {
   int blk_slot0;  // slot of the first element of the owning block (mm01.f:843-845 quirk)
   int epos0;      // position of the CTA's first element in the concatenated, unpadded element
                   // order of all owned blocks (estiff / pull_state addressing)
+  int blk_span;   // span of the owning block (mm10 small-strain curvature fit, mm10_a.f:1622)
 };
 
 // un-contracted, round-to-nearest operations (never fused by ptxas)

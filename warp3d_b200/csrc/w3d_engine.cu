@@ -373,6 +373,7 @@ int create_impl(w3d_engine *h) {
         d.nvalid = (b.span - i0 < EPC) ? b.span - i0 : EPC;
         d.blk_slot0 = b.slot0;
         d.epos0 = (int)(b.epos0 + i0);
+        d.blk_span = b.span;
       }
       const int padded = ((b.span + EPC - 1) / EPC) * EPC;
       for (int i = 0; i < padded; ++i) {

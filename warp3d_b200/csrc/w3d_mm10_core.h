@@ -1,10 +1,9 @@
-// w3d_mm10_core.h -- crystal-plasticity material update (mm10) for ONE Gauss point, written once
-// in plain C++ and compiled twice: by nvcc as device code for the engine, and by g++ as the CPU
-// restatement the parity tests check it against (the block driver under oracle/ includes this file).
-// Because the local Newton loops are tolerance-terminated, an independently written CPU copy
-// would not be comparable at 1e-10; the second compile checks the port (compiler, FMA, libm),
-// not the transcription.  Fidelity to the Fortran is argued by the citations below and by the
-// physics / known-answer tests (DESIGN.md "mm10").
+// w3d_mm10_core.h -- crystal-plasticity material update (mm10) for ONE Gauss point: the engine's
+// general core (any slip table up to NS systems, several crystal types), device code for k_mm10<NS>
+// and host code for the property set-up.  The arithmetic is re-ordered for the GPU (one power per
+// slip system per state, sums over slip systems taken before the 6x6 products, register-resident
+// LU); the parity tests check it against an INDEPENDENT statement-for-statement CPU restatement
+// of the Fortran that lives with the test infrastructure -- no file is shared with it.
 //
 // Follows reference src/: mm10_a.f (mm10 :29, mm10_a_do_crystal :204, mm10_a_store_crystal :290,
 // mm10_init_cc_hist0 :480, mm10_tangent :664, mm10_setup :852, mm10_store_cryhist :998,

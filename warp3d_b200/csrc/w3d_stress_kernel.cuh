@@ -555,8 +555,22 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
           for (int bb = 0; bb < 3; ++bb)   // Rt = Rp * R^T (mult_type_3t), column-major storage
             rt[bb * 3 + aa] = Rp[0 * 3 + aa] * R1[bb][0] + Rp[1 * 3 + aa] * R1[bb][1] + Rp[2 * 3 + aa] * R1[bb][2];
       } else {
+        // small strain: mm10_calc_grads copies the FIRST ngp*9 contiguous words of the block-local
+        // history array starting at elem_hist(1, rs, 1) (mm10_a_copy_vector(Rt3d, Rps, ngp*9),
+        // mm10_a.f:1622) -- word rs + k / span of block element 1 + mod(k, span) at Gauss point 1,
+        // whichever element is being fitted.  Reproduced literally (the bar is the reference's
+        // result): lane gp fills rt[gp][0..8] = flat[gp*9 ..].
 #pragma unroll
-        for (int k = 0; k < 9; ++k) rt[k] = Rp[k];
+        for (int k9 = 0; k9 < 9; ++k9) {
+          const int k = gp * 9 + k9;
+          const int i = k % cd.blk_span;
+          int word = a.cp_o_Rp + k / cd.blk_span;          // runs on into the next Gauss-point
+          const int plane = word / a.hist_size;            // plane of the (span, hist, ngp) array
+          word -= plane * a.hist_size;                     // for blocks of very few elements
+          const int q = word - a.cp_o_Rp;
+          rt[k9] = (a.step == 1) ? ((q == 0 || q == 4 || q == 8) ? 1.0 : 0.0)
+                                 : a.hist_n[(long long)word * ng + (long long)(cd.blk_slot0 + i) * 8 + plane];
+        }
       }
     }
     __syncwarp();
