@@ -1,0 +1,54 @@
+// Test harness (tests/ only): one Gauss-point update of mm10 through
+//   (a) the independent statement-for-statement restatement  oracle/w3d_oracle_mm10.h
+//   (b) the engine's fast lattice-frame core                 warp3d_b200/csrc/w3d_mm10_fast.h (host build)
+// on the same inputs.  Built on demand by tests/test_mm10_fast_core.py with g++.
+#include <cstring>
+#include <vector>
+
+#include "../../oracle/w3d_oracle_mm10.h"
+#include "../../warp3d_b200/csrc/w3d_mm10_fast.h"
+
+extern "C" int mm10_point_both(const double *ct /*344*/, int ncrystals, const double *angles, int angle_type,
+                               int step, const double *hist_n, const double *Rur, const double *uddt, double dt,
+                               int iter0off, int asym, const double *cgn, int taul, double *h1_lit,
+                               double *cgn1_lit, double *h1_fast, double *cgn1_fast, int *cuts /*2*/) {
+  const int nslip = (int)ct[337];
+  if (nslip > 12) return -1;
+  // ---- literal
+  {
+    using namespace w3do_mm10;
+    CrystalType c;
+    const size_t nd = 36 + 144 + 144 + 13;
+    std::memcpy(&c, ct, nd * sizeof(double));
+    const double *ti = ct + nd;
+    c.nslip = (int)ti[0]; c.num_hard = (int)ti[1]; c.h_type = (int)ti[2]; c.tang_calc = (int)ti[3];
+    c.miter = (int)ti[4]; c.solver = (int)ti[5]; c.alter_mode = (int)ti[6];
+    std::vector<Props<12>> P(ncrystals);
+    for (int k = 0; k < ncrystals; ++k) { std::memset(&P[k], 0, sizeof(Props<12>)); setup_props<12>(c, angles + 3 * k, angle_type, P[k]); }
+    const Layout L = Layout::make(c.nslip, c.num_hard);
+    const CHist hn{hist_n, 1};
+    const Hist h1{h1_lit, 1};
+    cuts[0] = gauss_point_update<12>(step, ncrystals, P.data(), L, hn, h1, Rur, uddt, dt, iter0off != 0, asym != 0, cgn, cgn1_lit) ? 1 : 0;
+  }
+  // ---- fast
+  {
+    using namespace w3d_mm10f;
+    static CrystalConsts K;
+    setup_consts(ct, K);
+    K.angle_type = angle_type;
+    g_host_ct = &K;
+    std::vector<FProps> P(ncrystals);
+    for (int k = 0; k < ncrystals; ++k)
+      if (!setup_fprops(ct, angles + 3 * k, angle_type, P[k])) return -2;
+    const LayoutF L = LayoutF::make(nslip);
+    const CHistF hn{hist_n, 1};
+    const HistF h1{h1_fast, 1};
+    double ws[WORK_DOUBLES + NSF];
+    const WorkF W{ws, 1};
+    const PointInF in{Rur, uddt, cgn, 1};
+    const bool cut = taul ? gauss_point_update_fast<true, NoSync>(step, ncrystals, P.data(), L, hn, h1, W, in, dt, iter0off != 0, asym != 0, cgn1_fast)
+                          : gauss_point_update_fast<false, NoSync>(step, ncrystals, P.data(), L, hn, h1, W, in, dt, iter0off != 0, asym != 0, cgn1_fast);
+    cuts[1] = cut ? 1 : 0;
+  }
+  return 0;
+}

@@ -4,10 +4,12 @@
 // 7x7 Newton update with line search and adaptive sub-incrementation, consistent tangent by
 // Schur complement, plastic rotation update and the output/history terms.
 // Inputs from the PHASE 1 kinematics launch (scratch: R(n+1), strain increment, energy factor).
+#include <cstdlib>
 #include <cstring>
 
 #include "w3d_cp_kernel.h"
 #include "w3d_mm10_core.h"
+#include "w3d_mm10_fast.h"
 
 namespace w3d {
 
@@ -77,6 +79,145 @@ __global__ void __launch_bounds__(TPB * MM10_GROUPS, MM10_MIN_CTAS) k_mm10(const
   for (int k = 0; k < 9; ++k) a.urcs_n1[k * ng + g] = cgn1[k];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path (w3d_mm10_fast.h): one crystal type, <= 12 slip systems.  Thread = Gauss point, 256
+// threads per CTA, one CTA per SM; no per-thread stack -- the slip tables are operands from
+// __constant__ memory, B6 / C B6 / B3 and the vectors that must survive the Jacobian sit in a
+// per-thread column of shared memory ([word][thread]: conflict-free).
+// ------------------------------------------------------------------------------------------------
+// CTA shape, measured on the 1 M-element mm10 workload (stress pass, 3 launches): 128 threads in
+// lock step, 2 CTAs per SM 45.6 ms; 256 threads, 1 CTA 46.3 ms; 64 threads, 4 CTAs 58.2 ms (four
+// instruction streams per SM); without the lock step 56.6 / 62.1 / 70.4 ms.  (Round-1 kernel:
+// 54.1 ms.)  With geometric hardening the column is 12 words longer: one CTA of 128 per SM.
+// the solver loop's lock step: one barrier per trip, loop ends when no thread of the CTA needs more
+struct CtaSync {
+  // barrier.red WITHOUT .aligned (what __syncthreads_or would emit): the lanes of a warp reach
+  // the loop top at different times -- those already done skip the trip's body -- and an aligned
+  // barrier executed by a diverged warp is undefined (it deadlocked).  Every thread of the CTA
+  // arrives exactly once per trip; nobody leaves the kernel before the last trip.
+  static __device__ __forceinline__ bool any(bool p) {
+    unsigned r;
+    __syncwarp();      // every lane of every warp comes through here once per trip
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pin, pout;\n\t"
+        "setp.ne.u32 pin, %1, 0;\n\t"
+        "barrier.cta.red.or.pred pout, 0, pin;\n\t"
+        "selp.u32 %0, 1, 0, pout;\n\t"
+        "}"
+        : "=r"(r)
+        : "r"((unsigned)(p ? 1u : 0u))
+        : "memory");
+    return r != 0;
+  }
+};
+#ifndef W3D_MM10F_THREADS
+#define W3D_MM10F_THREADS 128
+#endif
+#ifndef W3D_MM10F_LOCKSTEP
+#define W3D_MM10F_LOCKSTEP 1
+#endif
+#if W3D_MM10F_LOCKSTEP
+typedef CtaSync Mm10fSync;
+#else
+typedef w3d_mm10f::NoSync Mm10fSync;
+#endif
+template <bool TAUL>
+struct Mm10fShape {
+  static constexpr int THREADS = TAUL ? TPB : W3D_MM10F_THREADS;
+  static constexpr int MIN_CTAS = TAUL ? 1 : (W3D_MM10F_THREADS > 128 ? 1 : W3D_MM10F_THREADS > 64 ? 2 : 4);
+  static constexpr int SMEM_BYTES =
+      (w3d_mm10f::WORK_DOUBLES + (TAUL ? w3d_mm10f::NSF : 0)) * THREADS * (int)sizeof(double);
+};
+
+template <bool TAUL>
+__global__ void __launch_bounds__(Mm10fShape<TAUL>::THREADS, Mm10fShape<TAUL>::MIN_CTAS) k_mm10f(const CpArgs a) {
+  extern __shared__ double sWork[];   // [word][thread]
+  constexpr int MM10F_THREADS = Mm10fShape<TAUL>::THREADS;
+  // a CTA takes THREADS / 128 whole 16-element groups, or (64 threads) half a group
+  constexpr int GROUPS = MM10F_THREADS >= TPB ? MM10F_THREADS / TPB : 1;
+  constexpr int SPLIT = MM10F_THREADS >= TPB ? 1 : TPB / MM10F_THREADS;
+  const int grp = threadIdx.x / TPB;
+  const int tid = threadIdx.x % TPB + (blockIdx.x % SPLIT) * MM10F_THREADS;
+  const int idesc = (blockIdx.x / SPLIT) * GROUPS + grp;
+  const bool have = idesc < a.ncta;
+  const CtaDesc cd = a.cta[have ? idesc : a.ncta - 1];
+  const int el = tid >> 3, gp = tid & 7;
+  const int slot = cd.slot0 + (el < cd.nvalid ? el : cd.nvalid - 1);
+  const long long ng = a.ng;
+  const long long g = (long long)slot * 8 + gp;
+  const double efac = a.scratch[15 * ng + g];
+  // padding lanes and points whose det F was not positive (NaN marker: the kinematics already
+  // asked for a step cut) take no part in the update, only in the loop's barriers
+  const bool active = have && el < cd.nvalid && (efac == efac);
+  if (!active) {
+    for (int c = 0; c < a.ncrystals; ++c)
+      while (Mm10fSync::any(false)) {}
+    return;
+  }
+  double cgn1[9];
+  const w3d_mm10f::LayoutF L = w3d_mm10f::LayoutF::make(a.nslip);
+  const w3d_mm10f::FProps *P =
+      reinterpret_cast<const w3d_mm10f::FProps *>(a.props) + (size_t)slot * a.ncrystals;
+  const w3d_mm10f::CHistF hn{a.hist_n + g, ng};
+  const w3d_mm10f::HistF h1{a.hist_n1 + g, ng};
+  const w3d_mm10f::WorkF W{sWork + threadIdx.x, MM10F_THREADS};
+  const w3d_mm10f::PointInF in{a.scratch + g, a.scratch + 9 * ng + g, a.urcs_n + g, ng};
+  const bool cut = w3d_mm10f::gauss_point_update_fast<TAUL, Mm10fSync>(a.step, a.ncrystals, P, L, hn, h1, W, in, a.dt,
+                                                                     a.iter_0_extrapolate_off != 0, a.asymmetric != 0, cgn1);
+  if (cut) {
+    atomicOr(&a.flags[0], 1);
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) a.urcs_n1[k * ng + g] = cgn1[k];
+}
+
+bool mm10_fast_eligible(const double *crystal_types, int n_crystal_types) {
+  if (getenv("W3D_MM10_GENERIC")) return false;      // A/B switch: force the general kernel
+  if (n_crystal_types != 1) return false;
+  const int nslip = (int)crystal_types[337], num_hard = (int)crystal_types[338], h_type = (int)crystal_types[339];
+  return nslip >= 1 && nslip <= w3d_mm10f::NSF && num_hard == 1 && h_type == 1;
+}
+int mm10_fast_props_doubles() { return (int)(sizeof(w3d_mm10f::FProps) / sizeof(double)); }
+bool mm10_fast_setup_props_host(const double *ct, const double *angles, int angle_type, double *out) {
+  w3d_mm10f::FProps P;
+  if (!w3d_mm10f::setup_fprops(ct, angles, angle_type, P)) return false;
+  std::memcpy(out, &P, sizeof P);
+  return true;
+}
+int mm10_fast_consts_bytes() { return (int)sizeof(w3d_mm10f::CrystalConsts); }
+void mm10_fast_setup_consts_host(const double *ct, int angle_type, void *out) {
+  w3d_mm10f::CrystalConsts K;
+  std::memset(&K, 0, sizeof K);
+  w3d_mm10f::setup_consts(ct, K);
+  K.angle_type = angle_type;
+  std::memcpy(out, &K, sizeof K);
+}
+cudaError_t launch_mm10_fast(const CpArgs &a, int ncta, const void *consts, bool taul, cudaStream_t st) {
+  // the crystal-type table goes to __constant__ memory in stream order before every launch: two
+  // engines of one process (sequentially, as one handle per GPU prescribes) never see each
+  // other's table
+  cudaError_t e = cudaMemcpyToSymbolAsync(w3d_mm10f::c_mm10f, consts, sizeof(w3d_mm10f::CrystalConsts), 0,
+                                          cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  CpArgs b = a;
+  b.ncta = ncta;
+#ifdef W3D_MM10F_HIST
+  {
+    int *hp = a.flags + 2;
+    cudaMemcpyToSymbolAsync(w3d_mm10f::w3df_hist, &hp, sizeof hp, 0, cudaMemcpyHostToDevice, st);
+  }
+#endif
+  if (taul) k_mm10f<true><<<ncta, Mm10fShape<true>::THREADS, Mm10fShape<true>::SMEM_BYTES, st>>>(b);
+  else {
+    constexpr int T = Mm10fShape<false>::THREADS;
+    const int grid = T >= TPB ? (ncta + T / TPB - 1) / (T / TPB) : ncta * (TPB / T);
+    k_mm10f<false><<<grid, T, Mm10fShape<false>::SMEM_BYTES, st>>>(b);
+  }
+  return cudaGetLastError();
+}
+
 int mm10_props_doubles(int nslip) {
   return (int)((nslip <= 12 ? sizeof(Props<12>) : sizeof(Props<48>)) / sizeof(double));
 }
@@ -118,6 +259,10 @@ cudaError_t mm10_prepare_device() {
   cudaError_t e = cudaFuncSetAttribute(k_mm10<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM10_PROPS_SMEM_LIMIT);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_mm10<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM10_PROPS_SMEM_LIMIT);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_mm10f<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<false>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_mm10f<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<true>::SMEM_BYTES);
   return e;
 }
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {

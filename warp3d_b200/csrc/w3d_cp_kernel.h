@@ -28,7 +28,17 @@ void mm10_setup_props_host(const double *crystal_type_rec, const double *angles,
                            double *props_out);
 int mm10_hist_size(int nslip, int num_hard, int ncrystals);
 void mm10_layout_offsets(int nslip, int num_hard, int *o_gradfe, int *o_Rp0);
-// shared-memory opt-in of both instantiations on the current device (w3d_engine_create)
+// ---- fast path (w3d_mm10_fast.h): one crystal type with <= 12 slip systems, Voce hardening.
+// eligible: decided once at create; props: 128 doubles per (element, crystal); consts: the
+// crystal-type table that launch_mm10_fast uploads to __constant__ memory before the kernel
+bool mm10_fast_eligible(const double *crystal_types, int n_crystal_types);
+int mm10_fast_props_doubles();
+bool mm10_fast_setup_props_host(const double *crystal_type_rec, const double *angles, int angle_type,
+                                double *props_out);
+int mm10_fast_consts_bytes();
+void mm10_fast_setup_consts_host(const double *crystal_type_rec, int angle_type, void *consts_out);
+cudaError_t launch_mm10_fast(const CpArgs &a, int ncta, const void *consts, bool taul, cudaStream_t st);
+// shared-memory opt-in of every instantiation on the current device (w3d_engine_create)
 cudaError_t mm10_prepare_device();
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st);
 

@@ -8,6 +8,7 @@
 #include "../../include/w3d_engine.h"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -54,6 +55,8 @@ struct Segment {
   // crystal plasticity (mm10)
   double *d_cprops = nullptr, *scratch = nullptr;
   int ncrystals = 0, nslip = 0, num_hard = 0, o_gradfe = 0, o_Rp0 = 0;
+  bool cp_fast = false, cp_taul = false;   // fast lattice-frame kernel (w3d_mm10_fast.h); k_0 != 0
+  std::vector<char> cp_consts;             // its crystal-type table (host copy, uploaded per launch)
 };
 
 struct BlockInfo {
@@ -347,7 +350,7 @@ int create_impl(w3d_engine *h) {
   CUDA_TRY(cudaMemcpy(h->d_c, c.c, sizeof(double) * c.nodof, cudaMemcpyHostToDevice));
   CUDA_TRY(dalloc(&h->d_estiff, (size_t)h->n_owned_elems * 300));
   CUDA_TRY(dalloc(&h->d_scal, 4));
-  CUDA_TRY(dalloc(&h->d_flags, 2));
+  CUDA_TRY(dalloc(&h->d_flags, 64));   // [0] cut, [1] fatal, [2..] debug histogram (W3D_MM10F_HIST builds)
   CUDA_TRY(cudaMallocHost((void **)&h->h_pin, 8 * sizeof(double)));
   {
     double tab3[3][8][8];
@@ -405,7 +408,13 @@ int create_impl(w3d_engine *h) {
       // Kocks angles, Schmid tensors and elastic stiffness in the reference frame
       sg.ncrystals = c.cp_ncrystals;
       sg.nslip = (int)c.crystal_types[337];
-      const int pd = mm10_props_doubles(sg.nslip);
+      sg.cp_fast = mm10_fast_eligible(c.crystal_types, c.n_crystal_types);
+      if (sg.cp_fast) {
+        sg.cp_taul = c.crystal_types[36 + 288 + 5] != 0.0;      // k_o: geometric hardening
+        sg.cp_consts.resize(mm10_fast_consts_bytes());
+        mm10_fast_setup_consts_host(c.crystal_types, c.cp_angle_type, sg.cp_consts.data());
+      }
+      const int pd = sg.cp_fast ? mm10_fast_props_doubles() : mm10_props_doubles(sg.nslip);
       sg.num_hard = (int)c.crystal_types[338];
       mm10_layout_offsets(sg.nslip, sg.num_hard, &sg.o_gradfe, &sg.o_Rp0);
       std::vector<double> cp((size_t)sg.nslots * sg.ncrystals * pd, 0.0);
@@ -420,9 +429,14 @@ int create_impl(w3d_engine *h) {
             const int cnum = c.elem_cnum[k];
             if (cnum < 1 || cnum > c.n_crystal_types)
               return fail(W3D_ERR_CONFIG, "element %d crystal %d: crystal number %d outside 1..%d", elem, cr + 1, cnum, c.n_crystal_types);
-            mm10_setup_props_host(c.crystal_types + (size_t)(cnum - 1) * W3D_CRYSTAL_TYPE_DOUBLES,
-                                  c.elem_angles + 3 * k, c.cp_angle_type,
-                                  &cp[((size_t)(b.slot0 + i) * sg.ncrystals + cr) * pd]);
+            double *rec = &cp[((size_t)(b.slot0 + i) * sg.ncrystals + cr) * pd];
+            const double *ctr = c.crystal_types + (size_t)(cnum - 1) * W3D_CRYSTAL_TYPE_DOUBLES;
+            if (sg.cp_fast) {
+              if (!mm10_fast_setup_props_host(ctr, c.elem_angles + 3 * k, c.cp_angle_type, rec))
+                return fail(W3D_ERR_CONFIG, "element %d crystal %d: singular elastic stiffness", elem, cr + 1);
+            } else {
+              mm10_setup_props_host(ctr, c.elem_angles + 3 * k, c.cp_angle_type, rec);
+            }
           }
         }
       }
@@ -472,7 +486,7 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   const w3d_engine_config &c = h->cfg;
   CUDA_TRY(cudaMemsetAsync(h->d_ifv, 0, sizeof(double) * c.nodof, h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, 64 * sizeof(int), h->stream));
   int first = 1;
   for (auto &sg : h->segs) {
     StressArgs a{};
@@ -497,7 +511,8 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
       ca.iter_0_extrapolate_off = (iter == 0 && (!extrapolated_du || step == 1)) ? 1 : 0;   // rstgp1.f:4453-4457
       ca.asymmetric = c.asymmetric_assembly ? 1 : 0;
       ca.ncrystals = sg.ncrystals; ca.nslip = sg.nslip; ca.num_hard = sg.num_hard;
-      CUDA_TRY(launch_mm10(ca, sg.ncta, h->stream));
+      if (sg.cp_fast) CUDA_TRY(launch_mm10_fast(ca, sg.ncta, sg.cp_consts.data(), sg.cp_taul, h->stream));
+      else CUDA_TRY(launch_mm10(ca, sg.ncta, h->stream));
       CUDA_TRY((launch_stress<10, 2>(sg, a, h->stream)));
       h->launches += 3;
     } else if (sg.mat_type == 5) {
@@ -530,6 +545,13 @@ int fetch_scalars(w3d_engine *h, w3d_scalars *out) {
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   int flags[2];
   std::memcpy(flags, h->h_pin + 4, sizeof flags);
+  if (getenv("W3D_MM10F_HIST")) {     // debug: solver-loop trips per Gauss point (W3D_MM10F_HIST builds of w3d_cp.cu)
+    int hist[64];
+    cudaMemcpy(hist, h->d_flags, sizeof hist, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "mm10f trips histogram:");
+    for (int k = 2; k < 64; ++k) fprintf(stderr, " %d", hist[k]);
+    fprintf(stderr, "\n");
+  }
   w3d_scalars s{};
   s.material_cut_step = flags[0] ? 1 : 0;
   if (!s.material_cut_step) {
