@@ -314,8 +314,11 @@ def engine_arm(args):
     wd = workload_description(args.workload)
     TS = nprep + 1                      # the timed load step
     # seb: the deck's own domain column (2 domains) when run on 2 GPUs, slabs of blocks otherwise
+    # exchange step: inside the engine (C ABI, NCCL send/recv between neighbouring slabs); at N > 1
+    # rank 0 alone uploads u, du (NVLink broadcast) and every rank returns what it owns
     de = DomainEngine(model, rank, world, device=local,
-                      assign_slabs=not (WORKLOADS[args.workload][1] == "seb" and world == 2))
+                      assign_slabs=not (WORKLOADS[args.workload][1] == "seb" and world == 2),
+                      exchange=args.exchange, bcast_inputs=world > 1)
     eng = de.engine
     nodof, nel_own = model.nodof, eng.n_owned_elems
     ngp_total = model.noelem * 8
@@ -343,7 +346,7 @@ def engine_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    S = de.stream
+    S = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
 
     # ---- resident timing: K steps bracketed by barrier + synchronize, CUDA events on the stream
     for _ in range(max(args.warmup, 3)):
@@ -366,16 +369,35 @@ def engine_arm(args):
     t_stress = float(np.mean([ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]))
     t_tan = float(np.mean([ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)]))
 
+    # ---- the other exchange mode as a labelled variant (N > 1): same K steps, same bracketing
+    alt_ms, alt_mode = None, None
+    if world > 1:
+        alt_mode = "full" if args.exchange != "full" else "neighbours"
+        eng.comm_set_options(alt_mode, True)
+        for _ in range(3):
+            de.eps_sig_ifv_resident(TS, 1); de.tanstf_resident(TS, 1)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(S)
+        for k in range(args.steps):
+            de.eps_sig_ifv_resident(TS, 1); de.tanstf_resident(TS, 1)
+        b1.record(S)
+        barrier()
+        alt_ms = b0.elapsed_time(b1) / args.steps
+        eng.comm_set_options(args.exchange, True)
+
     # ---- end-to-end timing through the host-buffer calls (pinned host memory)
+    OWN = world > 1          # a rank copies back the dofs it owns, not the whole vector
+    own_first, own_n = de.owned_range()
     for _ in range(2):
-        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h); de.tanstf(TS, 1, est_h)
+        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h, owned_only=OWN); de.tanstf(TS, 1, est_h)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nrep_e2e = max(2, min(args.steps, 5))
     e0.record(S)
     w0 = time.perf_counter()
     for _ in range(nrep_e2e):
-        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
+        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h, owned_only=OWN)
         de.tanstf(TS, 1, est_h)
     e1.record(S)
     barrier()
@@ -397,13 +419,13 @@ def engine_arm(args):
     setup_s = time.perf_counter() - ts0
     kd_h, kc_h = pinned(st_["n_eqns"]), pinned(max(st_["ncoeff"], 1))
     for _ in range(2):
-        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
+        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h, owned_only=OWN)
         eng.tanstf_resident(TS, 1); eng.assemble(kd_h, kc_h)
     barrier()
     a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     a0.record(S)
     for _ in range(nrep_e2e):
-        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
+        de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h, owned_only=OWN)
         eng.tanstf_resident(TS, 1); eng.assemble(kd_h, kc_h)
     a1.record(S)
     for _ in range(nrep_e2e):
@@ -412,7 +434,7 @@ def engine_arm(args):
     barrier()
     asm = dict(ms=a0.elapsed_time(a1) / nrep_e2e, kernel_ms=a1.elapsed_time(a2) / nrep_e2e,
                neqns=st_["neqns"], ncoeff=st_["ncoeff"], setup_s=setup_s,
-               d2h=8 * nodof + 8 * (st_["n_eqns"] + st_["ncoeff"]))
+               d2h=8 * (own_n if OWN else nodof) + 8 * (st_["n_eqns"] + st_["ncoeff"]))
 
     # structure residual + convergence norms on the device (upres.f, cvtest.f:62-78): the internal
     # forces stay in HBM, 7 scalars come back.  Not part of the timed step; reported beside it.
@@ -428,7 +450,7 @@ def engine_arm(args):
     asm["residual_ms"] = r0.elapsed_time(r1) / 20
 
     t = torch.tensor([total_ms, t_stress, t_tan, e2e_ms, e2e_wall_ms, float(launches), asm["ms"], asm["kernel_ms"],
-                      float(asm["d2h"]), float(asm["ncoeff"])], dtype=torch.float64, device="cuda")
+                      float(asm["d2h"]), float(asm["ncoeff"]), alt_ms or 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         tl = t.clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -437,6 +459,7 @@ def engine_arm(args):
         asm["d2h"], asm["ncoeff"] = int(tl[8].item()), int(tl[9].item())     # bytes / terms over all ranks
     total_ms, t_stress, t_tan, e2e_ms, e2e_wall_ms = [float(x) for x in t[:5].tolist()]
     asm["ms"], asm["kernel_ms"] = float(t[6].item()), float(t[7].item())     # max over ranks
+    alt_ms = float(t[10].item()) or None
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
@@ -463,8 +486,12 @@ def engine_arm(args):
                         formulation="hex8 l3disop 2x2x2, geonl, bbar",
                         l2=("inputs_exceed_l2 (state >> 126 MB)" if model.noelem > 100000 else
                             "state fits L2 (small deck): launch-latency bound, not a roofline case"),
-                        partition=(f"{world} contiguous block slabs; resident pass: NCCL sum of ifv ({args.exchange}), "
-                                   f"e2e pass: full all-reduce") if world > 1 else "single GPU",
+                        partition=(f"{world} contiguous block slabs; exchange inside the engine (C ABI): "
+                                   + ("NCCL send/recv of the shared dofs between neighbouring domains"
+                                      if args.exchange != "full" else "ncclAllReduce of the whole ifv vector")
+                                   + " + one 5-double all-reduce of the scalars / cut flag; e2e: rank 0 uploads u, du "
+                                     "(ncclBroadcast), every rank returns the dofs and rows it owns")
+                        if world > 1 else "single GPU",
                         step="w3d_eps_sig_ifv + w3d_tanstf (one Newton iteration)"),
             stress_pass=dict(ms=t_stress, gp_updates_per_s=ngp_total / (t_stress * 1e-3)),
             stiffness_pass=dict(ms=t_tan, element_stiffnesses_per_s=model.noelem / (t_tan * 1e-3)),
@@ -480,9 +507,13 @@ def engine_arm(args):
                                             frac=ngp_own * other[2] / (other[1] * 1e-3) / 1e9 / peak),
                           fp64_peak_tflops=fp64_peak),
             e2e=dict(value=ngp_total / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, wall_ms_per_step=e2e_wall_ms,
-                     h2d_bytes_per_step=2 * 8 * nodof * world, d2h_bytes_per_step=8 * nodof * world + 8 * 300 * model.noelem,
+                     h2d_bytes_per_step=2 * 8 * nodof, d2h_bytes_per_step=8 * nodof + 8 * 300 * model.noelem,
                      note="pinned host buffers; u,du in; ifv and estiff(300,span) blocks out"),
             gpu_launches=launches, clocks=clocks,
+            exchange_variant=(dict(mode=alt_mode, ms_per_step=alt_ms, value=ngp_total / (alt_ms * 1e-3), unit=UNIT,
+                                   note="same K steps with the other exchange mode (full = ncclAllReduce of the whole "
+                                        "vector, the reference's wmpi_reduce_vec result on every rank)")
+                              if alt_ms else None),
             plastic_check=dict(plastic_work=sc["plastic_work"], internal_energy=sc["internal_energy"]),
         )
         if asm:
@@ -491,7 +522,7 @@ def engine_arm(args):
             line["e2e_element_blocks"] = line["e2e"]
             line["e2e"] = dict(
                 value=ngp_total / (asm["ms"] * 1e-3), unit=UNIT, ms_per_step=asm["ms"],
-                h2d_bytes_per_step=2 * 8 * nodof * world, d2h_bytes_per_step=asm["d2h"],
+                h2d_bytes_per_step=2 * 8 * nodof, d2h_bytes_per_step=asm["d2h"],
                 assemble_kernel_ms=asm["kernel_ms"], neqns=asm["neqns"], ncoeff=asm["ncoeff"],
                 structure_setup_s=asm["setup_s"],
                 note="pinned host buffers; u,du in; ifv, k_diag(neqns) and k_coeffs(ncoeff) out: w3d_eps_sig_ifv + "
@@ -544,8 +575,9 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="hex8_2m_mm01", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--exchange", default="interface", choices=["interface", "full"],
-                    help="N>1 resident pass: sum only the dofs shared between ranks, or the whole ifv vector")
+    ap.add_argument("--exchange", default="neighbours", choices=["neighbours", "full"],
+                    help="N>1: send/recv of the shared dofs between neighbouring domains, or all-reduce of the whole ifv "
+                         "vector; the other mode is timed as well and reported as exchange_variant")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define W3D_ABI_VERSION 2
+#define W3D_ABI_VERSION 3
 
 /* error codes (return values) */
 #define W3D_OK             0
@@ -36,6 +36,8 @@ extern "C" {
 #define W3D_ERR_ARG        4  /* bad argument (null pointer, block index out of range, ...)      */
 #define W3D_ERR_MM01_LAMBDA 5 /* mm01_general: negative plastic multiplier (mm01.f:878-881)      */
 #define W3D_ERR_DETF       6  /* det F <= 0 and the step is not adaptive (rstgp1.f:136-145)      */
+#define W3D_ERR_COMM       9  /* NCCL missing / failed, or a collective call on a handle without
+                                 a communicator                                                 */
 
 /* which = selector for w3d_push_state / w3d_pull_state.  Layout per block as in
  * mod_eleblocks.f:52-131 (blk is 1-based like the reference's block numbers):
@@ -169,6 +171,46 @@ void   *w3d_engine_stream(w3d_engine *h);
 int32_t w3d_engine_synchronize(w3d_engine *h);
 /* number of kernels the engine has launched since create (bench.py: gpu_launches) */
 int64_t w3d_engine_launch_count(const w3d_engine *h);
+
+/* ---- the exchange step between domains (one engine = one GPU = one MPI rank) -------------------
+ * Replaces what the reference's MPI build does at the end of drive_eps_sig_internal_forces:
+ * wmpi_reduce_vec(ifv, nodof) (drive_eps_sig_internal_forces.f:338-340), the reductions of
+ * internal_energy / plastic_work / sum_ifv / num_term_ifv and the logical OR of
+ * material_cut_step (:248-250, mpi_code_real.f wmpi_redlog).  Transport is NCCL over NVLink,
+ * bound at run time (dlopen of libnccl.so.2; W3D_NCCL_LIB overrides the name).
+ *
+ * Bootstrap as an MPI code does it: rank 0 calls w3d_comm_unique_id, the 128 bytes go to every
+ * rank by the caller's own means (MPI_Bcast in the reference), then every rank calls
+ * w3d_comm_init on its handle (created with cfg.myid = rank, cfg.numprocs = nranks).  From then
+ * on w3d_eps_sig_ifv / w3d_eps_sig_ifv_resident are COLLECTIVE calls: they end with the exchange
+ * of the internal forces and one 5-double all-reduce of the scalars and the cut flag, both on the
+ * engine's stream, and w3d_scalars holds the sums over all ranks on every rank.
+ *
+ * w3d_comm_set_options
+ *   exchange  1 (default): neighbour exchange.  Every engine knows from the replicated block
+ *             tables which dofs its own blocks share with each other rank (w3d_comm_plan).  The
+ *             partial sums on those dofs are packed, sent / received pairwise (grouped
+ *             ncclSend/ncclRecv) and added: every rank ends with the COMPLETE internal force on
+ *             every dof its own blocks touch, other entries keep this rank's partial (zero).
+ *             The full vector is the concatenation of what the ranks hold on the dofs they own
+ *             (w3d_comm_owned: the lowest rank touching a dof owns it).
+ *             0: ncclAllReduce of the whole vector -- the reference's result on every rank.
+ *   bcast_inputs  1: u and du given to rank 0 are broadcast over NVLink (ncclBroadcast) and the
+ *             pointers of the other ranks are ignored (may be NULL): one host->device copy per
+ *             iteration instead of one per GPU.  0 (default): every rank uploads its own copy,
+ *             as the reference's ranks hold them (replicated).                                    */
+int32_t w3d_comm_unique_id(uint8_t id[128]);
+int32_t w3d_comm_init(w3d_engine *h, const uint8_t id[128], int32_t rank, int32_t nranks);
+int32_t w3d_comm_set_options(w3d_engine *h, int32_t exchange, int32_t bcast_inputs);
+/* Host-only planning step (no GPU needed), the same routine the engine uses at create: for the
+ * domain `rank` of cfg, counts[r] = number of dofs shared with rank r (numprocs entries) and, when
+ * dofs != NULL, the 1-based dof lists concatenated in rank order, each ascending.  Both sides of
+ * a pair compute the same list.                                                                  */
+int32_t w3d_comm_plan(const w3d_engine_config *cfg, int32_t rank, int64_t *counts, int32_t *dofs);
+/* owned(nodof) = 1 where this rank owns the dof (lowest rank whose blocks touch it), else 0      */
+int32_t w3d_comm_owned(const w3d_engine_config *cfg, int32_t rank, uint8_t *owned);
+/* device -> host copy of ifv(first .. first+n-1), first 1-based: a rank returns only what it owns */
+int32_t w3d_download_ifv_range(w3d_engine *h, int32_t first, int32_t n, double *dst);
 
 /* ---- assembled equilibrium equations (SURVEY 8(f) NEXT-1), symmetric case -------------------
  * Replaces assemble_code.f: dof_map (:561-600), count_profile_symmetric (:20-250),

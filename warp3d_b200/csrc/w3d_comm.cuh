@@ -17,10 +17,8 @@
 //   0 = ncclAllReduce of the whole vector: the reference's semantics (every rank, hence root, holds
 //       the full vector).
 // The scalars and the cut flag travel as ONE 5-double all-reduce per pass.
+// (Included by w3d_engine.cu inside its anonymous namespace, after iprop(); <dlfcn.h> comes from there.)
 #pragma once
-#include <dlfcn.h>
-
-namespace {
 
 struct NcclUniqueId { char internal[128]; };
 typedef int (*nccl_get_unique_id_t)(NcclUniqueId *);
@@ -143,4 +141,3 @@ __global__ void k_scal_pack(const double *scal, const int *flags, double num_ter
   red[4] = flags[0] ? 1.0 : 0.0;
 }
 
-}  // namespace

@@ -7,6 +7,7 @@
 // usable every entry point returns W3D_ERR_CUDA.
 #include "../../include/w3d_engine.h"
 
+#include <dlfcn.h>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -19,6 +20,7 @@
 #include "w3d_cp_kernel.h"
 #include "w3d_assemble_data.h"
 #include "w3d_residual_data.h"
+#include <cstdint>
 #include <cmath>
 #include <algorithm>
 #include <type_traits>
@@ -73,8 +75,21 @@ struct BlockInfo {
 
 }  // namespace
 
+// exchange step between domains (w3d_comm.cuh)
+struct CommData {
+  void *comm = nullptr;              // ncclComm_t
+  int rank = 0, nranks = 1;
+  int exchange = 1, bcast_inputs = 0;
+  std::vector<long long> counts;     // dofs shared with each rank (host, from create)
+  std::vector<int32_t> dofs;         // concatenated lists, 1-based
+  long long ntot = 0;
+  int32_t *d_idx = nullptr;
+  double *d_send = nullptr, *d_recv = nullptr, *d_red = nullptr;   // d_red[8]
+};
+
 struct w3d_engine {
   w3d_engine_config cfg{};
+  CommData comm;
   std::string err;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -87,7 +102,7 @@ struct w3d_engine {
   int *d_flags = nullptr;           // [2]
   double *d_stage = nullptr;        // push/pull staging (one block)
   size_t stage_doubles = 0;
-  double *h_pin = nullptr;          // pinned: [0..3] scalars, then 2 ints of flags
+  double *h_pin = nullptr;          // pinned: [0..3] scalars, then 2 ints of flags, [8..15] reduced scalars
   int64_t launches = 0;
   double dt = 1.0;
   w3d_scalars last{};
@@ -120,6 +135,8 @@ inline float rprop(const w3d_engine_config &c, int row, int elem) {
 }
 // ifort logicals: .true. has the low bit set
 inline bool lprop(const w3d_engine_config &c, int row, int elem) { return (iprop(c, row, elem) & 1) != 0; }
+
+#include "w3d_comm.cuh"   // NCCL binding, neighbour plan, pack / add kernels
 
 // quad2 (getgpts.f:642-718) and deriv2 (derivs.f:283-343): WARP3D point and node ordering
 void shape_tables(double (*tab)[8][8]) {
@@ -225,7 +242,9 @@ void free_all(w3d_engine *h) {
   }
   h->assembly.release();
   h->residual.release();
-  cudaFree(h->d_c); cudaFree(h->d_u); cudaFree(h->d_du); cudaFree(h->d_ifv);
+  cudaFree(h->d_c); cudaFree(h->d_u); cudaFree(h->d_ifv);
+  cudaFree(h->comm.d_idx); cudaFree(h->comm.d_send); cudaFree(h->comm.d_recv); cudaFree(h->comm.d_red);
+  if (h->comm.comm && nccl_api()->comm_destroy) nccl_api()->comm_destroy(h->comm.comm);
   cudaFree(h->d_estiff); cudaFree(h->d_scal); cudaFree(h->d_flags); cudaFree(h->d_stage);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -341,17 +360,24 @@ int create_impl(w3d_engine *h) {
     epos += b.span;
   }
   h->n_owned_elems = epos;
+  if (c.numprocs > 1) {
+    // dofs shared with every other domain (used by the neighbour exchange after w3d_comm_init)
+    std::string perr;
+    const int prc = comm_plan(c, c.myid, h->comm.counts, h->comm.dofs, perr);
+    if (prc != W3D_OK && prc != W3D_ERR_UNSUPPORTED) return fail(prc, "interface plan: %s", perr.c_str());
+    if (prc == W3D_ERR_UNSUPPORTED) { h->comm.counts.clear(); h->comm.dofs.clear(); h->comm.exchange = 0; }
+  }
 
   // ---- global vectors
   CUDA_TRY(dalloc(&h->d_c, (size_t)c.nodof));
-  CUDA_TRY(dalloc(&h->d_u, (size_t)c.nodof));
-  CUDA_TRY(dalloc(&h->d_du, (size_t)c.nodof));
+  CUDA_TRY(dalloc(&h->d_u, 2 * (size_t)c.nodof));     // u and du contiguous: one broadcast moves both
+  h->d_du = h->d_u + c.nodof;
   CUDA_TRY(dalloc(&h->d_ifv, (size_t)c.nodof));
   CUDA_TRY(cudaMemcpy(h->d_c, c.c, sizeof(double) * c.nodof, cudaMemcpyHostToDevice));
   CUDA_TRY(dalloc(&h->d_estiff, (size_t)h->n_owned_elems * 300));
   CUDA_TRY(dalloc(&h->d_scal, 4));
   CUDA_TRY(dalloc(&h->d_flags, 64));   // [0] cut, [1] fatal, [2..] debug histogram (W3D_MM10F_HIST builds)
-  CUDA_TRY(cudaMallocHost((void **)&h->h_pin, 8 * sizeof(double)));
+  CUDA_TRY(cudaMallocHost((void **)&h->h_pin, 16 * sizeof(double)));
   {
     double tab3[3][8][8];
     shape_tables(tab3);
@@ -482,6 +508,58 @@ int create_impl(w3d_engine *h) {
   return W3D_OK;
 }
 
+// the exchange step after the stress kernels of all segments (stream-ordered, no host sync)
+int comm_exchange(w3d_engine *h) {
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  CommData &cm = h->comm;
+  NcclApi *api = nccl_api();
+  const int nodof = h->cfg.nodof;
+  if (cm.exchange == 1 && cm.ntot >= 0 && !cm.counts.empty()) {
+    if (cm.ntot > 0) {
+      const int grid = (int)std::min<long long>((cm.ntot + 255) / 256, 148 * 8);
+      k_iface_pack<<<grid, 256, 0, h->stream>>>(h->d_ifv, cm.d_idx, cm.d_send, cm.ntot);
+      NCCL_TRY(api->group_start());
+      long long off = 0;
+      for (int r = 0; r < cm.nranks; ++r) {
+        const long long n = cm.counts[r];
+        if (n > 0) {
+          NCCL_TRY(api->send(cm.d_send + off, (size_t)n, NCCL_FLOAT64, r, cm.comm, h->stream));
+          NCCL_TRY(api->recv(cm.d_recv + off, (size_t)n, NCCL_FLOAT64, r, cm.comm, h->stream));
+        }
+        off += n;
+      }
+      NCCL_TRY(api->group_end());
+      k_iface_add<<<grid, 256, 0, h->stream>>>(h->d_ifv, cm.d_idx, cm.d_recv, cm.ntot);
+      h->launches += 2;
+    }
+  } else {
+    NCCL_TRY(api->all_reduce(h->d_ifv, h->d_ifv, (size_t)nodof, NCCL_FLOAT64, NCCL_SUM, cm.comm, h->stream));
+  }
+  // internal_energy, plastic_work, sum_ifv, num_term_ifv and the cut flag: one all-reduce
+  k_scal_pack<<<1, 1, 0, h->stream>>>(h->d_scal, h->d_flags, 24.0 * (double)h->n_owned_elems, cm.d_red);
+  h->launches += 1;
+  NCCL_TRY(api->all_reduce(cm.d_red, cm.d_red, 5, NCCL_FLOAT64, NCCL_SUM, cm.comm, h->stream));
+  CUDA_TRY(cudaGetLastError());
+  return W3D_OK;
+}
+
+// host -> device copy of u, du; with bcast_inputs rank 0's copy goes to every rank over NVLink
+int upload_inputs(w3d_engine *h, const double *u, const double *du) {
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  const size_t nb = sizeof(double) * h->cfg.nodof;
+  CommData &cm = h->comm;
+  const bool bc = cm.comm && cm.bcast_inputs;
+  if (!bc || cm.rank == 0) {
+    if (!u || !du) return fail(W3D_ERR_ARG, "u / du are NULL");
+    CUDA_TRY(cudaMemcpyAsync(h->d_u, u, nb, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_du, du, nb, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (bc)
+    NCCL_TRY(nccl_api()->broadcast(h->d_u, h->d_u, 2 * (size_t)h->cfg.nodof, NCCL_FLOAT64, 0, cm.comm, h->stream));
+  h->have_vectors = true;
+  return W3D_OK;
+}
+
 int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   const w3d_engine_config &c = h->cfg;
@@ -535,6 +613,10 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
   }
   CUDA_TRY(cudaGetLastError());
   h->have_vectors = true;
+  if (h->comm.comm) {
+    const int rc = comm_exchange(h);
+    if (rc) return rc;
+  }
   return W3D_OK;
 }
 
@@ -542,6 +624,8 @@ int fetch_scalars(w3d_engine *h, w3d_scalars *out) {
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   CUDA_TRY(cudaMemcpyAsync(h->h_pin, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->h_pin + 4, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (h->comm.comm)
+    CUDA_TRY(cudaMemcpyAsync(h->h_pin + 8, h->comm.d_red, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   int flags[2];
   std::memcpy(flags, h->h_pin + 4, sizeof flags);
@@ -553,12 +637,21 @@ int fetch_scalars(w3d_engine *h, w3d_scalars *out) {
     fprintf(stderr, "\n");
   }
   w3d_scalars s{};
-  s.material_cut_step = flags[0] ? 1 : 0;
-  if (!s.material_cut_step) {
-    s.internal_energy = h->h_pin[0];
-    s.plastic_work = h->h_pin[1];
-    s.sum_ifv = h->h_pin[2];
-    s.num_term_ifv = 24 * (int64_t)h->n_owned_elems;
+  if (h->comm.comm) {     // sums over all ranks (wmpi_reduce_vec / wmpi_redlog)
+    const double *r = h->h_pin + 8;
+    s.material_cut_step = r[4] > 0.0 ? 1 : 0;
+    if (!s.material_cut_step) {
+      s.internal_energy = r[0]; s.plastic_work = r[1]; s.sum_ifv = r[2];
+      s.num_term_ifv = (int64_t)llround(r[3]);
+    }
+  } else {
+    s.material_cut_step = flags[0] ? 1 : 0;
+    if (!s.material_cut_step) {
+      s.internal_energy = h->h_pin[0];
+      s.plastic_work = h->h_pin[1];
+      s.sum_ifv = h->h_pin[2];
+      s.num_term_ifv = 24 * (int64_t)h->n_owned_elems;
+    }
   }
   h->last = s;
   if (out) *out = s;
@@ -642,18 +735,21 @@ const char *w3d_engine_last_error(const w3d_engine *h) { return h ? h->err.c_str
 
 int32_t w3d_eps_sig_ifv(w3d_engine *h, int32_t step, int32_t iter, int32_t extrapolated_du,
                         const double *u, const double *du, double *ifv, w3d_scalars *out) {
-  if (!h || !u || !du || !ifv) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
+  if (!h) return W3D_ERR_ARG;
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  // with a communicator ifv may be NULL (a rank that does not want the vector back; the owned
+  // part is fetched with w3d_download_ifv_range) and, with bcast_inputs, u / du on ranks > 0
+  if (!h->comm.comm && (!u || !du || !ifv)) return fail(W3D_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
   const size_t nb = sizeof(double) * h->cfg.nodof;
-  CUDA_TRY(cudaMemcpyAsync(h->d_u, u, nb, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_du, du, nb, cudaMemcpyHostToDevice, h->stream));
-  int rc = stress_resident(h, step, iter, extrapolated_du);
+  int rc = upload_inputs(h, u, du);
   if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(ifv, h->d_ifv, nb, cudaMemcpyDeviceToHost, h->stream));
+  rc = stress_resident(h, step, iter, extrapolated_du);
+  if (rc) return rc;
+  if (ifv) CUDA_TRY(cudaMemcpyAsync(ifv, h->d_ifv, nb, cudaMemcpyDeviceToHost, h->stream));
   w3d_scalars s;
   rc = fetch_scalars(h, &s);
-  if (s.material_cut_step) std::memset(ifv, 0, nb);   // :253-263
+  if (s.material_cut_step && ifv) std::memset(ifv, 0, nb);   // :253-263
   if (out) *out = s;
   return rc;
 }
@@ -664,10 +760,10 @@ int32_t w3d_tanstf(w3d_engine *h, int32_t step, int32_t iter, const double *u, c
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   CUDA_TRY(cudaSetDevice(h->device));
   const size_t nb = sizeof(double) * h->cfg.nodof;
+  (void)nb;
   if (u && du) {
-    CUDA_TRY(cudaMemcpyAsync(h->d_u, u, nb, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_du, du, nb, cudaMemcpyHostToDevice, h->stream));
-    h->have_vectors = true;
+    const int rcu = upload_inputs(h, u, du);
+    if (rcu) return rcu;
   } else if (!h->have_vectors) {
     return fail(W3D_ERR_ARG, "w3d_tanstf: u/du are NULL and no displacement vectors are resident");
   }
@@ -771,14 +867,101 @@ int32_t w3d_device_vectors(w3d_engine *h, double **d_u, double **d_du, double **
   return W3D_OK;
 }
 int32_t w3d_upload_displacements(w3d_engine *h, const double *u, const double *du) {
-  if (!h || !u || !du) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
+  if (!h) return W3D_ERR_ARG;
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   CUDA_TRY(cudaSetDevice(h->device));
-  const size_t nb = sizeof(double) * h->cfg.nodof;
-  CUDA_TRY(cudaMemcpyAsync(h->d_u, u, nb, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_du, du, nb, cudaMemcpyHostToDevice, h->stream));
+  const int rc = upload_inputs(h, u, du);
+  if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  h->have_vectors = true;
+  return W3D_OK;
+}
+int32_t w3d_download_ifv_range(w3d_engine *h, int32_t first, int32_t n, double *dst) {
+  if (!h || !dst) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  if (first < 1 || n < 0 || (long long)first + n - 1 > h->cfg.nodof) return fail(W3D_ERR_ARG, "dof range %d..%d outside 1..%d", first, first + n - 1, h->cfg.nodof);
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(dst, h->d_ifv + (first - 1), sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return W3D_OK;
+}
+
+int32_t w3d_comm_unique_id(uint8_t id[128]) {
+  NcclApi *api = nccl_api();
+  if (!id || !api->lib || !api->error.empty()) { g_create_error = api->error.empty() ? "null argument" : api->error; return W3D_ERR_COMM; }
+  NcclUniqueId u;
+  const int r = api->get_unique_id(&u);
+  if (r != 0) { g_create_error = std::string("ncclGetUniqueId: ") + api->get_error_string(r); return W3D_ERR_COMM; }
+  std::memcpy(id, u.internal, 128);
+  return W3D_OK;
+}
+int32_t w3d_comm_init(w3d_engine *h, const uint8_t id[128], int32_t rank, int32_t nranks) {
+  if (!h || !id) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  NcclApi *api = nccl_api();
+  if (!api->lib || !api->error.empty()) return fail(W3D_ERR_COMM, "NCCL not usable: %s", api->error.c_str());
+  if (h->comm.comm) return fail(W3D_ERR_COMM, "communicator already initialised");
+  if (nranks != h->cfg.numprocs || rank != h->cfg.myid)
+    return fail(W3D_ERR_CONFIG, "rank %d of %d does not match the engine's myid %d / numprocs %d", rank, nranks, h->cfg.myid, h->cfg.numprocs);
+  CUDA_TRY(cudaSetDevice(h->device));
+  NcclUniqueId u;
+  std::memcpy(u.internal, id, 128);
+  void *comm = nullptr;
+  NCCL_TRY(api->comm_init_rank(&comm, nranks, u, rank));
+  CommData &cm = h->comm;
+  cm.comm = comm; cm.rank = rank; cm.nranks = nranks;
+  cm.ntot = 0;
+  for (long long n : cm.counts) cm.ntot += n;
+  CUDA_TRY(dalloc(&cm.d_red, 8));
+  if (cm.ntot > 0) {
+    CUDA_TRY(dalloc(&cm.d_idx, (size_t)cm.ntot));
+    CUDA_TRY(dalloc(&cm.d_send, (size_t)cm.ntot));
+    CUDA_TRY(dalloc(&cm.d_recv, (size_t)cm.ntot));
+    CUDA_TRY(cudaMemcpy(cm.d_idx, cm.dofs.data(), sizeof(int32_t) * cm.ntot, cudaMemcpyHostToDevice));
+  }
+  int nnb = 0;
+  for (long long n : cm.counts) nnb += n > 0;
+  fprintf(stderr, "w3d_comm: rank %d of %d on device %d, %d neighbour domain(s), %lld shared dofs of %d\n", rank, nranks,
+          h->device, nnb, cm.ntot, h->cfg.nodof);
+  return W3D_OK;
+}
+int32_t w3d_comm_set_options(w3d_engine *h, int32_t exchange, int32_t bcast_inputs) {
+  if (!h) return W3D_ERR_ARG;
+  if (exchange != 0 && exchange != 1) return h->fail(W3D_ERR_ARG, "exchange must be 0 (all-reduce) or 1 (neighbours)");
+  if (exchange == 1 && h->comm.counts.empty() && h->cfg.numprocs > 1) return h->fail(W3D_ERR_UNSUPPORTED, "no neighbour plan for this model (more than 64 domains)");
+  h->comm.exchange = exchange;
+  h->comm.bcast_inputs = bcast_inputs ? 1 : 0;
+  return W3D_OK;
+}
+int32_t w3d_comm_plan(const w3d_engine_config *cfg, int32_t rank, int64_t *counts, int32_t *dofs) {
+  if (!cfg || !counts || rank < 0 || rank >= (cfg->numprocs > 0 ? cfg->numprocs : 1)) return W3D_ERR_ARG;
+  std::vector<long long> cnt;
+  std::vector<int32_t> d;
+  std::string err;
+  const int rc = comm_plan(*cfg, rank, cnt, d, err);
+  if (rc) { g_create_error = err; return rc; }
+  for (size_t r = 0; r < cnt.size(); ++r) counts[r] = cnt[r];
+  if (dofs) std::memcpy(dofs, d.data(), sizeof(int32_t) * d.size());
+  return W3D_OK;
+}
+int32_t w3d_comm_owned(const w3d_engine_config *cfg, int32_t rank, uint8_t *owned) {
+  if (!cfg || !owned || !cfg->elblks || !cfg->edest || !cfg->props) return W3D_ERR_ARG;
+  const w3d_engine_config &c = *cfg;
+  const int np = c.numprocs > 0 ? c.numprocs : 1;
+  std::vector<int32_t> low((size_t)c.nodof, np);
+  long long tab = 0;
+  for (int blk = 0; blk < c.nelblk; ++blk) {
+    const int span = c.elblks[4 * blk + 0], felem = c.elblks[4 * blk + 1];
+    const int dom = np > 1 ? c.elblks[4 * blk + 2] : 0;
+    if (span <= 0 || felem < 1 || felem + span - 1 > c.noelem || dom < 0 || dom >= np) return W3D_ERR_CONFIG;
+    const int totdof = iprop(c, 2, felem) * iprop(c, 4, felem);
+    for (long long k = 0; k < (long long)totdof * span; ++k) {
+      const int32_t e = c.edest[tab + k];
+      if (e < 1 || e > c.nodof) return W3D_ERR_CONFIG;
+      if (dom < low[(size_t)e - 1]) low[(size_t)e - 1] = dom;
+    }
+    tab += (long long)totdof * span;
+  }
+  for (int d = 0; d < c.nodof; ++d) owned[d] = (low[d] == rank) ? 1 : 0;
   return W3D_OK;
 }
 int32_t w3d_download_ifv(w3d_engine *h, double *ifv) {

@@ -3,109 +3,93 @@
 The reference's MPI build gives every rank the blocks whose ``elblks(2,blk) == myid``
 (src/drive_eps_sig_internal_forces.f:166) and sums the internal-force vector with
 ``wmpi_reduce_vec(ifv, nodof)`` plus three scalar reductions and a logical OR for the step-cut flag
-(:248-250, :338-340).  Here the ranks are GPUs of one box: the only exchange step of the path is
-that sum, done with NCCL (``torch.distributed``) directly on the engine's device vector, on the
-engine's own stream, so it is ordered after the stress kernel without a host round trip.
-State never migrates; the stiffness pass needs no collective.
+(:248-250, :338-340).  Here the ranks are GPUs of one box and the exchange step lives BEHIND THE
+C ABI (include/w3d_engine.h: w3d_comm_unique_id / w3d_comm_init): NCCL send/receive pairs between
+neighbouring domains (or one all-reduce of the whole vector, the reference's semantics) and one
+5-double all-reduce for the scalars, all on the engine's own stream.  A Fortran MPI caller reaches
+exactly the same code.  This module only does what the MPI layer of the caller would do: it hands
+rank 0's NCCL id to the other ranks (``torch.distributed`` object broadcast; any transport would
+do) and assigns contiguous block slabs to ranks.  State never migrates; the stiffness pass needs
+no collective.
 """
 from __future__ import annotations
 
 import numpy as np
 
-from .engine import Engine
+from .engine import Engine, comm_owned, comm_unique_id
 from .model import Model, slab_domains
 
 
-class _DevVec:
-    """Expose an engine-owned device vector to torch through __cuda_array_interface__."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr="<f8", data=(int(ptr), False),
-                                             version=2)
+def share_unique_id(rank: int, world: int, group=None):
+    """rank 0 creates the NCCL id through the C ABI, everybody receives it."""
+    if world == 1:
+        return comm_unique_id()
+    import torch.distributed as dist
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
 
 
 class DomainEngine:
-    """Engine of one rank plus the interface-force sum across ranks."""
+    """Engine of one rank; the cross-rank sum of the internal forces happens inside the engine."""
 
     def __init__(self, model: Model, rank: int, world: int, device: int = -1, group=None,
-                 assign_slabs: bool = True):
-        import torch
-        self.torch = torch
+                 assign_slabs: bool = True, exchange: str = "neighbours", bcast_inputs: bool = False):
         self.rank, self.world, self.group = rank, world, group
         if world > 1 and assign_slabs:
             model.elblks[:, 2] = slab_domains(model, world)
         self.model = model
         self.engine = Engine(model, device=device, myid=rank, numprocs=world)
-        pu, pdu, pf = self.engine.device_vectors()
-        dev = torch.device("cuda", torch.cuda.current_device() if device < 0 else device)
-        self.stream = torch.cuda.ExternalStream(self.engine.stream, device=dev)
-        self.d_ifv = torch.as_tensor(_DevVec(pf, model.nodof), device=dev)
-        self.d_u = torch.as_tensor(_DevVec(pu, model.nodof), device=dev)
-        self.d_du = torch.as_tensor(_DevVec(pdu, model.nodof), device=dev)
-        self._scal = torch.zeros(4, dtype=torch.float64, device=dev)
-        # interface dofs = dofs touched by the blocks of more than one rank (identical, sorted list
-        # on every rank since the block tables are replicated): the only entries of ifv that need
-        # the cross-rank sum when the caller stays on the device
-        self.interface_idx = None
+        self.bcast_inputs = bool(bcast_inputs) and world > 1
         if world > 1:
-            off = model.block_offsets(24)
-            ed = model.edest.astype(np.int64) - 1
-            touched = np.zeros((world, model.nodof), dtype=bool)
-            for blk in range(model.nelblk):
-                touched[int(model.elblks[blk, 2]), ed[off[blk]:off[blk + 1]]] = True
-            shared = np.nonzero(touched.sum(axis=0) > 1)[0]
-            self.interface_idx = torch.as_tensor(shared, dtype=torch.int64, device=dev)
-            self._ibuf = torch.zeros(len(shared), dtype=torch.float64, device=dev)
+            self.engine.comm_init(share_unique_id(rank, world, group), rank, world)
+            self.engine.comm_set_options(exchange, self.bcast_inputs)
+        self._owned = None
+
+    # ---- which part of the full vector this rank returns
+    def owned_mask(self):
+        """dofs this rank owns (lowest rank whose blocks touch a dof): the full ifv is the
+        concatenation of every rank's owned entries."""
+        if self._owned is None:
+            self._owned = (comm_owned(self.model, self.rank, self.world) if self.world > 1
+                           else np.ones(self.model.nodof, dtype=bool))
+        return self._owned
+
+    def owned_range(self):
+        """(first 1-based, n) of the smallest contiguous dof range holding every owned dof; for slab
+        partitions of a structured mesh the range holds nothing else."""
+        idx = np.nonzero(self.owned_mask())[0]
+        if len(idx) == 0:
+            return 1, 0
+        return int(idx[0]) + 1, int(idx[-1] - idx[0]) + 1
 
     # ---- device-resident Newton-iteration pieces
-    def eps_sig_ifv_resident(self, step, itr, exchange="full"):
-        """stress/ifv kernel for the owned blocks, then the NCCL sum of ifv over ranks.
-        exchange="full": all-reduce of the whole vector (the reference's wmpi_reduce_vec; every
-        rank ends with the complete ifv).  exchange="interface": only the dofs shared between
-        ranks are summed (packed gather -> all-reduce -> scatter); each rank then holds the
-        correct ifv on every dof its own blocks touch, which is all a device-resident caller
-        needs, and the message shrinks from nodof to the slab faces."""
+    def eps_sig_ifv_resident(self, step, itr, exchange=None):
+        """stress / ifv kernels of the owned blocks, then the exchange step, inside the engine."""
         self.engine.eps_sig_ifv_resident(step, itr)
-        if self.world > 1:
-            import torch.distributed as dist
-            with self.torch.cuda.stream(self.stream):
-                if exchange == "interface":
-                    self.torch.index_select(self.d_ifv, 0, self.interface_idx, out=self._ibuf)
-                    dist.all_reduce(self._ibuf, op=dist.ReduceOp.SUM, group=self.group)
-                    self.d_ifv.index_copy_(0, self.interface_idx, self._ibuf)
-                else:
-                    dist.all_reduce(self.d_ifv, op=dist.ReduceOp.SUM, group=self.group)
 
     def tanstf_resident(self, step, itr):
         self.engine.tanstf_resident(step, itr)
 
     def scalars(self):
-        """block scalars summed over ranks, cut flag OR-ed (wmpi_redlog / wmpi_reduce_vec)."""
-        sc = self.engine.last_scalars()
-        if self.world > 1:
-            import torch.distributed as dist
-            t = self._scal
-            t.copy_(self.torch.tensor([sc["internal_energy"], sc["plastic_work"], sc["sum_ifv"],
-                                       float(sc["num_term_ifv"])], dtype=self.torch.float64))
-            dist.all_reduce(t, group=self.group)
-            cut = self.torch.tensor([1.0 if sc["material_cut_step"] else 0.0], device=t.device)
-            dist.all_reduce(cut, op=dist.ReduceOp.MAX, group=self.group)
-            v = t.cpu().numpy()
-            sc = dict(internal_energy=float(v[0]), plastic_work=float(v[1]), sum_ifv=float(v[2]),
-                      num_term_ifv=int(round(v[3])), material_cut_step=bool(cut.item() > 0))
-            if sc["material_cut_step"]:
-                sc.update(internal_energy=0.0, plastic_work=0.0, sum_ifv=0.0, num_term_ifv=0)
-        return sc
+        """block scalars summed over ranks, cut flag OR-ed: already done by the engine."""
+        return self.engine.last_scalars()
 
     # ---- the reference-facing calls with host buffers
-    def drive_eps_sig_internal_forces(self, step, itr, u, du, ifv=None):
-        self.engine.upload_displacements(u, du)
-        self.eps_sig_ifv_resident(step, itr)
-        sc = self.scalars()
-        ifv = self.engine.download_ifv(ifv)
-        if sc["material_cut_step"]:
-            ifv[:] = 0.0
-        return ifv, sc
+    def drive_eps_sig_internal_forces(self, step, itr, u, du, ifv=None, owned_only=False):
+        """ifv: the full vector on this rank (every rank holds every dof its blocks touch; with
+        exchange="full" all of it).  owned_only: copy back only this rank's owned range."""
+        if self.bcast_inputs and self.rank != 0:
+            u = du = None
+        if owned_only:
+            _, sc = self.engine.drive_eps_sig_internal_forces(step, itr, u, du, ifv=False)
+            first, n = self.owned_range()
+            out = ifv[first - 1:first - 1 + n] if ifv is not None else None
+            out = self.engine.download_ifv_range(first, n, out)
+            if sc["material_cut_step"]:
+                out[:] = 0.0
+            return out, sc
+        return self.engine.drive_eps_sig_internal_forces(step, itr, u, du, ifv)
 
     def tanstf(self, step, itr, out=None):
         self.engine.tanstf_resident(step, itr)

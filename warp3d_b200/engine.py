@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("W3D_ENGINE_LIB") or os.path.join(_HERE, "libw3d_engine.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 (HIST_N, HIST_N1, EPS_N, EPS_N1, URCS_N, URCS_N1, ROT_N, ROT_N1, CEP, ESTIFF, ELEM_VOL) = range(11)
 _STATE_WHICH = dict(history=HIST_N, history1=HIST_N1, eps_n=EPS_N, eps_n1=EPS_N1, urcs_n=URCS_N,
                     urcs_n1=URCS_N1, rot_n=ROT_N, rot_n1=ROT_N1, cep=CEP, estiff=ESTIFF,
@@ -36,6 +36,8 @@ EXPORTS = (
     "w3d_download_estiff", "w3d_set_time_step",
     "w3d_assemble_setup", "w3d_assemble_structure", "w3d_assemble", "w3d_assemble_rows",
     "w3d_residual_set_loads", "w3d_residual", "w3d_residual_device",
+    "w3d_comm_unique_id", "w3d_comm_init", "w3d_comm_set_options", "w3d_comm_plan", "w3d_comm_owned",
+    "w3d_download_ifv_range",
 )
 
 
@@ -139,6 +141,15 @@ def lib():
         L.w3d_download_estiff.argtypes = [C.c_void_p, C.c_void_p]
         L.w3d_set_time_step.restype = C.c_int32
         L.w3d_set_time_step.argtypes = [C.c_void_p, C.c_double]
+        for name in ("w3d_comm_unique_id", "w3d_comm_init", "w3d_comm_set_options", "w3d_comm_plan",
+                     "w3d_comm_owned", "w3d_download_ifv_range"):
+            getattr(L, name).restype = C.c_int32
+        L.w3d_comm_unique_id.argtypes = [C.c_void_p]
+        L.w3d_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        L.w3d_comm_set_options.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.w3d_comm_plan.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.w3d_comm_owned.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.w3d_download_ifv_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -152,6 +163,76 @@ def _f64(a):
     return a
 
 
+def make_config(m: Model, device: int = -1, myid: int = 0, numprocs: int = 1):
+    """w3d_engine_config for a model (the tables a Fortran caller would pass after its *_init
+    routines).  Returns (cfg, keep-alive list of the arrays the pointers refer to)."""
+    keep = [np.ascontiguousarray(x) for x in
+            (m.elblks.astype(np.int32), m.props.astype(np.int32), m.matprp.astype(np.float32),
+             m.c.astype(np.float64), m.edest.astype(np.int32), m.cdest.astype(np.int32),
+             m.hist_size.astype(np.int32))]
+    cfg = _Config()
+    cfg.abi_version = ABI_VERSION
+    cfg.mxvl, cfg.mxelpr, cfg.mxmtpr = max(MXVL, int(m.elblks[:, 0].max())), MXELPR, MXMTPR
+    cfg.nelblk, cfg.noelem, cfg.nonode, cfg.nodof = m.nelblk, m.noelem, m.nonode, m.nodof
+    cfg.myid, cfg.numprocs = myid, numprocs
+    (cfg.elblks, cfg.props, cfg.matprp, cfg.c, cfg.edest, cfg.cdest,
+     cfg.history_blk_list) = [_ptr(x) for x in keep]
+    cfg.nmat = keep[2].shape[0]
+    cfg.eps_bbar = m.eps_bbar
+    cfg.qbar_flag = int(m.qbar_flag)
+    cfg.beta_fact = m.beta_fact
+    cfg.adaptive_flag = int(m.adaptive_flag)
+    cfg.device = device
+    if getattr(m, "crystal_types", None) is not None:      # mm10 input tables
+        ct = np.ascontiguousarray(m.crystal_types, dtype=np.float64)
+        cn = np.ascontiguousarray(m.elem_cnum, dtype=np.int32)
+        ang = np.ascontiguousarray(m.elem_angles, dtype=np.float64)
+        keep += [ct, cn, ang]
+        cfg.crystal_types, cfg.elem_cnum, cfg.elem_angles = _ptr(ct), _ptr(cn), _ptr(ang)
+        cfg.n_crystal_types, cfg.cp_ncrystals = ct.shape[0], int(m.ncrystals)
+        cfg.cp_angle_type = int(m.angle_type)
+        cfg.asymmetric_assembly = int(m.asymmetric_assembly)
+    return cfg, keep
+
+
+def comm_plan(model: Model, rank: int, numprocs: int):
+    """w3d_comm_plan (host only, no GPU): the dofs domain `rank` shares with every other domain,
+    as a list of 1-based ascending int32 arrays indexed by rank."""
+    L = lib()
+    cfg, keep = make_config(model, -1, rank, numprocs)
+    counts = np.zeros(numprocs, dtype=np.int64)
+    rc = L.w3d_comm_plan(C.byref(cfg), C.c_int32(rank), _ptr(counts), None)
+    if rc:
+        raise EngineError(rc, L.w3d_engine_last_error(None).decode())
+    dofs = np.zeros(max(int(counts.sum()), 1), dtype=np.int32)
+    rc = L.w3d_comm_plan(C.byref(cfg), C.c_int32(rank), _ptr(counts), _ptr(dofs))
+    if rc:
+        raise EngineError(rc, L.w3d_engine_last_error(None).decode())
+    off = np.concatenate([[0], np.cumsum(counts)])
+    return [dofs[off[r]:off[r + 1]].copy() for r in range(numprocs)]
+
+
+def comm_owned(model: Model, rank: int, numprocs: int):
+    """w3d_comm_owned: boolean mask of the dofs `rank` owns (lowest rank whose blocks touch it)."""
+    L = lib()
+    cfg, keep = make_config(model, -1, rank, numprocs)
+    owned = np.zeros(model.nodof, dtype=np.uint8)
+    rc = L.w3d_comm_owned(C.byref(cfg), C.c_int32(rank), _ptr(owned))
+    if rc:
+        raise EngineError(rc, "w3d_comm_owned failed")
+    return owned.astype(bool)
+
+
+def comm_unique_id():
+    """w3d_comm_unique_id (rank 0): 128 bytes to hand to every rank's comm_init."""
+    L = lib()
+    buf = (C.c_uint8 * 128)()
+    rc = L.w3d_comm_unique_id(buf)
+    if rc:
+        raise EngineError(rc, L.w3d_engine_last_error(None).decode())
+    return bytes(buf)
+
+
 class Engine:
     """One engine instance = one GPU = one MPI rank's share of the element blocks."""
 
@@ -159,32 +240,7 @@ class Engine:
         self.model = model
         self._L = lib()
         m = model
-        keep = [np.ascontiguousarray(x) for x in
-                (m.elblks.astype(np.int32), m.props.astype(np.int32), m.matprp.astype(np.float32),
-                 m.c.astype(np.float64), m.edest.astype(np.int32), m.cdest.astype(np.int32),
-                 m.hist_size.astype(np.int32))]
-        cfg = _Config()
-        cfg.abi_version = ABI_VERSION
-        cfg.mxvl, cfg.mxelpr, cfg.mxmtpr = max(MXVL, int(m.elblks[:, 0].max())), MXELPR, MXMTPR
-        cfg.nelblk, cfg.noelem, cfg.nonode, cfg.nodof = m.nelblk, m.noelem, m.nonode, m.nodof
-        cfg.myid, cfg.numprocs = myid, numprocs
-        (cfg.elblks, cfg.props, cfg.matprp, cfg.c, cfg.edest, cfg.cdest,
-         cfg.history_blk_list) = [_ptr(x) for x in keep]
-        cfg.nmat = keep[2].shape[0]
-        cfg.eps_bbar = m.eps_bbar
-        cfg.qbar_flag = int(m.qbar_flag)
-        cfg.beta_fact = m.beta_fact
-        cfg.adaptive_flag = int(m.adaptive_flag)
-        cfg.device = device
-        if getattr(m, "crystal_types", None) is not None:      # mm10 input tables
-            ct = np.ascontiguousarray(m.crystal_types, dtype=np.float64)
-            cn = np.ascontiguousarray(m.elem_cnum, dtype=np.int32)
-            ang = np.ascontiguousarray(m.elem_angles, dtype=np.float64)
-            keep += [ct, cn, ang]
-            cfg.crystal_types, cfg.elem_cnum, cfg.elem_angles = _ptr(ct), _ptr(cn), _ptr(ang)
-            cfg.n_crystal_types, cfg.cp_ncrystals = ct.shape[0], int(m.ncrystals)
-            cfg.cp_angle_type = int(m.angle_type)
-            cfg.asymmetric_assembly = int(m.asymmetric_assembly)
+        cfg, keep = make_config(m, device, myid, numprocs)
         h = C.c_void_p()
         rc = self._L.w3d_engine_create(C.byref(cfg), C.byref(h))
         if rc:
@@ -223,6 +279,23 @@ class Engine:
     def synchronize(self):
         self._check(self._L.w3d_engine_synchronize(self._h))
 
+    # ---- exchange step between domains (NCCL behind the C ABI)
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._L.w3d_comm_init(self._h, buf, C.c_int32(rank), C.c_int32(nranks)))
+        self.comm_active = True
+
+    def comm_set_options(self, exchange="neighbours", bcast_inputs=False):
+        mode = {"neighbours": 1, "interface": 1, "full": 0, "allreduce": 0}[exchange]
+        self._check(self._L.w3d_comm_set_options(self._h, C.c_int32(mode), C.c_int32(int(bcast_inputs))))
+
+    def download_ifv_range(self, first, n, out=None):
+        """ifv(first .. first+n-1), first 1-based."""
+        if out is None:
+            out = np.empty(n)
+        self._check(self._L.w3d_download_ifv_range(self._h, C.c_int32(first), C.c_int32(n), _ptr(out)))
+        return out
+
     # ---- the reference's drivers
     def set_time_step(self, dt):
         self._check(self._L.w3d_set_time_step(self._h, float(dt)))
@@ -230,9 +303,12 @@ class Engine:
     def drive_eps_sig_internal_forces(self, step, itr, u, du, ifv=None):
         """Strain recovery, material update, internal forces for all owned blocks.
         Returns (ifv, scalars); ifv is this rank's contribution."""
-        u, du = _f64(u), _f64(du)
+        u = None if u is None else _f64(u)       # None: only with a communicator (see w3d_engine.h)
+        du = None if du is None else _f64(du)
         if ifv is None:
             ifv = np.empty(self.model.nodof)
+        elif ifv is False:                       # communicator: this rank does not want ifv back
+            ifv = None
         sc = _Scalars()
         rc = self._L.w3d_eps_sig_ifv(self._h, step, itr, int(self.model.extrapolated_du), _ptr(u),
                                      _ptr(du), _ptr(ifv), C.byref(sc))
@@ -330,7 +406,8 @@ class Engine:
         return pu.value, pdu.value, pf.value
 
     def upload_displacements(self, u, du):
-        u, du = _f64(u), _f64(du)
+        u = None if u is None else _f64(u)
+        du = None if du is None else _f64(du)
         self._check(self._L.w3d_upload_displacements(self._h, _ptr(u), _ptr(du)))
 
     def download_ifv(self, ifv=None):
