@@ -126,6 +126,21 @@ void make_cp_icp(int n, int *cp, int *dcp, int *icp /* (utsz,2) column-major */)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Contraction convention of the noise-amplifying chain (coordinates -> Jacobian -> Gamma -> theta
+// -> F -> C -> Cardano -> U^-1 -> R).  The reference's closed-form polar decomposition turns a
+// 1-ulp change of C into ~1e-9 of R for small strains, so "the reference's result" is defined
+// only up to the compiler's choice of fused multiply-adds (ifort -O3 contracts; which products it
+// fuses is not visible from the source).  The restatement therefore FIXES one pattern -- the one
+// an optimising compiler produces when it contracts left to right:
+//     a*b + c*d + e*f  ->  fma(e, f, fma(c, d, a*b)),    a*b - c*d  ->  fma(a, b, -(c*d)),
+//     s = s + a*b      ->  fma(a, b, s)
+// -- and writes it out explicitly (the file is compiled with -ffp-contract=off, so nothing else
+// is fused).  The engine evaluates the same chain with the same fused operations in the same
+// order, which makes it bit-identical up to libm's atan2 / sincos.
+// ---------------------------------------------------------------------------------------------
+static inline double fm(double a, double b, double c) { return std::fma(a, b, c); }
+
+// ---------------------------------------------------------------------------------------------
 // gtmat1.f:300-507 (jacob1), 3-D solid branch
 // ---------------------------------------------------------------------------------------------
 void jacob1(int span, double *jac /*(mxvl,3,3)*/, double *dj, double *gama /*(mxvl,3,3)*/,
@@ -136,35 +151,39 @@ void jacob1(int span, double *jac /*(mxvl,3,3)*/, double *dj, double *gama /*(mx
   for (int k = 0; k < 9 * mxvl; ++k) { jac[k] = 0.0; gama[k] = 0.0; }
   for (int j = 1; j <= nnode; ++j) {
     for (int i = 0; i < span; ++i) {
-      JAC(i, 1, 1) = JAC(i, 1, 1) + nxi[j - 1] * CE(i, j);
-      JAC(i, 1, 2) = JAC(i, 1, 2) + nxi[j - 1] * CE(i, nnode + j);
-      JAC(i, 1, 3) = JAC(i, 1, 3) + nxi[j - 1] * CE(i, 2 * nnode + j);
-      JAC(i, 2, 1) = JAC(i, 2, 1) + neta[j - 1] * CE(i, j);
-      JAC(i, 2, 2) = JAC(i, 2, 2) + neta[j - 1] * CE(i, nnode + j);
-      JAC(i, 2, 3) = JAC(i, 2, 3) + neta[j - 1] * CE(i, 2 * nnode + j);
-      JAC(i, 3, 1) = JAC(i, 3, 1) + nzeta[j - 1] * CE(i, j);
-      JAC(i, 3, 2) = JAC(i, 3, 2) + nzeta[j - 1] * CE(i, nnode + j);
-      JAC(i, 3, 3) = JAC(i, 3, 3) + nzeta[j - 1] * CE(i, 2 * nnode + j);
+      JAC(i, 1, 1) = fm(nxi[j - 1], CE(i, j), JAC(i, 1, 1));
+      JAC(i, 1, 2) = fm(nxi[j - 1], CE(i, nnode + j), JAC(i, 1, 2));
+      JAC(i, 1, 3) = fm(nxi[j - 1], CE(i, 2 * nnode + j), JAC(i, 1, 3));
+      JAC(i, 2, 1) = fm(neta[j - 1], CE(i, j), JAC(i, 2, 1));
+      JAC(i, 2, 2) = fm(neta[j - 1], CE(i, nnode + j), JAC(i, 2, 2));
+      JAC(i, 2, 3) = fm(neta[j - 1], CE(i, 2 * nnode + j), JAC(i, 2, 3));
+      JAC(i, 3, 1) = fm(nzeta[j - 1], CE(i, j), JAC(i, 3, 1));
+      JAC(i, 3, 2) = fm(nzeta[j - 1], CE(i, nnode + j), JAC(i, 3, 2));
+      JAC(i, 3, 3) = fm(nzeta[j - 1], CE(i, 2 * nnode + j), JAC(i, 3, 3));
     }
   }
   double j1[mxvl], j2[mxvl], j3[mxvl];
   for (int i = 0; i < span; ++i) {
-    j1[i] = JAC(i, 2, 2) * JAC(i, 3, 3) - JAC(i, 2, 3) * JAC(i, 3, 2);
-    j2[i] = JAC(i, 2, 1) * JAC(i, 3, 3) - JAC(i, 2, 3) * JAC(i, 3, 1);
-    j3[i] = JAC(i, 2, 1) * JAC(i, 3, 2) - JAC(i, 2, 2) * JAC(i, 3, 1);
-    dj[i] = JAC(i, 1, 1) * j1[i] - JAC(i, 1, 2) * j2[i] + JAC(i, 1, 3) * j3[i];
+    j1[i] = fm(JAC(i, 2, 2), JAC(i, 3, 3), -(JAC(i, 2, 3) * JAC(i, 3, 2)));
+    j2[i] = fm(JAC(i, 2, 1), JAC(i, 3, 3), -(JAC(i, 2, 3) * JAC(i, 3, 1)));
+    j3[i] = fm(JAC(i, 2, 1), JAC(i, 3, 2), -(JAC(i, 2, 2) * JAC(i, 3, 1)));
+    dj[i] = fm(JAC(i, 1, 3), j3[i], fm(-JAC(i, 1, 2), j2[i], JAC(i, 1, 1) * j1[i]));
   }
   // gtmat1.f:445-459: non-positive det only produces warnings; no state change.
   for (int i = 0; i < span; ++i) {
-    GAM(i, 1, 1) = j1[i] / dj[i];
-    GAM(i, 2, 1) = -j2[i] / dj[i];
-    GAM(i, 3, 1) = j3[i] / dj[i];
-    GAM(i, 1, 2) = (JAC(i, 3, 2) * JAC(i, 1, 3) - JAC(i, 1, 2) * JAC(i, 3, 3)) / dj[i];
-    GAM(i, 2, 2) = (JAC(i, 1, 1) * JAC(i, 3, 3) - JAC(i, 3, 1) * JAC(i, 1, 3)) / dj[i];
-    GAM(i, 3, 2) = (JAC(i, 1, 2) * JAC(i, 3, 1) - JAC(i, 1, 1) * JAC(i, 3, 2)) / dj[i];
-    GAM(i, 1, 3) = (JAC(i, 1, 2) * JAC(i, 2, 3) - JAC(i, 1, 3) * JAC(i, 2, 2)) / dj[i];
-    GAM(i, 2, 3) = (JAC(i, 1, 3) * JAC(i, 2, 1) - JAC(i, 1, 1) * JAC(i, 2, 3)) / dj[i];
-    GAM(i, 3, 3) = (JAC(i, 1, 1) * JAC(i, 2, 2) - JAC(i, 1, 2) * JAC(i, 2, 1)) / dj[i];
+    // division by the common determinant as ONE reciprocal and nine products -- what the
+    // reference's build does with these statements (ifort -O3 runs with -no-prec-div); part of the
+    // contraction convention above
+    const double rdj = 1.0 / dj[i];
+    GAM(i, 1, 1) = j1[i] * rdj;
+    GAM(i, 2, 1) = -j2[i] * rdj;
+    GAM(i, 3, 1) = j3[i] * rdj;
+    GAM(i, 1, 2) = fm(JAC(i, 3, 2), JAC(i, 1, 3), -(JAC(i, 1, 2) * JAC(i, 3, 3))) * rdj;
+    GAM(i, 2, 2) = fm(JAC(i, 1, 1), JAC(i, 3, 3), -(JAC(i, 3, 1) * JAC(i, 1, 3))) * rdj;
+    GAM(i, 3, 2) = fm(JAC(i, 1, 2), JAC(i, 3, 1), -(JAC(i, 1, 1) * JAC(i, 3, 2))) * rdj;
+    GAM(i, 1, 3) = fm(JAC(i, 1, 2), JAC(i, 2, 3), -(JAC(i, 1, 3) * JAC(i, 2, 2))) * rdj;
+    GAM(i, 2, 3) = fm(JAC(i, 1, 3), JAC(i, 2, 1), -(JAC(i, 1, 1) * JAC(i, 2, 3))) * rdj;
+    GAM(i, 3, 3) = fm(JAC(i, 1, 1), JAC(i, 2, 2), -(JAC(i, 1, 2) * JAC(i, 2, 1))) * rdj;
   }
 #undef JAC
 #undef CE
@@ -209,22 +228,22 @@ void tcomp1(int span, double *theta /*(mxvl,9)*/, const double *nxi, const doubl
   for (int k = 0; k < 9 * mxvl; ++k) theta[k] = 0.0;
   for (int j = 1; j <= nnode; ++j)
     for (int i = 0; i < span; ++i) {
-      THT(i, j, 1) = GAM(i, 1, 1) * nxi[j - 1] + GAM(i, 1, 2) * neta[j - 1] + GAM(i, 1, 3) * nzeta[j - 1];
-      THT(i, j, 2) = GAM(i, 2, 1) * nxi[j - 1] + GAM(i, 2, 2) * neta[j - 1] + GAM(i, 2, 3) * nzeta[j - 1];
-      THT(i, j, 3) = GAM(i, 3, 1) * nxi[j - 1] + GAM(i, 3, 2) * neta[j - 1] + GAM(i, 3, 3) * nzeta[j - 1];
+      THT(i, j, 1) = fm(GAM(i, 1, 3), nzeta[j - 1], fm(GAM(i, 1, 2), neta[j - 1], GAM(i, 1, 1) * nxi[j - 1]));
+      THT(i, j, 2) = fm(GAM(i, 2, 3), nzeta[j - 1], fm(GAM(i, 2, 2), neta[j - 1], GAM(i, 2, 1) * nxi[j - 1]));
+      THT(i, j, 3) = fm(GAM(i, 3, 3), nzeta[j - 1], fm(GAM(i, 3, 2), neta[j - 1], GAM(i, 3, 1) * nxi[j - 1]));
     }
   const int tpos1 = nnode, tpos2 = 2 * nnode;
   for (int j = 1; j <= nnode; ++j)
     for (int i = 0; i < span; ++i) {
-      TH(i, 1) = TH(i, 1) + THT(i, j, 1) * UE(i, j);
-      TH(i, 2) = TH(i, 2) + THT(i, j, 1) * UE(i, tpos1 + j);
-      TH(i, 3) = TH(i, 3) + THT(i, j, 1) * UE(i, tpos2 + j);
-      TH(i, 4) = TH(i, 4) + THT(i, j, 2) * UE(i, j);
-      TH(i, 5) = TH(i, 5) + THT(i, j, 2) * UE(i, tpos1 + j);
-      TH(i, 6) = TH(i, 6) + THT(i, j, 2) * UE(i, tpos2 + j);
-      TH(i, 7) = TH(i, 7) + THT(i, j, 3) * UE(i, j);
-      TH(i, 8) = TH(i, 8) + THT(i, j, 3) * UE(i, tpos1 + j);
-      TH(i, 9) = TH(i, 9) + THT(i, j, 3) * UE(i, tpos2 + j);
+      TH(i, 1) = fm(THT(i, j, 1), UE(i, j), TH(i, 1));
+      TH(i, 2) = fm(THT(i, j, 1), UE(i, tpos1 + j), TH(i, 2));
+      TH(i, 3) = fm(THT(i, j, 1), UE(i, tpos2 + j), TH(i, 3));
+      TH(i, 4) = fm(THT(i, j, 2), UE(i, j), TH(i, 4));
+      TH(i, 5) = fm(THT(i, j, 2), UE(i, tpos1 + j), TH(i, 5));
+      TH(i, 6) = fm(THT(i, j, 2), UE(i, tpos2 + j), TH(i, 6));
+      TH(i, 7) = fm(THT(i, j, 3), UE(i, j), TH(i, 7));
+      TH(i, 8) = fm(THT(i, j, 3), UE(i, tpos1 + j), TH(i, 8));
+      TH(i, 9) = fm(THT(i, j, 3), UE(i, tpos2 + j), TH(i, 9));
     }
 #undef THT
 #undef UE
@@ -247,10 +266,10 @@ void fcomp1(int span, double *f /*(mxvl,3,3)*/, double *df, const double *theta,
     F3(f, i, 3, 3) = TH(i, 9) + one;
   }
   for (int i = 0; i < span; ++i) {
-    const double f1 = F3(f, i, 2, 2) * F3(f, i, 3, 3) - F3(f, i, 2, 3) * F3(f, i, 3, 2);
-    const double f2 = F3(f, i, 2, 1) * F3(f, i, 3, 3) - F3(f, i, 2, 3) * F3(f, i, 3, 1);
-    const double f3 = F3(f, i, 2, 1) * F3(f, i, 3, 2) - F3(f, i, 2, 2) * F3(f, i, 3, 1);
-    df[i] = F3(f, i, 1, 1) * f1 - F3(f, i, 1, 2) * f2 + F3(f, i, 1, 3) * f3;
+    const double f1 = fm(F3(f, i, 2, 2), F3(f, i, 3, 3), -(F3(f, i, 2, 3) * F3(f, i, 3, 2)));
+    const double f2 = fm(F3(f, i, 2, 1), F3(f, i, 3, 3), -(F3(f, i, 2, 3) * F3(f, i, 3, 1)));
+    const double f3 = fm(F3(f, i, 2, 1), F3(f, i, 3, 2), -(F3(f, i, 2, 2) * F3(f, i, 3, 1)));
+    df[i] = fm(F3(f, i, 1, 3), f3, fm(-F3(f, i, 1, 2), f2, F3(f, i, 1, 1) * f1));
   }
   error = 0;
   for (int i = 0; i < span; ++i)
@@ -273,12 +292,12 @@ static void evcmp1_new(int span, const double *c /*(mxvl,6)*/, double *lamda /*(
     const double ee = m23 * m23;
     const double ff = m13 * m13;
     const double m = m11 + m22 + m33;
-    const double c1 = (m11 * m22 + m11 * m33 + m22 * m33) - (dd + ee + ff);
-    const double c0 = m33 * dd + m11 * ee + m22 * ff - m11 * m22 * m33 - two * m13 * de;
-    const double p = m * m - three * c1;
-    const double q = m * (p - onept5 * c1) - thirteenpt5 * c0;
+    const double c1 = fm(m22, m33, fm(m11, m33, m11 * m22)) - (dd + ee + ff);
+    const double c0 = fm(-(two * m13), de, fm(-(m11 * m22), m33, fm(m22, ff, fm(m11, ee, m33 * dd))));
+    const double p = fm(m, m, -(three * c1));
+    const double q = fm(m, fm(-onept5, c1, p), -(thirteenpt5 * c0));
     const double sqrtp = std::sqrt(std::fabs(p));
-    double phi = twentyseven * (quarter * c1 * c1 * (p - c1) + c0 * (q + sixpt75 * c0));
+    double phi = twentyseven * fm(c0, fm(sixpt75, c0, q), quarter * c1 * c1 * (p - c1));
     phi = third * std::atan2(std::sqrt(std::fabs(phi)), q);
     const double cphi = sqrtp * std::cos(phi);
     const double sphi = iroot3 * sqrtp * std::sin(phi);
@@ -309,20 +328,21 @@ void rtcmp1(int span, const double *f /*(mxvl,3,3)*/, double *r /*(mxvl,3,3)*/) 
   const double one = 1.0, two = 2.0;
   // ivcmp1
   for (int i = 0; i < span; ++i) {
-    CW(i, 1) = F3(f, i, 1, 1) * F3(f, i, 1, 1) + F3(f, i, 2, 1) * F3(f, i, 2, 1) + F3(f, i, 3, 1) * F3(f, i, 3, 1);
-    CW(i, 2) = F3(f, i, 1, 1) * F3(f, i, 1, 2) + F3(f, i, 2, 1) * F3(f, i, 2, 2) + F3(f, i, 3, 1) * F3(f, i, 3, 2);
-    CW(i, 3) = F3(f, i, 1, 2) * F3(f, i, 1, 2) + F3(f, i, 2, 2) * F3(f, i, 2, 2) + F3(f, i, 3, 2) * F3(f, i, 3, 2);
-    CW(i, 4) = F3(f, i, 1, 1) * F3(f, i, 1, 3) + F3(f, i, 2, 1) * F3(f, i, 2, 3) + F3(f, i, 3, 1) * F3(f, i, 3, 3);
-    CW(i, 5) = F3(f, i, 1, 2) * F3(f, i, 1, 3) + F3(f, i, 2, 2) * F3(f, i, 2, 3) + F3(f, i, 3, 2) * F3(f, i, 3, 3);
-    CW(i, 6) = F3(f, i, 1, 3) * F3(f, i, 1, 3) + F3(f, i, 2, 3) * F3(f, i, 2, 3) + F3(f, i, 3, 3) * F3(f, i, 3, 3);
+#define DOT3(a1, b1, a2, b2, a3, b3) fm(a3, b3, fm(a2, b2, (a1) * (b1)))
+    CW(i, 1) = DOT3(F3(f, i, 1, 1), F3(f, i, 1, 1), F3(f, i, 2, 1), F3(f, i, 2, 1), F3(f, i, 3, 1), F3(f, i, 3, 1));
+    CW(i, 2) = DOT3(F3(f, i, 1, 1), F3(f, i, 1, 2), F3(f, i, 2, 1), F3(f, i, 2, 2), F3(f, i, 3, 1), F3(f, i, 3, 2));
+    CW(i, 3) = DOT3(F3(f, i, 1, 2), F3(f, i, 1, 2), F3(f, i, 2, 2), F3(f, i, 2, 2), F3(f, i, 3, 2), F3(f, i, 3, 2));
+    CW(i, 4) = DOT3(F3(f, i, 1, 1), F3(f, i, 1, 3), F3(f, i, 2, 1), F3(f, i, 2, 3), F3(f, i, 3, 1), F3(f, i, 3, 3));
+    CW(i, 5) = DOT3(F3(f, i, 1, 2), F3(f, i, 1, 3), F3(f, i, 2, 2), F3(f, i, 2, 3), F3(f, i, 3, 2), F3(f, i, 3, 3));
+    CW(i, 6) = DOT3(F3(f, i, 1, 3), F3(f, i, 1, 3), F3(f, i, 2, 3), F3(f, i, 2, 3), F3(f, i, 3, 3), F3(f, i, 3, 3));
   }
   for (int i = 0; i < span; ++i) {
-    CC6(i, 1) = CW(i, 1) * CW(i, 1) + CW(i, 2) * CW(i, 2) + CW(i, 4) * CW(i, 4);
-    CC6(i, 2) = CW(i, 1) * CW(i, 2) + CW(i, 2) * CW(i, 3) + CW(i, 4) * CW(i, 5);
-    CC6(i, 3) = CW(i, 2) * CW(i, 2) + CW(i, 3) * CW(i, 3) + CW(i, 5) * CW(i, 5);
-    CC6(i, 4) = CW(i, 1) * CW(i, 4) + CW(i, 2) * CW(i, 5) + CW(i, 4) * CW(i, 6);
-    CC6(i, 5) = CW(i, 2) * CW(i, 4) + CW(i, 3) * CW(i, 5) + CW(i, 5) * CW(i, 6);
-    CC6(i, 6) = CW(i, 4) * CW(i, 4) + CW(i, 5) * CW(i, 5) + CW(i, 6) * CW(i, 6);
+    CC6(i, 1) = DOT3(CW(i, 1), CW(i, 1), CW(i, 2), CW(i, 2), CW(i, 4), CW(i, 4));
+    CC6(i, 2) = DOT3(CW(i, 1), CW(i, 2), CW(i, 2), CW(i, 3), CW(i, 4), CW(i, 5));
+    CC6(i, 3) = DOT3(CW(i, 2), CW(i, 2), CW(i, 3), CW(i, 3), CW(i, 5), CW(i, 5));
+    CC6(i, 4) = DOT3(CW(i, 1), CW(i, 4), CW(i, 2), CW(i, 5), CW(i, 4), CW(i, 6));
+    CC6(i, 5) = DOT3(CW(i, 2), CW(i, 4), CW(i, 3), CW(i, 5), CW(i, 5), CW(i, 6));
+    CC6(i, 6) = DOT3(CW(i, 4), CW(i, 4), CW(i, 5), CW(i, 5), CW(i, 6), CW(i, 6));
   }
   evcmp1_new(span, c, ev.data());
   for (int i = 0; i < span; ++i) {
@@ -333,33 +353,34 @@ void rtcmp1(int span, const double *f /*(mxvl,3,3)*/, double *r /*(mxvl,3,3)*/) 
   for (int i = 0; i < span; ++i) {
     const double e1 = ev[0 * mxvl + i], e2 = ev[1 * mxvl + i], e3 = ev[2 * mxvl + i];
     iu[i] = e1 + e2 + e3;
-    iiu[i] = e1 * e2 + e2 * e3 + e1 * e3;
+    iiu[i] = DOT3(e1, e2, e2, e3, e1, e3);
     iiiu[i] = e1 * e2 * e3;
   }
   // irscp1
   for (int i = 0; i < span; ++i) {
-    const double a2 = one / (iiiu[i] * (iu[i] * iiu[i] - iiiu[i]));
-    const double b2 = iu[i] * iiu[i] * iiu[i] - iiiu[i] * (iu[i] * iu[i] + iiu[i]);
-    const double c2 = -iiiu[i] - iu[i] * (iu[i] * iu[i] - two * iiu[i]);
+    const double a2 = one / (iiiu[i] * fm(iu[i], iiu[i], -iiiu[i]));
+    const double b2 = fm(iu[i] * iiu[i], iiu[i], -(iiiu[i] * fm(iu[i], iu[i], iiu[i])));
+    const double c2 = fm(-iu[i], fm(iu[i], iu[i], -(two * iiu[i])), -iiiu[i]);
     const double d2 = iu[i];
-    UI(i, 1) = a2 * (b2 + c2 * CW(i, 1) + d2 * CC6(i, 1));
-    UI(i, 2) = a2 * (c2 * CW(i, 2) + d2 * CC6(i, 2));
-    UI(i, 3) = a2 * (b2 + c2 * CW(i, 3) + d2 * CC6(i, 3));
-    UI(i, 4) = a2 * (c2 * CW(i, 4) + d2 * CC6(i, 4));
-    UI(i, 5) = a2 * (c2 * CW(i, 5) + d2 * CC6(i, 5));
-    UI(i, 6) = a2 * (b2 + c2 * CW(i, 6) + d2 * CC6(i, 6));
+    UI(i, 1) = a2 * fm(d2, CC6(i, 1), fm(c2, CW(i, 1), b2));
+    UI(i, 2) = a2 * fm(d2, CC6(i, 2), c2 * CW(i, 2));
+    UI(i, 3) = a2 * fm(d2, CC6(i, 3), fm(c2, CW(i, 3), b2));
+    UI(i, 4) = a2 * fm(d2, CC6(i, 4), c2 * CW(i, 4));
+    UI(i, 5) = a2 * fm(d2, CC6(i, 5), c2 * CW(i, 5));
+    UI(i, 6) = a2 * fm(d2, CC6(i, 6), fm(c2, CW(i, 6), b2));
   }
   // rtcmp1
   for (int i = 0; i < span; ++i) {
-    F3(r, i, 1, 1) = F3(f, i, 1, 1) * UI(i, 1) + F3(f, i, 1, 2) * UI(i, 2) + F3(f, i, 1, 3) * UI(i, 4);
-    F3(r, i, 1, 2) = F3(f, i, 1, 1) * UI(i, 2) + F3(f, i, 1, 2) * UI(i, 3) + F3(f, i, 1, 3) * UI(i, 5);
-    F3(r, i, 1, 3) = F3(f, i, 1, 1) * UI(i, 4) + F3(f, i, 1, 2) * UI(i, 5) + F3(f, i, 1, 3) * UI(i, 6);
-    F3(r, i, 2, 1) = F3(f, i, 2, 1) * UI(i, 1) + F3(f, i, 2, 2) * UI(i, 2) + F3(f, i, 2, 3) * UI(i, 4);
-    F3(r, i, 2, 2) = F3(f, i, 2, 1) * UI(i, 2) + F3(f, i, 2, 2) * UI(i, 3) + F3(f, i, 2, 3) * UI(i, 5);
-    F3(r, i, 2, 3) = F3(f, i, 2, 1) * UI(i, 4) + F3(f, i, 2, 2) * UI(i, 5) + F3(f, i, 2, 3) * UI(i, 6);
-    F3(r, i, 3, 1) = F3(f, i, 3, 1) * UI(i, 1) + F3(f, i, 3, 2) * UI(i, 2) + F3(f, i, 3, 3) * UI(i, 4);
-    F3(r, i, 3, 2) = F3(f, i, 3, 1) * UI(i, 2) + F3(f, i, 3, 2) * UI(i, 3) + F3(f, i, 3, 3) * UI(i, 5);
-    F3(r, i, 3, 3) = F3(f, i, 3, 1) * UI(i, 4) + F3(f, i, 3, 2) * UI(i, 5) + F3(f, i, 3, 3) * UI(i, 6);
+    F3(r, i, 1, 1) = DOT3(F3(f, i, 1, 1), UI(i, 1), F3(f, i, 1, 2), UI(i, 2), F3(f, i, 1, 3), UI(i, 4));
+    F3(r, i, 1, 2) = DOT3(F3(f, i, 1, 1), UI(i, 2), F3(f, i, 1, 2), UI(i, 3), F3(f, i, 1, 3), UI(i, 5));
+    F3(r, i, 1, 3) = DOT3(F3(f, i, 1, 1), UI(i, 4), F3(f, i, 1, 2), UI(i, 5), F3(f, i, 1, 3), UI(i, 6));
+    F3(r, i, 2, 1) = DOT3(F3(f, i, 2, 1), UI(i, 1), F3(f, i, 2, 2), UI(i, 2), F3(f, i, 2, 3), UI(i, 4));
+    F3(r, i, 2, 2) = DOT3(F3(f, i, 2, 1), UI(i, 2), F3(f, i, 2, 2), UI(i, 3), F3(f, i, 2, 3), UI(i, 5));
+    F3(r, i, 2, 3) = DOT3(F3(f, i, 2, 1), UI(i, 4), F3(f, i, 2, 2), UI(i, 5), F3(f, i, 2, 3), UI(i, 6));
+    F3(r, i, 3, 1) = DOT3(F3(f, i, 3, 1), UI(i, 1), F3(f, i, 3, 2), UI(i, 2), F3(f, i, 3, 3), UI(i, 4));
+    F3(r, i, 3, 2) = DOT3(F3(f, i, 3, 1), UI(i, 2), F3(f, i, 3, 2), UI(i, 3), F3(f, i, 3, 3), UI(i, 5));
+    F3(r, i, 3, 3) = DOT3(F3(f, i, 3, 1), UI(i, 4), F3(f, i, 3, 2), UI(i, 5), F3(f, i, 3, 3), UI(i, 6));
+#undef DOT3
   }
 #undef CC6
 #undef CW

@@ -416,7 +416,7 @@ static void rstgp(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int g
     const double half = 0.5;
     for (int j = 1; j <= bi.ndof * nnode; ++j)
       for (int i = 0; i < span; ++i) {
-        V2(lw.uenh, i, j) = V2(lw.ue, i, j) + half * V2(lw.due, i, j);
+        V2(lw.uenh, i, j) = std::fma(half, V2(lw.due, i, j), V2(lw.ue, i, j));   // contraction convention, w3d_oracle.cpp
         V2(lw.uen1, i, j) = V2(lw.ue, i, j) + V2(lw.due, i, j);
       }
     int error = 0;

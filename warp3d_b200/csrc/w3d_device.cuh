@@ -6,10 +6,16 @@
 // structure-of-arrays  a[component][element_slot*8 + gp]  so each warp access is one 256 B line.
 //
 // Numerical contract (see DESIGN.md "parity"):  the chain  coordinates/displacements -> Gamma_0 ->
-// F -> C -> Cardano eigenvalues  is evaluated with explicitly rounded, un-contracted operations
-// in the reference's statement order (gtmat1.f:300-507, 522-674, 1031-1210), because the
+// F -> C -> Cardano eigenvalues -> U^-1 -> R  is evaluated with explicitly rounded operations in
+// the reference's statement order (gtmat1.f:300-507, 522-674, 1031-1210), because the
 // reference's closed-form polar decomposition amplifies a 1-ulp change of C into ~1e-9 of R for
-// strains below ~5e-3.  Everything downstream is well conditioned and uses FMA freely.
+// strains below ~5e-3.  Products and sums are fused in ONE fixed pattern -- left-to-right
+// contraction, a*b + c*d + e*f -> fma(e, f, fma(c, d, a*b)), a*b - c*d -> fma(a, b, -(c*d)),
+// s + a*b -> fma(a, b, s) -- written out with xf() below; the CPU restatement the parity tests
+// use states the same pattern (an optimising compiler such as the reference's own contracts
+// these expressions too; which products it fuses is not visible from the source, so the pattern
+// is a convention either way).  ~450 fewer FP64 instructions per Gauss point than the un-fused
+// chain of round 1.  Everything downstream is well conditioned and uses FMA freely.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -35,6 +41,11 @@ struct CtaDesc {
 __device__ __forceinline__ double xm(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double xa(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double xs(double a, double b) { return __dsub_rn(a, b); }
+// the fused operation of the contraction convention (never split or re-associated by ptxas)
+__device__ __forceinline__ double xf(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ double xdot3(double a1, double b1, double a2, double b2, double a3, double b3) {
+  return xf(a3, b3, xf(a2, b2, xm(a1, b1)));
+}
 // a / b, correctly rounded like __ddiv_rn, without the division's ~65-instruction subroutine for
 // a == 0.  That subroutine runs whenever the quotient is zero or subnormal, and zero numerators
 // are the rule, not the exception, on this path: the off-diagonal cofactors of an axis-aligned
@@ -65,29 +76,30 @@ __device__ __forceinline__ void jacobian(const double (&nx)[8], const double (&n
       for (int c = 0; c < 3; ++c) J[r][c] = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      J[0][0] = xa(J[0][0], xm(nx[j], X[j]));
-      J[0][1] = xa(J[0][1], xm(nx[j], Y[j]));
-      J[0][2] = xa(J[0][2], xm(nx[j], Z[j]));
-      J[1][0] = xa(J[1][0], xm(ne[j], X[j]));
-      J[1][1] = xa(J[1][1], xm(ne[j], Y[j]));
-      J[1][2] = xa(J[1][2], xm(ne[j], Z[j]));
-      J[2][0] = xa(J[2][0], xm(nz[j], X[j]));
-      J[2][1] = xa(J[2][1], xm(nz[j], Y[j]));
-      J[2][2] = xa(J[2][2], xm(nz[j], Z[j]));
+      J[0][0] = xf(nx[j], X[j], J[0][0]);
+      J[0][1] = xf(nx[j], Y[j], J[0][1]);
+      J[0][2] = xf(nx[j], Z[j], J[0][2]);
+      J[1][0] = xf(ne[j], X[j], J[1][0]);
+      J[1][1] = xf(ne[j], Y[j], J[1][1]);
+      J[1][2] = xf(ne[j], Z[j], J[1][2]);
+      J[2][0] = xf(nz[j], X[j], J[2][0]);
+      J[2][1] = xf(nz[j], Y[j], J[2][1]);
+      J[2][2] = xf(nz[j], Z[j], J[2][2]);
     }
-    const double j1 = xs(xm(J[1][1], J[2][2]), xm(J[1][2], J[2][1]));
-    const double j2 = xs(xm(J[1][0], J[2][2]), xm(J[1][2], J[2][0]));
-    const double j3 = xs(xm(J[1][0], J[2][1]), xm(J[1][1], J[2][0]));
-    dj = xa(xs(xm(J[0][0], j1), xm(J[0][1], j2)), xm(J[0][2], j3));
-    G[0][0] = xdiv(j1, dj);
-    G[1][0] = xdiv(-j2, dj);
-    G[2][0] = xdiv(j3, dj);
-    G[0][1] = xdiv(xs(xm(J[2][1], J[0][2]), xm(J[0][1], J[2][2])), dj);
-    G[1][1] = xdiv(xs(xm(J[0][0], J[2][2]), xm(J[2][0], J[0][2])), dj);
-    G[2][1] = xdiv(xs(xm(J[0][1], J[2][0]), xm(J[0][0], J[2][1])), dj);
-    G[0][2] = xdiv(xs(xm(J[0][1], J[1][2]), xm(J[0][2], J[1][1])), dj);
-    G[1][2] = xdiv(xs(xm(J[0][2], J[1][0]), xm(J[0][0], J[1][2])), dj);
-    G[2][2] = xdiv(xs(xm(J[0][0], J[1][1]), xm(J[0][1], J[1][0])), dj);
+    const double j1 = xf(J[1][1], J[2][2], -xm(J[1][2], J[2][1]));
+    const double j2 = xf(J[1][0], J[2][2], -xm(J[1][2], J[2][0]));
+    const double j3 = xf(J[1][0], J[2][1], -xm(J[1][1], J[2][0]));
+    dj = xf(J[0][2], j3, xf(-J[0][1], j2, xm(J[0][0], j1)));
+    const double rdj = __ddiv_rn(1.0, dj);      // one reciprocal, nine products (convention)
+    G[0][0] = xm(j1, rdj);
+    G[1][0] = xm(-j2, rdj);
+    G[2][0] = xm(j3, rdj);
+    G[0][1] = xm(xf(J[2][1], J[0][2], -xm(J[0][1], J[2][2])), rdj);
+    G[1][1] = xm(xf(J[0][0], J[2][2], -xm(J[2][0], J[0][2])), rdj);
+    G[2][1] = xm(xf(J[0][1], J[2][0], -xm(J[0][0], J[2][1])), rdj);
+    G[0][2] = xm(xf(J[0][1], J[1][2], -xm(J[0][2], J[1][1])), rdj);
+    G[1][2] = xm(xf(J[0][2], J[1][0], -xm(J[0][0], J[1][2])), rdj);
+    G[2][2] = xm(xf(J[0][0], J[1][1], -xm(J[0][1], J[1][0])), rdj);
   } else {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -129,18 +141,18 @@ __device__ __forceinline__ void polar_rotation(const double (&F)[3][3], double (
   const double third = 1.0 / 3.0;                          // constants module: one/three
   const double iroot3 = 0x1.279a74590331dp-1;              // one/sqrt(three) as IEEE evaluates it
   // metric tensor C = F^T F (symmetric storage 11,12,22,13,23,33) and C*C
-  const double c1 = xa(xa(xm(F[0][0], F[0][0]), xm(F[1][0], F[1][0])), xm(F[2][0], F[2][0]));
-  const double c2 = xa(xa(xm(F[0][0], F[0][1]), xm(F[1][0], F[1][1])), xm(F[2][0], F[2][1]));
-  const double c3 = xa(xa(xm(F[0][1], F[0][1]), xm(F[1][1], F[1][1])), xm(F[2][1], F[2][1]));
-  const double c4 = xa(xa(xm(F[0][0], F[0][2]), xm(F[1][0], F[1][2])), xm(F[2][0], F[2][2]));
-  const double c5 = xa(xa(xm(F[0][1], F[0][2]), xm(F[1][1], F[1][2])), xm(F[2][1], F[2][2]));
-  const double c6 = xa(xa(xm(F[0][2], F[0][2]), xm(F[1][2], F[1][2])), xm(F[2][2], F[2][2]));
-  const double cc1 = xa(xa(xm(c1, c1), xm(c2, c2)), xm(c4, c4));
-  const double cc2 = xa(xa(xm(c1, c2), xm(c2, c3)), xm(c4, c5));
-  const double cc3 = xa(xa(xm(c2, c2), xm(c3, c3)), xm(c5, c5));
-  const double cc4 = xa(xa(xm(c1, c4), xm(c2, c5)), xm(c4, c6));
-  const double cc5 = xa(xa(xm(c2, c4), xm(c3, c5)), xm(c5, c6));
-  const double cc6 = xa(xa(xm(c4, c4), xm(c5, c5)), xm(c6, c6));
+  const double c1 = xdot3(F[0][0], F[0][0], F[1][0], F[1][0], F[2][0], F[2][0]);
+  const double c2 = xdot3(F[0][0], F[0][1], F[1][0], F[1][1], F[2][0], F[2][1]);
+  const double c3 = xdot3(F[0][1], F[0][1], F[1][1], F[1][1], F[2][1], F[2][1]);
+  const double c4 = xdot3(F[0][0], F[0][2], F[1][0], F[1][2], F[2][0], F[2][2]);
+  const double c5 = xdot3(F[0][1], F[0][2], F[1][1], F[1][2], F[2][1], F[2][2]);
+  const double c6 = xdot3(F[0][2], F[0][2], F[1][2], F[1][2], F[2][2], F[2][2]);
+  const double cc1 = xdot3(c1, c1, c2, c2, c4, c4);
+  const double cc2 = xdot3(c1, c2, c2, c3, c4, c5);
+  const double cc3 = xdot3(c2, c2, c3, c3, c5, c5);
+  const double cc4 = xdot3(c1, c4, c2, c5, c4, c6);
+  const double cc5 = xdot3(c2, c4, c3, c5, c5, c6);
+  const double cc6 = xdot3(c4, c4, c5, c5, c6, c6);
   // Cardano eigenvalues of C
   const double m11 = c1, m12 = c2, m13 = c4, m22 = c3, m23 = c5, m33 = c6;
   const double de = xm(m12, m23);
@@ -148,14 +160,12 @@ __device__ __forceinline__ void polar_rotation(const double (&F)[3][3], double (
   const double ee = xm(m23, m23);
   const double ff = xm(m13, m13);
   const double m = xa(xa(m11, m22), m33);
-  const double cc1e = xs(xa(xa(xm(m11, m22), xm(m11, m33)), xm(m22, m33)), xa(xa(dd, ee), ff));
-  const double c0 = xs(xs(xa(xa(xm(m33, dd), xm(m11, ee)), xm(m22, ff)), xm(xm(m11, m22), m33)),
-                       xm(xm(two, m13), de));
-  const double p = xs(xm(m, m), xm(three, cc1e));
-  const double q = xs(xm(m, xs(p, xm(onept5, cc1e))), xm(thirteenpt5, c0));
+  const double cc1e = xs(xf(m22, m33, xf(m11, m33, xm(m11, m22))), xa(xa(dd, ee), ff));
+  const double c0 = xf(-xm(two, m13), de, xf(-xm(m11, m22), m33, xf(m22, ff, xf(m11, ee, xm(m33, dd)))));
+  const double p = xf(m, m, -xm(three, cc1e));
+  const double q = xf(m, xf(-onept5, cc1e, p), -xm(thirteenpt5, c0));
   const double sqrtp = sqrt(fabs(p));
-  double phi = xm(twentyseven, xa(xm(xm(xm(quarter, cc1e), cc1e), xs(p, cc1e)),
-                                  xm(c0, xa(q, xm(sixpt75, c0)))));
+  double phi = xm(twentyseven, xf(c0, xf(sixpt75, c0, q), xm(xm(xm(quarter, cc1e), cc1e), xs(p, cc1e))));
   // the argument is a difference of nearly equal numbers and comes out exactly zero at a good
   // share of the points: atan2(+0, q) is 0 or pi by the sign of q -- the same bits without the
   // slow paths of sqrt(0) and of the zero quotient inside atan2
@@ -176,25 +186,25 @@ __device__ __forceinline__ void polar_rotation(const double (&F)[3][3], double (
   if (e3 < e2) { const double s = e2; e2 = e3; e3 = s; }
   e1 = sqrt(e1); e2 = sqrt(e2); e3 = sqrt(e3);
   const double iu = xa(xa(e1, e2), e3);
-  const double iiu = xa(xa(xm(e1, e2), xm(e2, e3)), xm(e1, e3));
+  const double iiu = xdot3(e1, e2, e2, e3, e1, e3);
   const double iiiu = xm(xm(e1, e2), e3);
   // irscp1
-  const double a2 = __ddiv_rn(one, xm(iiiu, xs(xm(iu, iiu), iiiu)));
-  const double b2 = xs(xm(xm(iu, iiu), iiu), xm(iiiu, xa(xm(iu, iu), iiu)));
-  const double c2m = xs(-iiiu, xm(iu, xs(xm(iu, iu), xm(two, iiu))));
+  const double a2 = __ddiv_rn(one, xm(iiiu, xf(iu, iiu, -iiiu)));
+  const double b2 = xf(xm(iu, iiu), iiu, -xm(iiiu, xf(iu, iu, iiu)));
+  const double c2m = xf(-iu, xf(iu, iu, -xm(two, iiu)), -iiiu);
   const double d2 = iu;
-  const double u1 = xm(a2, xa(xa(b2, xm(c2m, c1)), xm(d2, cc1)));
-  const double u2 = xm(a2, xa(xm(c2m, c2), xm(d2, cc2)));
-  const double u3 = xm(a2, xa(xa(b2, xm(c2m, c3)), xm(d2, cc3)));
-  const double u4 = xm(a2, xa(xm(c2m, c4), xm(d2, cc4)));
-  const double u5 = xm(a2, xa(xm(c2m, c5), xm(d2, cc5)));
-  const double u6 = xm(a2, xa(xa(b2, xm(c2m, c6)), xm(d2, cc6)));
+  const double u1 = xm(a2, xf(d2, cc1, xf(c2m, c1, b2)));
+  const double u2 = xm(a2, xf(d2, cc2, xm(c2m, c2)));
+  const double u3 = xm(a2, xf(d2, cc3, xf(c2m, c3, b2)));
+  const double u4 = xm(a2, xf(d2, cc4, xm(c2m, c4)));
+  const double u5 = xm(a2, xf(d2, cc5, xm(c2m, c5)));
+  const double u6 = xm(a2, xf(d2, cc6, xf(c2m, c6, b2)));
   // rtcmp1: R = F * Ui
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    R[r][0] = xa(xa(xm(F[r][0], u1), xm(F[r][1], u2)), xm(F[r][2], u4));
-    R[r][1] = xa(xa(xm(F[r][0], u2), xm(F[r][1], u3)), xm(F[r][2], u5));
-    R[r][2] = xa(xa(xm(F[r][0], u4), xm(F[r][1], u5)), xm(F[r][2], u6));
+    R[r][0] = xdot3(F[r][0], u1, F[r][1], u2, F[r][2], u4);
+    R[r][1] = xdot3(F[r][0], u2, F[r][1], u3, F[r][2], u5);
+    R[r][2] = xdot3(F[r][0], u4, F[r][1], u5, F[r][2], u6);
   }
 }
 

@@ -117,10 +117,10 @@ __device__ __forceinline__ void jacobian_smem(const double (*sN)[8][8], int gp, 
     } else if (MODE == 2) {
       x = (x + U[j]) + DU[j]; y = (y + U[8 + j]) + DU[8 + j]; z = (z + U[16 + j]) + DU[16 + j];
     }
-    if (EXACT) {
-      J[0][0] = xa(J[0][0], xm(nx, x)); J[0][1] = xa(J[0][1], xm(nx, y)); J[0][2] = xa(J[0][2], xm(nx, z));
-      J[1][0] = xa(J[1][0], xm(ne, x)); J[1][1] = xa(J[1][1], xm(ne, y)); J[1][2] = xa(J[1][2], xm(ne, z));
-      J[2][0] = xa(J[2][0], xm(nz, x)); J[2][1] = xa(J[2][1], xm(nz, y)); J[2][2] = xa(J[2][2], xm(nz, z));
+    if (EXACT) {     // contraction convention of the noise-amplifying chain (w3d_device.cuh)
+      J[0][0] = xf(nx, x, J[0][0]); J[0][1] = xf(nx, y, J[0][1]); J[0][2] = xf(nx, z, J[0][2]);
+      J[1][0] = xf(ne, x, J[1][0]); J[1][1] = xf(ne, y, J[1][1]); J[1][2] = xf(ne, z, J[1][2]);
+      J[2][0] = xf(nz, x, J[2][0]); J[2][1] = xf(nz, y, J[2][1]); J[2][2] = xf(nz, z, J[2][2]);
     } else {
       J[0][0] = fma(nx, x, J[0][0]); J[0][1] = fma(nx, y, J[0][1]); J[0][2] = fma(nx, z, J[0][2]);
       J[1][0] = fma(ne, x, J[1][0]); J[1][1] = fma(ne, y, J[1][1]); J[1][2] = fma(ne, z, J[1][2]);
@@ -128,19 +128,20 @@ __device__ __forceinline__ void jacobian_smem(const double (*sN)[8][8], int gp, 
     }
   }
   if (EXACT) {
-    const double j1 = xs(xm(J[1][1], J[2][2]), xm(J[1][2], J[2][1]));
-    const double j2 = xs(xm(J[1][0], J[2][2]), xm(J[1][2], J[2][0]));
-    const double j3 = xs(xm(J[1][0], J[2][1]), xm(J[1][1], J[2][0]));
-    dj = xa(xs(xm(J[0][0], j1), xm(J[0][1], j2)), xm(J[0][2], j3));
-    G[0][0] = xdiv(j1, dj);
-    G[1][0] = xdiv(-j2, dj);
-    G[2][0] = xdiv(j3, dj);
-    G[0][1] = xdiv(xs(xm(J[2][1], J[0][2]), xm(J[0][1], J[2][2])), dj);
-    G[1][1] = xdiv(xs(xm(J[0][0], J[2][2]), xm(J[2][0], J[0][2])), dj);
-    G[2][1] = xdiv(xs(xm(J[0][1], J[2][0]), xm(J[0][0], J[2][1])), dj);
-    G[0][2] = xdiv(xs(xm(J[0][1], J[1][2]), xm(J[0][2], J[1][1])), dj);
-    G[1][2] = xdiv(xs(xm(J[0][2], J[1][0]), xm(J[0][0], J[1][2])), dj);
-    G[2][2] = xdiv(xs(xm(J[0][0], J[1][1]), xm(J[0][1], J[1][0])), dj);
+    const double j1 = xf(J[1][1], J[2][2], -xm(J[1][2], J[2][1]));
+    const double j2 = xf(J[1][0], J[2][2], -xm(J[1][2], J[2][0]));
+    const double j3 = xf(J[1][0], J[2][1], -xm(J[1][1], J[2][0]));
+    dj = xf(J[0][2], j3, xf(-J[0][1], j2, xm(J[0][0], j1)));
+    const double rdj = __ddiv_rn(1.0, dj);      // one reciprocal, nine products (convention)
+    G[0][0] = xm(j1, rdj);
+    G[1][0] = xm(-j2, rdj);
+    G[2][0] = xm(j3, rdj);
+    G[0][1] = xm(xf(J[2][1], J[0][2], -xm(J[0][1], J[2][2])), rdj);
+    G[1][1] = xm(xf(J[0][0], J[2][2], -xm(J[2][0], J[0][2])), rdj);
+    G[2][1] = xm(xf(J[0][1], J[2][0], -xm(J[0][0], J[2][1])), rdj);
+    G[0][2] = xm(xf(J[0][1], J[1][2], -xm(J[0][2], J[1][1])), rdj);
+    G[1][2] = xm(xf(J[0][2], J[1][0], -xm(J[0][0], J[1][2])), rdj);
+    G[2][2] = xm(xf(J[0][0], J[1][1], -xm(J[0][1], J[1][0])), rdj);
   } else {
     const double j1 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
     const double j2 = J[1][0] * J[2][2] - J[1][2] * J[2][0];
@@ -191,9 +192,9 @@ __device__ __forceinline__ void jacobian_matrix_exact(const double (*sN)[8][8], 
   for (int j = 0; j < 8; ++j) {
     const double nx = sN[0][j][gp], ne = sN[1][j][gp], nz = sN[2][j][gp];
     const double x = C[j], y = C[8 + j], z = C[16 + j];
-    J[0][0] = xa(J[0][0], xm(nx, x)); J[0][1] = xa(J[0][1], xm(nx, y)); J[0][2] = xa(J[0][2], xm(nx, z));
-    J[1][0] = xa(J[1][0], xm(ne, x)); J[1][1] = xa(J[1][1], xm(ne, y)); J[1][2] = xa(J[1][2], xm(ne, z));
-    J[2][0] = xa(J[2][0], xm(nz, x)); J[2][1] = xa(J[2][1], xm(nz, y)); J[2][2] = xa(J[2][2], xm(nz, z));
+    J[0][0] = xf(nx, x, J[0][0]); J[0][1] = xf(nx, y, J[0][1]); J[0][2] = xf(nx, z, J[0][2]);
+    J[1][0] = xf(ne, x, J[1][0]); J[1][1] = xf(ne, y, J[1][1]); J[1][2] = xf(ne, z, J[1][2]);
+    J[2][0] = xf(nz, x, J[2][0]); J[2][1] = xf(nz, y, J[2][1]); J[2][2] = xf(nz, z, J[2][2]);
   }
 }
 
@@ -310,19 +311,19 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
 #pragma unroll 1
       for (int j = 0; j < 8; ++j) {
         const double nx = sN[0][j][gp], ne = sN[1][j][gp], nz = sN[2][j][gp];
-        const double tx = xa(xa(xm(G0[0][0], nx), xm(G0[0][1], ne)), xm(G0[0][2], nz));
-        const double ty = xa(xa(xm(G0[1][0], nx), xm(G0[1][1], ne)), xm(G0[1][2], nz));
-        const double tz = xa(xa(xm(G0[2][0], nx), xm(G0[2][1], ne)), xm(G0[2][2], nz));
+        const double tx = xdot3(G0[0][0], nx, G0[0][1], ne, G0[0][2], nz);
+        const double ty = xdot3(G0[1][0], nx, G0[1][1], ne, G0[1][2], nz);
+        const double tz = xdot3(G0[2][0], nx, G0[2][1], ne, G0[2][2], nz);
         const double u0 = U[j], v0 = U[8 + j], w0 = U[16 + j];
         const double du = DU[j], dv = DU[8 + j], dw = DU[16 + j];
         const double u1 = xa(u0, du), v1 = xa(v0, dv), w1 = xa(w0, dw);          // uen1
-        const double uh = xa(u0, xm(0.5, du)), vh = xa(v0, xm(0.5, dv)), wh = xa(w0, xm(0.5, dw));
-        t1[0] = xa(t1[0], xm(tx, u1)); t1[1] = xa(t1[1], xm(tx, v1)); t1[2] = xa(t1[2], xm(tx, w1));
-        t1[3] = xa(t1[3], xm(ty, u1)); t1[4] = xa(t1[4], xm(ty, v1)); t1[5] = xa(t1[5], xm(ty, w1));
-        t1[6] = xa(t1[6], xm(tz, u1)); t1[7] = xa(t1[7], xm(tz, v1)); t1[8] = xa(t1[8], xm(tz, w1));
-        th[0] = xa(th[0], xm(tx, uh)); th[1] = xa(th[1], xm(tx, vh)); th[2] = xa(th[2], xm(tx, wh));
-        th[3] = xa(th[3], xm(ty, uh)); th[4] = xa(th[4], xm(ty, vh)); th[5] = xa(th[5], xm(ty, wh));
-        th[6] = xa(th[6], xm(tz, uh)); th[7] = xa(th[7], xm(tz, vh)); th[8] = xa(th[8], xm(tz, wh));
+        const double uh = xf(0.5, du, u0), vh = xf(0.5, dv, v0), wh = xf(0.5, dw, w0);
+        t1[0] = xf(tx, u1, t1[0]); t1[1] = xf(tx, v1, t1[1]); t1[2] = xf(tx, w1, t1[2]);
+        t1[3] = xf(ty, u1, t1[3]); t1[4] = xf(ty, v1, t1[4]); t1[5] = xf(ty, w1, t1[5]);
+        t1[6] = xf(tz, u1, t1[6]); t1[7] = xf(tz, v1, t1[7]); t1[8] = xf(tz, w1, t1[8]);
+        th[0] = xf(tx, uh, th[0]); th[1] = xf(tx, vh, th[1]); th[2] = xf(tx, wh, th[2]);
+        th[3] = xf(ty, uh, th[3]); th[4] = xf(ty, vh, th[4]); th[5] = xf(ty, wh, th[5]);
+        th[6] = xf(tz, uh, th[6]); th[7] = xf(tz, vh, th[7]); th[8] = xf(tz, wh, th[8]);
       }
       // fcomp1 (gtmat1.f:601-674)
       double F1[3][3], Fh[3][3];
@@ -332,20 +333,25 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
       Fh[0][0] = xa(th[0], 1.0); Fh[0][1] = th[3]; Fh[0][2] = th[6];
       Fh[1][0] = th[1]; Fh[1][1] = xa(th[4], 1.0); Fh[1][2] = th[7];
       Fh[2][0] = th[2]; Fh[2][1] = th[5]; Fh[2][2] = xa(th[8], 1.0);
-      const double f1 = xs(xm(F1[1][1], F1[2][2]), xm(F1[1][2], F1[2][1]));
-      const double f2 = xs(xm(F1[1][0], F1[2][2]), xm(F1[1][2], F1[2][0]));
-      const double f3 = xs(xm(F1[1][0], F1[2][1]), xm(F1[1][1], F1[2][0]));
-      const double dfn1 = xa(xs(xm(F1[0][0], f1), xm(F1[0][1], f2)), xm(F1[0][2], f3));
-      const double h1 = xs(xm(Fh[1][1], Fh[2][2]), xm(Fh[1][2], Fh[2][1]));
-      const double h2 = xs(xm(Fh[1][0], Fh[2][2]), xm(Fh[1][2], Fh[2][0]));
-      const double h3 = xs(xm(Fh[1][0], Fh[2][1]), xm(Fh[1][1], Fh[2][0]));
-      const double dfh = xa(xs(xm(Fh[0][0], h1), xm(Fh[0][1], h2)), xm(Fh[0][2], h3));
+      const double f1 = xf(F1[1][1], F1[2][2], -xm(F1[1][2], F1[2][1]));
+      const double f2 = xf(F1[1][0], F1[2][2], -xm(F1[1][2], F1[2][0]));
+      const double f3 = xf(F1[1][0], F1[2][1], -xm(F1[1][1], F1[2][0]));
+      const double dfn1 = xf(F1[0][2], f3, xf(-F1[0][1], f2, xm(F1[0][0], f1)));
+      const double h1 = xf(Fh[1][1], Fh[2][2], -xm(Fh[1][2], Fh[2][1]));
+      const double h2 = xf(Fh[1][0], Fh[2][2], -xm(Fh[1][2], Fh[2][0]));
+      const double h3 = xf(Fh[1][0], Fh[2][1], -xm(Fh[1][1], Fh[2][0]));
+      const double dfh = xf(Fh[0][2], h3, xf(-Fh[0][1], h2, xm(Fh[0][0], h1)));
       error = !(dfn1 > 1.0e-20) || !(dfh > 1.0e-20);
       efac = dfn1 * dj0 * a.beta_fact * weight;
       if (!error) {
-        // one copy of the (large) polar-decomposition code, executed twice: keeps the kernel
-        // within the instruction cache
+        // both decompositions (n+1 and n+1/2) in flight together: two independent chains of
+        // sqrt / atan2 / sincos for the FP64 pipe (2 M mesh: 4.00 -> 3.84 ms); W3D_POLAR_ROLLED
+        // keeps one copy of the code executed twice
+#if defined(W3D_POLAR_ROLLED)
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
         for (int w = 0; w < 2; ++w) {
           double F[3][3], R[3][3];
 #pragma unroll
