@@ -246,6 +246,16 @@ int32_t w3d_assemble_structure(w3d_engine *h, int32_t *dof_eqn_map, int32_t *eqn
  * (n_eqns) / k_coeffs (ncoeff): host buffers for this domain's rows, or both NULL to leave the
  * result in device memory.                                                                       */
 int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs);
+/* Replaces convert_vss_csr (drive_assemble_solve.f:1501-1590) as drive_assemble_solve.f:757 calls
+ * it for hypre and for asymmetric assembly: the full, structurally symmetric CSR pattern of the
+ * structure (per row: lower terms, diagonal, upper terms, columns ascending; k_ptrs(neqns+1)
+ * 1-based offsets, nnz = neqns + 2 ncoeff) -- bit-exact integers -- and, in k_coeffs(nnz), the
+ * values of the last w3d_assemble in that pattern (the symmetric stiffness in full storage).  Any
+ * pointer may be NULL.  One domain.  Not built: assem_by_row_asymmetric's VALUES for an
+ * unsymmetric element stiffness (needs the full 24 x 24 element matrices, which k_tanstf does not
+ * form).                                                                                          */
+int32_t w3d_assemble_csr(w3d_engine *h, int64_t *nnz, int32_t *k_ptrs, int32_t *k_indexes,
+                         double *k_coeffs);
 
 /* ---- structure residual and its norms (SURVEY 8(f) NEXT-2) ------------------------------------
  * Replaces upres_iter_0 (upres.f:13-77), upres (upres.f:121-226) and the residual loop of cvtest

@@ -253,6 +253,19 @@ def assemble(oracle: "Oracle", estiff, s):
     return kd, kc[:s["ncoeff"]]
 
 
+def convert_vss_csr(s):
+    """convert_vss_csr (drive_assemble_solve.f:1501): (ptrs (neqns+1), indexes (nnz)), 1-based."""
+    L = lib()
+    L.w3do_convert_vss_csr.restype = C.c_int64
+    neq, nco = s["neqns"], s["ncoeff"]
+    ptrs = np.zeros(neq + 1, dtype=np.int32)
+    idx = np.zeros(neq + 2 * nco, dtype=np.int32)
+    ki = np.ascontiguousarray(s["k_indexes"] if nco else np.zeros(1, dtype=np.int32))
+    nnz = L.w3do_convert_vss_csr(C.c_int32(neq), C.c_int64(nco), _ptr(s["k_ptrs"]), _ptr(ki), _ptr(ptrs), _ptr(idx))
+    assert nnz == neq + 2 * nco
+    return ptrs, idx
+
+
 # ---- structure residual and its norms (upres.f, cvtest.f:62-78) -----------------------------------
 def _f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)

@@ -164,4 +164,58 @@ void w3do_assemble(const w3do_model *m, const double *estiff, int32_t neqns,
   }
 }
 
+
+// convert_vss_csr (drive_assemble_solve.f:1501-1590), statement for statement (1-based arrays kept
+// through the V() accessors): upper-triangle VSS pattern -> full structurally symmetric CSR.
+// ptrs(neqns+1), indexes(2*ncoeff+neqns); returns nnz.
+int64_t w3do_convert_vss_csr(int32_t neqns, int64_t ncoeff, const int32_t *vss_ptrs,
+                             const int32_t *vss_indexes, int32_t *ptrs, int32_t *indexes) {
+#define VP(i) vss_ptrs[(i)-1]
+#define VI(i) vss_indexes[(i)-1]
+#define P(i) ptrs[(i)-1]
+#define IX(i) indexes[(i)-1]
+  const int64_t nnz = (int64_t)neqns + 2 * ncoeff;
+  std::vector<int32_t> workv((size_t)neqns, 0);
+#define WK(i) workv[(i)-1]
+  for (int i = 1; i <= neqns + 1; ++i) P(i) = 0;
+  for (int i = 1; i <= neqns; ++i) P(i) = VP(i);
+  for (int i = 1; i <= neqns; ++i) P(i) = P(i) + 1;
+  for (int64_t i = 1; i <= ncoeff; ++i) {
+    P(VI(i)) = P(VI(i)) + 1;
+    WK(VI(i)) = WK(VI(i)) + 1;
+  }
+  for (int i = 2; i <= neqns; ++i) P(i) = P(i - 1) + P(i);
+  for (int i = neqns + 1; i >= 2; --i) P(i) = P(i - 1) + 1;
+  P(1) = 1;
+  for (int64_t i = 1; i <= nnz; ++i) IX(i) = 0;
+  int64_t sft = 1, j = 1;
+  for (int i = 1; i <= neqns; ++i) {
+    int64_t o = P(i) + WK(i);
+    IX(o) = i;
+    o = o + 1;
+    for (j = sft; j <= sft + VP(i) - 1; ++j) {
+      IX(o) = VI(j);
+      o = o + 1;
+    }
+    sft = j;
+  }
+  for (int i = 1; i <= neqns; ++i) WK(i) = 0;
+  sft = 1;
+  for (int c = 1; c <= neqns; ++c) {
+    for (j = sft; j <= sft + VP(c) - 1; ++j) {
+      const int r = VI(j);
+      const int64_t o = P(r) + WK(r);
+      IX(o) = c;
+      WK(r) = WK(r) + 1;
+    }
+    sft = j;
+  }
+#undef VP
+#undef VI
+#undef P
+#undef IX
+#undef WK
+  return nnz;
+}
+
 }  // extern "C"

@@ -161,3 +161,60 @@ def test_device_assembly_by_domains_adds_up_to_the_one_domain_result(ndom):
     assert np.array_equal(kc_sum[once[rows]], kc1[once[rows]])
     scale = max(abs(kd1).max(), abs(kc1).max())                 # interface rows: one more rounding
     assert abs(kd_sum - kd1).max() <= 1e-14 * scale and abs(kc_sum - kc1).max() <= 1e-14 * scale
+
+
+def _full_csr(ptrs, idx, val, n):
+    return sp.csr_matrix((val, idx.astype(np.int64) - 1, ptrs.astype(np.int64) - 1), shape=(n, n))
+
+
+def test_convert_vss_csr_restatement_is_the_full_sorted_pattern():
+    """convert_vss_csr (drive_assemble_solve.f:1501): the restatement's CSR pattern equals the
+    pattern of the symmetric matrix scipy assembles -- offsets 1-based, columns ascending, lower
+    terms before the diagonal before the upper terms, nnz = neqns + 2 ncoeff."""
+    m, cst = _case(nx=5, ny=4, nz=3, seed=21, block_size=9)
+    o, st = op.Oracle(m), new_state(m)
+    (step, iters), = list(load_path(m, nsteps=1, strain=3.0e-3))
+    for itr, u, du in iters:
+        o.eps_sig_ifv(st, step, itr, u, du)
+    ek = o.tanstf(st, step, itr, u, du)
+    s = op.assemble_structure(o, cst)
+    ptrs, idx = op.convert_vss_csr(s)
+    neq = s["neqns"]
+    assert ptrs[0] == 1 and ptrs[-1] == neq + 2 * s["ncoeff"] + 1 and len(idx) == neq + 2 * s["ncoeff"]
+    for r in range(neq):
+        cols = idx[ptrs[r] - 1:ptrs[r + 1] - 1]
+        assert np.all(np.diff(cols) > 0) and (r + 1) in cols
+    # the same pattern built independently: upper terms, their mirror images and the diagonal
+    rows = np.repeat(np.arange(neq), s["k_ptrs"])
+    cols = s["k_indexes"].astype(np.int64) - 1
+    full = sp.coo_matrix((np.ones(3 * 0 + 2 * len(cols) + neq),
+                          (np.concatenate([rows, cols, np.arange(neq)]), np.concatenate([cols, rows, np.arange(neq)]))),
+                         shape=(neq, neq)).tocsr()
+    full.sort_indices()
+    assert np.array_equal(full.indptr + 1, ptrs) and np.array_equal(full.indices + 1, idx)
+    assert full.data.max() == 1.0          # no term listed twice
+
+
+@pytest.mark.gpu
+def test_device_csr_pattern_bit_exact_and_values():
+    """w3d_assemble_csr: the integers equal the restatement of convert_vss_csr bit for bit; the
+    values are the symmetric stiffness in full storage (upper terms mirrored)."""
+    from warp3d_b200.engine import Engine
+    m, cst = _case(nx=6, ny=5, nz=4, seed=11, block_size=13)
+    e, o, st = Engine(m), op.Oracle(m), new_state(m)
+    (step, iters), = list(load_path(m, nsteps=1, strain=3.0e-3))
+    for itr, u, du in iters:
+        e.drive_eps_sig_internal_forces(step, itr, u, du)
+    e.tanstf(step, itr, u, du, to_host=False)
+    sg = e.assemble_setup(cst)
+    kd, kc = e.assemble()
+    ptrs, idx, val = e.assemble_csr()
+    so = op.assemble_structure(o, cst)
+    ptrs_o, idx_o = op.convert_vss_csr(so)
+    assert np.array_equal(ptrs, ptrs_o) and np.array_equal(idx, idx_o)        # integers: bit exact
+    neq = sg["neqns"]
+    K = _full_csr(ptrs, idx, val, neq)
+    A = _vss_to_csr(sg, kd, kc)                                                # upper + upper^T + diag
+    assert abs(K - A).max() == 0.0
+    assert abs(K - K.T).max() == 0.0
+    e.close()

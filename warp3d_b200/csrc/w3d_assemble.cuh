@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(128) k_assemble_rows(
 // Measured on the 2 M-element mesh: 44 ms (thread per equation, scattered global
 // read-modify-writes) -> this kernel.
 constexpr int ASM_WARPS = 4;       // warps (nodes) per CTA
-constexpr int ASM_MAXROW = 192;    // longest row this kernel takes (81 on a structured hex8 mesh)
+constexpr int ASM_MAXROW = 96;     // longest row this kernel takes (81 on a structured hex8 mesh); 14 KB of
+                                   // shared memory per CTA -> 16 CTAs = 64 warps per SM
 __global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_nodes(
     int node0, int nonode, int eq0, const int32_t *__restrict__ dof_eqn, const int32_t *__restrict__ inv_ptr,
     const int32_t *__restrict__ inv_epos, const int8_t *__restrict__ inv_lnode,
@@ -97,17 +98,36 @@ __global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_nodes(
     if (lane == 0) sdiag[w][c] = 0.0;
   }
   __syncwarp();
-  for (int j = inv_ptr[node]; j < inv_ptr[node + 1]; ++j) {   // elements on the node, ascending
+  // elements on the node, ascending.  The loads of element j+1 (its equation numbers and the three
+  // stiffness terms of this lane's column) are issued before the shared-memory search-and-add of
+  // element j: the chain index -> equation numbers / terms -> search -> add no longer runs at
+  // global-memory latency once per element.
+  const int jbeg = inv_ptr[node], jend = inv_ptr[node + 1];
+  int scol_n = 0;
+  double v_n[3] = {0.0, 0.0, 0.0};
+  auto fetch = [&](int j) {
     const long long e = inv_epos[j];
     const int ln = inv_lnode[j];
-    const int scol = (lane < 24) ? eeqn[e * 24 + lane] : 0;
-    const double *ek = estiff + e * 300;
+    if (lane < 24) {
+      scol_n = eeqn[e * 24 + lane];
+      const double *ek = estiff + e * 300;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int erow = c * 8 + ln;
+        const int hi = max(lane, erow), lo = min(lane, erow);
+        v_n[c] = ek[(hi * (hi + 1)) / 2 + lo];                      // dcp(max) - |ecol - erow|
+      }
+    }
+  };
+  if (jbeg < jend) fetch(jbeg);
+  for (int j = jbeg; j < jend; ++j) {
+    const int scol = scol_n;
+    const double v3[3] = {v_n[0], v_n[1], v_n[2]};
+    if (j + 1 < jend) fetch(j + 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       if (srow[c] == 0 || lane >= 24 || scol < srow[c]) continue;   // constrained / lower triangle
-      const int erow = c * 8 + ln;
-      const int hi = max(lane, erow), lo = min(lane, erow);
-      const double v = ek[(hi * (hi + 1)) / 2 + lo];                // dcp(max) - |ecol - erow|
+      const double v = v3[c];
       if (scol == srow[c]) {
         sdiag[w][c] += v;                                           // one lane per element
       } else {
@@ -126,6 +146,16 @@ __global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_nodes(
     if (srow[c] == 0) continue;
     for (int k = lane; k < n[c]; k += 32) kcoef[rs[c] + k] = sval[w][c][k];
     if (lane == 0) kdiag[srow[c] - 1 - eq0] = sdiag[w][c];
+  }
+}
+
+// values of the assembled upper triangle into the full CSR pattern (diagonal, upper and the
+// mirrored lower terms): one gather per stored term
+__global__ void k_csr_fill(const int32_t *__restrict__ src, const double *__restrict__ kdiag,
+                           const double *__restrict__ kcoef, double *__restrict__ val, long long nnz) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nnz; k += (long long)gridDim.x * blockDim.x) {
+    const int32_t s = src[k];
+    val[k] = (s < 0) ? kdiag[-(s + 1)] : kcoef[s];
   }
 }
 
@@ -238,27 +268,55 @@ int32_t w3d_assemble_setup(w3d_engine *h, const int32_t *cstmap, const int32_t *
   A.neq_local = A.node_first_eqn[node_hi] - A.eq0;
   if (A.neq_local <= 0) return h->fail(W3D_ERR_CONFIG, "assembly: no free dof on this domain's nodes");
   const int nloc = A.neq_local;
-  // ---- sparsity: per equation the distinct columns right of the diagonal, ascending
+  // ---- sparsity: per equation the distinct columns right of the diagonal, ascending.  The up
+  //      to three equations of a node see the same elements, so the node's sorted list of distinct
+  //      equations is formed once and every row takes its tail; node ranges are dealt to host
+  //      threads (6.1 M equations: 4.6 s single-threaded in round 1).
   A.k_ptrs.assign(nloc, 0);
-  A.k_indexes.clear();
-  A.k_indexes.reserve((size_t)nloc * 40);
   std::vector<long long> row_start(nloc + 1, 0);
-  std::vector<int32_t> cand;
-  cand.reserve(27 * 3 * 8);
-  for (int r = 0; r < nloc; ++r) {
-    const int srow = A.eq0 + r + 1;
-    const int nd = A.eqn_node_map[A.eq0 + r] - 1;
-    cand.clear();
-    for (int j = ptr_all[nd]; j < ptr_all[nd + 1]; ++j) {
-      const int32_t *q = &eeqn_all[(size_t)inv_all[j] * 24];
-      for (int k = 0; k < 24; ++k)
-        if (q[k] > srow) cand.push_back(q[k]);
+  {
+    const int nnode_loc = node_hi - node_lo;
+    unsigned nthr = std::thread::hardware_concurrency();
+    nthr = std::max(1u, std::min(nthr, 32u));
+    if (nnode_loc < 4096) nthr = 1;
+    std::vector<std::vector<int32_t>> part(nthr);
+    std::vector<std::thread> pool;
+    auto work = [&](unsigned t) {
+      const int na = node_lo + (int)((long long)nnode_loc * t / nthr), nb = node_lo + (int)((long long)nnode_loc * (t + 1) / nthr);
+      std::vector<int32_t> &out = part[t];
+      out.reserve((size_t)(nb - na) * 3 * 40);
+      std::vector<int32_t> cand;
+      cand.reserve(27 * 24);
+      for (int nd = na; nd < nb; ++nd) {
+        const int r0 = A.node_first_eqn[nd], r1 = A.node_first_eqn[nd + 1];   // equations of this node
+        if (r1 <= r0) continue;
+        cand.clear();
+        for (int j = ptr_all[nd]; j < ptr_all[nd + 1]; ++j) {
+          const int32_t *q = &eeqn_all[(size_t)inv_all[j] * 24];
+          for (int k = 0; k < 24; ++k)
+            if (q[k] > r0 + 1) cand.push_back(q[k]);
+        }
+        std::sort(cand.begin(), cand.end());
+        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+        for (int r = r0; r < r1; ++r) {
+          const int srow = r + 1;
+          const auto first = std::upper_bound(cand.begin(), cand.end(), srow);
+          A.k_ptrs[r - A.eq0] = (int32_t)(cand.end() - first);
+          out.insert(out.end(), first, cand.end());
+        }
+      }
+    };
+    for (unsigned t = 1; t < nthr; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    for (int r = 0; r < nloc; ++r) row_start[r + 1] = row_start[r] + A.k_ptrs[r];
+    A.k_indexes.resize((size_t)row_start[nloc]);
+    size_t off = 0;
+    for (unsigned t = 0; t < nthr; ++t) {
+      if (!part[t].empty()) std::memcpy(A.k_indexes.data() + off, part[t].data(), sizeof(int32_t) * part[t].size());
+      off += part[t].size();
+      std::vector<int32_t>().swap(part[t]);
     }
-    std::sort(cand.begin(), cand.end());
-    cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
-    A.k_ptrs[r] = (int32_t)cand.size();
-    A.k_indexes.insert(A.k_indexes.end(), cand.begin(), cand.end());
-    row_start[r + 1] = row_start[r] + (long long)cand.size();
   }
   A.ncoeff = row_start[nloc];
   // ---- upload
@@ -368,6 +426,86 @@ int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs) {
   if (k_diag) CUDA_TRY(cudaMemcpyAsync(k_diag, A.d_kdiag, sizeof(double) * (size_t)A.neq_local, cudaMemcpyDeviceToHost, h->stream));
   if (k_coeffs && A.ncoeff) CUDA_TRY(cudaMemcpyAsync(k_coeffs, A.d_kcoef, sizeof(double) * (size_t)A.ncoeff, cudaMemcpyDeviceToHost, h->stream));
   if (k_diag || k_coeffs) CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return W3D_OK;
+}
+
+
+// convert_vss_csr (drive_assemble_solve.f:1501-1590): the upper-triangle VSS pattern turned into
+// the full, structurally symmetric CSR pattern (per row: lower terms, diagonal, upper terms;
+// columns ascending; 1-based offsets in k_ptrs(neqns+1)) that the reference hands to hypre and to
+// the asymmetric Pardiso path -- same statements, same order, so the integers are the
+// reference's.  k_coeffs (nnz) receives the values of the last w3d_assemble in that pattern
+// (upper terms mirrored into the lower triangle: the symmetric stiffness in full storage).  Any
+// pointer may be NULL; the pattern is built on the first call after w3d_assemble_setup.  One
+// domain only (the reference converts on root after the merge).
+int32_t w3d_assemble_csr(w3d_engine *h, int64_t *nnz_out, int32_t *k_ptrs, int32_t *k_indexes, double *k_coeffs) {
+  if (!h) return W3D_ERR_ARG;
+  AssemblyData &A = h->assembly;
+  if (!A.ready) return h->fail(W3D_ERR_ARG, "w3d_assemble_setup has not been called");
+  auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  if (A.neq_local != A.neqns) return fail(W3D_ERR_UNSUPPORTED, "w3d_assemble_csr: one domain only (rows %d of %d held here)", A.neq_local, A.neqns);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int neqns = A.neqns;
+  const long long ncoeff = A.ncoeff;
+  if (!A.csr_ready) {
+    const long long nnz = (long long)neqns + 2 * ncoeff;
+    if (nnz > 2147483000LL) return fail(W3D_ERR_UNSUPPORTED, "w3d_assemble_csr: %lld terms exceed default-integer offsets", nnz);
+    const int32_t *vss_ptrs = A.k_ptrs.data();
+    const int32_t *vss_indexes = A.k_indexes.data();
+    std::vector<int32_t> &ptrs = A.csr_ptrs, &indexes = A.csr_indexes;
+    std::vector<int32_t> src((size_t)nnz), work((size_t)neqns, 0);
+    ptrs.assign((size_t)neqns + 1, 0);
+    indexes.assign((size_t)nnz, 0);
+    // number of terms per row: upper terms + diagonal + terms per column
+    for (int i = 0; i < neqns; ++i) ptrs[i] = vss_ptrs[i] + 1;
+    for (long long i = 0; i < ncoeff; ++i) {
+      ptrs[vss_indexes[i] - 1] += 1;
+      work[vss_indexes[i] - 1] += 1;
+    }
+    // convert to 1-based offsets
+    for (int i = 1; i < neqns; ++i) ptrs[i] = ptrs[i - 1] + ptrs[i];
+    for (int i = neqns; i >= 1; --i) ptrs[i] = ptrs[i - 1] + 1;
+    ptrs[0] = 1;
+    // upper triangle and diagonal
+    long long sidx = 0;
+    for (int i = 0; i < neqns; ++i) {
+      long long o = (long long)ptrs[i] - 1 + work[i];      // the diagonal's slot (0-based)
+      indexes[o] = i + 1;
+      src[o] = -(i + 1);
+      ++o;
+      for (int j = 0; j < vss_ptrs[i]; ++j, ++sidx, ++o) {
+        indexes[o] = vss_indexes[sidx];
+        src[o] = (int32_t)sidx;
+      }
+    }
+    // lower triangle: row r, column c, columns strictly increasing
+    std::fill(work.begin(), work.end(), 0);
+    sidx = 0;
+    for (int cc = 0; cc < neqns; ++cc)
+      for (int j = 0; j < vss_ptrs[cc]; ++j, ++sidx) {
+        const int r = vss_indexes[sidx] - 1;
+        const long long o = (long long)ptrs[r] - 1 + work[r];
+        indexes[o] = cc + 1;
+        src[o] = (int32_t)sidx;
+        work[r] += 1;
+      }
+    A.csr_nnz = nnz;
+    CUDA_TRY(cudaMalloc((void **)&A.d_csr_src, sizeof(int32_t) * (size_t)nnz));
+    CUDA_TRY(cudaMemcpy(A.d_csr_src, src.data(), sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void **)&A.d_csr_val, sizeof(double) * (size_t)nnz));
+    A.csr_ready = true;
+  }
+  if (nnz_out) *nnz_out = A.csr_nnz;
+  if (k_ptrs) std::memcpy(k_ptrs, A.csr_ptrs.data(), sizeof(int32_t) * A.csr_ptrs.size());
+  if (k_indexes) std::memcpy(k_indexes, A.csr_indexes.data(), sizeof(int32_t) * A.csr_indexes.size());
+  if (k_coeffs) {
+    const int grid = (int)std::min<long long>((A.csr_nnz + 255) / 256, 148LL * 16);
+    k_csr_fill<<<grid, 256, 0, h->stream>>>(A.d_csr_src, A.d_kdiag, A.d_kcoef, A.d_csr_val, A.csr_nnz);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(k_coeffs, A.d_csr_val, sizeof(double) * (size_t)A.csr_nnz, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
   return W3D_OK;
 }
 

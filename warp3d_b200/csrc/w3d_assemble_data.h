@@ -33,13 +33,19 @@ struct AssemblyData {
   int max_row = 0;                   // longest row (terms right of the diagonal)
   int32_t *d_eeqn = nullptr;         // (24, n_owned_elems) equation number of each element dof, 0 = constrained
   double *d_kdiag = nullptr, *d_kcoef = nullptr;
+  // full structurally symmetric CSR (convert_vss_csr), built on first request
+  bool csr_ready = false;
+  long long csr_nnz = 0;
+  std::vector<int32_t> csr_ptrs, csr_indexes;   // (neqns + 1) 1-based offsets, (nnz) 1-based columns
+  int32_t *d_csr_src = nullptr;                 // (nnz) >= 0: index into k_coeffs, < 0: -(row + 1) of k_diag
+  double *d_csr_val = nullptr;
   void release() {
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (int k = 0; k < NCHUNK; ++k)
       if (chunk_done[k]) cudaEventDestroy(chunk_done[k]);
     cudaFree(d_eqn_node); cudaFree(d_eqn_comp); cudaFree(d_row_start); cudaFree(d_kidx);
     cudaFree(d_inv_ptr); cudaFree(d_inv_epos); cudaFree(d_inv_lnode); cudaFree(d_eeqn); cudaFree(d_dof_eqn);
-    cudaFree(d_kdiag); cudaFree(d_kcoef);
+    cudaFree(d_kdiag); cudaFree(d_kcoef); cudaFree(d_csr_src); cudaFree(d_csr_val);
     *this = AssemblyData();
   }
 };

@@ -34,7 +34,7 @@ EXPORTS = (
     "w3d_tanstf_resident", "w3d_last_scalars", "w3d_engine_stream", "w3d_engine_synchronize",
     "w3d_engine_launch_count", "w3d_upload_displacements", "w3d_download_ifv",
     "w3d_download_estiff", "w3d_set_time_step",
-    "w3d_assemble_setup", "w3d_assemble_structure", "w3d_assemble", "w3d_assemble_rows",
+    "w3d_assemble_setup", "w3d_assemble_structure", "w3d_assemble", "w3d_assemble_rows", "w3d_assemble_csr",
     "w3d_residual_set_loads", "w3d_residual", "w3d_residual_device",
     "w3d_comm_unique_id", "w3d_comm_init", "w3d_comm_set_options", "w3d_comm_plan", "w3d_comm_owned",
     "w3d_download_ifv_range",
@@ -365,6 +365,17 @@ class Engine:
             return k_diag, k_coeffs[:self._ncoeff]
         self._check(self._L.w3d_assemble(self._h, None, None))
         return None, None
+
+    def assemble_csr(self, values=True):
+        """convert_vss_csr: (k_ptrs (neqns+1, 1-based), k_indexes (nnz, 1-based), k_coeffs (nnz) or
+        None) -- the full structurally symmetric CSR of the last assemble()."""
+        nnz = C.c_int64()
+        self._check(self._L.w3d_assemble_csr(self._h, C.byref(nnz), None, None, None))
+        ptrs = np.empty(self._neqns + 1, dtype=np.int32)
+        idx = np.empty(nnz.value, dtype=np.int32)
+        val = np.empty(nnz.value) if values else None
+        self._check(self._L.w3d_assemble_csr(self._h, C.byref(nnz), _ptr(ptrs), _ptr(idx), _ptr(val)))
+        return ptrs, idx, val
 
     # ---- structure residual and its norms (upres.f, cvtest.f:62-78)
     def residual_set_loads(self, cstmap, pbar, load=None, mdiag=None, velocity=None, accel=None,
