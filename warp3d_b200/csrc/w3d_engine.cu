@@ -86,6 +86,11 @@ struct CommData {
   long long ntot = 0;
   int32_t *d_idx = nullptr;
   double *d_send = nullptr, *d_recv = nullptr, *d_red = nullptr;   // d_red[8]
+  // the exchange runs on its own stream so that the stiffness pass (which reads neither ifv nor
+  // the scalars) overlaps it; whoever touches ifv / the scalars next joins first (comm_join)
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+  bool pending = false;
 };
 
 struct w3d_engine {
@@ -97,6 +102,7 @@ struct w3d_engine {
   std::vector<BlockInfo> blocks;
   std::vector<Segment> segs;
   long long n_owned_elems = 0;
+  int dof_lo = 0, dof_hi = 0;       // [dof_lo, dof_hi): the structure dofs this engine's blocks touch
   double *d_c = nullptr, *d_u = nullptr, *d_du = nullptr, *d_ifv = nullptr;
   double *d_estiff = nullptr;       // (300, n_owned_elems)
   double *d_scal = nullptr;         // [4]
@@ -245,6 +251,9 @@ void free_all(w3d_engine *h) {
   h->residual.release();
   cudaFree(h->d_c); cudaFree(h->d_u); cudaFree(h->d_ifv);
   cudaFree(h->comm.d_idx); cudaFree(h->comm.d_send); cudaFree(h->comm.d_recv); cudaFree(h->comm.d_red);
+  if (h->comm.stream) cudaStreamDestroy(h->comm.stream);
+  if (h->comm.ev_start) cudaEventDestroy(h->comm.ev_start);
+  if (h->comm.ev_done) cudaEventDestroy(h->comm.ev_done);
   if (h->comm.comm && nccl_api()->comm_destroy) nccl_api()->comm_destroy(h->comm.comm);
   cudaFree(h->d_estiff); cudaFree(h->d_scal); cudaFree(h->d_flags); cudaFree(h->d_stage);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -361,6 +370,20 @@ int create_impl(w3d_engine *h) {
     epos += b.span;
   }
   h->n_owned_elems = epos;
+  {
+    // the internal-force vector is only ever written inside the dof range of the owned blocks
+    // (a slab of the structure when there are several domains): only that range is zeroed per pass
+    int lo = c.nodof, hi = 0;
+    for (const BlockInfo &b : h->blocks) {
+      if (!b.owned) continue;
+      for (long long k = 0; k < (long long)b.totdof * b.span; ++k) {
+        const int32_t e = c.edest[b.tab_off + k];
+        if (e >= 1 && e <= c.nodof) { lo = std::min(lo, e - 1); hi = std::max(hi, (int)e); }
+      }
+    }
+    h->dof_lo = hi > lo ? lo : 0;
+    h->dof_hi = hi > lo ? hi : 0;
+  }
   if (c.numprocs > 1) {
     // dofs shared with every other domain (used by the neighbour exchange after w3d_comm_init)
     std::string perr;
@@ -510,37 +533,70 @@ int create_impl(w3d_engine *h) {
 }
 
 // the exchange step after the stress kernels of all segments (stream-ordered, no host sync)
+// deterministic fixed-order reduction of the per-CTA partial sums of every segment into d_scal
+void reduce_scalars(w3d_engine *h, cudaStream_t st) {
+  int first = 1;
+  for (auto &sg : h->segs) {
+    if (sg.ncta > 4096) {   // two fixed-order stages (still deterministic)
+      double *tmp = sg.partials + (size_t)sg.ncta * 4;
+      k_reduce_partials_stage1<<<REDUCE_STAGE1_CTAS, 256, 0, st>>>(sg.partials, sg.ncta, tmp);
+      k_reduce_partials<<<1, 256, 0, st>>>(tmp, REDUCE_STAGE1_CTAS, h->d_scal, first ? 0 : 1);
+      h->launches += 2;
+    } else {
+      k_reduce_partials<<<1, 256, 0, st>>>(sg.partials, sg.ncta, h->d_scal, first ? 0 : 1);
+      h->launches += 1;
+    }
+    first = 0;
+  }
+}
+
+// make the engine's stream wait for an exchange still in flight on the communication stream
+int comm_join(w3d_engine *h) {
+  if (!h->comm.pending) return W3D_OK;
+  h->comm.pending = false;
+  if (cudaStreamWaitEvent(h->stream, h->comm.ev_done, 0) != cudaSuccess)
+    return h->fail(W3D_ERR_CUDA, "cudaStreamWaitEvent on the exchange failed");
+  return W3D_OK;
+}
+
 int comm_exchange(w3d_engine *h) {
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   CommData &cm = h->comm;
   NcclApi *api = nccl_api();
   const int nodof = h->cfg.nodof;
+  // everything below goes to the communication stream, after the stress kernels of this pass
+  CUDA_TRY(cudaEventRecord(cm.ev_start, h->stream));
+  CUDA_TRY(cudaStreamWaitEvent(cm.stream, cm.ev_start, 0));
+  cudaStream_t cs = cm.stream;
+  reduce_scalars(h, cs);
   if (cm.exchange == 1 && cm.ntot >= 0 && !cm.counts.empty()) {
     if (cm.ntot > 0) {
       const int grid = (int)std::min<long long>((cm.ntot + 255) / 256, 148 * 8);
-      k_iface_pack<<<grid, 256, 0, h->stream>>>(h->d_ifv, cm.d_idx, cm.d_send, cm.ntot);
+      k_iface_pack<<<grid, 256, 0, cs>>>(h->d_ifv, cm.d_idx, cm.d_send, cm.ntot);
       NCCL_TRY(api->group_start());
       long long off = 0;
       for (int r = 0; r < cm.nranks; ++r) {
         const long long n = cm.counts[r];
         if (n > 0) {
-          NCCL_TRY(api->send(cm.d_send + off, (size_t)n, NCCL_FLOAT64, r, cm.comm, h->stream));
-          NCCL_TRY(api->recv(cm.d_recv + off, (size_t)n, NCCL_FLOAT64, r, cm.comm, h->stream));
+          NCCL_TRY(api->send(cm.d_send + off, (size_t)n, NCCL_FLOAT64, r, cm.comm, cs));
+          NCCL_TRY(api->recv(cm.d_recv + off, (size_t)n, NCCL_FLOAT64, r, cm.comm, cs));
         }
         off += n;
       }
       NCCL_TRY(api->group_end());
-      k_iface_add<<<grid, 256, 0, h->stream>>>(h->d_ifv, cm.d_idx, cm.d_recv, cm.ntot);
+      k_iface_add<<<grid, 256, 0, cs>>>(h->d_ifv, cm.d_idx, cm.d_recv, cm.ntot);
       h->launches += 2;
     }
   } else {
-    NCCL_TRY(api->all_reduce(h->d_ifv, h->d_ifv, (size_t)nodof, NCCL_FLOAT64, NCCL_SUM, cm.comm, h->stream));
+    NCCL_TRY(api->all_reduce(h->d_ifv, h->d_ifv, (size_t)nodof, NCCL_FLOAT64, NCCL_SUM, cm.comm, cs));
   }
   // internal_energy, plastic_work, sum_ifv, num_term_ifv and the cut flag: one all-reduce
-  k_scal_pack<<<1, 1, 0, h->stream>>>(h->d_scal, h->d_flags, 24.0 * (double)h->n_owned_elems, cm.d_red);
+  k_scal_pack<<<1, 1, 0, cs>>>(h->d_scal, h->d_flags, 24.0 * (double)h->n_owned_elems, cm.d_red);
   h->launches += 1;
-  NCCL_TRY(api->all_reduce(cm.d_red, cm.d_red, 5, NCCL_FLOAT64, NCCL_SUM, cm.comm, h->stream));
+  NCCL_TRY(api->all_reduce(cm.d_red, cm.d_red, 5, NCCL_FLOAT64, NCCL_SUM, cm.comm, cs));
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(cm.ev_done, cs));
+  cm.pending = true;
   return W3D_OK;
 }
 
@@ -555,6 +611,10 @@ int upload_inputs(w3d_engine *h, const double *u, const double *du) {
     CUDA_TRY(cudaMemcpyAsync(h->d_u, u, nb, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_du, du, nb, cudaMemcpyHostToDevice, h->stream));
   }
+  if (bc) {
+    const int rj = comm_join(h);     // one NCCL operation of this communicator at a time
+    if (rj) return rj;
+  }
   if (bc)
     NCCL_TRY(nccl_api()->broadcast(h->d_u, h->d_u, 2 * (size_t)h->cfg.nodof, NCCL_FLOAT64, 0, cm.comm, h->stream));
   h->have_vectors = true;
@@ -564,7 +624,11 @@ int upload_inputs(w3d_engine *h, const double *u, const double *du) {
 int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   const w3d_engine_config &c = h->cfg;
-  CUDA_TRY(cudaMemsetAsync(h->d_ifv, 0, sizeof(double) * c.nodof, h->stream));
+  { const int rj = comm_join(h); if (rj) return rj; }
+  if (h->comm.comm && h->comm.exchange == 0)      // the all-reduce leaves sums in every entry
+    CUDA_TRY(cudaMemsetAsync(h->d_ifv, 0, sizeof(double) * c.nodof, h->stream));
+  else if (h->dof_hi > h->dof_lo)
+    CUDA_TRY(cudaMemsetAsync(h->d_ifv + h->dof_lo, 0, sizeof(double) * (size_t)(h->dof_hi - h->dof_lo), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, 64 * sizeof(int), h->stream));
   int first = 1;
   for (auto &sg : h->segs) {
@@ -601,17 +665,10 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
       CUDA_TRY((launch_stress<1, 0>(sg, a, h->stream)));
       h->launches += 1;
     }
-    if (sg.ncta > 4096) {   // two fixed-order stages (still deterministic)
-      double *tmp = sg.partials + (size_t)sg.ncta * 4;
-      k_reduce_partials_stage1<<<REDUCE_STAGE1_CTAS, 256, 0, h->stream>>>(sg.partials, sg.ncta, tmp);
-      k_reduce_partials<<<1, 256, 0, h->stream>>>(tmp, REDUCE_STAGE1_CTAS, h->d_scal, first ? 0 : 1);
-      h->launches += 2;
-    } else {
-      k_reduce_partials<<<1, 256, 0, h->stream>>>(sg.partials, sg.ncta, h->d_scal, first ? 0 : 1);
-      h->launches += 1;
-    }
-    first = 0;
   }
+  // energy / plastic work / sum |f| of the pass: on the engine's stream, or -- with a communicator
+  // -- on the communication stream in front of the scalar all-reduce (off the critical path)
+  if (!h->comm.comm) reduce_scalars(h, h->stream);
   CUDA_TRY(cudaGetLastError());
   h->have_vectors = true;
   if (h->comm.comm) {
@@ -623,6 +680,7 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
 
 int fetch_scalars(w3d_engine *h, w3d_scalars *out) {
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
+  { const int rj = comm_join(h); if (rj) return rj; }
   CUDA_TRY(cudaMemcpyAsync(h->h_pin, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->h_pin + 4, h->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (h->comm.comm)
@@ -726,6 +784,7 @@ int32_t w3d_engine_create(const w3d_engine_config *cfg, w3d_engine **handle) {
 int32_t w3d_engine_destroy(w3d_engine *h) {
   if (!h) return W3D_ERR_ARG;
   cudaSetDevice(h->device);
+  if (h->comm.stream) cudaStreamSynchronize(h->comm.stream);
   cudaStreamSynchronize(h->stream);
   free_all(h);
   delete h;
@@ -747,6 +806,7 @@ int32_t w3d_eps_sig_ifv(w3d_engine *h, int32_t step, int32_t iter, int32_t extra
   if (rc) return rc;
   rc = stress_resident(h, step, iter, extrapolated_du);
   if (rc) return rc;
+  { const int rj = comm_join(h); if (rj) return rj; }
   if (ifv) CUDA_TRY(cudaMemcpyAsync(ifv, h->d_ifv, nb, cudaMemcpyDeviceToHost, h->stream));
   w3d_scalars s;
   rc = fetch_scalars(h, &s);
@@ -864,6 +924,7 @@ int32_t w3d_device_vectors(w3d_engine *h, double **d_u, double **d_du, double **
   if (d_u) *d_u = h->d_u;
   if (d_du) *d_du = h->d_du;
   if (d_ifv) *d_ifv = h->d_ifv;
+  comm_join(h);
   h->have_vectors = true;
   return W3D_OK;
 }
@@ -881,6 +942,7 @@ int32_t w3d_download_ifv_range(w3d_engine *h, int32_t first, int32_t n, double *
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   if (first < 1 || n < 0 || (long long)first + n - 1 > h->cfg.nodof) return fail(W3D_ERR_ARG, "dof range %d..%d outside 1..%d", first, first + n - 1, h->cfg.nodof);
   CUDA_TRY(cudaSetDevice(h->device));
+  { const int rj = comm_join(h); if (rj) return rj; }
   CUDA_TRY(cudaMemcpyAsync(dst, h->d_ifv + (first - 1), sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return W3D_OK;
@@ -913,6 +975,9 @@ int32_t w3d_comm_init(w3d_engine *h, const uint8_t id[128], int32_t rank, int32_
   cm.ntot = 0;
   for (long long n : cm.counts) cm.ntot += n;
   CUDA_TRY(dalloc(&cm.d_red, 8));
+  CUDA_TRY(cudaStreamCreateWithFlags(&cm.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&cm.ev_start, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&cm.ev_done, cudaEventDisableTiming));
   if (cm.ntot > 0) {
     CUDA_TRY(dalloc(&cm.d_idx, (size_t)cm.ntot));
     CUDA_TRY(dalloc(&cm.d_send, (size_t)cm.ntot));
@@ -931,6 +996,9 @@ int32_t w3d_comm_set_options(w3d_engine *h, int32_t exchange, int32_t bcast_inpu
   if (exchange == 1 && h->comm.counts.empty() && h->cfg.numprocs > 1) return h->fail(W3D_ERR_UNSUPPORTED, "no neighbour plan for this model (more than 64 domains)");
   h->comm.exchange = exchange;
   h->comm.bcast_inputs = bcast_inputs ? 1 : 0;
+  cudaSetDevice(h->device);
+  comm_join(h);
+  cudaMemsetAsync(h->d_ifv, 0, sizeof(double) * h->cfg.nodof, h->stream);   // no stale sums of the other mode
   return W3D_OK;
 }
 int32_t w3d_comm_plan(const w3d_engine_config *cfg, int32_t rank, int64_t *counts, int32_t *dofs) {
@@ -969,6 +1037,7 @@ int32_t w3d_download_ifv(w3d_engine *h, double *ifv) {
   if (!h || !ifv) return h ? h->fail(W3D_ERR_ARG, "null argument") : W3D_ERR_ARG;
   auto fail = [&](int code, const char *fmt, auto... args) { return h->fail(code, fmt, args...); };
   CUDA_TRY(cudaSetDevice(h->device));
+  { const int rj = comm_join(h); if (rj) return rj; }
   CUDA_TRY(cudaMemcpyAsync(ifv, h->d_ifv, sizeof(double) * h->cfg.nodof, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return W3D_OK;
@@ -1000,6 +1069,7 @@ void *w3d_engine_stream(w3d_engine *h) { return h ? (void *)h->stream : nullptr;
 int32_t w3d_engine_synchronize(w3d_engine *h) {
   if (!h) return W3D_ERR_ARG;
   cudaSetDevice(h->device);
+  if (comm_join(h)) return W3D_ERR_CUDA;
   return cudaStreamSynchronize(h->stream) == cudaSuccess ? W3D_OK : h->fail(W3D_ERR_CUDA, "stream synchronize failed");
 }
 int64_t w3d_engine_launch_count(const w3d_engine *h) { return h ? h->launches : -1; }

@@ -177,6 +177,7 @@ int32_t w3d_residual(w3d_engine *h, int32_t iter, double dt, double nbeta, doubl
   if (!h->have_vectors) return h->fail(W3D_ERR_ARG, "w3d_residual before any stress pass (no internal forces)");
   if (iter < 0 || !(dt > 0.0) || !(nbeta > 0.0)) return h->fail(W3D_ERR_ARG, "residual: bad iter / dt / nbeta");
   CUDA_TRY(cudaSetDevice(h->device));
+  { const int rj = comm_join(h); if (rj) return rj; }   // the internal forces must be complete
   ResidualArgs a{};
   a.nodof = h->cfg.nodof;
   a.iter = iter;

@@ -248,7 +248,12 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
   const int nblk = (l < 4) ? 5 : 4;   // pairs {l, l+4} belong to lanes 0..3
   double SV[3] = {0.0, 0.0, 0.0};     // sum over Gauss points of m^T D* Bbar_l  (B-bar only)
 
-#pragma unroll 1
+#ifndef TANSTF_P_UNROLL
+#define TANSTF_P_UNROLL 1
+#endif
+#define W3D_PRAGMA_(x) _Pragma(#x)
+#define W3D_UNROLL_N(n) W3D_PRAGMA_(unroll n)
+  W3D_UNROLL_N(TANSTF_P_UNROLL)
   for (int p = 0; p < 8; ++p) {
     const double *pr = er + p * GPREC;
     // D* (lower triangle) and D* m
