@@ -23,6 +23,7 @@
 extern "C" { long long w3d_mm10_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }
 #endif
 #include "w3d_oracle_mm05.h"   // per-point mm05 restatement (independent of the product)
+#include "w3d_oracle_mm03.h"   // mm03 (mises) restatement (independent of the product)
 
 namespace w3do {
 
@@ -264,6 +265,96 @@ static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
   store_cep(span, gpn, gbl_cep, cep.data());
 }
 
+// drive_03_update (rstgp1.f:1418-1990) -> mm03p (mm03.f:10), mm03 (:2063), cnst3 (:3252); mises
+// material without voids, constant or power-law hardening (w3d_oracle_mm03.h).  Property
+// vectors: setup_mm03_rknstr (rknstr.f:1142-1215).  Not segmental, no temperatures, no fgm.
+static void drive_03_update(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int gpn,
+                            int step, int iter, const double *uddt_displ, double *gbl_cep,
+                            bool &material_cut_step, int *fatal) {
+  using namespace w3do_mm03;
+  const int span = bi.span;
+  const double trans_factor = 0.95;
+  std::vector<double> cep(mxvl * 36, 0.0);
+  double *urcs_n = &lw.urcs_blk_n[(size_t)(gpn - 1) * nstrs * mxvl];
+  double *urcs_n1 = &lw.urcs_blk_n1[(size_t)(gpn - 1) * nstrs * mxvl];
+  double *hist = &lw.elem_hist[(size_t)(gpn - 1) * bi.hist_size * span];
+  double *hist1 = &lw.elem_hist1[(size_t)(gpn - 1) * bi.hist_size * span];
+  double *rtse = &lw.rtse[(size_t)(gpn - 1) * nstr * mxvl];
+  if (bi.hist_size != HIST) { *fatal = 5; return; }
+  if ((iprop(m, 24, bi.felem) & 4) != 0) { *fatal = 3; return; }          // segmental curves
+  std::vector<Props> P(span);
+  std::vector<Point> pt(span);
+  for (int i = 0; i < span; ++i) {
+    const int elem = bi.felem + i;
+    Props &p = P[i];
+    p.e = rprop(m, 7, elem); p.nu = rprop(m, 8, elem); p.h_fixed = rprop(m, 15, elem);
+    p.sigyld = rprop(m, 23, elem); p.n_power = rprop(m, 21, elem); p.eps_ref = rprop(m, 22, elem);
+    p.m_power = rprop(m, 20, elem); p.f0 = rprop(m, 26, elem);
+    p.q1 = rprop(m, 27, elem); p.q2 = rprop(m, 28, elem); p.q3 = rprop(m, 29, elem);
+    p.nucleation = (iprop(m, 30, elem) & 1) != 0;
+    if (p.f0 > 0.0 || p.nucleation) { *fatal = 3; return; }                // Gurson: not restated
+    // copy_sigyld_vec (rstgp1.f:1898-1906): reduced for the cubic transition
+    if (p.n_power > 0.0) p.sigyld = p.sigyld * trans_factor;
+    for (int k = 0; k < 6; ++k) pt[i].deps[k] = uddt_displ[(size_t)k * mxvl + i] + 0.0;   // + uddt_temps
+    for (int k = 0; k < 9; ++k) { pt[i].stress_n[k] = urcs_n[(size_t)k * mxvl + i]; pt[i].stress_n1[k] = 0.0; }
+    for (int k = 0; k < HIST; ++k) {
+      pt[i].history[k] = hist[(size_t)k * span + i];
+      pt[i].history1[k] = hist1[(size_t)k * span + i];
+    }
+    for (int k = 0; k < 6; ++k) pt[i].stress_n1_elas[k] = rtse[(size_t)k * mxvl + i];
+    pt[i].null_point = false; pt[i].nonlinear_flag = false;
+    pt[i].p_trial = pt[i].q_trial = pt[i].yld_func = 0.0;
+  }
+  const bool nonlinear_update = iter >= 1 || m->extrapolated_du != 0;
+  const bool adaptive = m->adaptive_flag != 0 && step > 1;
+  const bool allow_cut = adaptive && (iprop(m, 24, bi.felem) & 2) != 0;    // rknstr.f:1213-1214
+  if (nonlinear_update) {
+    const bool process_block = mm03p(step, span, pt.data(), P.data());
+    if (process_block) {
+      for (int i = 0; i < span; ++i) {
+        if (pt[i].null_point) continue;
+        if (!pt[i].nonlinear_flag) continue;
+        if (mm03(P[i], m->dt, pt[i])) {
+          if (allow_cut) { material_cut_step = true; return; }
+          *fatal = 7;                                                       // abort_job
+          return;
+        }
+      }
+    }
+    for (int i = 0; i < span; ++i) {
+      double D[6][6];
+      cnst3(iter, P[i], pt[i].stress_n1_elas, pt[i].history, pt[i].history1, D);
+      for (int r = 1; r <= 6; ++r) for (int c = 1; c <= 6; ++c) Q6(cep, i, r, c) = D[r - 1][c - 1];
+    }
+    for (int i = 0; i < span; ++i) {
+      for (int k = 0; k < 9; ++k) urcs_n1[(size_t)k * mxvl + i] = pt[i].stress_n1[k];   // drive_03_update_c
+      for (int k = 0; k < HIST; ++k) hist1[(size_t)k * span + i] = pt[i].history1[k];
+      for (int k = 0; k < 6; ++k) rtse[(size_t)k * mxvl + i] = pt[i].stress_n1_elas[k];
+    }
+  } else {
+    // drive_03_update_b / _e: linear-elastic [D], no history update
+    const double one = 1.0, two = 2.0;
+    for (int i = 0; i < span; ++i) {
+      const double e = P[i].e, nu = P[i].nu;
+      const double c1 = (e / ((one + nu) * (one - two * nu)));
+      const double c2 = (one - nu) * c1;
+      const double c3 = ((one - two * nu) / two) * c1;
+      const double c4 = nu * c1;
+      Q6(cep, i, 1, 1) = c2; Q6(cep, i, 2, 2) = c2; Q6(cep, i, 3, 3) = c2;
+      Q6(cep, i, 4, 4) = c3; Q6(cep, i, 5, 5) = c3; Q6(cep, i, 6, 6) = c3;
+      Q6(cep, i, 1, 2) = c4; Q6(cep, i, 1, 3) = c4; Q6(cep, i, 2, 1) = c4;
+      Q6(cep, i, 3, 1) = c4; Q6(cep, i, 2, 3) = c4; Q6(cep, i, 3, 2) = c4;
+    }
+    for (int k = 1; k <= 6; ++k)
+      for (int i = 0; i < mxvl; ++i) V2(urcs_n1, i, k) = V2(urcs_n, i, k);
+    for (int k = 1; k <= 6; ++k)
+      for (int mm = 1; mm <= 6; ++mm)
+        for (int i = 0; i < span; ++i)
+          V2(urcs_n1, i, k) = V2(urcs_n1, i, k) + Q6(cep, i, mm, k) * pt[i].deps[mm - 1];
+  }
+  store_cep(span, gpn, gbl_cep, cep.data());
+}
+
 // drive_10_update (rstgp1.f:4327-4513) -> mm10 (mm10_a.f:29).  The per-Gauss-point crystal update
 // is the statement-for-statement restatement in w3d_oracle_mm10.h; this wrapper supplies the
 // reference's block-local layouts.
@@ -445,6 +536,10 @@ static void rstgp(const w3do_model *m, const BlockInfo &bi, LocalWork &lw, int g
       break;
     case 5:
       drive_05_update(m, bi, lw, gpn, step, iter, uddt.data(), gbl_cep, material_cut_step, fatal);
+      if (material_cut_step || *fatal) return;
+      break;
+    case 3:
+      drive_03_update(m, bi, lw, gpn, step, iter, uddt.data(), gbl_cep, material_cut_step, fatal);
       if (material_cut_step || *fatal) return;
       break;
     case 10:

@@ -192,7 +192,7 @@ static void do_nlek_block(const w3do_model *m, const BlockPtrs &bp, int blk, int
     *fatal = 4;
     return;
   }
-  if (bi.mat_type != 1 && bi.mat_type != 5 && bi.mat_type != 10) {
+  if (bi.mat_type != 1 && bi.mat_type != 3 && bi.mat_type != 5 && bi.mat_type != 10) {   // drive_03_cnst = extract_D_symmetric (gptns1.f:939-950)
     *fatal = 3;
     return;
   }

@@ -19,6 +19,7 @@
 #include "w3d_stress_kernel.cuh"
 #include "w3d_tanstf_kernel.cuh"
 #include "w3d_cp_kernel.h"
+#include "w3d_mm03_kernel.h"
 #include "w3d_assemble_data.h"
 #include "w3d_residual_data.h"
 #include <cstdint>
@@ -57,6 +58,8 @@ struct Segment {
          *hist_n1 = nullptr, *elem_vol = nullptr, *partials = nullptr;
   // crystal plasticity (mm10)
   double *d_cprops = nullptr, *scratch = nullptr;
+  int mm03_allow_cut = 0;
+  int2 *d_mm03_blocks = nullptr;     // mm03: (first slot, span) of every element block of the segment
   int ncrystals = 0, nslip = 0, num_hard = 0, o_gradfe = 0, o_Rp0 = 0;
   bool cp_fast = false, cp_taul = false;   // fast lattice-frame kernel (w3d_mm10_fast.h); k_0 != 0
   std::vector<char> cp_consts;             // its crystal-type table (host copy, uploaded per launch)
@@ -245,7 +248,7 @@ void free_all(w3d_engine *h) {
     cudaFree(s.eps_n); cudaFree(s.eps_n1); cudaFree(s.urcs_n); cudaFree(s.urcs_n1);
     cudaFree(s.rot_n); cudaFree(s.rot_n1); cudaFree(s.cep); cudaFree(s.hist_n);
     cudaFree(s.hist_n1); cudaFree(s.elem_vol); cudaFree(s.partials);
-    cudaFree(s.d_cprops); cudaFree(s.scratch);
+    cudaFree(s.d_cprops); cudaFree(s.scratch); cudaFree(s.d_mm03_blocks);
   }
   h->assembly.release();
   h->residual.release();
@@ -325,8 +328,19 @@ int create_impl(w3d_engine *h) {
     if (!b.owned) continue;
     if (b.elem_type != 2 || b.nnode != 8 || b.ndof != 3 || b.ngp != 8)
       return fail(W3D_ERR_UNSUPPORTED, "block %d: element type %d (%d nodes, %d points): only hex8 l3disop 2x2x2", blk + 1, b.elem_type, b.nnode, b.ngp);
-    if (b.mat_type != 1 && b.mat_type != 5 && b.mat_type != 10)
-      return fail(W3D_ERR_UNSUPPORTED, "block %d: material model %d not built yet (mm01, mm05, mm10)", blk + 1, b.mat_type);
+    if (b.mat_type != 1 && b.mat_type != 3 && b.mat_type != 5 && b.mat_type != 10)
+      return fail(W3D_ERR_UNSUPPORTED, "block %d: material model %d not built yet (mm01, mm03, mm05, mm10)", blk + 1, b.mat_type);
+    if (b.mat_type == 3) {
+      // the mises path of mm03: no voids, no nucleation, no segmental curves (mm03.f:2163, rknstr.f:816-819)
+      if (b.hist_size != 15) return fail(W3D_ERR_CONFIG, "block %d: mm03 history size %d != 15", blk + 1, b.hist_size);
+      for (int i = 0; i < b.span; ++i) {
+        const int el = b.felem + i;
+        if (rprop(c, 26, el) > 0.0f || (iprop(c, 30, el) & 1))
+          return fail(W3D_ERR_UNSUPPORTED, "block %d element %d: Gurson material (f0 > 0 or nucleation) not built; mm03 mises only", blk + 1, el);
+        if (iprop(c, 24, el) & 4)
+          return fail(W3D_ERR_UNSUPPORTED, "block %d element %d: segmental stress-strain curves not built", blk + 1, el);
+      }
+    }
     if (b.mat_type == 5) {
       if (b.hist_size != 14) return fail(W3D_ERR_CONFIG, "block %d: mm05 history size %d != 14", blk + 1, b.hist_size);
       if (!c.matprp || b.matnum < 1 || b.matnum > c.nmat || c.mxmtpr < 64)
@@ -407,6 +421,7 @@ int create_impl(w3d_engine *h) {
     shape_tables(tab3);
     CUDA_TRY(cudaMemcpyToSymbol(c_shape, tab3, sizeof tab3));
     CUDA_TRY(mm05_set_shape_table(&tab3[0][0][0], sizeof tab3));
+    CUDA_TRY(mm03_set_shape_table(&tab3[0][0][0], sizeof tab3));
   }
 
   // ---- per-segment tables and state
@@ -447,6 +462,10 @@ int create_impl(w3d_engine *h) {
         p[3] = rprop(c, 15, elem); p[4] = rprop(c, 23, elem); p[5] = lprop(c, 17, elem) ? 1.0f : 0.0f;
         if (b.mat_type == 5)   // setup_mm05_rknstr (rknstr.f:1234-1317): mm05_props = matprp(55:64)
           for (int k = 0; k < 10; ++k) p[6 + k] = c.matprp[(size_t)(b.matnum - 1) * c.mxmtpr + 54 + k];
+        if (b.mat_type == 3) {   // setup_mm03_rknstr (rknstr.f:1142-1215)
+          p[6] = rprop(c, 21, elem); p[7] = rprop(c, 20, elem); p[8] = rprop(c, 22, elem);
+          p[9] = rprop(c, 27, elem); p[10] = rprop(c, 28, elem); p[11] = rprop(c, 29, elem);
+        }
       }
       for (int w = 0; w <= W3D_ELEM_VOL; ++w) {
         const long long n = block_doubles(w, b);
@@ -500,6 +519,17 @@ int create_impl(w3d_engine *h) {
     CUDA_TRY(cudaMemcpy(sg.d_edest, ed.data(), sizeof(int32_t) * ed.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(dalloc(&sg.d_cdest, cdv.size()));
     CUDA_TRY(cudaMemcpy(sg.d_cdest, cdv.data(), sizeof(int32_t) * cdv.size(), cudaMemcpyHostToDevice));
+    if (sg.mat_type == 3) {
+      std::vector<int2> bd;
+      for (int blk : sg.blocks) bd.push_back(make_int2(h->blocks[blk].slot0, h->blocks[blk].span));
+      CUDA_TRY(cudaMalloc((void **)&sg.d_mm03_blocks, sizeof(int2) * bd.size()));
+      CUDA_TRY(cudaMemcpy(sg.d_mm03_blocks, bd.data(), sizeof(int2) * bd.size(), cudaMemcpyHostToDevice));
+      CUDA_TRY(dalloc(&sg.scratch, (size_t)16 * sg.nslots * 8));
+      // allow_cut (rknstr.f:1213-1214): bit 2 of iprops(24) of the material; one flag per segment
+      sg.mm03_allow_cut = 1;
+      for (int blk : sg.blocks)
+        if (!(iprop(c, 24, h->blocks[blk].felem) & 2)) sg.mm03_allow_cut = 0;
+    }
     CUDA_TRY(dalloc(&sg.d_eprops, ep.size()));
     CUDA_TRY(cudaMemcpy(sg.d_eprops, ep.data(), sizeof(float) * ep.size(), cudaMemcpyHostToDevice));
     const size_t ng = (size_t)sg.ng;
@@ -526,6 +556,7 @@ int create_impl(w3d_engine *h) {
   CUDA_TRY((stress_prepare_device<10, 1>()));
   CUDA_TRY((stress_prepare_device<10, 2>()));
   CUDA_TRY(mm05_prepare_device());
+  CUDA_TRY(mm03_prepare_device());
   CUDA_TRY(mm10_prepare_device());
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaGetLastError());
@@ -657,6 +688,19 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
       if (sg.cp_fast) CUDA_TRY(launch_mm10_fast(ca, sg.ncta, sg.cp_consts.data(), sg.cp_taul, h->stream));
       else CUDA_TRY(launch_mm10(ca, sg.ncta, h->stream));
       CUDA_TRY((launch_stress<10, 2>(sg, a, h->stream)));
+      h->launches += 3;
+    } else if (sg.mat_type == 3) {
+      // drive_03_update: kinematics -> k_mm03 (one CTA per element block) -> internal force
+      a.scratch = sg.scratch;
+      CUDA_TRY(launch_stress_mm03(sg.geonl, sg.bbar, 1, sg.ncta, a, h->stream));
+      Mm03Args ma{};
+      ma.blocks = sg.d_mm03_blocks; ma.eprops = sg.d_eprops; ma.hist_n = sg.hist_n; ma.urcs_n = sg.urcs_n;
+      ma.scratch = sg.scratch; ma.hist_n1 = sg.hist_n1; ma.urcs_n1 = sg.urcs_n1; ma.cep = sg.cep;
+      ma.flags = h->d_flags; ma.ng = sg.ng; ma.dt = h->dt; ma.step = step; ma.iter = iter;
+      ma.allow_cut = (a.adaptive && sg.mm03_allow_cut) ? 1 : 0;
+      ma.nonlinear_update = a.nonlinear_update;
+      CUDA_TRY(launch_mm03(ma, (int)sg.blocks.size(), h->stream));
+      CUDA_TRY(launch_stress_mm03(sg.geonl, sg.bbar, 2, sg.ncta, a, h->stream));
       h->launches += 3;
     } else if (sg.mat_type == 5) {
       CUDA_TRY(launch_stress_mm05(sg.geonl, sg.bbar, sg.ncta, a, h->stream));

@@ -541,6 +541,11 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
       for (int q = 0; q < 9; ++q) cgn1[q] = 0.0;
     }
   }
+  if (MAT == 3) {
+    // PHASE 2: stresses at n+1 and [D] come from k_mm03 (w3d_mm03.cu)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) cgn1[k] = a.urcs_n1[k * ng + g];
+  }
   if (MAT == 10) {
     // PHASE 2: stresses at n+1 come from k_mm10
 #pragma unroll

@@ -23,7 +23,7 @@ MXELPR = 43    # param_def: mxelpr
 MXMTPR = 300   # param_def: mxmtpr
 NSTR = 6
 NSTRS = 9
-HIST_SIZE = {1: 11, 5: 14}   # mm01.f:976, mm05.f:4136
+HIST_SIZE = {1: 11, 3: 15, 5: 14}   # mm01.f:976, mm03.f:1623-1640, mm05.f:4136
 CEP_SIZE = 21
 
 # WARP3D hex8 (l3disop) node ordering in (xi, eta, zeta) -- src/derivs.f:283-343
@@ -240,6 +240,12 @@ def build_hex8_model(coords, incid, materials=None, elem_material=None, geonl=Tr
         matprp[mi, 3] = mat.tan_e
         matprp[mi, 4] = mat.yld_pt
         matprp[mi, 8] = mat.mat_type
+        if mat.mat_type == 3:
+            # `mises` card (inmat.f:816-823, defaults :307-327): m_power, n_power, ref_eps rows
+            # 10-12; f0 = 0, q1 = q2 = q3 = 0, no nucleation
+            matprp[mi, 9] = mat.extra.get("m_power", 0.0)
+            matprp[mi, 10] = mat.extra.get("n_power", 0.0)
+            matprp[mi, 11] = mat.extra.get("ref_eps", 0.0)
         for row, val in mat.extra.get("matprp", {}).items():
             matprp[mi, row - 1] = val
     props = np.zeros((noelem, MXELPR), dtype=np.int32)
@@ -264,6 +270,14 @@ def build_hex8_model(coords, incid, materials=None, elem_material=None, geonl=Tr
     props[:, 18] = -1 if bbar else 0
     props[:, 22] = _f32_bits(matprp[mi, 4])
     props[:, 24] = matprp[mi, 8].astype(np.int32)
+    is3 = props[:, 24] == 3
+    if is3.any():      # elprp.f:869-897: the rows mm03 reads
+        d = matprp[mi, 11].astype(np.float64)
+        eta32 = np.where(d != 0.0, 1.0 / np.where(d != 0.0, d, 1.0), 0.0).astype(np.float32)
+        for word, col in ((19, matprp[mi, 9]), (20, matprp[mi, 10]), (21, eta32), (25, matprp[mi, 13]),
+                          (26, matprp[mi, 14]), (27, matprp[mi, 15]), (28, matprp[mi, 16]),
+                          (30, matprp[mi, 18]), (31, matprp[mi, 19]), (32, matprp[mi, 20])):
+            props[:, word] = np.where(is3, _f32_bits(col.astype(np.float32)), props[:, word])
     props[:, 37] = elem_material
     props[:, 41] = -1
 
