@@ -561,10 +561,106 @@ def engine_arm(args):
                     peak_kind="measured DFMA throughput (tools/fp64_peak.cu, profiles/r01_fp64_peak.json)",
                     note="algorithmic flops = per-operation counts of the algorithm as implemented "
                          "(DESIGN.md 3.3) x operation counters of the CPU restatement on a sub-box")
-        print(json.dumps(line), flush=True)
     de.close()
+    # ---- BASELINE.json configs[4] (1 M-element mm10 polycrystal) on the same ranks: a sub-object of
+    #      the same line, so the 1/2/4/8-GPU runs of the default command carry its scaling curve too
+    second = None
+    if args.workload == "hex8_2m_mm01" and not args.no_mm10:
+        try:
+            second = config5_leg(args, rank, world, local)
+        except Exception as ex:          # never lose the headline line to the secondary leg
+            second = dict(workload="hex8_1m_mm10", error=f"{type(ex).__name__}: {ex}")
+    if rank == 0:
+        if second is not None:
+            line["mm10"] = second
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def config5_leg(args, rank, world, local):
+    """hex8_1m_mm10 (BASELINE.json configs[4]) with the blocks partitioned over the same ranks:
+    K timed Newton iterations (stress pass = kinematics + k_mm10f + internal force, then tangent),
+    bracketed like the headline workload; max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from warp3d_b200.distributed import DomainEngine
+    name = "hex8_1m_mm10"
+    model, du_step, nprep = make_workload(name)
+    wd = workload_description(name)
+    TS = nprep + 1
+    de = DomainEngine(model, rank, world, device=local, assign_slabs=True, exchange=args.exchange,
+                      bcast_inputs=world > 1)
+    eng = de.engine
+    nodof = model.nodof
+    u_h = torch.zeros(nodof, dtype=torch.float64, pin_memory=True).numpy()
+    du_h = torch.empty(nodof, dtype=torch.float64, pin_memory=True).numpy()
+    ifv_h = torch.empty(nodof, dtype=torch.float64, pin_memory=True).numpy()
+    du_h[:] = du_step
+    for step in range(1, nprep + 1):
+        de.drive_eps_sig_internal_forces(step, 0, u_h, du_h, ifv_h)
+        de.drive_eps_sig_internal_forces(step, 1, u_h, du_h, ifv_h)
+        de.update(); de.adaptive_save()
+        u_h[:] = u_h + du_step
+    de.drive_eps_sig_internal_forces(TS, 0, u_h, du_h, ifv_h)
+    _, sc = de.drive_eps_sig_internal_forces(TS, 1, u_h, du_h, ifv_h)
+    if sc["material_cut_step"]:
+        de.close()
+        return dict(workload=name, error="the workload asked for a step cut")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    S = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+    K = max(3, min(args.steps, 10))
+    for _ in range(3):
+        de.eps_sig_ifv_resident(TS, 1, exchange=args.exchange); de.tanstf_resident(TS, 1)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
+    l0 = eng.launch_count
+    ev[0].record(S)
+    for k in range(K):
+        de.eps_sig_ifv_resident(TS, 1, exchange=args.exchange)
+        ev[2 * k + 1].record(S)
+        de.tanstf_resident(TS, 1)
+        ev[2 * k + 2].record(S)
+    barrier()
+    launches = eng.launch_count - l0
+    t = torch.tensor([ev[0].elapsed_time(ev[-1]) / K,
+                      float(np.mean([ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(K)])),
+                      float(np.mean([ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(K)]))],
+                     dtype=torch.float64, device="cuda")
+    nl = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)
+    ms, t_stress, t_tan = [float(x) for x in t.tolist()]
+    nel_own = eng.n_owned_elems
+    de.close()
+    ngp = model.noelem * 8
+    out = dict(workload=name, config="BASELINE.json configs[4]", elements=model.noelem, gauss_points=ngp,
+               material=wd["material"], n_gpus=world, steps=K, warmup=3, ms_per_step=ms,
+               value=ngp / (ms * 1e-3), unit=UNIT, scaling="strong",
+               stress_pass=dict(ms=t_stress, gp_updates_per_s=ngp / (t_stress * 1e-3),
+                                kernels="k_eps_sig_ifv<10,phase 1> + k_mm10f + k_eps_sig_ifv<10,phase 2>"),
+               stiffness_pass=dict(ms=t_tan), gpu_launches=int(nl.item()),
+               plastic_check=dict(plastic_work=sc["plastic_work"], internal_energy=sc["internal_energy"]))
+    pk = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
+    if rank == 0 and world == 1 and not args.no_cpu and os.path.exists(pk):
+        with open(pk) as f:
+            fp64_peak = json.load(f).get("dfma_tflops")
+        ops = mm10_operation_counts(name)
+        fl = mm10_flops_per_gp(ops)
+        tf = nel_own * 8 * fl / (t_stress * 1e-3) / 1e12
+        out["roofline"] = dict(bound="fp64", achieved=tf, peak=fp64_peak, unit="TFLOP/s", frac=tf / fp64_peak,
+                               flops_per_gp=fl, launch_ms=t_stress,
+                               peak_kind="measured DFMA throughput of tools/fp64_peak.cu (own microbenchmark, "
+                                         "profiles/r01_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure",
+                               note="algorithmic flops = per-operation counts of the algorithm as implemented x "
+                                    "operation counters of the CPU restatement on a sub-box")
+    return out
 
 
 def main():
@@ -575,6 +671,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="hex8_2m_mm01", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-mm10", action="store_true",
+                    help="skip the hex8_1m_mm10 sub-object (BASELINE.json configs[4]) of the default workload")
     ap.add_argument("--exchange", default="neighbours", choices=["neighbours", "full"],
                     help="N>1: send/recv of the shared dofs between neighbouring domains, or all-reduce of the whole ifv "
                          "vector; the other mode is timed as well and reported as exchange_variant")
