@@ -290,7 +290,7 @@ def reference_arm(args):
                                   stress_gp_per_s=ngp / t_s, stiffness_elem_per_s=m.noelem / t_k),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def engine_arm(args):
@@ -573,7 +573,7 @@ def engine_arm(args):
     if rank == 0:
         if second is not None:
             line["mm10"] = second
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -663,6 +663,29 @@ def config5_leg(args, rank, world, local):
     return out
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries below us write to file descriptor 1 on their
+    own (NCCL prints its version banner there whenever the harness sets NCCL_DEBUG, whatever
+    NCCL_DEBUG_FILE says): keep a private duplicate of the real stdout for the result line and
+    point descriptor 1 at stderr for everybody else, child processes included."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -677,6 +700,7 @@ def main():
                     help="N>1: send/recv of the shared dofs between neighbouring domains, or all-reduce of the whole ifv "
                          "vector; the other mode is timed as well and reported as exchange_variant")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         reference_arm(args)
     else:
