@@ -12,6 +12,15 @@
  * NOT restated (the product refuses the same inputs): Gurson branch (mm03s and friends),
  * segmental curves (mm03sc), temperature dependence, fgm properties, killed elements.
  *
+ * PARITY STATUS: **parity unpinned** against Fortran output.  The reference ships no golden vectors
+ * for mm03, and every known answer of its verification suite that uses a `mises` material on hex8
+ * (test18, test57, test88, test89, testH/I: verification/run_tests.py) is a J-integral or a crack-
+ * growth result, i.e. needs the domain integral / element extinction that stay with the reference;
+ * the Fortran cannot be compiled here.  What stands in: line-by-line transcription with citations,
+ * the physical checks of tests/test_mm03_core.py (yield surface, uniaxial power-law curve, finite-
+ * difference tangent, patch test) and the function-level dump replay of fortran/w3d_dump_hook.f +
+ * tools/compare_fortran_dump.py for whoever has ifort.
+ *
  * Literal oddities kept on purpose:
  *  - mm03's `third` is the REAL*4 literal 0.3333333333 widened (0.3333333432674408), so the
  *    mean stress removed in the radial return is off by 3e-8 relative (:2130-2131, :3064-3074);
