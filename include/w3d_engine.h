@@ -288,7 +288,13 @@ int32_t w3d_residual_set_loads(w3d_engine *h, const w3d_residual_loads *loads);
  * forces of the last stress pass and the du it was given.  res: host (nodof) or NULL to leave it
  * on the device (w3d_residual_device).  res(i) follows the reference's expression and operation
  * order; the three sums are fixed-order tree sums (run-to-run reproducible, equal to the
- * reference's sequential sums to rounding); num_term_loads and res_max_dof are exact.             */
+ * reference's sequential sums to rounding); num_term_loads and res_max_dof are exact.
+ * Several domains (w3d_comm_init): collective.  After the neighbour exchange a rank's internal
+ * forces are complete only on the dofs its own blocks touch, so every rank evaluates the dofs it
+ * OWNS (w3d_comm_owned: the ranks' owned sets tile the vector), res is zero elsewhere -- the sum
+ * of the ranks' res vectors is the structure residual -- and the norms come back summed over the
+ * ranks (one small all-reduce), the same on every rank.  After the all-reduce mode every rank
+ * holds the whole force vector and evaluates all of it.                                           */
 int32_t w3d_residual(w3d_engine *h, int32_t iter, double dt, double nbeta, double *res,
                      w3d_residual_norms *out);
 int32_t w3d_residual_device(w3d_engine *h, double **d_res);

@@ -34,6 +34,15 @@ def main():
     orc.eps_sig_ifv(so, 1, 0, u, du)
     f_ref, sc_ref = orc.eps_sig_ifv(so, 1, 1, u, du)
     scale = np.abs(f_ref).max()
+    # one-domain residual and norms from the CPU restatement (upres + cvtest residual loop)
+    cst = np.zeros(m.nodof, dtype=np.int32)
+    xs = m.c.reshape(-1, 3)[:, 0]
+    cst.reshape(-1, 3)[xs <= xs.min() + 1e-9] = 1
+    rng = np.random.default_rng(3)
+    pbar = scale * 0.3 * rng.normal(size=m.nodof); load = scale * 0.1 * rng.normal(size=m.nodof)
+    from oracle import oracle_py as op
+    res_ref, nrm_ref = op.upres(cst, pbar, load, f_ref, du, 1.0, 0.25)
+    nrm_ref.update(op.cvtest_residual(res_ref))
     ok = True
     for exchange, bcast in (("neighbours", False), ("full", False), ("neighbours", True)):
         de = DomainEngine(m, rank, world, device=local, exchange=exchange, bcast_inputs=bcast)
@@ -54,11 +63,24 @@ def main():
         fo, _ = de.drive_eps_sig_internal_forces(1, 1, uu, dd, owned_only=True)
         e3 = float(np.abs(fo - f_ref[first - 1:first - 1 + n])[own[first - 1:first - 1 + n]].max() / scale)
         es = max(abs(sc[k] - sc_ref[k]) / abs(sc_ref[k]) for k in ("internal_energy", "plastic_work", "sum_ifv"))
+        # structure residual and its norms (w3d_residual is collective with several domains): the
+        # norms equal the one-domain ones on every rank, the ranks' res vectors add up to the
+        # structure residual (neighbour mode: each rank evaluates the dofs it owns)
+        de.engine.residual_set_loads(cst, pbar=pbar, load=load)
+        res, nrm = de.engine.residual(1, 1.0, 0.25)
+        rsum = torch.from_numpy(res.copy()).cuda()
+        if exchange == "neighbours":
+            dist.all_reduce(rsum)
+        er = float(np.abs(rsum.cpu().numpy() - res_ref).max() / np.abs(res_ref).max())
+        en = max(abs(nrm[k] - nrm_ref[k]) / abs(nrm_ref[k]) for k in ("norm_res", "mgload", "sum_loads", "res_max"))
+        good_res = (er < 1e-10 and en < 1e-12 and nrm["num_term_loads"] == nrm_ref["num_term_loads"]
+                    and nrm["res_max_dof"] == nrm_ref["res_max_dof"])
         good = (max(e1, e2, e3) < 1e-10 and es < 1e-10 and sc["num_term_ifv"] == sc_ref["num_term_ifv"]
-                and not sc["material_cut_step"])
+                and not sc["material_cut_step"] and good_res)
         ok = ok and good
         print(f"rank {rank}/{world} exchange={exchange} bcast={bcast}: touched {e1:.1e} owned-concat {e2:.1e} "
-              f"owned-range {e3:.1e} scalars {es:.1e} num_term {sc['num_term_ifv']} -> {'OK' if good else 'MISMATCH'}",
+              f"owned-range {e3:.1e} scalars {es:.1e} num_term {sc['num_term_ifv']} residual {er:.1e} norms {en:.1e} "
+              f"max dof {nrm['res_max_dof']} -> {'OK' if good else 'MISMATCH'}",
               flush=True)
         de.close()
     dist.barrier()

@@ -89,6 +89,12 @@ struct CommData {
   long long ntot = 0;
   int32_t *d_idx = nullptr;
   double *d_send = nullptr, *d_recv = nullptr, *d_red = nullptr;   // d_red[8]
+  // dofs this rank OWNS (lowest domain among those whose blocks touch the dof; untouched dofs go
+  // to rank 0): the ranks' owned sets tile 1..nodof, so sums over owned dofs all-reduce to the
+  // structure's (w3d_residual after a neighbour exchange)
+  std::vector<uint8_t> owned;        // host, from create
+  uint8_t *d_owned = nullptr;
+  double *d_rred = nullptr;          // 4 sums + 3 doubles per rank for the residual norms
   // the exchange runs on its own stream so that the stiffness pass (which reads neither ifv nor
   // the scalars) overlaps it; whoever touches ifv / the scalars next joins first (comm_join)
   cudaStream_t stream = nullptr;
@@ -254,6 +260,7 @@ void free_all(w3d_engine *h) {
   h->residual.release();
   cudaFree(h->d_c); cudaFree(h->d_u); cudaFree(h->d_ifv);
   cudaFree(h->comm.d_idx); cudaFree(h->comm.d_send); cudaFree(h->comm.d_recv); cudaFree(h->comm.d_red);
+  cudaFree(h->comm.d_owned); cudaFree(h->comm.d_rred);
   if (h->comm.stream) cudaStreamDestroy(h->comm.stream);
   if (h->comm.ev_start) cudaEventDestroy(h->comm.ev_start);
   if (h->comm.ev_done) cudaEventDestroy(h->comm.ev_done);
@@ -404,6 +411,9 @@ int create_impl(w3d_engine *h) {
     const int prc = comm_plan(c, c.myid, h->comm.counts, h->comm.dofs, perr);
     if (prc != W3D_OK && prc != W3D_ERR_UNSUPPORTED) return fail(prc, "interface plan: %s", perr.c_str());
     if (prc == W3D_ERR_UNSUPPORTED) { h->comm.counts.clear(); h->comm.dofs.clear(); h->comm.exchange = 0; }
+    h->comm.owned.assign((size_t)c.nodof, 0);
+    const int orc = w3d_comm_owned(&c, c.myid, h->comm.owned.data());
+    if (orc != W3D_OK) return fail(orc, "ownership of the dofs: block table inconsistent");
   }
 
   // ---- global vectors
@@ -1028,6 +1038,11 @@ int32_t w3d_comm_init(w3d_engine *h, const uint8_t id[128], int32_t rank, int32_
     CUDA_TRY(dalloc(&cm.d_recv, (size_t)cm.ntot));
     CUDA_TRY(cudaMemcpy(cm.d_idx, cm.dofs.data(), sizeof(int32_t) * cm.ntot, cudaMemcpyHostToDevice));
   }
+  if (!cm.owned.empty()) {
+    CUDA_TRY(cudaMalloc((void **)&cm.d_owned, cm.owned.size()));
+    CUDA_TRY(cudaMemcpy(cm.d_owned, cm.owned.data(), cm.owned.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(dalloc(&cm.d_rred, 4 + 3 * (size_t)nranks));
+  }
   int nnb = 0;
   for (long long n : cm.counts) nnb += n > 0;
   fprintf(stderr, "w3d_comm: rank %d of %d on device %d, %d neighbour domain(s), %lld shared dofs of %d\n", rank, nranks,
@@ -1074,7 +1089,8 @@ int32_t w3d_comm_owned(const w3d_engine_config *cfg, int32_t rank, uint8_t *owne
     }
     tab += (long long)totdof * span;
   }
-  for (int d = 0; d < c.nodof; ++d) owned[d] = (low[d] == rank) ? 1 : 0;
+  // a dof no block touches (an unconnected node) belongs to rank 0
+  for (int d = 0; d < c.nodof; ++d) owned[d] = (low[d] == rank || (low[d] == np && rank == 0)) ? 1 : 0;
   return W3D_OK;
 }
 int32_t w3d_download_ifv(w3d_engine *h, double *ifv) {

@@ -23,6 +23,7 @@ struct ResidualArgs {
   const double *pbar, *load, *mdiag, *vel, *acc, *cf, *dlag, *du, *ifv;
   double *res;
   ResidualPartial *part;
+  const unsigned char *owned;   // several domains, neighbour exchange: the dofs this rank owns (else null)
 };
 
 __device__ __forceinline__ double ld0(const double *v, int i) { return v ? v[i] : 0.0; }
@@ -72,6 +73,10 @@ __device__ __forceinline__ void cta_reduce(ResidualPartial &p, ResidualPartial *
 __global__ void __launch_bounds__(RES_TPB) k_residual(const ResidualArgs a) {
   ResidualPartial p{0.0, 0.0, 0.0, 0.0, 0, 0, 0, 0.0};
   for (int i = blockIdx.x * RES_TPB + threadIdx.x; i < a.nodof; i += gridDim.x * RES_TPB) {
+    if (a.owned && !a.owned[i]) {   // another rank's dof: its internal force is not complete here
+      a.res[i] = 0.0;
+      continue;
+    }
     const bool constrained = a.cstmap[i] != 0;
     const double du = a.du[i], ifv = a.ifv[i], md = ld0(a.mdiag, i), cf = ld0(a.cf, i);
     const double inertia = __dmul_rn(__dmul_rn(md, du), a.nfac);
@@ -139,6 +144,29 @@ int res_upload(w3d_engine *h, T **dst, const T *src, size_t n) {
   return W3D_OK;
 }
 
+// several domains: the norms of the structure from the ranks' owned parts.  [0..3] = the three sums
+// and the number of load terms (added by ncclAllReduce), then one (max |res|, dof, res) triple per
+// rank, zero except the rank's own (the same all-reduce gathers them)
+__global__ void k_residual_pack(const ResidualPartial *p, double *red, int rank, int nranks) {
+  for (int k = threadIdx.x; k < 4 + 3 * nranks; k += blockDim.x) red[k] = 0.0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    red[0] = p->sum_res2; red[1] = p->mgload2; red[2] = p->sum_loads; red[3] = (double)p->num_term_loads;
+    red[4 + 3 * rank] = p->max_abs; red[5 + 3 * rank] = (double)p->max_dof; red[6 + 3 * rank] = p->res_at_max;
+  }
+}
+__global__ void k_residual_unpack(const double *red, int nranks, ResidualPartial *p) {
+  ResidualPartial t{red[0], red[1], red[2], 0.0, (long long)red[3], 0, 0, 0.0};
+  for (int r = 0; r < nranks; ++r) {     // cvtest.f:70-73 over the whole vector: largest, lowest dof among equals
+    const double ab = red[4 + 3 * r];
+    const int dof = (int)red[5 + 3 * r];
+    if (dof != 0 && (t.max_dof == 0 || ab > t.max_abs || (ab == t.max_abs && dof < t.max_dof))) {
+      t.max_abs = ab; t.max_dof = dof; t.res_at_max = red[6 + 3 * r];
+    }
+  }
+  *p = t;
+}
+
 }  // namespace
 
 extern "C" {
@@ -190,11 +218,24 @@ int32_t w3d_residual(w3d_engine *h, int32_t iter, double dt, double nbeta, doubl
   a.cf = R.d_cf; a.dlag = R.d_dlag; a.du = h->d_du; a.ifv = h->d_ifv;
   a.res = R.d_res;
   a.part = R.d_part;
+  // several domains after a neighbour exchange: every rank evaluates the dofs it owns (their
+  // internal forces are complete there) and the norms are summed over the ranks; after the
+  // all-reduce mode every rank holds the whole vector and evaluates all of it
+  const bool split = h->comm.comm && h->comm.exchange == 1 && h->comm.d_owned;
+  a.owned = split ? h->comm.d_owned : nullptr;
   const int ncta = std::min((a.nodof + RES_TPB - 1) / RES_TPB, RES_MAX_CTAS);
   k_residual<<<ncta, RES_TPB, 0, h->stream>>>(a);
   k_residual_finish<<<1, RES_TPB, 0, h->stream>>>(R.d_part, ncta, R.d_res);
   h->launches += 2;
   CUDA_TRY(cudaGetLastError());
+  if (split) {
+    CommData &cm = h->comm;
+    k_residual_pack<<<1, 64, 0, h->stream>>>(R.d_part + RES_MAX_CTAS, cm.d_rred, cm.rank, cm.nranks);
+    NCCL_TRY(nccl_api()->all_reduce(cm.d_rred, cm.d_rred, 4 + 3 * (size_t)cm.nranks, NCCL_FLOAT64, NCCL_SUM, cm.comm, h->stream));
+    k_residual_unpack<<<1, 1, 0, h->stream>>>(cm.d_rred, cm.nranks, R.d_part + RES_MAX_CTAS);
+    h->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  }
   CUDA_TRY(cudaMemcpyAsync(R.h_part, R.d_part + RES_MAX_CTAS, sizeof(ResidualPartial), cudaMemcpyDeviceToHost, h->stream));
   if (res) CUDA_TRY(cudaMemcpyAsync(res, R.d_res, sizeof(double) * a.nodof, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
