@@ -47,6 +47,8 @@ WORKLOADS = {
     # BASELINE.json configs[1]: the reference's fracture_models/seb deck with mm01 (17 318 hex8, the
     # deck's 137 user blocks and 2 domains, consistent q off); mesh from tests/golden/seb_deck.npz
     "seb_mm01": (None, "seb", None),
+    # the same deck AS SHIPPED: material `mises e 200e9 nu 0.3 yld_pt 400e6 n_power 10` = mm03
+    "seb_mm03": (None, "seb", None),
 }
 # mm10 workload: fcc (12 slip systems), Voce hardening with the property values of
 # verification/test82/voche_model/warp3d_voche.inp:6-10, one crystal per element, Kocks angles
@@ -63,7 +65,7 @@ def make_workload(name, dims=None):
     dims = dims or wdims
     if kind == "seb":
         from warp3d_b200 import seb_bend_field, seb_model
-        m, cons = seb_model()
+        m, cons = seb_model(material="mises" if name == "seb_mm03" else "bilinear")
         m.deck_constraints = cons
         # one converged step of the bending field at 0.75 of the first-yield scale, then the timed
         # iteration adds the same again: ~90 % of the points are plastic in it
@@ -88,6 +90,11 @@ def make_workload(name, dims=None):
 
 def workload_description(name):
     kind = WORKLOADS[name][1]
+    if kind == "seb" and name == "seb_mm03":
+        # 15 history words instead of 11, and the three-launch structure: 2 x 128 B of scratch
+        return dict(material="mm03 mises, the deck's own card (e 200e9 nu 0.3 yld_pt 400e6 n_power 10), "
+                             "fracture_models/seb mesh and blocking, consistent q off",
+                    bytes_stress=776.0 + 64.0 + 256.0, bytes_tanstf=708.0)
     if kind == "seb":
         return dict(material="mm01 bilinear (deck card switched from mises: e 200e9 nu 0.3 yld_pt 400e6 tan_e 2e9), "
                              "fracture_models/seb mesh and blocking, consistent q off",
@@ -467,7 +474,8 @@ def engine_arm(args):
         value = ngp_total / (ms_per_step * 1e-3)
         # dominant kernel = the one with the longer average launch; per-launch units = owned GPs
         ngp_own = nel_own * 8
-        sname = "k_eps_sig_ifv<phase 1,2> + k_mm10" if WORKLOADS[args.workload][1] == "mm10" else "k_eps_sig_ifv"
+        sname = ("k_eps_sig_ifv<phase 1,2> + k_mm10f" if WORKLOADS[args.workload][1] == "mm10" else
+                 "k_eps_sig_ifv<phase 1,2> + k_mm03" if args.workload == "seb_mm03" else "k_eps_sig_ifv")
         k_name, k_ms, k_bytes = (("k_tanstf", t_tan, wd["bytes_tanstf"]) if t_tan >= t_stress
                                  else (sname, t_stress, wd["bytes_stress"]))
         ach = ngp_own * k_bytes / (k_ms * 1e-3) / 1e9

@@ -59,7 +59,7 @@ struct Segment {
   // crystal plasticity (mm10)
   double *d_cprops = nullptr, *scratch = nullptr;
   int mm03_allow_cut = 0;
-  int2 *d_mm03_blocks = nullptr;     // mm03: (first slot, span) of every element block of the segment
+  int *d_mm03_active = nullptr;      // mm03: [slot / 16][8] live-point flags of the element blocks (k_mm03_flags)
   int ncrystals = 0, nslip = 0, num_hard = 0, o_gradfe = 0, o_Rp0 = 0;
   bool cp_fast = false, cp_taul = false;   // fast lattice-frame kernel (w3d_mm10_fast.h); k_0 != 0
   std::vector<char> cp_consts;             // its crystal-type table (host copy, uploaded per launch)
@@ -254,7 +254,7 @@ void free_all(w3d_engine *h) {
     cudaFree(s.eps_n); cudaFree(s.eps_n1); cudaFree(s.urcs_n); cudaFree(s.urcs_n1);
     cudaFree(s.rot_n); cudaFree(s.rot_n1); cudaFree(s.cep); cudaFree(s.hist_n);
     cudaFree(s.hist_n1); cudaFree(s.elem_vol); cudaFree(s.partials);
-    cudaFree(s.d_cprops); cudaFree(s.scratch); cudaFree(s.d_mm03_blocks);
+    cudaFree(s.d_cprops); cudaFree(s.scratch); cudaFree(s.d_mm03_active);
   }
   h->assembly.release();
   h->residual.release();
@@ -530,10 +530,7 @@ int create_impl(w3d_engine *h) {
     CUDA_TRY(dalloc(&sg.d_cdest, cdv.size()));
     CUDA_TRY(cudaMemcpy(sg.d_cdest, cdv.data(), sizeof(int32_t) * cdv.size(), cudaMemcpyHostToDevice));
     if (sg.mat_type == 3) {
-      std::vector<int2> bd;
-      for (int blk : sg.blocks) bd.push_back(make_int2(h->blocks[blk].slot0, h->blocks[blk].span));
-      CUDA_TRY(cudaMalloc((void **)&sg.d_mm03_blocks, sizeof(int2) * bd.size()));
-      CUDA_TRY(cudaMemcpy(sg.d_mm03_blocks, bd.data(), sizeof(int2) * bd.size(), cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMalloc((void **)&sg.d_mm03_active, sizeof(int) * 8 * (size_t)(sg.nslots / EPC)));
       CUDA_TRY(dalloc(&sg.scratch, (size_t)16 * sg.nslots * 8));
       // allow_cut (rknstr.f:1213-1214): bit 2 of iprops(24) of the material; one flag per segment
       sg.mm03_allow_cut = 1;
@@ -704,14 +701,16 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
       a.scratch = sg.scratch;
       CUDA_TRY(launch_stress_mm03(sg.geonl, sg.bbar, 1, sg.ncta, a, h->stream));
       Mm03Args ma{};
-      ma.blocks = sg.d_mm03_blocks; ma.eprops = sg.d_eprops; ma.hist_n = sg.hist_n; ma.urcs_n = sg.urcs_n;
+      ma.cta = sg.d_cta; ma.blk_active = sg.d_mm03_active; ma.eprops = sg.d_eprops; ma.hist_n = sg.hist_n; ma.urcs_n = sg.urcs_n;
       ma.scratch = sg.scratch; ma.hist_n1 = sg.hist_n1; ma.urcs_n1 = sg.urcs_n1; ma.cep = sg.cep;
       ma.flags = h->d_flags; ma.ng = sg.ng; ma.dt = h->dt; ma.step = step; ma.iter = iter;
       ma.allow_cut = (a.adaptive && sg.mm03_allow_cut) ? 1 : 0;
       ma.nonlinear_update = a.nonlinear_update;
-      CUDA_TRY(launch_mm03(ma, (int)sg.blocks.size(), h->stream));
+      if (ma.nonlinear_update)
+        CUDA_TRY(cudaMemsetAsync(sg.d_mm03_active, 0, sizeof(int) * 8 * (size_t)(sg.nslots / EPC), h->stream));
+      CUDA_TRY(launch_mm03(ma, sg.ncta, h->stream));
       CUDA_TRY(launch_stress_mm03(sg.geonl, sg.bbar, 2, sg.ncta, a, h->stream));
-      h->launches += 3;
+      h->launches += ma.nonlinear_update ? 4 : 3;
     } else if (sg.mat_type == 5) {
       CUDA_TRY(launch_stress_mm05(sg.geonl, sg.bbar, sg.ncta, a, h->stream));
       h->launches += 1;
