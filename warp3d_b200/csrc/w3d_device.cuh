@@ -37,6 +37,9 @@ struct CtaDesc {
   int blk_span;   // span of the owning block (mm10 small-strain curvature fit, mm10_a.f:1622)
 };
 
+// L2 prefetch of the line holding p (no register, no shared memory, no wait)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // un-contracted, round-to-nearest operations (never fused by ptxas)
 __device__ __forceinline__ double xm(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double xa(double a, double b) { return __dadd_rn(a, b); }

@@ -103,6 +103,41 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
     }
     cp_async_commit();
   }
+  // ---- L2 prefetch for a CTA that will start soon (AHEAD CTAs later = a slot offset: slots are
+  //      laid out in CTA order; approximate where blocks are padded, it is only a hint): its
+  //      state stream and index tables are then L2 hits instead of HBM round trips under load.
+  //      Measured on the 2 M-element mesh (launch, ms): none 4.144; 74 / 148 / 222 CTAs ahead
+  //      3.966 / 3.966 / 3.964; 444 3.987; 888 4.212 (evicted again before use).  The same hint
+  //      in the stress kernel changed nothing (3.720 vs 3.725: its state is consumed after the
+  //      long kinematics, the stream is already hidden) and was left out.
+#ifndef TANSTF_PREFETCH_AHEAD
+#define TANSTF_PREFETCH_AHEAD 148
+#endif
+  if (TANSTF_PREFETCH_AHEAD > 0) {
+    const long long pslot = (long long)slot + (long long)TANSTF_PREFETCH_AHEAD * EPC;
+    const long long pg = pslot * 8 + gp;
+    if (pg < ng) {
+      if ((tid & 3) == 0) {      // one request per 32-byte sector of the 8-byte SoA streams
+        if (a.d_from_hist) {
+#pragma unroll 1
+          for (int k = 0; k < 36; ++k) prefetch_l2(a.hist_n1 + (long long)k * ng + pg);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 21; ++k) prefetch_l2(a.cep + (long long)k * ng + pg);
+        }
+        if (GEONL) {
+#pragma unroll
+          for (int q9 = 0; q9 < 9; ++q9) prefetch_l2(a.rot_n1 + (long long)q9 * ng + pg);
+#pragma unroll
+          for (int q6 = 0; q6 < 6; ++q6) prefetch_l2(a.urcs_n1 + (long long)q6 * ng + pg);
+        }
+      }
+      if (gp < 3) {              // 96 B of dof numbers and 96 B of coordinate numbers per element
+        prefetch_l2(a.cdest + (size_t)pslot * 24 + gp * 8);
+        if (GEONL) prefetch_l2(a.edest + (size_t)pslot * 24 + gp * 8);
+      }
+    }
+  }
   // ---- dptstf: coordinates of node `gp` on the n+1 configuration, staged in the N slots
   {
     double vc[3], vu[3], vdu[3];
