@@ -217,6 +217,8 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
 
   const int tid = threadIdx.x;
   for (int k = tid; k < 192; k += STPB) (&sN[0][0][0])[k] = (&c_shape[0][0][0])[k];
+  __syncthreads();   // the shape table is the only CTA-wide exchange before the final partial sums:
+                     // a warp owns 4 whole elements, their staging below needs a warp barrier only
 
   const int idesc = blockIdx.x * STRESS_GROUPS + tid / TPB;   // this thread's 16-element group
   const bool have = idesc < a.ncta;
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(STPB, STRESS_MIN_CTAS) k_eps_sig_ifv(const Str
       }
     }
   }
-  __syncthreads();
+  __syncwarp();
 
   const double *C = sC[el], *U = sU[el], *DU = sDU[el];
   const double beta_b = (1.0 - a.eps_bbar) * (1.0 / 3.0);   // bmod.f: beta = (1-eps)/3

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
   __shared__ double sN[3][8][8];
   const int tid = threadIdx.x;
   for (int k = tid; k < 192; k += TPB) (&sN[0][0][0])[k] = (&c_shape[0][0][0])[k];
+  __syncthreads();   // the only CTA-wide barrier: everything below is exchanged within a warp (4 whole elements)
 
   const CtaDesc cd = a.cta[blockIdx.x];
   const int el = tid >> 3, gp = tid & 7;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(TPB, TANSTF_MIN_CTAS) k_tanstf(const TanstfArg
       sV[k * 8 + gp] = x;   // temporary: coordinates [comp][node]
     }
   }
-  __syncthreads();
+  __syncwarp();
   double nx[8], ne[8], nz[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { nx[j] = sN[0][j][gp]; ne[j] = sN[1][j][gp]; nz[j] = sN[2][j][gp]; }
