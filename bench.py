@@ -98,7 +98,7 @@ def workload_description(name):
     if kind == "seb":
         return dict(material="mm01 bilinear (deck card switched from mises: e 200e9 nu 0.3 yld_pt 400e6 tan_e 2e9), "
                              "fracture_models/seb mesh and blocking, consistent q off",
-                    bytes_stress=776.0, bytes_tanstf=708.0, flops_stress=3573.0, flops_tanstf=4540.0)
+                    bytes_stress=776.0, bytes_tanstf=708.0, flops_stress=3225.0, flops_tanstf=4540.0)
     if kind.startswith("mm05"):
         # as mm01 with 14 history words per point instead of 11 (3 x 8 B more each way)
         return dict(material={"mm05_fa": "mm05 cyclic, nonlinear_hardening (q_u 100e6, b_u 20, h_u 10e9, gamma_u 50)",
@@ -106,18 +106,18 @@ def workload_description(name):
                     bytes_stress=776.0 + 48.0, bytes_tanstf=708.0)
     if kind == "mm01":
         # FP64 flops per Gauss point: 2 x DFMA + DMUL + DADD executed (predicated-on thread
-        # instructions / Gauss points) from the ncu per-instruction counts of the two kernels on the
-        # 50 %-plastic workload (profiles/r01_summary.md "mm01 instruction mix"); the hand count of
-        # the algorithm agrees to a few percent
+        # instructions / Gauss points) from the per-instruction counts of the round-2 ncu captures
+        # of the two kernels on the 50 %-plastic workload (profiles/r02_summary.md "instruction
+        # mix": stress kernel 1 264 DFMA + 497 DMUL + 201 DADD, stiffness kernel 1 974 + 424 + 170)
         return dict(material="mm01 bilinear (E=200e9 as real*4, nu=0.3, yld=400e6, tan_e=E/100)"
                              + (", beta 0.5 (mixed hardening)" if name.endswith("_beta05") else "")
                              + (", stretch scaled to stay elastic" if name.endswith("_elastic") else ""),
-                    bytes_stress=776.0, bytes_tanstf=708.0, flops_stress=3573.0, flops_tanstf=4540.0,
+                    bytes_stress=776.0, bytes_tanstf=708.0, flops_stress=3225.0, flops_tanstf=4540.0,
                     # measured DRAM bytes per Gauss point (dram__bytes_read + write of one `ncu --set
-                    # full` launch on hex8_256k_mm01 / 2 097 152 points,
-                    # profiles/r01_final_mm01_*_256k_ncu.csv)
-                    dram_stress=(532.444928e6 + 1046.123e6) / 2097152.0,
-                    dram_tanstf=(674.460672e6 + 582.819328e6) / 2097152.0)
+                    # full` launch on hex8_256k_mm01 / 2 097 152 points: round-2 captures,
+                    # profiles/r02_stress_256k_details.csv, profiles/r02_tanstf_256k_v2_details.csv)
+                    dram_stress=(531.654400e6 + 1011.120e6) / 2097152.0,
+                    dram_tanstf=(674.907648e6 + 582.138112e6) / 2097152.0)
     # per Gauss point: history 2 x 158 x 8, urcs 2 x 72, eps 2 x 48, rot 72, scratch 2 x 128,
     # crystal properties 1448/8, element vectors 120  (DESIGN.md "mm10")
     return dict(material="mm10 crystal plasticity: fcc 12 slip, Voce (test82/voche_model values), 1 crystal/element",
@@ -545,10 +545,10 @@ def engine_arm(args):
                 note="w3d_residual (upres + cvtest residual loop), residual left on the device; the call "
                      "includes the read-back of the 7 scalars (one stream synchronisation)")
         if "flops_stress" in wd and fp64_peak:
-            # both mm01 kernels are at the FP64 ridge (4.6 and 6.4 flop/B against 36.4 TFLOP/s /
-            # 6.55 TB/s = 5.6 flop/B), and a DMUL or DADD occupies the pipe like a DFMA: with 2 639
-            # and 2 568 FP64 instructions per point the pipe floors are 2.3 ms each for 16 M points,
-            # above the HBM floors of 1.9 and 1.7 ms.  State them against the DFMA peak as well.
+            # both mm01 kernels sit near the FP64 ridge (4.2 and 6.4 flop/B against 36.4 TFLOP/s /
+            # 6.55 TB/s = 5.6 flop/B), and a DMUL or DADD occupies the pipe like a DFMA: with 1 962
+            # and 2 567 FP64 instructions per point the pipe floors are 1.7 and 2.3 ms for 16 M
+            # points, beside HBM floors of 1.9 and 1.7 ms.  State them against the DFMA peak as well.
             fs = ngp_own * wd["flops_stress"] / (t_stress * 1e-3) / 1e12
             ft = ngp_own * wd["flops_tanstf"] / (t_tan * 1e-3) / 1e12
             line["roofline"]["fp64"] = dict(
