@@ -18,7 +18,7 @@ from oracle.oracle_py import Oracle  # noqa: E402
 from warp3d_b200 import Material, build_structured_hex8, new_state  # noqa: E402
 
 
-def _records(m, mat, path):
+def _records(m, mat, path, hist=11, mat_type=1):
     """run the load path on the restatement and cut one record per (block, iteration)"""
     o, st = Oracle(m), new_state(m)
     off24 = m.block_offsets(24)
@@ -35,11 +35,11 @@ def _records(m, mat, path):
                     off = m.block_offsets(8 * k)
                     return a[off[blk]:off[blk + 1]].reshape(span, 8, k).copy()
 
-                recs.append(dict(blk=blk + 1, step=step, iter=itr, span=span, ngp=8, hist=11, totdof=24, mat=1,
+                recs.append(dict(blk=blk + 1, step=step, iter=itr, span=span, ngp=8, hist=hist, totdof=24, mat=mat_type,
                                  geonl=True, bbar=True, felem=m.felem(blk), ce_0=m.c[ed], ue=u[ed], due=du[ed],
-                                 hist_n=cut(before.history, 11), urcs_n=cut(before.urcs_n, 9),
+                                 hist_n=cut(before.history, hist), urcs_n=cut(before.urcs_n, 9),
                                  eps_n=cut(before.eps_n, 6), ddtse=cut(st.eps_n1, 6) - cut(before.eps_n, 6),
-                                 urcs_n1=cut(st.urcs_n1, 9), hist_n1=cut(st.history1, 11), rot_n1=cut(st.rot_n1, 9)))
+                                 urcs_n1=cut(st.urcs_n1, 9), hist_n1=cut(st.history1, hist), rot_n1=cut(st.rot_n1, 9)))
         o.update(st); o.adaptive_save(st)
     return recs
 
@@ -69,6 +69,20 @@ def test_dump_records_round_trip_and_replay(tmp_path):
         for name, (d, s) in res.items():
             assert d <= 1e-12 * max(s, 1e-300), (rec["blk"], rec["step"], rec["iter"], name, d, s)
         nplastic += int((rec["hist_n1"][:, :, 3].view(np.int64) & 0xFFFFFFFF == 1).sum())
+    assert nplastic > 0
+
+
+def test_dump_replay_of_mises_blocks(tmp_path):
+    """the same for blocks of material model 3 (`mises ... n_power`: what the seb and test_1 decks ship)"""
+    mat = Material(mat_type=3, e=200.0e9, nu=0.3, yld_pt=400.0e6, tan_e=0.0, extra={"n_power": 10.0})
+    m = build_structured_hex8(4, 3, 2, materials=[mat], coord_jitter=0.1, seed=9, block_size=7, dt=1.0e6)
+    recs = _records(m, mat, load_path(m, nsteps=2, strain=2.5e-3), hist=15, mat_type=3)
+    nplastic = 0
+    for rec in cfd.read_records(_write(tmp_path, recs)):
+        assert rec["mat"] == 3 and rec["hist"] == 15
+        for name, (d, s) in cfd.replay(rec, mat, dt=1.0e6).items():
+            assert d <= 1e-12 * max(s, 1e-300), (rec["blk"], rec["step"], rec["iter"], name, d, s)
+        nplastic += int((rec["hist_n1"][:, :, 5].view(np.int64) & 0xFFFFFFFF == 1).sum())
     assert nplastic > 0
 
 

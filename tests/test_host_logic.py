@@ -78,3 +78,25 @@ def test_every_bench_workload_builds_and_states_its_algorithmic_bytes():
     assert beta == np.float32(0.5)
     e, p = (abs(bench.make_workload(w, (2, 2, 2))[1]).max() for w in ("hex8_2m_mm01_elastic", "hex8_2m_mm01"))
     assert e < 0.5 * p                                           # the elastic variant stays under yield
+
+
+def test_mises_material_words_follow_elprp():
+    """`properties mises e .. nu .. yld_pt .. n_power ..` (inmat.f:816-823, defaults :307-327) ->
+    element property words of elprp.f:866-897: 15 = h (0 for tan_e 0), 20 m_power, 21 n_power,
+    22 = 1 / ref_eps (or 0), 23 yield stress, 25 model 3, 26 f0 = 0, 27-29 q1-q3 = 0, 30 no
+    nucleation; history size 15 (mm03_set_sizes, mm03.f:1623-1640)."""
+    import numpy as np
+    from warp3d_b200 import Material, build_structured_hex8
+    mat = Material(mat_type=3, e=200.0e9, nu=0.3, yld_pt=400.0e6, tan_e=0.0,
+                   extra=dict(n_power=10.0, m_power=12.0, ref_eps=0.5))
+    m = build_structured_hex8(3, 2, 2, materials=[mat], block_size=5)
+    f32 = m.props.view(np.float32)
+    assert (m.hist_size == 15).all()
+    assert (m.props[:, 24] == 3).all()
+    assert (f32[:, 14] == 0.0).all() and (f32[:, 22] == np.float32(400.0e6)).all()
+    assert (f32[:, 19] == np.float32(12.0)).all() and (f32[:, 20] == np.float32(10.0)).all()
+    assert (f32[:, 21] == np.float32(2.0)).all()                 # eta = 1 / D
+    assert (f32[:, 25:29] == 0.0).all() and (m.props[:, 29] == 0).all()
+    # a bilinear material leaves those words untouched (zero)
+    m1 = build_structured_hex8(3, 2, 2, block_size=5)
+    assert (m1.props[:, 19:22] == 0).all() and (m1.hist_size == 11).all()

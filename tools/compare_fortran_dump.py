@@ -8,6 +8,8 @@ with records written from the restatement itself.
 
 usage: compare_fortran_dump.py w3d_dump.bin --e 200e9 --nu 0.3 --yld 400e6 --tan-e 2e9 [--beta 1]
                                [--engine] [--eps-bbar 0] [--no-qbar]
+       compare_fortran_dump.py w3d_dump.bin --mises --e 200e9 --nu 0.3 --yld 400e6 --n-power 10
+                               [--m-power 0 --ref-eps 0] [--dt 1e6] ...      (blocks of model 3)
 
 Record (little endian): 13 x int32 header (magic 87033001, blk, step, iter, span, ngp, hist_size,
 totdof, mxvl, mat_type, geonl, bbar, felem) then float64 arrays in Fortran order:
@@ -82,7 +84,7 @@ def write_record(f, rec, mxvl=128):
     gp_block(rec["ddtse"]); gp_block(rec["urcs_n1"]); hist_block(rec["hist_n1"]); gp_block(rec["rot_n1"])
 
 
-def replay(rec, material, eps_bbar=0.0, qbar=True, use_engine=False):
+def replay(rec, material, eps_bbar=0.0, qbar=True, use_engine=False, dt=1.0):
     """Returns dict name -> (max abs difference, scale) for eps_n1, urcs_n1, hist_n1, rot_n1."""
     from oracle.oracle_py import Oracle
     from warp3d_b200 import build_hex8_model, new_state
@@ -91,7 +93,7 @@ def replay(rec, material, eps_bbar=0.0, qbar=True, use_engine=False):
     coords = np.stack([ce[:, 0:8], ce[:, 8:16], ce[:, 16:24]], axis=2).reshape(-1, 3)
     incid = (np.arange(span * 8).reshape(span, 8) + 1).astype(np.int32)
     m = build_hex8_model(coords, incid, materials=[material], geonl=rec["geonl"], bbar=rec["bbar"],
-                         block_size=128, eps_bbar=eps_bbar, qbar_flag=qbar)
+                         block_size=128, eps_bbar=eps_bbar, qbar_flag=qbar, dt=dt)
 
     def nodal(a):                                               # (span, 24) -> (nodof,)
         return np.stack([a[:, 0:8], a[:, 8:16], a[:, 16:24]], axis=2).reshape(-1)
@@ -131,16 +133,23 @@ def main():
     ap.add_argument("--yld", type=float, required=True); ap.add_argument("--tan-e", type=float, required=True)
     ap.add_argument("--beta", type=float, default=1.0); ap.add_argument("--eps-bbar", type=float, default=0.0)
     ap.add_argument("--no-qbar", action="store_true"); ap.add_argument("--engine", action="store_true")
+    ap.add_argument("--mises", action="store_true", help="the blocks use the `mises` card (material model 3)")
+    ap.add_argument("--n-power", type=float, default=0.0); ap.add_argument("--m-power", type=float, default=0.0)
+    ap.add_argument("--ref-eps", type=float, default=0.0); ap.add_argument("--dt", type=float, default=1.0)
     a = ap.parse_args()
     from warp3d_b200 import Material
-    mat = Material(mat_type=1, e=a.e, nu=a.nu, yld_pt=a.yld, tan_e=a.tan_e, beta=a.beta)
+    if a.mises:
+        mat = Material(mat_type=3, e=a.e, nu=a.nu, yld_pt=a.yld, tan_e=a.tan_e, beta=1.0,
+                       extra=dict(n_power=a.n_power, m_power=a.m_power, ref_eps=a.ref_eps))
+    else:
+        mat = Material(mat_type=1, e=a.e, nu=a.nu, yld_pt=a.yld, tan_e=a.tan_e, beta=a.beta)
     worst = {}
     n = 0
     for rec in read_records(a.dump):
-        if rec["mat"] != 1:
+        if rec["mat"] != mat.mat_type:
             print(f"block {rec['blk']}: material model {rec['mat']} -- give the model's properties through the API")
             continue
-        r = replay(rec, mat, a.eps_bbar, not a.no_qbar, a.engine)
+        r = replay(rec, mat, a.eps_bbar, not a.no_qbar, a.engine, dt=a.dt)
         n += 1
         for k, (d, s) in r.items():
             rel = d / s if s > 0 else d
