@@ -110,7 +110,11 @@ typedef struct w3d_scalars {
 typedef struct w3d_engine w3d_engine;   /* opaque */
 
 /* Build the device-side model: block tables, index maps, property vectors, zeroed state with
- * R = I (history_cep_init / rotation_init, reopen.f:1015-1176).                                 */
+ * R = I (history_cep_init / rotation_init, reopen.f:1015-1176).
+ * Built: hex8 (l3disop, 2x2x2), geonl and small strain, B-bar on/off; material models 1 (mm01
+ * bilinear), 3 (mm03 `mises`: no voids, no nucleation, no segmental curves), 5 (mm05, both
+ * options), 10 (mm10, Voce hardening, <= 48 slip systems).  Anything else in the tables returns
+ * W3D_ERR_UNSUPPORTED here, for the whole model -- the caller keeps its own path for that model. */
 int32_t w3d_engine_create(const w3d_engine_config *cfg, w3d_engine **handle);
 int32_t w3d_engine_destroy(w3d_engine *handle);
 /* last error text for this handle (or for a failed create when handle == NULL) */
