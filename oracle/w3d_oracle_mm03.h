@@ -22,10 +22,12 @@
  * tools/compare_fortran_dump.py for whoever has ifort.
  *
  * Literal oddities kept on purpose:
- *  - mm03's `third` is the REAL*4 literal 0.3333333333 widened (0.3333333432674408), so the
- *    mean stress removed in the radial return is off by 3e-8 relative (:2130-2131, :3064-3074);
- *    mm03p uses 1.d0/3.d0; cnst3 uses 0.333333333d0 and 0.6666666667d0.
- *  - mm03q's tolerances are REAL*4 literals 0.000001 widened (:2843).
+ *  - mm03's `third` is the bare literal 0.3333333333 of a DATA statement (:2130-2131): ten digits
+ *    in double under -fpconstant (the default here, W3DO3_K), 0.3333333432674408 if the compiler
+ *    evaluated it in single -- the mean stress removed in the radial return (:3064-3074) is off by
+ *    1e-10 or 3e-8 relative accordingly; mm03p uses 1.d0/3.d0; cnst3 uses 0.333333333d0 and
+ *    0.6666666667d0.
+ *  - mm03q's tolerances are bare literals 0.000001 (:2843), same switch.
  *  - the state flag (+1 / -1) lives in the LOW 32-bit word of history word 6 through an
  *    EQUIVALENCE (:316-317, :2124): the double is a denormal.  The high word is 0 from the step-1
  *    set-up; where the Fortran leaves it undefined (all-null block, :66-67) this file writes 0.
@@ -42,6 +44,16 @@
 #include <cstring>
 
 namespace w3do_mm03 {
+
+// The reference is built with ifort -fpconstant (src/Makefile.linux_Intel.inc:101): a bare REAL*4
+// literal that initialises a double is evaluated in double (same convention as the
+// mm05 restatement).  -DW3D_MM03_DATA_SINGLE evaluates them in single instead (0.3333333333 ->
+// 0.3333333432674408, 0.000001 -> 9.99999997e-07).
+#ifdef W3D_MM03_DATA_SINGLE
+#define W3DO3_K(x) ((double)(x##f))
+#else
+#define W3DO3_K(x) (x)
+#endif
 
 constexpr int HIST = 15;       // mm03_set_sizes (mm03.f:1623-1640)
 
@@ -244,7 +256,7 @@ struct Shared {
       h, q_trial, deq, dep, h_new, f_new, time_incr, newyld, threeg, mpoweri, h_constant, sbar_new,
       eps_o, h_inviscid, inviscid_stress, hprime_init, sig_cur_min_val;
   double zero = 0.0, half = 0.5, one = 1.0, two = 2.0, three = 3.0,
-         third = (double)0.3333333333f, six = 6.0;       // data statement of REAL*4 literals (:2130)
+         third = W3DO3_K(0.3333333333), six = 6.0;       // data statement of bare literals (:2130)
   bool rate_depen, consth, power_law;
   int vm_converge;
 
@@ -268,7 +280,7 @@ struct Shared {
 
   // mm03q (mm03.f:2820-3100)
   void mm03q(double *newsig) {
-    const double toler = (double)0.000001f, sig_tol = (double)0.000001f, unused = (double)-1.11e30f;
+    const double toler = W3DO3_K(0.000001), sig_tol = W3DO3_K(0.000001), unused = -W3DO3_K(1.11e30);
     double newyld_high, newyld_mid, deplas_low, deplas_high, resid_high, fl, fh, deplas = 0.0,
            deplas_riddr, deplas_mid, resid_mid, sridder, deplas_new, resid_new, resid, resid_low;
     int iconverge = 0;
@@ -349,7 +361,7 @@ struct Shared {
     // 1000: (:3031-3076)
     if (iconverge == 3 || iconverge == 5) mm03qq(deplas, newyld, resid);
     if (deplas <= zero) {
-      if (std::fabs(deplas) > (double)0.001f * eps_o) vm_converge = 3;
+      if (std::fabs(deplas) > W3DO3_K(0.001) * eps_o) vm_converge = 3;
     }
     h = h_inviscid;
     if (rate_depen) {

@@ -668,7 +668,6 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
   else if (h->dof_hi > h->dof_lo)
     CUDA_TRY(cudaMemsetAsync(h->d_ifv + h->dof_lo, 0, sizeof(double) * (size_t)(h->dof_hi - h->dof_lo), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, 64 * sizeof(int), h->stream));
-  int first = 1;
   for (auto &sg : h->segs) {
     StressArgs a{};
     a.cta = sg.d_cta; a.edest = sg.d_edest; a.cdest = sg.d_cdest; a.eprops = sg.d_eprops;
@@ -741,13 +740,15 @@ int fetch_scalars(w3d_engine *h, w3d_scalars *out) {
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   int flags[2];
   std::memcpy(flags, h->h_pin + 4, sizeof flags);
-  if (getenv("W3D_MM10F_HIST")) {     // debug: solver-loop trips per Gauss point (W3D_MM10F_HIST builds of w3d_cp.cu)
+#ifdef W3D_MM10F_HIST
+  {                                   // debug builds only: solver-loop trips per Gauss point (w3d_cp.cu)
     int hist[64];
     cudaMemcpy(hist, h->d_flags, sizeof hist, cudaMemcpyDeviceToHost);
     fprintf(stderr, "mm10f trips histogram:");
     for (int k = 2; k < 64; ++k) fprintf(stderr, " %d", hist[k]);
     fprintf(stderr, "\n");
   }
+#endif
   w3d_scalars s{};
   if (h->comm.comm) {     // sums over all ranks (wmpi_reduce_vec / wmpi_redlog)
     const double *r = h->h_pin + 8;

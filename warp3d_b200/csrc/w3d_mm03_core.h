@@ -11,9 +11,10 @@
 // temperatures and fgm properties are refused by w3d_engine_create.
 //
 // Kept on purpose (the reference's numbers are the bar):
-//  * mm03's mean-stress factor is the REAL*4 literal 0.3333333333 (mm03.f:2131); cnst3's are
-//    0.333333333d0 / 0.6666666667d0 / 1.224744871d0 (:3291-3292); mm03q's tolerances and the
-//    -1.11e30 start value are REAL*4 literals (:2843);
+//  * mm03's mean-stress factor is the bare literal 0.3333333333 (mm03.f:2131), mm03q's tolerances
+//    and its -1.11e30 start value are bare literals too (:2843): evaluated in double, as the
+//    reference's -fpconstant build does (W3D_MM03_DATA_SINGLE: in single); cnst3's are
+//    0.333333333d0 / 0.6666666667d0 / 1.224744871d0 (:3291-3292);
 //  * history word 6 carries the state (+1 plastic, -1 elastic) in its low 32 bits (:2124);
 //  * a block whose points are ALL null at this Gauss point (sum |deps| <= 2e-13) copies the
 //    state at n and marks every point elastic (:63-79): `block_null`, decided by the caller over
@@ -31,6 +32,12 @@
 #endif
 
 namespace w3d_mm03 {
+
+#ifdef W3D_MM03_DATA_SINGLE
+#define W3D3_K(x) ((double)(x##f))
+#else
+#define W3D3_K(x) (x)
+#endif
 
 constexpr int HIST = 15;
 enum { OK = 0, NO_CONVERGENCE = 1 };
@@ -309,8 +316,8 @@ W3D3_HD inline int update(int step, int iter, const Props &P, double dt, bool bl
     for (int k = 0; k < 6; ++k) h1[9 + k] = h[9 + k] + uddt[k];
   } else {
     // ---- plastic loading: Ridder's method on the plastic strain increment (mm03q)
-    const double third_r4 = (double)0.3333333333f;
-    const double toler = (double)0.000001f, sig_tol = (double)0.000001f;
+    const double third_r4 = W3D3_K(0.3333333333);
+    const double toler = W3D3_K(0.000001), sig_tol = W3D3_K(0.000001);
     const double shear_mod = 0.5 * e / (1.0 + nu);
     Return R;
     R.e = e; R.sigma_o = P.sigyld; R.n_power = P.n_power; R.m_power = P.m_power; R.eps_ref = P.eps_ref;
@@ -332,7 +339,7 @@ W3D3_HD inline int update(int step, int iter, const Props &P, double dt, bool bl
       else if (fabs(f_hi) <= sig_tol * sbar) { d = hi; newyld = yld_hi; }
       else return NO_CONVERGENCE;
     } else {
-      double last = (double)-1.11e30f;
+      double last = -W3D3_K(1.11e30);
       bool done = false;
       for (int loop = 1; loop <= 20 && !done; ++loop) {
         const double mid = 0.5 * (lo + hi);
