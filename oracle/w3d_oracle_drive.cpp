@@ -23,6 +23,7 @@
 extern "C" { long long w3d_mm10_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }
 #endif
 #include "w3d_oracle_mm05.h"   // per-point mm05 restatement (independent of the product)
+#include "w3d_oracle_mm05_fa.h"   // nonlinear_hardening option of mm05: second, block-form restatement
 #include "w3d_oracle_mm03.h"   // mm03 (mises) restatement (independent of the product)
 
 namespace w3do {
@@ -230,6 +231,47 @@ static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
   const bool adaptive_possible = m->adaptive_flag != 0 && step > 1;
   if (bi.hist_size != 14 || !m->matprp) { *fatal = 5; return; }
   if (matprp(m, 58, bi.matnum) == 0.0f) { *fatal = 3; return; }   // option flag not set (inmat.f:2220, :2272)
+  if (matprp(m, 58, bi.matnum) > 0.0f && nonlinear_update) {
+    // nonlinear_hardening: the block-form restatement (w3d_oracle_mm05_fa.h), arrays as the
+    // reference passes them: drive_05_update_c (rstgp1.f:2627-2700) -> mm05 -> mm05_fa, then cnst5
+    namespace fa = w3do_mm05_fa;
+    std::vector<double> mmp((size_t)span * 10), tr((size_t)span * 6), sn((size_t)span * 9), s1((size_t)span * 9, 0.0),
+        dp((size_t)span * 6), hn((size_t)span * 14), h1((size_t)span * 14);
+    for (int i = 0; i < span; ++i) {
+      const int elem = bi.felem + i;
+      lw.e_vec[i] = rprop(m, 7, elem); lw.nu_vec[i] = rprop(m, 8, elem); lw.sigyld_vec[i] = rprop(m, 23, elem);
+      for (int k = 0; k < 10; ++k) mmp[(size_t)i * 10 + k] = matprp(m, 55 + k, bi.matnum);
+      for (int k = 0; k < 9; ++k) sn[(size_t)i * 9 + k] = urcs_n[(size_t)k * mxvl + i];
+      for (int k = 0; k < 6; ++k) dp[(size_t)i * 6 + k] = uddt_displ[(size_t)k * mxvl + i] + 0.0;
+      for (int k = 0; k < 14; ++k) {
+        hn[(size_t)i * 14 + k] = hist[(size_t)k * span + i];
+        h1[(size_t)i * 14 + k] = hist1[(size_t)k * span + i];
+      }
+    }
+    fa::Block B;
+    B.span = span;
+    B.mm_props = reinterpret_cast<double (*)[10]>(mmp.data());
+    B.e_vec = lw.e_vec; B.nu_vec = lw.nu_vec; B.sigyld_vec = lw.sigyld_vec;
+    B.trial = reinterpret_cast<double (*)[6]>(tr.data());
+    B.stress_n = reinterpret_cast<double (*)[9]>(sn.data());
+    B.stress_np1 = reinterpret_cast<double (*)[9]>(s1.data());
+    B.deps = reinterpret_cast<double (*)[6]>(dp.data());
+    B.history_n = reinterpret_cast<double (*)[14]>(hn.data());
+    B.history_np1 = reinterpret_cast<double (*)[14]>(h1.data());
+    const int rc = fa::mm05_fa(step, iter, B, adaptive_possible);
+    if (rc == fa::CUT) { material_cut_step = true; return; }
+    if (rc != fa::OK) { *fatal = rc; return; }
+    std::vector<double> dm((size_t)span * 36);
+    fa::cnst5_fa(B, reinterpret_cast<double (*)[6][6]>(dm.data()));
+    for (int i = 0; i < span; ++i) {
+      for (int k = 0; k < 9; ++k) urcs_n1[(size_t)k * mxvl + i] = s1[(size_t)i * 9 + k];
+      for (int k = 0; k < 14; ++k) hist1[(size_t)k * span + i] = h1[(size_t)i * 14 + k];
+      for (int r = 1; r <= 6; ++r)
+        for (int c = 1; c <= 6; ++c) Q6(cep, i, r, c) = dm[(size_t)i * 36 + (r - 1) * 6 + (c - 1)];
+    }
+    store_cep(span, gpn, gbl_cep, cep.data());
+    return;
+  }
   for (int i = 0; i < span; ++i) {
     const int elem = bi.felem + i;
     Props P;

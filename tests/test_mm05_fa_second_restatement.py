@@ -1,0 +1,88 @@
+"""mm05, nonlinear_hardening option: the two CPU restatements kept under oracle/ against each
+other.  w3d_oracle_mm05.h (per point) is the transcription the engine's device core descends
+from; w3d_oracle_mm05_fa.h (block form, the one the oracle driver now uses for this option) was
+written a second time directly from src/mm05.f in round 2 without consulting the first.  Agreement
+of the two on cyclic strain paths -- stresses, every history word, the consistent tangent, the
+sub-increment counts and the state flag bit for bit -- is what makes the engine's 1e-10 parity for
+this option a check of the transcription and not only of the port."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "native", "mm05_fa_check.cpp")
+LIB = os.path.join(ROOT, "build", "tests", "libmm05_fa_check.so")
+
+
+def _lib():
+    deps = [SRC, os.path.join(ROOT, "oracle", "w3d_oracle_mm05.h"), os.path.join(ROOT, "oracle", "w3d_oracle_mm05_fa.h")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB, SRC], check=True)
+    L = C.CDLL(LIB)
+    L.mm05_fa_both.restype = C.c_int
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def both(props, step, it, hist, cgn, uddt, adaptive=True):
+    L = _lib()
+    n = props.shape[0]
+    out = []
+    for _ in range(2):
+        out.append(dict(h1=np.zeros((n, 14)), cgn1=np.zeros((n, 9)), D=np.zeros((n, 36)), trial=np.zeros((n, 6)),
+                        rc=np.zeros(n, dtype=np.int32)))
+    a, b = out
+    assert L.mm05_fa_both(n, step, it, int(adaptive), _p(props), _p(hist), _p(cgn), _p(uddt),
+                          _p(a["h1"]), _p(a["cgn1"]), _p(a["D"]), _p(a["trial"]), _p(a["rc"]),
+                          _p(b["h1"]), _p(b["cgn1"]), _p(b["D"]), _p(b["trial"]), _p(b["rc"])) == 0
+    return a, b
+
+
+CASES = {
+    # e, nu, sigyld, then mm_props(1:6) = Q_bar, b, H_bar, +1, gamma, sig_tol (3-D values, as inmat.f stores them)
+    "steel": (200.0e9, 0.3, 400.0e6, 100.0e6, 20.0 * np.sqrt(2.0 / 3.0), 10.0e9 * 2.0 / 3.0, 1.0, 50.0 * np.sqrt(2.0 / 3.0), 0.001),
+    "ksi_strong_recall": (30000.0, 0.3, 60.0, 25.0, 12.0, 900.0, 1.0, 120.0, 0.0005),
+    "no_recall_linear_kinematic": (70.0e3, 0.33, 250.0, 0.0, 1.0, 2000.0, 1.0, 0.0, 0.002),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_two_restatements_agree_on_cyclic_paths(case):
+    e, nu, sy, q, b, h, flag, gam, tol = CASES[case]
+    span = 32
+    props = np.tile(np.array([e, nu, sy, q, b, h, flag, gam, tol, 0, 0, 0, 0], dtype=float), (span, 1)).copy()
+    rng = np.random.default_rng(len(case))
+    eps_y = sy / e
+    hist = np.zeros((span, 14)); cgn = np.zeros((span, 9))
+    direction = rng.normal(size=(span, 6)); direction[:, :3] -= 0.9 * direction[:, :3].mean(axis=1, keepdims=True)
+    direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    worst, nyield, nsub_max = {}, 0, 0
+    for step in range(1, 13):
+        sgn = -1.0 if (step // 3) % 2 else 1.0                       # cyclic: reverse every three steps
+        for it in ((0, 1, 2) if step > 1 else (1, 2)):
+            uddt = sgn * 1.6 * eps_y * (direction + 0.2 * rng.normal(size=(span, 6))) * (0.5 if it == 0 else 1.0)
+            uddt[5] = 0.0                                            # a point with no strain increment
+            a, bb = both(props, step, it, hist, cgn, uddt)
+            assert (a["rc"] == 0).all() and (bb["rc"] == 0).all(), (step, it, a["rc"], bb["rc"])
+            assert np.array_equal(a["h1"][:, 3].view(np.int64), bb["h1"][:, 3].view(np.int64)), "state flags"
+            assert np.array_equal(a["h1"][:, 11], bb["h1"][:, 11]), "sub-increment counts"
+            for name, key, sl in (("stress", "cgn1", slice(0, 6)), ("energy", "cgn1", slice(6, 9)), ("D", "D", slice(0, 36)),
+                                  ("trial", "trial", slice(0, 6)), ("lambda", "h1", slice(0, 1)), ("k", "h1", slice(1, 2)),
+                                  ("aps", "h1", slice(2, 3)), ("H", "h1", slice(4, 5)), ("alpha", "h1", slice(5, 11))):
+                x, y = a[key][:, sl], bb[key][:, sl]
+                scale = max(np.abs(x).max(), 1e-300)
+                worst[name] = max(worst.get(name, 0.0), float(np.abs(x - y).max() / scale))
+            st = a["h1"][:, 3].view(np.int64) & 0xFFFFFFFF
+            nyield += int((st == 1).sum()); nsub_max = max(nsub_max, int(a["h1"][:, 11].max()))
+        hist, cgn = bb["h1"].copy(), bb["cgn1"].copy()
+    assert nyield > 200 and nsub_max >= 3, (nyield, nsub_max)
+    bad = {k: v for k, v in worst.items() if v > 1e-12}
+    assert not bad, (bad, worst)
