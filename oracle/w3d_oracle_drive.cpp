@@ -24,6 +24,7 @@ extern "C" { long long w3d_mm10_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }
 #endif
 #include "w3d_oracle_mm05.h"   // per-point mm05 restatement (independent of the product)
 #include "w3d_oracle_mm05_fa.h"   // nonlinear_hardening option of mm05: second, block-form restatement
+#include "w3d_oracle_mm05_gp.h"   // generalized_plasticity option: the same
 #include "w3d_oracle_mm03.h"   // mm03 (mises) restatement (independent of the product)
 
 namespace w3do {
@@ -231,10 +232,13 @@ static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
   const bool adaptive_possible = m->adaptive_flag != 0 && step > 1;
   if (bi.hist_size != 14 || !m->matprp) { *fatal = 5; return; }
   if (matprp(m, 58, bi.matnum) == 0.0f) { *fatal = 3; return; }   // option flag not set (inmat.f:2220, :2272)
-  if (matprp(m, 58, bi.matnum) > 0.0f && nonlinear_update) {
-    // nonlinear_hardening: the block-form restatement (w3d_oracle_mm05_fa.h), arrays as the
-    // reference passes them: drive_05_update_c (rstgp1.f:2627-2700) -> mm05 -> mm05_fa, then cnst5
+  if (nonlinear_update) {
+    // both options through the block-form restatements (w3d_oracle_mm05_fa.h / _gp.h), arrays as
+    // the reference passes them: drive_05_update_c (rstgp1.f:2627-2700) -> mm05 -> mm05_fa or
+    // mm05_gp, then cnst5 / cnst5_gp
     namespace fa = w3do_mm05_fa;
+    namespace gp = w3do_mm05_gp;
+    const bool generalized_pl = matprp(m, 58, bi.matnum) < 0.0f;
     std::vector<double> mmp((size_t)span * 10), tr((size_t)span * 6), sn((size_t)span * 9), s1((size_t)span * 9, 0.0),
         dp((size_t)span * 6), hn((size_t)span * 14), h1((size_t)span * 14);
     for (int i = 0; i < span; ++i) {
@@ -258,11 +262,18 @@ static void drive_05_update(const w3do_model *m, const BlockInfo &bi, LocalWork 
     B.deps = reinterpret_cast<double (*)[6]>(dp.data());
     B.history_n = reinterpret_cast<double (*)[14]>(hn.data());
     B.history_np1 = reinterpret_cast<double (*)[14]>(h1.data());
-    const int rc = fa::mm05_fa(step, iter, B, adaptive_possible);
+    // generalized plasticity: setup_mm05_rknstr (rknstr.f:1282-1293), gp_tau_vec = matprp(56)
+    std::vector<double> hu(span, (double)matprp(m, 55, bi.matnum)), tau(span, (double)matprp(m, 56, bi.matnum)),
+        bu(span, (double)matprp(m, 57, bi.matnum)), du(span, (double)matprp(m, 59, bi.matnum));
+    gp::GpVectors V{lw.e_vec, lw.e_vec, lw.nu_vec, lw.nu_vec, lw.sigyld_vec, lw.sigyld_vec, hu.data(), hu.data(),
+                    bu.data(), bu.data(), du.data(), du.data(), tau.data()};
+    const int rc = generalized_pl ? gp::mm05_gp(step, iter, B, V, adaptive_possible)
+                                  : fa::mm05_fa(step, iter, B, adaptive_possible);
     if (rc == fa::CUT) { material_cut_step = true; return; }
     if (rc != fa::OK) { *fatal = rc; return; }
     std::vector<double> dm((size_t)span * 36);
-    fa::cnst5_fa(B, reinterpret_cast<double (*)[6][6]>(dm.data()));
+    if (generalized_pl) gp::cnst5_gp(B, V, reinterpret_cast<double (*)[6][6]>(dm.data()));
+    else fa::cnst5_fa(B, reinterpret_cast<double (*)[6][6]>(dm.data()));
     for (int i = 0; i < span; ++i) {
       for (int k = 0; k < 9; ++k) urcs_n1[(size_t)k * mxvl + i] = s1[(size_t)i * 9 + k];
       for (int k = 0; k < 14; ++k) hist1[(size_t)k * span + i] = h1[(size_t)i * 14 + k];

@@ -6,8 +6,9 @@
  * round 2 directly from the Fortran, in the Fortran's own BLOCK form -- every routine loops over
  * the `span` elements of a block at one Gauss point, arrays are (element, component) -- without
  * consulting the per-point version.  tests/test_mm05_fa_second_restatement.py holds the two
- * restatements against each other; the oracle driver uses this one for the nonlinear_hardening
- * option, so the engine's 1e-10 parity for that option is against an independently written checker.
+ * restatements against each other; the oracle driver uses this one (and w3d_oracle_mm05_gp.h for
+ * the other option), so the engine's 1e-10 parity for mm05 is against an independently written
+ * checker.
  *
  *   mm05_fa                   src/mm05.f:288-422
  *   mm05_fa_step1_set         :424-480

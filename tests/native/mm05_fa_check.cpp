@@ -1,12 +1,13 @@
-// Test harness (tests/ only): one element block at one Gauss point, nonlinear_hardening option of
-// mm05, through the two restatements kept under oracle/:
+// Test harness (tests/ only): one element block at one Gauss point, either option of mm05 (sign of
+// mm_props(4)), through the two restatements kept under oracle/:
 //   (a) w3d_oracle_mm05.h     per point, the transcription the engine's device core descends from
-//   (b) w3d_oracle_mm05_fa.h  block form, written a second time directly from mm05.f (round 2)
+//   (b) w3d_oracle_mm05_fa.h / _gp.h  block form, written a second time directly from mm05.f (round 2)
 // Built on demand by tests/test_mm05_fa_second_restatement.py with g++.
 #include <vector>
 
 #include "../../oracle/w3d_oracle_mm05.h"
 #include "../../oracle/w3d_oracle_mm05_fa.h"
+#include "../../oracle/w3d_oracle_mm05_gp.h"
 
 // props per element: e, nu, sigyld, mm_props(1:10); arrays [span][...] row-major.
 extern "C" int mm05_fa_both(int span, int step, int iter, int adaptive, const double *props, const double *hist_n,
@@ -54,9 +55,23 @@ extern "C" int mm05_fa_both(int span, int step, int iter, int adaptive, const do
     B.deps = reinterpret_cast<double (*)[6]>(dp.data());
     B.history_n = reinterpret_cast<double (*)[14]>(hn.data());
     B.history_np1 = reinterpret_cast<double (*)[14]>(h1_b);
-    const int rc = fa::mm05_fa(step, iter, B, adaptive != 0);
+    // option by the sign of mm_props(4) = matprp(58); generalized plasticity: h_u = matprp(55),
+    // tau = matprp(56), beta_u = matprp(57), delta_u = matprp(59) (rknstr.f:1282-1293)
+    namespace gp = w3do_mm05_gp;
+    std::vector<double> hu(span), tau(span), bu(span), du(span);
+    for (int i = 0; i < span; ++i) {
+      hu[i] = mmp[(size_t)i * 10 + 0]; tau[i] = mmp[(size_t)i * 10 + 1];
+      bu[i] = mmp[(size_t)i * 10 + 2]; du[i] = mmp[(size_t)i * 10 + 4];
+    }
+    gp::GpVectors V{e.data(), e.data(), nu.data(), nu.data(), sy.data(), sy.data(), hu.data(), hu.data(),
+                    bu.data(), bu.data(), du.data(), du.data(), tau.data()};
+    const bool generalized = mmp[3] < 0.0;
+    const int rc = generalized ? gp::mm05_gp(step, iter, B, V, adaptive != 0) : fa::mm05_fa(step, iter, B, adaptive != 0);
     for (int i = 0; i < span; ++i) rc_b[i] = rc;
-    if (rc == fa::OK) fa::cnst5_fa(B, reinterpret_cast<double (*)[6][6]>(d_b));
+    if (rc == fa::OK) {
+      if (generalized) gp::cnst5_gp(B, V, reinterpret_cast<double (*)[6][6]>(d_b));
+      else fa::cnst5_fa(B, reinterpret_cast<double (*)[6][6]>(d_b));
+    }
   }
   return 0;
 }

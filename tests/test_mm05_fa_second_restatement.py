@@ -1,6 +1,5 @@
-"""mm05, nonlinear_hardening option: the two CPU restatements kept under oracle/ against each
-other.  w3d_oracle_mm05.h (per point) is the transcription the engine's device core descends
-from; w3d_oracle_mm05_fa.h (block form, the one the oracle driver now uses for this option) was
+"""mm05, both options: the two CPU restatements kept under oracle/ against each other.  w3d_oracle_mm05.h (per point) is the transcription the engine's device core descends
+from; w3d_oracle_mm05_fa.h / w3d_oracle_mm05_gp.h (block form, the ones the oracle driver now uses) were
 written a second time directly from src/mm05.f in round 2 without consulting the first.  Agreement
 of the two on cyclic strain paths -- stresses, every history word, the consistent tangent, the
 sub-increment counts and the state flag bit for bit -- is what makes the engine's 1e-10 parity for
@@ -19,7 +18,7 @@ LIB = os.path.join(ROOT, "build", "tests", "libmm05_fa_check.so")
 
 
 def _lib():
-    deps = [SRC, os.path.join(ROOT, "oracle", "w3d_oracle_mm05.h"), os.path.join(ROOT, "oracle", "w3d_oracle_mm05_fa.h")]
+    deps = [SRC] + [os.path.join(ROOT, "oracle", f) for f in ("w3d_oracle_mm05.h", "w3d_oracle_mm05_fa.h", "w3d_oracle_mm05_gp.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB, SRC], check=True)
@@ -51,6 +50,10 @@ CASES = {
     "steel": (200.0e9, 0.3, 400.0e6, 100.0e6, 20.0 * np.sqrt(2.0 / 3.0), 10.0e9 * 2.0 / 3.0, 1.0, 50.0 * np.sqrt(2.0 / 3.0), 0.001),
     "ksi_strong_recall": (30000.0, 0.3, 60.0, 25.0, 12.0, 900.0, 1.0, 120.0, 0.0005),
     "no_recall_linear_kinematic": (70.0e3, 0.33, 250.0, 0.0, 1.0, 2000.0, 1.0, 0.0, 0.002),
+    # generalized_plasticity (flag -1): mm_props(1:6) = gp_h_u, gp_tau, gp_beta_u, -1, gp_delta_u, sig_tol
+    # (the reference's own values of verification/test39 / testP, ksi; then mixed hardening)
+    "gp_test39_kinematic": (30000.0, 0.3, 60.0, 400.0, 0.0, 200.0, -1.0, 0.010, 0.0001),
+    "gp_mixed_hardening": (30000.0, 0.3, 60.0, 900.0, 0.4, 150.0, -1.0, 25.0, 0.0002),
 }
 
 
@@ -84,5 +87,8 @@ def test_two_restatements_agree_on_cyclic_paths(case):
             nyield += int((st == 1).sum()); nsub_max = max(nsub_max, int(a["h1"][:, 11].max()))
         hist, cgn = bb["h1"].copy(), bb["cgn1"].copy()
     assert nyield > 200 and nsub_max >= 3, (nyield, nsub_max)
+    # generalized plasticity, steps that start outside the yield surface: the golden-section
+    # search compares function values that differ by rounding noise near the minimum (mm05.f:3290-
+    # 3350), so two transcriptions agree only as far as they are statement-identical; they are
     bad = {k: v for k, v in worst.items() if v > 1e-12}
     assert not bad, (bad, worst)
