@@ -149,6 +149,111 @@ __global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_nodes(
   }
 }
 
+// Where every element term lands, worked out once per constraint set: for incidence j (element j of
+// a node's list), lane = element column, one byte per equation of the node -- the position in the
+// row (0..ASM_MAXROW-1), 0xFE = the diagonal, 0xFF = not stored (lower triangle / constrained).
+// k_assemble_nodes spent its time on the three binary searches per lane and element (issue slots
+// 69 % busy, profiles/r02_assemble_256k_details.csv); with the map the same additions in the same
+// order need one 4-byte load instead.
+__global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_build_map(
+    int node0, int nonode, int eq0, const int32_t *__restrict__ dof_eqn, const int32_t *__restrict__ inv_ptr,
+    const int32_t *__restrict__ inv_epos, const int32_t *__restrict__ eeqn,
+    const long long *__restrict__ row_start, const int32_t *__restrict__ kidx, int inc0,
+    uint32_t *__restrict__ posmap) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int node = node0 + blockIdx.x * ASM_WARPS + w;
+  if (node >= nonode || lane >= 24) return;
+  int srow[3], n[3];
+  long long rs[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    srow[c] = dof_eqn[3 * node + c];
+    rs[c] = srow[c] ? row_start[srow[c] - 1 - eq0] : 0;
+    n[c] = srow[c] ? (int)(row_start[srow[c] - eq0] - rs[c]) : 0;
+  }
+  for (int j = inv_ptr[node]; j < inv_ptr[node + 1]; ++j) {
+    const int scol = eeqn[(long long)inv_epos[j] * 24 + lane];
+    uint32_t code = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uint32_t k = 0xFFu;
+      if (srow[c] != 0 && scol >= srow[c]) {
+        if (scol == srow[c]) {
+          k = 0xFEu;
+        } else {
+          int a = 0, b = n[c];
+          while (a < b) {
+            const int m = (a + b) >> 1;
+            if (kidx[rs[c] + m] < scol) a = m + 1; else b = m;
+          }
+          k = (uint32_t)a;
+        }
+      }
+      code |= k << (8 * c);
+    }
+    posmap[(long long)(j - inc0) * 24 + lane] = code;
+  }
+}
+
+__global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_nodes_mapped(
+    int node0, int nonode, int eq0, const int32_t *__restrict__ dof_eqn, const int32_t *__restrict__ inv_ptr,
+    const int32_t *__restrict__ inv_epos, const int8_t *__restrict__ inv_lnode, const double *__restrict__ estiff,
+    const long long *__restrict__ row_start, int inc0, const uint32_t *__restrict__ posmap,
+    double *__restrict__ kdiag, double *__restrict__ kcoef) {
+  __shared__ double sval[ASM_WARPS][3][ASM_MAXROW];
+  __shared__ double sdiag[ASM_WARPS][3];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int node = node0 + blockIdx.x * ASM_WARPS + w;
+  if (node >= nonode) return;
+  int srow[3], n[3];
+  long long rs[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    srow[c] = dof_eqn[3 * node + c];
+    rs[c] = srow[c] ? row_start[srow[c] - 1 - eq0] : 0;
+    n[c] = srow[c] ? (int)(row_start[srow[c] - eq0] - rs[c]) : 0;
+    for (int k = lane; k < n[c]; k += 32) sval[w][c][k] = 0.0;
+    if (lane == 0) sdiag[w][c] = 0.0;
+  }
+  __syncwarp();
+  const int jbeg = inv_ptr[node], jend = inv_ptr[node + 1];
+  uint32_t code_n = 0xFFFFFFu;
+  double v_n[3] = {0.0, 0.0, 0.0};
+  auto fetch = [&](int j) {
+    if (lane < 24) {
+      code_n = posmap[(long long)(j - inc0) * 24 + lane];
+      const int ln = inv_lnode[j];
+      const double *ek = estiff + (long long)inv_epos[j] * 300;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int erow = c * 8 + ln;
+        const int hi = max(lane, erow), lo = min(lane, erow);
+        v_n[c] = ek[(hi * (hi + 1)) / 2 + lo];
+      }
+    }
+  };
+  if (jbeg < jend) fetch(jbeg);
+  for (int j = jbeg; j < jend; ++j) {       // elements on the node, ascending: the reference's order of additions
+    const uint32_t code = code_n;
+    const double v3[3] = {v_n[0], v_n[1], v_n[2]};
+    if (j + 1 < jend) fetch(j + 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t k = (code >> (8 * c)) & 0xFFu;
+      if (lane >= 24 || k == 0xFFu) continue;
+      if (k == 0xFEu) sdiag[w][c] += v3[c];          // one lane per element and equation
+      else sval[w][c][k] += v3[c];                   // distinct terms within an element
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (srow[c] == 0) continue;
+    for (int k = lane; k < n[c]; k += 32) kcoef[rs[c] + k] = sval[w][c][k];
+    if (lane == 0) kdiag[srow[c] - 1 - eq0] = sdiag[w][c];
+  }
+}
+
 // values of the assembled upper triangle into the full CSR pattern (diagonal, upper and the
 // mirrored lower terms): one gather per stored term
 __global__ void k_csr_fill(const int32_t *__restrict__ src, const double *__restrict__ kdiag,
@@ -346,6 +451,28 @@ int32_t w3d_assemble_setup(w3d_engine *h, const int32_t *cstmap, const int32_t *
   for (int r = 0; r < nloc; ++r) A.max_row = std::max(A.max_row, (int)A.k_ptrs[r]);
   CUDA_TRY(cudaMalloc((void **)&A.d_kdiag, sizeof(double) * (size_t)nloc));
   CUDA_TRY(cudaMalloc((void **)&A.d_kcoef, sizeof(double) * (size_t)(A.ncoeff ? A.ncoeff : 1)));
+  // position map of every element term (k_assemble_build_map), 96 B per (node, element) incidence;
+  // skipped when it would not fit comfortably (the searching kernel is used then)
+  cudaFree(A.d_posmap); A.d_posmap = nullptr;
+  if (A.max_row <= ASM_MAXROW && A.node_hi > A.node_lo) {
+    A.inc0 = inv_ptr[A.node_lo];
+    const long long ninc = (long long)inv_ptr[A.node_hi] - A.inc0;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t need = sizeof(uint32_t) * 24 * (size_t)(ninc > 0 ? ninc : 1);
+    if (need < free_b / 4 && cudaMalloc((void **)&A.d_posmap, need) == cudaSuccess) {
+      const int nn = A.node_hi - A.node_lo;
+      k_assemble_build_map<<<(nn + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
+          A.node_lo, A.node_hi, A.eq0, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_eeqn, A.d_row_start, A.d_kidx,
+          A.inc0, A.d_posmap);
+      h->launches += 1;
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+    } else {
+      cudaGetLastError();
+      A.d_posmap = nullptr;
+    }
+  }
   A.ready = true;
   if (neqns_out) *neqns_out = neq;
   if (ncoeff_out) *ncoeff_out = A.ncoeff;
@@ -392,9 +519,14 @@ int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs) {
     for (int k = 0; k < nchunk; ++k) {
       const int na = A.node_lo + (int)((long long)nnode * k / nchunk), nb = A.node_lo + (int)((long long)nnode * (k + 1) / nchunk);
       if (nb <= na) continue;
-      k_assemble_nodes<<<(nb - na + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
-          na, nb, A.eq0, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn, h->d_estiff,
-          A.d_row_start, A.d_kidx, A.d_kdiag, A.d_kcoef);
+      if (A.d_posmap)
+        k_assemble_nodes_mapped<<<(nb - na + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
+            na, nb, A.eq0, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, h->d_estiff, A.d_row_start, A.inc0,
+            A.d_posmap, A.d_kdiag, A.d_kcoef);
+      else
+        k_assemble_nodes<<<(nb - na + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
+            na, nb, A.eq0, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn, h->d_estiff,
+            A.d_row_start, A.d_kidx, A.d_kdiag, A.d_kcoef);
       CUDA_TRY(cudaGetLastError());
       h->launches += 1;
       CUDA_TRY(cudaEventRecord(A.chunk_done[k], h->stream));
@@ -411,7 +543,11 @@ int32_t w3d_assemble(w3d_engine *h, double *k_diag, double *k_coeffs) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return W3D_OK;
   }
-  if (A.max_row <= ASM_MAXROW) {
+  if (A.max_row <= ASM_MAXROW && A.d_posmap) {
+    k_assemble_nodes_mapped<<<(A.node_hi - A.node_lo + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
+        A.node_lo, A.node_hi, A.eq0, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, h->d_estiff, A.d_row_start,
+        A.inc0, A.d_posmap, A.d_kdiag, A.d_kcoef);
+  } else if (A.max_row <= ASM_MAXROW) {
     k_assemble_nodes<<<(A.node_hi - A.node_lo + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, h->stream>>>(
         A.node_lo, A.node_hi, A.eq0, A.d_dof_eqn, A.d_inv_ptr, A.d_inv_epos, A.d_inv_lnode, A.d_eeqn, h->d_estiff,
         A.d_row_start, A.d_kidx, A.d_kdiag, A.d_kcoef);

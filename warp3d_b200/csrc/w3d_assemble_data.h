@@ -24,6 +24,8 @@ struct AssemblyData {
   int32_t *d_inv_ptr = nullptr;      // (nonode + 1) into the two lists below
   int32_t *d_inv_epos = nullptr;     // position of the element in d_estiff / d_eeqn
   int8_t *d_inv_lnode = nullptr;     // local node number (0..7) of the node in that element
+  uint32_t *d_posmap = nullptr;      // [incidence - inc0][24]: row positions of the 3 x 24 terms (k_assemble_build_map)
+  int inc0 = 0;                      // first incidence (d_inv_ptr[node_lo]) the map covers
   int32_t *d_dof_eqn = nullptr;      // (nodof) equation number of each structure dof, 0 = constrained
   static constexpr int NCHUNK = 8;   // node ranges whose copy to the host overlaps the next range's assembly
   std::vector<long long> h_row_start;   // (neq_local + 1) host copy of d_row_start
@@ -44,7 +46,7 @@ struct AssemblyData {
     for (int k = 0; k < NCHUNK; ++k)
       if (chunk_done[k]) cudaEventDestroy(chunk_done[k]);
     cudaFree(d_eqn_node); cudaFree(d_eqn_comp); cudaFree(d_row_start); cudaFree(d_kidx);
-    cudaFree(d_inv_ptr); cudaFree(d_inv_epos); cudaFree(d_inv_lnode); cudaFree(d_eeqn); cudaFree(d_dof_eqn);
+    cudaFree(d_inv_ptr); cudaFree(d_inv_epos); cudaFree(d_inv_lnode); cudaFree(d_posmap); cudaFree(d_eeqn); cudaFree(d_dof_eqn);
     cudaFree(d_kdiag); cudaFree(d_kcoef); cudaFree(d_csr_src); cudaFree(d_csr_val);
     *this = AssemblyData();
   }
