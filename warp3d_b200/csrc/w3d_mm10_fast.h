@@ -296,7 +296,9 @@ W3DF_HD inline void unit_dev(const double *D, double (&d)[6]) {   // mm10_solve_
 // here are I + small terms).  All indices are compile-time: A stays in registers.  Returns 7 when
 // done, else the first column j that needs an interchange -- columns < j are eliminated exactly
 // as the pivoting routine would have done, so lu7_slow can take over from there.
-W3DF_HD inline int lu7_nopivot(double (&A)[7][7], double (&rinv)[7]) {
+// The reciprocal of each pivot replaces the pivot itself (the diagonal of U is only ever used as a
+// divisor): no second array of seven doubles to keep alive next to the 49 of the matrix.
+W3DF_HD inline int lu7_nopivot(double (&A)[7][7]) {
   int jstop = 7;
   W3DF_UNROLL
   for (int j = 0; j < 7; ++j) {
@@ -309,7 +311,7 @@ W3DF_HD inline int lu7_nopivot(double (&A)[7][7], double (&rinv)[7]) {
         jstop = j;
       } else {
         const double r = 1.0 / A[j][j];
-        rinv[j] = r;
+        A[j][j] = r;
         W3DF_UNROLL
         for (int i = j + 1; i < 7; ++i) {
           A[i][j] *= r;
@@ -322,7 +324,7 @@ W3DF_HD inline int lu7_nopivot(double (&A)[7][7], double (&rinv)[7]) {
   return jstop;
 }
 // forward / back substitution with the factors of lu7_nopivot
-W3DF_HD inline void lu7_apply(const double (&A)[7][7], const double (&rinv)[7], double (&b)[7]) {
+W3DF_HD inline void lu7_apply(const double (&A)[7][7], double (&b)[7]) {
   W3DF_UNROLL
   for (int i = 0; i < 7; ++i)
     W3DF_UNROLL
@@ -331,7 +333,7 @@ W3DF_HD inline void lu7_apply(const double (&A)[7][7], const double (&rinv)[7], 
   for (int i = 6; i >= 0; --i) {
     W3DF_UNROLL
     for (int j = i + 1; j < 7; ++j) b[i] -= A[i][j] * b[j];
-    b[i] *= rinv[i];
+    b[i] *= A[i][i];          // the pivot's reciprocal (lu7_nopivot)
   }
 }
 // The rare case: finish the factorisation from column j0 with partial pivoting (DGETF2: pivot =
@@ -344,7 +346,7 @@ static W3DF_HD W3DF_NOINLINE void lu7_slow(double *A /*[49] row-major*/, int j0,
   W3DF_ROLLED
   for (int j = 0; j < 7; ++j) {
     piv[j] = j;
-    if (j < j0) { rinv[j] = 1.0 / A[j * 7 + j]; continue; }
+    if (j < j0) { rinv[j] = A[j * 7 + j]; continue; }   // columns done by lu7_nopivot hold 1 / pivot
     int p = j;
     double amax = fabs(A[j * 7 + j]);
     for (int i = j + 1; i < 7; ++i)
@@ -986,8 +988,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     for (int r = 0; r < 7; ++r)
       W3DF_UNROLL
       for (int cc = 0; cc < 7; ++cc) A[r][cc] = -A[r][cc];
-    double rinv[7];
-    const int jstop = lu7_nopivot(A, rinv);
+    const int jstop = lu7_nopivot(A);
     if (tangent_pass) {
       // mm10_tangent: JJ^-1 C = leading block of J^-1 [C; 0]
       double JR[6][6];
@@ -998,7 +999,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
           W3DF_UNROLL
           for (int r = 0; r < 6; ++r) b[r] = -P.C[r][cc];
           b[6] = 0.0;
-          lu7_apply(A, rinv, b);
+          lu7_apply(A, b);
           W3DF_UNROLL
           for (int r = 0; r < 6; ++r) JR[r][cc] = b[r];
         }
@@ -1030,7 +1031,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     W3DF_UNROLL
     for (int k = 0; k < 7; ++k) dx[k] = Rv[k];
     if (jstop == 7) {
-      lu7_apply(A, rinv, dx);
+      lu7_apply(A, dx);
     } else {
       double Am[49], Bm[7];
       W3DF_UNROLL
