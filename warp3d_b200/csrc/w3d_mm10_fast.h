@@ -141,7 +141,11 @@ struct WorkF {
   int wss;
   W3DF_HD volatile double &operator()(int k) const { return ws[k * wss]; }
 };
-enum { O_B6 = 0, O_CB = 36, O_B3 = 72, O_K0 = 81, O_OST = 87, O_XP = 93, O_RV = 100, O_TL = 107 };
+// O_SC: loop-carried scalars of the solver that are touched once per sub-increment or once per
+// trip (sub-increment fraction and step, hardening state at the sub-increment start, first
+// residual norm): in the column they cost a shared-memory access instead of a register or -- what
+// ptxas made of them -- a spill slot served from L2
+enum { O_B6 = 0, O_CB = 36, O_B3 = 72, O_K0 = 81, O_OST = 87, O_XP = 93, O_RV = 100, O_SC = 107, O_TL = 111 };
 // Inputs of one Gauss point, re-read from memory where they are used (set-up, sub-increment
 // start, output) instead of being carried in registers through the solver loop: rot_blk_n1
 // (column-major 9), the un-rotated strain increment (6), urcs at n (9) -- strided like history
@@ -152,7 +156,7 @@ struct PointInF {
   W3DF_HD double uddt(int k) const { return ud[(long long)k * stride]; }
   W3DF_HD double urcs_n(int k) const { return cgn[(long long)k * stride]; }
 };
-constexpr int WORK_DOUBLES = 107;          // + NSF with geometric hardening (tau_l)
+constexpr int WORK_DOUBLES = 111;          // + NSF with geometric hardening (tau_l)
 
 // ---- small dense helpers (mm10_a.f:1431 rt2rve, :1492 rt2rvw, mm10_b.f:1513 symsw) -------------
 W3DF_HD inline void rt2rve(const double (&rt)[3][3], double (&rv)[6][6]) {
@@ -559,10 +563,11 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   const int miter = W3DF_CT.miter;
   double xt[7], dx[7], Rv[7];
   double tinc = dt, dg, tt_rate = 0.0;
-  double frac = 0.0, stepf = 1.0, ott = x[6];
+  volatile double &frac = W(O_SC + 0), &stepf = W(O_SC + 1), &ott = W(O_SC + 2), &inR1 = W(O_SC + 3);
+  frac = 0.0; stepf = 1.0; ott = x[6]; inR1 = 0.0;
   int cuts = 0, stage, iter = 0, ls = 0;
   bool full = false, tangent_pass = false, failed = false;
-  double inR1 = 0.0, inR = 0.0, ls1 = 0.0, ls2 = 0.0, alpha = 1.0, nR = 0.0;
+  double inR = 0.0, ls1 = 0.0, ls2 = 0.0, alpha = 1.0, nR = 0.0;
   W3DF_UNROLL
   for (int k = 0; k < 6; ++k) W(O_OST + k) = x[k];
   W3DF_UNROLL
