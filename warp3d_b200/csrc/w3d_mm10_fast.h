@@ -565,8 +565,10 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   double tinc = dt, dg, tt_rate = 0.0;
   volatile double &frac = W(O_SC + 0), &stepf = W(O_SC + 1), &ott = W(O_SC + 2), &inR1 = W(O_SC + 3);
   frac = 0.0; stepf = 1.0; ott = x[6]; inR1 = 0.0;
-  int cuts = 0, stage, iter = 0, ls = 0;
-  bool full = false, tangent_pass = false, failed = false;
+  // loop control packed into one register (each of these was a register or a spill slot of its own)
+  struct { unsigned cuts : 4, stage : 4, iter : 12, ls : 8, full : 1, tangent_pass : 1, failed : 1, begin_sub : 1; } ct;
+  ct.cuts = 0; ct.stage = 0; ct.iter = 0; ct.ls = 0;
+  ct.full = 0; ct.tangent_pass = 0; ct.failed = 0;
   double inR = 0.0, ls1 = 0.0, ls2 = 0.0, alpha = 1.0, nR = 0.0;
   W3DF_UNROLL
   for (int k = 0; k < 6; ++k) W(O_OST + k) = x[k];
@@ -577,16 +579,16 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   int w3df_trips = 0;
 #endif
   double r2c = 0.0, ttrc = 0.0;   // hardening residual and rate of the state last evaluated
-  bool begin_sub = true;
+  ct.begin_sub = 1;
   for (;;) {
     if (!SYNC::any(!done)) break;
     if (done) continue;
 #ifdef W3D_MM10F_HIST
     ++w3df_trips;
 #endif
-    if (begin_sub) {
+    if (ct.begin_sub) {
       // (sub-)increment set-up: curr%D, curr%tinc, curr%dg; k0 = n%stress + C D; predictor start
-      begin_sub = false;
+      ct.begin_sub = false;
       const double fr = elastic ? 1.0 : (stepf + frac);
       double D[6];
       W3DF_UNROLL
@@ -605,7 +607,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) xt[k] = x[k];
       if (elastic) {
-        stage = ST_ELASTIC;
+        ct.stage = ST_ELASTIC;
       } else {
         double d1[6], d2[6], nd[6];
         W3DF_UNROLL
@@ -616,14 +618,14 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
         const double t2 = d1[3] * d2[3] + d1[4] * d2[4] + d1[5] * d2[5];
         const double cos_ang = fmax(t1 + t2, 0.0);
         xt[6] = x[6] + cos_ang * n_tt_rate * (dt * stepf);
-        stage = ST_INIT_PRED;
+        ct.stage = ST_INIT_PRED;
       }
-      full = false;
-      iter = 0;
+      ct.full = false;
+      ct.iter = 0;
     }
 
-    bool newton = tangent_pass;
-    if (!tangent_pass) {
+    bool newton = ct.tangent_pass;
+    if (!ct.tangent_pass) {
       // ================= residual at xt (mm10_formR1, mm10_formR2) =================
       double dot;
       {
@@ -694,7 +696,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
           ttrc = (h - n_tt) / tinc;
           r2c = tt - h;
         }
-        if (full) {
+        if (ct.full) {
           tt_rate = ttrc;
           Rv[6] = r2c;
           dot = dot + Rv[6] * Rv[6];
@@ -702,7 +704,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
           Rv[6] = 0.0;
         }
       }
-      if (stage == ST_ELASTIC) {
+      if (ct.stage == ST_ELASTIC) {
         // mm10_solve_strup_a: elastic stiffness as tangent; stress corrected for creep only
         W3DF_UNROLL
         for (int k = 0; k < 6; ++k) x[k] = x[k] - Rv[k];
@@ -711,7 +713,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       }
       nR = sqrt(dot);
       bool check = false;
-      if (stage == ST_INIT_PRED) {
+      if (ct.stage == ST_INIT_PRED) {
         inR1 = nR;
         W3DF_UNROLL
         for (int k = 0; k < 7; ++k) x[k] = xt[k];     // x(7) = predicted tau_tilde x2
@@ -719,33 +721,33 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       } else {   // ST_LS
         const double nlsx = ls1 + ls2 * alpha;
         const double nRs = 0.5 * dot;
-        if ((nRs <= nlsx) || (ls > mls)) {
+        if ((nRs <= nlsx) || (ct.ls > mls)) {
           W3DF_UNROLL
           for (int k = 0; k < 7; ++k) x[k] = xt[k];
-          iter = iter + 1;
-          bool bad = iter > miter;
+          ct.iter = ct.iter + 1;
+          bool bad = ct.iter > miter;
           W3DF_UNROLL
           for (int k = 0; k < 7; ++k) bad = bad || (x[k] != x[k]);
-          if (bad) failed = true;
+          if (bad) ct.failed = true;
           else check = true;
         } else {
           alpha = red * alpha;
-          ls = ls + 1;
+          ct.ls = ct.ls + 1;
           W3DF_UNROLL
           for (int k = 0; k < 7; ++k) xt[k] = x[k] + alpha * dx[k];
         }
       }
       if (check) {
-        const bool cont = full ? (((nR > W3DF_CT.atol) && (nR / inR > W3DF_CT.rtol)) || (iter < mmin))
+        const bool cont = ct.full ? (((nR > W3DF_CT.atol) && (nR / inR > W3DF_CT.rtol)) || (ct.iter < mmin))
                                : ((nR > W3DF_CT.atol1) && (nR / inR1 > W3DF_CT.rtol1));
         if (cont) {
           newton = true;
-        } else if (!full) {
+        } else if (!ct.full) {
           // predictor converged: material update from the predicted state (mm10_solve_update).
           // Its first residual is the one just formed plus the hardening entry; the loop test
           // holds for iter = 0 < mmin, so the first update pass follows in this same trip
-          full = true;
-          iter = 0;
+          ct.full = true;
+          ct.iter = 0;
           tt_rate = ttrc;
           Rv[6] = r2c;
           dot = dot + Rv[6] * Rv[6];
@@ -760,40 +762,40 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
           ott = x[6];
           frac = frac + stepf;
           if (frac < 1.0) {
-            begin_sub = true;
+            ct.begin_sub = true;
           } else {
             // tangent of the last solver pass: re-form its Jacobian at the state it was formed at
-            tangent_pass = true;
+            ct.tangent_pass = true;
             newton = true;
           }
         }
       }
-      if (failed) {
+      if (ct.failed) {
         // mm10_solve failed (predictor or update): back to the last good state, halve the step
-        failed = false;
+        ct.failed = false;
         W3DF_UNROLL
         for (int k = 0; k < 6; ++k) x[k] = W(O_OST + k);
         x[6] = ott;
         stepf = stepf * 0.5;
-        cuts = cuts + 1;
-        if (cuts > mcuts) { cut = true; done = true; continue; }
-        begin_sub = true;
+        ct.cuts = ct.cuts + 1;
+        if (ct.cuts > mcuts) { cut = true; done = true; continue; }
+        ct.begin_sub = true;
       }
     }
     if (!newton) continue;
 
     // ================= Jacobian at x (mm10_formJ) and the Newton step =================
     // (the residual is parked in the workspace while the Jacobian is accumulated: registers)
-    if (!tangent_pass) {
+    if (!ct.tangent_pass) {
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) W(O_RV + k) = Rv[k];
     }
     // the state the Jacobian is formed at: x, or for the tangent the state of the last solver
     // pass (the converged state stays in the workspace: O_OST and ott)
-    if (tangent_pass) {
+    if (ct.tangent_pass) {
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) x[k] = W(O_XP + k);
-    } else if (full) {
+    } else if (ct.full) {
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) W(O_XP + k) = x[k];
     }
@@ -814,7 +816,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       const HardF ht = hard_term(tt);
       const double mitv = -1.0 / W3DF_CT.tau_v;
       double hp0 = 0.0, sg0 = 1.0, rx0 = 0.0;
-      if (!TAUL && full) {
+      if (!TAUL && ct.full) {
         hp0 = pow1(W3DF_CT.voche_ie, W3DF_CT.voche_m, fabs(ht.a));
         sg0 = sgn1(ht.a);
         rx0 = 1.0 / fabs(ht.a);
@@ -862,7 +864,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
           const double fw = si + rs[q] * cv;                    // mm10_form_wp for mm10_IW
           W3DF_UNROLL
           for (int a = 0; a < 3; ++a) wpl[a] = wpl[a] + fw * W3DF_CT.qcr[i][a];
-          if (full) {
+          if (ct.full) {
             const double dgdh = -nott * si;                     // mm10_dgdh_voche
             W3DF_UNROLL
             for (int k = 0; k < 6; ++k) a6[k] = a6[k] + dgdh * W3DF_CT.mc[i][k];
@@ -912,7 +914,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
           for (int k = 0; k < 6; ++k) v = v + cb[k] * M[k][cc];
           Pm[r][cc] = v;
         }
-        if (full) {                        // J12 = CB a6' + 2 symsw(T, B3 q3'), first part
+        if (ct.full) {                        // J12 = CB a6' + 2 symsw(T, B3 q3'), first part
           double v = cb[0] * a6[0];
           W3DF_UNROLL
           for (int k = 1; k < 6; ++k) v = v + cb[k] * a6[k];
@@ -932,7 +934,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
           for (int k = 1; k < 6; ++k) v = v + Pm[r][k] * bc[k];
           A[r][cc] = v;
         }
-        if (full) {                        // J21 = -sc B6 et'
+        if (ct.full) {                        // J21 = -sc B6 et'
           double v = bc[0] * et[0];
           W3DF_UNROLL
           for (int k = 1; k < 6; ++k) v = v + bc[k] * et[k];
@@ -954,7 +956,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       }
       W3DF_UNROLL
       for (int r = 0; r < 6; ++r) A[r][r] = A[r][r] + 1.0;
-      if (full) {
+      if (ct.full) {
         double q3r[3], sq[6];
         W3DF_UNROLL
         for (int a = 0; a < 3; ++a)
@@ -974,7 +976,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       }
     }
     // here A holds J.  Line-search terms need trans(J) R before the factorisation destroys J.
-    if (!tangent_pass) {
+    if (!ct.tangent_pass) {
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) Rv[k] = W(O_RV + k);
       double dotR = 0.0;
@@ -994,7 +996,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       W3DF_UNROLL
       for (int cc = 0; cc < 7; ++cc) A[r][cc] = -A[r][cc];
     const int jstop = lu7_nopivot(A);
-    if (tangent_pass) {
+    if (ct.tangent_pass) {
       // mm10_tangent: JJ^-1 C = leading block of J^-1 [C; 0]
       double JR[6][6];
       if (jstop == 7) {
@@ -1054,10 +1056,10 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     for (int k = 0; k < 7; ++k) ls2 = ls2 + dx[k] * xt[k];
     ls2 = c_ls * ls2;
     alpha = 1.0;
-    ls = 0;
+    ct.ls = 0;
     W3DF_UNROLL
     for (int k = 0; k < 7; ++k) xt[k] = x[k] + alpha * dx[k];
-    stage = ST_LS;
+    ct.stage = ST_LS;
   }
 
 #if defined(W3D_MM10F_HIST) && defined(__CUDA_ARCH__)
