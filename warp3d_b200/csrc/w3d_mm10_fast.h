@@ -561,7 +561,9 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   const double c_ls = 1.0e-4, red = 0.5;
   const int mls = 10, mmin = 1, mcuts = 4;
   const int miter = W3DF_CT.miter;
-  double xt[7], dx[7], Rv[7];
+  // carried across the trips: x and the step dx; the trial point x + alpha dx is re-formed at the
+  // top of a trip (seven doubles fewer to keep live through the Jacobian)
+  double dx[7], Rv[7];
   double tinc = dt, dg, tt_rate = 0.0;
   volatile double &frac = W(O_SC + 0), &stepf = W(O_SC + 1), &ott = W(O_SC + 2), &inR1 = W(O_SC + 3);
   frac = 0.0; stepf = 1.0; ott = x[6]; inR1 = 0.0;
@@ -604,8 +606,10 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
         W(O_K0 + r) = v;
       }
       x[6] = n_tt;   // "some subroutines modify n%tau_tilde in setup": tt restarts from n
+      // trial point of this trip: x itself, hardening entry moved by the predictor below
+      alpha = 1.0;
       W3DF_UNROLL
-      for (int k = 0; k < 7; ++k) xt[k] = x[k];
+      for (int k = 0; k < 7; ++k) dx[k] = 0.0;
       if (elastic) {
         ct.stage = ST_ELASTIC;
       } else {
@@ -617,7 +621,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
         const double t1 = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
         const double t2 = d1[3] * d2[3] + d1[4] * d2[4] + d1[5] * d2[5];
         const double cos_ang = fmax(t1 + t2, 0.0);
-        xt[6] = x[6] + cos_ang * n_tt_rate * (dt * stepf);
+        dx[6] = cos_ang * n_tt_rate * (dt * stepf);
         ct.stage = ST_INIT_PRED;
       }
       ct.full = false;
@@ -628,6 +632,9 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     if (!ct.tangent_pass) {
       // ================= residual at xt (mm10_formR1, mm10_formR2) =================
       double dot;
+      double xt[7];
+      W3DF_UNROLL
+      for (int k = 0; k < 7; ++k) xt[k] = x[k] + alpha * dx[k];
       {
         double sp[6];
         W3DF_UNROLL
@@ -733,8 +740,6 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
         } else {
           alpha = red * alpha;
           ct.ls = ct.ls + 1;
-          W3DF_UNROLL
-          for (int k = 0; k < 7; ++k) xt[k] = x[k] + alpha * dx[k];
         }
       }
       if (check) {
@@ -976,6 +981,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       }
     }
     // here A holds J.  Line-search terms need trans(J) R before the factorisation destroys J.
+    double jtr[7];
     if (!ct.tangent_pass) {
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) Rv[k] = W(O_RV + k);
@@ -984,11 +990,11 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       for (int k = 0; k < 7; ++k) dotR = dotR + Rv[k] * Rv[k];
       ls1 = 0.5 * dotR;
       W3DF_UNROLL
-      for (int k = 0; k < 7; ++k) {   // trans(J) R, kept in dx until the solve
+      for (int k = 0; k < 7; ++k) {   // trans(J) R, folded into ls2 after the solve
         double sj = 0.0;
         W3DF_UNROLL
         for (int r = 0; r < 7; ++r) sj = sj + A[r][k] * Rv[r];
-        xt[k] = sj;
+        jtr[k] = sj;
       }
     }
     W3DF_UNROLL
@@ -1053,12 +1059,10 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     }
     ls2 = 0.0;
     W3DF_UNROLL
-    for (int k = 0; k < 7; ++k) ls2 = ls2 + dx[k] * xt[k];
+    for (int k = 0; k < 7; ++k) ls2 = ls2 + dx[k] * jtr[k];
     ls2 = c_ls * ls2;
     alpha = 1.0;
     ct.ls = 0;
-    W3DF_UNROLL
-    for (int k = 0; k < 7; ++k) xt[k] = x[k] + alpha * dx[k];
     ct.stage = ST_LS;
   }
 
