@@ -3,6 +3,7 @@
 //   (b) the engine's fast lattice-frame core                 warp3d_b200/csrc/w3d_mm10_fast.h (host build)
 // on the same inputs.  Built on demand by tests/test_mm10_fast_core.py with g++.
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "../../oracle/w3d_oracle_mm10.h"
@@ -46,8 +47,14 @@ extern "C" int mm10_point_both(const double *ct /*344*/, int ncrystals, const do
     double ws[WORK_DOUBLES + NSF];
     const WorkF W{ws, 1};
     const PointInF in{Rur, uddt, cgn, 1};
-    const bool cut = taul ? gauss_point_update_fast<true, NoSync>(step, ncrystals, P.data(), L, hn, h1, W, in, dt, iter0off != 0, asym != 0, cgn1_fast)
-                          : gauss_point_update_fast<false, NoSync>(step, ncrystals, P.data(), L, hn, h1, W, in, dt, iter0off != 0, asym != 0, cgn1_fast);
+    // as k_mm10f instantiates it: one crystal per element -> tangent stored ahead by the Newton passes
+    auto run = [&](auto taul_c, auto single_c) {
+      return gauss_point_update_fast<decltype(taul_c)::value, NoSync, decltype(single_c)::value>(
+          step, ncrystals, P.data(), L, hn, h1, W, in, dt, iter0off != 0, asym != 0, cgn1_fast);
+    };
+    const bool single = (ncrystals == 1);
+    const bool cut = taul ? (single ? run(std::true_type{}, std::true_type{}) : run(std::true_type{}, std::false_type{}))
+                          : (single ? run(std::false_type{}, std::true_type{}) : run(std::false_type{}, std::false_type{}));
     cuts[1] = cut ? 1 : 0;
   }
   return 0;

@@ -130,7 +130,9 @@ struct Mm10fShape {
       (w3d_mm10f::WORK_DOUBLES + (TAUL ? w3d_mm10f::NSF : 0)) * THREADS * (int)sizeof(double);
 };
 
-template <bool TAUL>
+// SINGLE: one crystal per element -- the tangent is stored ahead by the Newton passes
+// (w3d_mm10_fast.h, TANGENT_AHEAD)
+template <bool TAUL, bool SINGLE>
 __global__ void __launch_bounds__(Mm10fShape<TAUL>::THREADS, Mm10fShape<TAUL>::MIN_CTAS) k_mm10f(const CpArgs a) {
   extern __shared__ double sWork[];   // [word][thread]
   constexpr int MM10F_THREADS = Mm10fShape<TAUL>::THREADS;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(Mm10fShape<TAUL>::THREADS, Mm10fShape<TAUL>::M
   const w3d_mm10f::HistF h1{a.hist_n1 + g, ng};
   const w3d_mm10f::WorkF W{sWork + threadIdx.x, MM10F_THREADS};
   const w3d_mm10f::PointInF in{a.scratch + g, a.scratch + 9 * ng + g, a.urcs_n + g, ng};
-  const bool cut = w3d_mm10f::gauss_point_update_fast<TAUL, Mm10fSync>(a.step, a.ncrystals, P, L, hn, h1, W, in, a.dt,
+  const bool cut = w3d_mm10f::gauss_point_update_fast<TAUL, Mm10fSync, SINGLE>(a.step, a.ncrystals, P, L, hn, h1, W, in, a.dt,
                                                                      a.iter_0_extrapolate_off != 0, a.asymmetric != 0, cgn1);
   if (cut) {
     atomicOr(&a.flags[0], 1);
@@ -209,11 +211,15 @@ cudaError_t launch_mm10_fast(const CpArgs &a, int ncta, const void *consts, bool
     cudaMemcpyToSymbolAsync(w3d_mm10f::w3df_hist, &hp, sizeof hp, 0, cudaMemcpyHostToDevice, st);
   }
 #endif
-  if (taul) k_mm10f<true><<<ncta, Mm10fShape<true>::THREADS, Mm10fShape<true>::SMEM_BYTES, st>>>(b);
-  else {
+  const bool single = (a.ncrystals == 1);
+  if (taul) {
+    if (single) k_mm10f<true, true><<<ncta, Mm10fShape<true>::THREADS, Mm10fShape<true>::SMEM_BYTES, st>>>(b);
+    else k_mm10f<true, false><<<ncta, Mm10fShape<true>::THREADS, Mm10fShape<true>::SMEM_BYTES, st>>>(b);
+  } else {
     constexpr int T = Mm10fShape<false>::THREADS;
     const int grid = T >= TPB ? (ncta + T / TPB - 1) / (T / TPB) : ncta * (TPB / T);
-    k_mm10f<false><<<grid, T, Mm10fShape<false>::SMEM_BYTES, st>>>(b);
+    if (single) k_mm10f<false, true><<<grid, T, Mm10fShape<false>::SMEM_BYTES, st>>>(b);
+    else k_mm10f<false, false><<<grid, T, Mm10fShape<false>::SMEM_BYTES, st>>>(b);
   }
   return cudaGetLastError();
 }
@@ -260,9 +266,13 @@ cudaError_t mm10_prepare_device() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_mm10<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM10_PROPS_SMEM_LIMIT);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_mm10f<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<false>::SMEM_BYTES);
+    e = cudaFuncSetAttribute(k_mm10f<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<false>::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_mm10f<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<true>::SMEM_BYTES);
+    e = cudaFuncSetAttribute(k_mm10f<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<false>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_mm10f<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<true>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_mm10f<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<true>::SMEM_BYTES);
   return e;
 }
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {

@@ -404,7 +404,12 @@ W3DF_HD inline HardF hard_term(double tt) {
 // mm10_store_cryhist.  Returns true when the crystal asks for a global step cut.
 // n_* : state at n of this crystal; R: rot_blk_n1 (3x3); W: per-thread workspace column.
 // ------------------------------------------------------------------------------------------------
-template <bool TAUL, class SYNC>
+// TANGENT_AHEAD (single crystal): every full Newton pass also solves for the tangent columns with
+// the factors it has in registers and stores them (unsymmetrised) in history at n+1; the pass that
+// turns out to be the last one has then left exactly what mm10_tangent forms from the Jacobian
+// of the last solver pass, and the separate trip that re-forms and re-factors that Jacobian is
+// not needed.  With several crystals the tangents are summed, so the separate trip stays.
+template <bool TAUL, class SYNC, bool TANGENT_AHEAD>
 W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const PointInF &in,
                                         double n_tt, double n_tt_rate, double dt,
                                         bool iter_0_extrapolate_off, bool asymmetric, bool init,
@@ -567,6 +572,8 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   double tinc = dt, dg, tt_rate = 0.0;
   volatile double &frac = W(O_SC + 0), &stepf = W(O_SC + 1), &ott = W(O_SC + 2), &inR1 = W(O_SC + 3);
   frac = 0.0; stepf = 1.0; ott = x[6]; inR1 = 0.0;
+  // the separate tangent trip exists only without TANGENT_AHEAD
+#define W3DF_TP (!TANGENT_AHEAD && ct.tangent_pass)
   // loop control packed into one register (each of these was a register or a spill slot of its own)
   struct { unsigned cuts : 4, stage : 4, iter : 12, ls : 8, full : 1, tangent_pass : 1, failed : 1, begin_sub : 1; } ct;
   ct.cuts = 0; ct.stage = 0; ct.iter = 0; ct.ls = 0;
@@ -628,8 +635,8 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       ct.iter = 0;
     }
 
-    bool newton = ct.tangent_pass;
-    if (!ct.tangent_pass) {
+    bool newton = W3DF_TP;
+    if (!W3DF_TP) {
       // ================= residual at xt (mm10_formR1, mm10_formR2) =================
       double dot;
       double xt[7];
@@ -768,6 +775,8 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
           frac = frac + stepf;
           if (frac < 1.0) {
             ct.begin_sub = true;
+          } else if (TANGENT_AHEAD) {
+            done = true;      // the last full Newton pass has stored the tangent columns
           } else {
             // tangent of the last solver pass: re-form its Jacobian at the state it was formed at
             ct.tangent_pass = true;
@@ -791,16 +800,16 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
 
     // ================= Jacobian at x (mm10_formJ) and the Newton step =================
     // (the residual is parked in the workspace while the Jacobian is accumulated: registers)
-    if (!ct.tangent_pass) {
+    if (!W3DF_TP) {
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) W(O_RV + k) = Rv[k];
     }
     // the state the Jacobian is formed at: x, or for the tangent the state of the last solver
     // pass (the converged state stays in the workspace: O_OST and ott)
-    if (ct.tangent_pass) {
+    if (W3DF_TP) {
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) x[k] = W(O_XP + k);
-    } else if (ct.full) {
+    } else if (ct.full && !TANGENT_AHEAD) {
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) W(O_XP + k) = x[k];
     }
@@ -982,7 +991,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     }
     // here A holds J.  Line-search terms need trans(J) R before the factorisation destroys J.
     double jtr[7];
-    if (!ct.tangent_pass) {
+    if (!W3DF_TP) {
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) Rv[k] = W(O_RV + k);
       double dotR = 0.0;
@@ -1002,7 +1011,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       W3DF_UNROLL
       for (int cc = 0; cc < 7; ++cc) A[r][cc] = -A[r][cc];
     const int jstop = lu7_nopivot(A);
-    if (ct.tangent_pass) {
+    if (W3DF_TP) {
       // mm10_tangent: JJ^-1 C = leading block of J^-1 [C; 0]
       double JR[6][6];
       if (jstop == 7) {
@@ -1043,7 +1052,36 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     }
     W3DF_UNROLL
     for (int k = 0; k < 7; ++k) dx[k] = Rv[k];
-    if (jstop == 7) {
+    if (TANGENT_AHEAD && ct.full) {
+      // tangent columns of this pass: leading block of J^-1 [C; 0] (mm10_tangent), c == 0
+      if (jstop == 7) {
+        W3DF_ROLLED
+        for (int cc = 0; cc < 6; ++cc) {
+          double b[7];
+          W3DF_UNROLL
+          for (int r = 0; r < 6; ++r) b[r] = -P.C[r][cc];
+          b[6] = 0.0;
+          lu7_apply(A, b);
+          W3DF_UNROLL
+          for (int r = 0; r < 6; ++r) h1[L.o_D() + cc * 6 + r] = b[r];
+        }
+        lu7_apply(A, dx);
+      } else {
+        double Am[49], Bm[49];
+        W3DF_UNROLL
+        for (int r = 0; r < 7; ++r)
+          W3DF_UNROLL
+          for (int cc = 0; cc < 7; ++cc) Am[r * 7 + cc] = A[r][cc];
+        for (int r = 0; r < 7; ++r) {
+          for (int cc = 0; cc < 6; ++cc) Bm[r * 7 + cc] = (r < 6) ? -P.C[r][cc] : 0.0;
+          Bm[r * 7 + 6] = dx[r];
+        }
+        lu7_slow(Am, jstop, Bm, 7);
+        for (int r = 0; r < 6; ++r)
+          for (int cc = 0; cc < 6; ++cc) h1[L.o_D() + cc * 6 + r] = Bm[r * 7 + cc];
+        for (int k = 0; k < 7; ++k) dx[k] = Bm[k * 7 + 6];
+      }
+    } else if (jstop == 7) {
       lu7_apply(A, dx);
     } else {
       double Am[49], Bm[7];
@@ -1104,6 +1142,17 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     W3DF_UNROLL
     for (int k = 0; k < 6; ++k) bad = bad || (x[k] != x[k]);
     if (bad) return true;
+  }
+  if (TANGENT_AHEAD && !asymmetric) {
+    // mm10_a_make_symm_1 on the columns the last full Newton pass stored
+    W3DF_UNROLL
+    for (int cc = 1; cc < 6; ++cc)
+      W3DF_UNROLL
+      for (int r = 0; r < cc; ++r) {
+        const double t = (h1[L.o_D() + cc * 6 + r] + h1[L.o_D() + r * 6 + cc]) * 0.5;
+        h1[L.o_D() + cc * 6 + r] = t;
+        h1[L.o_D() + r * 6 + cc] = t;
+      }
   }
   W3DF_UNROLL
   for (int k = 0; k < 6; ++k) { h1[L.c_stress(c) + k] = x[k]; acc.sig[k] = acc.sig[k] + x[k]; }
@@ -1369,10 +1418,11 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   return false;
 }
 
+#undef W3DF_TP
 // mm10 (mm10_a.f:29): all crystals of one Gauss point.  hn / h1: history at n / n+1; props:
 // ncrystals consecutive FProps records of this element; Rur: rot_blk_n1 column-major 9; uddt:
 // un-rotated strain increment; cgn / cgn1: urcs at n / n+1 (9).  true = step cut requested.
-template <bool TAUL, class SYNC>
+template <bool TAUL, class SYNC, bool TANGENT_AHEAD = false>
 W3DF_HD inline bool gauss_point_update_fast(int step, int ncrystals, const FProps *props, const LayoutF &L,
                                             const CHistF &hn, const HistF &h1, const WorkF &W,
                                             const PointInF &in, double dt, bool iter_0_extrapolate_off,
@@ -1394,7 +1444,7 @@ W3DF_HD inline bool gauss_point_update_fast(int step, int ncrystals, const FProp
     }
     const double n_tt = init ? W3DF_CT.tau_y + 1.0e-5 : hn[L.c_tt(c)];      // mm10_init_voche
     const double n_tt_rate = init ? 0.0 : hn[L.c_rate(c)];
-    cut = crystal_update_fast<TAUL, SYNC>(props[c], W, in, n_tt, n_tt_rate, dt, iter_0_extrapolate_off,
+    cut = crystal_update_fast<TAUL, SYNC, TANGENT_AHEAD>(props[c], W, in, n_tt, n_tt_rate, dt, iter_0_extrapolate_off,
                                           asymmetric, init, L, c, hn, h1, acc);
   }
   if (cut) return true;
