@@ -47,14 +47,20 @@ extern "C" int mm10_point_both(const double *ct /*344*/, int ncrystals, const do
     double ws[WORK_DOUBLES + NSF];
     const WorkF W{ws, 1};
     const PointInF in{Rur, uddt, cgn, 1};
-    // as k_mm10f instantiates it: one crystal per element -> tangent stored ahead by the Newton passes
-    auto run = [&](auto taul_c, auto single_c) {
-      return gauss_point_update_fast<decltype(taul_c)::value, NoSync, decltype(single_c)::value>(
+    // as launch_mm10_fast picks the k_mm10f instantiation: one crystal per element -> tangent stored
+    // ahead by the Newton passes; rate exponent 19 compiled in
+    auto run = [&](auto taul_c, auto single_c, auto rate_c) {
+      return gauss_point_update_fast<decltype(taul_c)::value, NoSync, decltype(single_c)::value, decltype(rate_c)::value>(
           step, ncrystals, P.data(), L, hn, h1, W, in, dt, iter0off != 0, asym != 0, cgn1_fast);
     };
+    using T = std::true_type;
+    using F = std::false_type;
+    using RT = std::integral_constant<int, -1>;
+    using E19 = std::integral_constant<int, 19>;
     const bool single = (ncrystals == 1);
-    const bool cut = taul ? (single ? run(std::true_type{}, std::true_type{}) : run(std::true_type{}, std::false_type{}))
-                          : (single ? run(std::false_type{}, std::true_type{}) : run(std::false_type{}, std::false_type{}));
+    const bool e19 = (g_host_ct->rate_ie == 19);
+    const bool cut = taul ? (single ? run(T{}, T{}, RT{}) : run(T{}, F{}, RT{}))
+                          : (single ? (e19 ? run(F{}, T{}, E19{}) : run(F{}, T{}, RT{})) : run(F{}, F{}, RT{}));
     cuts[1] = cut ? 1 : 0;
   }
   return 0;

@@ -4,7 +4,7 @@ w3d_mm10_fast.h, from an ncu source-page CSV and nvdisasm -g of the SAME build.
 usage: ncu_regions_mm10f.py <source.csv> <nvdisasm -g output> [kernel substring]"""
 import collections, csv, re, sys
 src_csv, sass = sys.argv[1:3]
-kern = sys.argv[3] if len(sys.argv) > 3 else 'k_mm10fILb0'
+kern = sys.argv[3] if len(sys.argv) > 3 else 'k_mm10fILb0ELb1'
 cur = None; infn = False; off2 = {}
 for line in open(sass):
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', line)
@@ -20,8 +20,8 @@ import os
 src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'warp3d_b200', 'csrc', 'w3d_mm10_fast.h')).read().split('\n')
 def find(s): return [i + 1 for i, l in enumerate(src) if s in l][0]
 marks = [('helpers', 1), ('setup', find('// ---- mm10_setup: B6 = RE E6')), ('strup_init', find('// ---- mm10_solve_strup')),
-         ('looptop', find('if (!SYNC::any(!done)) break;')), ('begin_sub', find('if (begin_sub) {')),
-         ('residual', find('// ================= residual at xt')), ('stage logic', find('if (stage == ST_ELASTIC) {')),
+         ('looptop', find('if (!SYNC::any(!done)) break;')), ('begin_sub', find('if (ct.begin_sub) {')),
+         ('residual', find('// ================= residual at xt')), ('stage logic', find('if (ct.stage == ST_ELASTIC) {')),
          ('jacobian', find('// ================= Jacobian at x')), ('lu+solve', find('const int jstop = lu7_nopivot')),
          ('after loop', find('if (idle) return false;')), ('output', find('// ---- mm10_output (mm10_a.f:3493)')),
          ('rotation', find('// ---- mm10_update_rotation')), ('gauss_point', find('W3DF_HD inline bool gauss_point_update_fast')),

@@ -132,7 +132,9 @@ struct Mm10fShape {
 
 // SINGLE: one crystal per element -- the tangent is stored ahead by the Newton passes
 // (w3d_mm10_fast.h, TANGENT_AHEAD)
-template <bool TAUL, bool SINGLE>
+// RATE_E: rate exponent harden_n - 1 fixed at compile time (19: harden_n 20 of verification/test82
+// and test74), or -1 = read from the crystal table at run time
+template <bool TAUL, bool SINGLE, int RATE_E>
 __global__ void __launch_bounds__(Mm10fShape<TAUL>::THREADS, Mm10fShape<TAUL>::MIN_CTAS) k_mm10f(const CpArgs a) {
   extern __shared__ double sWork[];   // [word][thread]
   constexpr int MM10F_THREADS = Mm10fShape<TAUL>::THREADS;
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(Mm10fShape<TAUL>::THREADS, Mm10fShape<TAUL>::M
   const w3d_mm10f::HistF h1{a.hist_n1 + g, ng};
   const w3d_mm10f::WorkF W{sWork + threadIdx.x, MM10F_THREADS};
   const w3d_mm10f::PointInF in{a.scratch + g, a.scratch + 9 * ng + g, a.urcs_n + g, ng};
-  const bool cut = w3d_mm10f::gauss_point_update_fast<TAUL, Mm10fSync, SINGLE>(a.step, a.ncrystals, P, L, hn, h1, W, in, a.dt,
+  const bool cut = w3d_mm10f::gauss_point_update_fast<TAUL, Mm10fSync, SINGLE, RATE_E>(a.step, a.ncrystals, P, L, hn, h1, W, in, a.dt,
                                                                      a.iter_0_extrapolate_off != 0, a.asymmetric != 0, cgn1);
   if (cut) {
     atomicOr(&a.flags[0], 1);
@@ -212,14 +214,17 @@ cudaError_t launch_mm10_fast(const CpArgs &a, int ncta, const void *consts, bool
   }
 #endif
   const bool single = (a.ncrystals == 1);
+  const bool e19 = (static_cast<const w3d_mm10f::CrystalConsts *>(consts)->rate_ie == 19);
   if (taul) {
-    if (single) k_mm10f<true, true><<<ncta, Mm10fShape<true>::THREADS, Mm10fShape<true>::SMEM_BYTES, st>>>(b);
-    else k_mm10f<true, false><<<ncta, Mm10fShape<true>::THREADS, Mm10fShape<true>::SMEM_BYTES, st>>>(b);
+    const int T = Mm10fShape<true>::THREADS, S = Mm10fShape<true>::SMEM_BYTES;
+    if (single) k_mm10f<true, true, -1><<<ncta, T, S, st>>>(b);
+    else k_mm10f<true, false, -1><<<ncta, T, S, st>>>(b);
   } else {
-    constexpr int T = Mm10fShape<false>::THREADS;
+    constexpr int T = Mm10fShape<false>::THREADS, S = Mm10fShape<false>::SMEM_BYTES;
     const int grid = T >= TPB ? (ncta + T / TPB - 1) / (T / TPB) : ncta * (TPB / T);
-    if (single) k_mm10f<false, true><<<grid, T, Mm10fShape<false>::SMEM_BYTES, st>>>(b);
-    else k_mm10f<false, false><<<grid, T, Mm10fShape<false>::SMEM_BYTES, st>>>(b);
+    if (single && e19) k_mm10f<false, true, 19><<<grid, T, S, st>>>(b);
+    else if (single) k_mm10f<false, true, -1><<<grid, T, S, st>>>(b);
+    else k_mm10f<false, false, -1><<<grid, T, S, st>>>(b);
   }
   return cudaGetLastError();
 }
@@ -265,14 +270,14 @@ cudaError_t mm10_prepare_device() {
   cudaError_t e = cudaFuncSetAttribute(k_mm10<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM10_PROPS_SMEM_LIMIT);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_mm10<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM10_PROPS_SMEM_LIMIT);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_mm10f<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<false>::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_mm10f<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<false>::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_mm10f<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<true>::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_mm10f<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mm10fShape<true>::SMEM_BYTES);
+  auto opt_in = [&](auto kernel, int bytes) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  };
+  opt_in(k_mm10f<false, false, -1>, Mm10fShape<false>::SMEM_BYTES);
+  opt_in(k_mm10f<false, true, -1>, Mm10fShape<false>::SMEM_BYTES);
+  opt_in(k_mm10f<false, true, 19>, Mm10fShape<false>::SMEM_BYTES);
+  opt_in(k_mm10f<true, false, -1>, Mm10fShape<true>::SMEM_BYTES);
+  opt_in(k_mm10f<true, true, -1>, Mm10fShape<true>::SMEM_BYTES);
   return e;
 }
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {

@@ -263,6 +263,16 @@ W3DF_HD inline void pow4(int ie, double e, double (&b)[CH], double (&r)[CH]) {
     for (int q = 0; q < CH; ++q) b[q] = b[q] * b[q];
   }
 }
+// RATE_E >= 0: the rate exponent is known when the kernel is compiled (no dispatch per call)
+template <int RATE_E>
+W3DF_HD inline void pow_rate(double (&b)[CH], double (&r)[CH]) {
+  if (RATE_E >= 0) {
+    W3DF_UNROLL
+    for (int q = 0; q < CH; ++q) r[q] = pow_const<(RATE_E >= 0 ? RATE_E : 0)>(b[q]);
+  } else {
+    pow4(W3DF_CT.rate_ie, W3DF_CT.rate_n - 1.0, b, r);
+  }
+}
 W3DF_HD inline double pow1(int ie, double e, double x) {
   if (ie < 0) return pow_general(x, e);
   double r = 1.0, b = x;
@@ -409,7 +419,7 @@ W3DF_HD inline HardF hard_term(double tt) {
 // turns out to be the last one has then left exactly what mm10_tangent forms from the Jacobian
 // of the last solver pass, and the separate trip that re-forms and re-factors that Jacobian is
 // not needed.  With several crystals the tangents are summed, so the separate trip stays.
-template <bool TAUL, class SYNC, bool TANGENT_AHEAD>
+template <bool TAUL, class SYNC, bool TANGENT_AHEAD, int RATE_E>
 W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const PointInF &in,
                                         double n_tt, double n_tt_rate, double dt,
                                         bool iter_0_extrapolate_off, bool asymmetric, bool init,
@@ -672,7 +682,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
                     sp[3] * W3DF_CT.mc[i][3] + sp[4] * W3DF_CT.mc[i][4] + sp[5] * W3DF_CT.mc[i][5];
             b[q] = fabs(rs[q] * itt);
           }
-          pow4(W3DF_CT.rate_ie, W3DF_CT.rate_n - 1.0, b, pw);
+          pow_rate<RATE_E>(b, pw);
           W3DF_UNROLL
           for (int q = 0; q < CH; ++q) {
             const int i = i0 + q;
@@ -858,7 +868,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
                   sp[3] * W3DF_CT.mc[i][3] + sp[4] * W3DF_CT.mc[i][4] + sp[5] * W3DF_CT.mc[i][5];
           b[q] = fabs(rs[q] * itt);
         }
-        pow4(W3DF_CT.rate_ie, W3DF_CT.rate_n - 1.0, b, pw);
+        pow_rate<RATE_E>(b, pw);
         W3DF_UNROLL
         for (int q = 0; q < CH; ++q) {
           const int i = i0 + q;
@@ -1195,7 +1205,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
                 sp[3] * W3DF_CT.mc[i][3] + sp[4] * W3DF_CT.mc[i][4] + sp[5] * W3DF_CT.mc[i][5];
         b[q] = fabs(rs[q] * itt);
       }
-      pow4(W3DF_CT.rate_ie, W3DF_CT.rate_n - 1.0, b, pw);
+      pow_rate<RATE_E>(b, pw);
       W3DF_UNROLL
       for (int q = 0; q < CH; ++q) {
         const int i = i0 + q;
@@ -1313,7 +1323,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
                   sp[3] * W3DF_CT.mc[i][3] + sp[4] * W3DF_CT.mc[i][4] + sp[5] * W3DF_CT.mc[i][5];
           b[q] = fabs(rs[q] * itt);
         }
-        pow4(W3DF_CT.rate_ie, W3DF_CT.rate_n - 1.0, b, pw);
+        pow_rate<RATE_E>(b, pw);
         W3DF_UNROLL
         for (int q = 0; q < CH; ++q) {
           const int i = i0 + q;
@@ -1422,7 +1432,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
 // mm10 (mm10_a.f:29): all crystals of one Gauss point.  hn / h1: history at n / n+1; props:
 // ncrystals consecutive FProps records of this element; Rur: rot_blk_n1 column-major 9; uddt:
 // un-rotated strain increment; cgn / cgn1: urcs at n / n+1 (9).  true = step cut requested.
-template <bool TAUL, class SYNC, bool TANGENT_AHEAD = false>
+template <bool TAUL, class SYNC, bool TANGENT_AHEAD = false, int RATE_E = -1>
 W3DF_HD inline bool gauss_point_update_fast(int step, int ncrystals, const FProps *props, const LayoutF &L,
                                             const CHistF &hn, const HistF &h1, const WorkF &W,
                                             const PointInF &in, double dt, bool iter_0_extrapolate_off,
@@ -1444,7 +1454,7 @@ W3DF_HD inline bool gauss_point_update_fast(int step, int ncrystals, const FProp
     }
     const double n_tt = init ? W3DF_CT.tau_y + 1.0e-5 : hn[L.c_tt(c)];      // mm10_init_voche
     const double n_tt_rate = init ? 0.0 : hn[L.c_rate(c)];
-    cut = crystal_update_fast<TAUL, SYNC, TANGENT_AHEAD>(props[c], W, in, n_tt, n_tt_rate, dt, iter_0_extrapolate_off,
+    cut = crystal_update_fast<TAUL, SYNC, TANGENT_AHEAD, RATE_E>(props[c], W, in, n_tt, n_tt_rate, dt, iter_0_extrapolate_off,
                                           asymmetric, init, L, c, hn, h1, acc);
   }
   if (cut) return true;
