@@ -6,6 +6,9 @@
 // Inputs from the PHASE 1 kinematics launch (scratch: R(n+1), strain increment, energy factor).
 #include <cstdlib>
 #include <cstring>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "w3d_cp_kernel.h"
 #include "w3d_mm10_core.h"
@@ -144,16 +147,25 @@ __global__ void __launch_bounds__(Mm10fShape<TAUL>::THREADS, Mm10fShape<TAUL>::M
   const int grp = threadIdx.x / TPB;
   const int tid = threadIdx.x % TPB + (blockIdx.x % SPLIT) * MM10F_THREADS;
   const int idesc = (blockIdx.x / SPLIT) * GROUPS + grp;
-  const bool have = idesc < a.ncta;
-  const CtaDesc cd = a.cta[have ? idesc : a.ncta - 1];
   const int el = tid >> 3, gp = tid & 7;
-  const int slot = cd.slot0 + (el < cd.nvalid ? el : cd.nvalid - 1);
+  const int pos = idesc * EPC + el;          // position in the schedule (a.order)
+  bool have;
+  int slot;
+  if (a.order) {
+    have = pos < a.n_el;
+    slot = a.order[have ? pos : a.n_el - 1];
+  } else {
+    const bool desc = idesc < a.ncta;
+    const CtaDesc cd = a.cta[desc ? idesc : a.ncta - 1];
+    have = desc && el < cd.nvalid;
+    slot = cd.slot0 + (el < cd.nvalid ? el : cd.nvalid - 1);
+  }
   const long long ng = a.ng;
   const long long g = (long long)slot * 8 + gp;
   const double efac = a.scratch[15 * ng + g];
   // padding lanes and points whose det F was not positive (NaN marker: the kinematics already
   // asked for a step cut) take no part in the update, only in the loop's barriers
-  const bool active = have && el < cd.nvalid && (efac == efac);
+  const bool active = have && (efac == efac);
   if (!active) {
     for (int c = 0; c < a.ncrystals; ++c)
       while (Mm10fSync::any(false)) {}
@@ -167,8 +179,11 @@ __global__ void __launch_bounds__(Mm10fShape<TAUL>::THREADS, Mm10fShape<TAUL>::M
   const w3d_mm10f::HistF h1{a.hist_n1 + g, ng};
   const w3d_mm10f::WorkF W{sWork + threadIdx.x, MM10F_THREADS};
   const w3d_mm10f::PointInF in{a.scratch + g, a.scratch + 9 * ng + g, a.urcs_n + g, ng};
+  unsigned trips = 0;
   const bool cut = w3d_mm10f::gauss_point_update_fast<TAUL, Mm10fSync, SINGLE, RATE_E>(a.step, a.ncrystals, P, L, hn, h1, W, in, a.dt,
-                                                                     a.iter_0_extrapolate_off != 0, a.asymmetric != 0, cgn1);
+                                                                     a.iter_0_extrapolate_off != 0, a.asymmetric != 0, cgn1,
+                                                                     &trips);
+  if (a.trips) atomicMax(&a.trips[pos], (int)trips);
   if (cut) {
     atomicOr(&a.flags[0], 1);
     return;
@@ -177,11 +192,50 @@ __global__ void __launch_bounds__(Mm10fShape<TAUL>::THREADS, Mm10fShape<TAUL>::M
   for (int k = 0; k < 9; ++k) a.urcs_n1[k * ng + g] = cgn1[k];
 }
 
+// ---- Mm10Schedule: see w3d_cp_kernel.h
+struct Mm10Schedule {
+  int n_el = 0;
+  int *order[2] = {nullptr, nullptr};   // element slots, current order in order[cur]
+  int *trips = nullptr, *keys_out = nullptr;
+  void *tmp = nullptr;
+  size_t tmp_bytes = 0;
+  int cur = 0;
+  bool have_trips = false;
+};
+void mm10_schedule_destroy(Mm10Schedule *s) {
+  if (!s) return;
+  cudaFree(s->order[0]); cudaFree(s->order[1]); cudaFree(s->trips); cudaFree(s->keys_out); cudaFree(s->tmp);
+  delete s;
+}
+cudaError_t mm10_schedule_create(const CtaDesc *host_cta, int ncta, Mm10Schedule **out) {
+  *out = nullptr;
+  std::vector<int> slots;
+  for (int i = 0; i < ncta; ++i)
+    for (int e = 0; e < host_cta[i].nvalid; ++e) slots.push_back(host_cta[i].slot0 + e);
+  if (slots.empty()) return cudaSuccess;
+  Mm10Schedule *s = new Mm10Schedule;
+  s->n_el = (int)slots.size();
+  const size_t bytes = sizeof(int) * slots.size();
+  cudaError_t e = cudaMalloc((void **)&s->order[0], bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&s->order[1], bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&s->trips, bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&s->keys_out, bytes);
+  if (e == cudaSuccess)
+    e = cub::DeviceRadixSort::SortPairsDescending(nullptr, s->tmp_bytes, s->trips, s->keys_out, s->order[0], s->order[1],
+                                                  s->n_el, 0, 8);
+  if (e == cudaSuccess) e = cudaMalloc(&s->tmp, s->tmp_bytes ? s->tmp_bytes : 1);
+  if (e == cudaSuccess) e = cudaMemcpy(s->order[0], slots.data(), bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { mm10_schedule_destroy(s); return e; }
+  *out = s;
+  return cudaSuccess;
+}
+
 bool mm10_fast_eligible(const double *crystal_types, int n_crystal_types) {
   if (getenv("W3D_MM10_GENERIC")) return false;      // A/B switch: force the general kernel
   if (n_crystal_types != 1) return false;
   const int nslip = (int)crystal_types[337], num_hard = (int)crystal_types[338], h_type = (int)crystal_types[339];
-  return nslip >= 1 && nslip <= w3d_mm10f::NSF && num_hard == 1 && h_type == 1;
+  const int miter = (int)crystal_types[341];      // the loop's iteration counter holds 8 bits
+  return nslip >= 1 && nslip <= w3d_mm10f::NSF && num_hard == 1 && h_type == 1 && miter <= 250;
 }
 int mm10_fast_props_doubles() { return (int)(sizeof(w3d_mm10f::FProps) / sizeof(double)); }
 bool mm10_fast_setup_props_host(const double *ct, const double *angles, int angle_type, double *out) {
@@ -198,7 +252,8 @@ void mm10_fast_setup_consts_host(const double *ct, int angle_type, void *out) {
   K.angle_type = angle_type;
   std::memcpy(out, &K, sizeof K);
 }
-cudaError_t launch_mm10_fast(const CpArgs &a, int ncta, const void *consts, bool taul, cudaStream_t st) {
+cudaError_t launch_mm10_fast(const CpArgs &a, int ncta, const void *consts, bool taul, Mm10Schedule *sched,
+                             cudaStream_t st) {
   // the crystal-type table goes to __constant__ memory in stream order before every launch: two
   // engines of one process (sequentially, as one handle per GPU prescribes) never see each
   // other's table
@@ -207,6 +262,22 @@ cudaError_t launch_mm10_fast(const CpArgs &a, int ncta, const void *consts, bool
   if (e != cudaSuccess) return e;
   CpArgs b = a;
   b.ncta = ncta;
+  b.order = nullptr; b.trips = nullptr; b.n_el = 0;
+  if (sched) {
+    if (sched->have_trips) {
+      // keys: trip counts by position of the previous pass (saturated at 255: 8 bits)
+      e = cub::DeviceRadixSort::SortPairsDescending(sched->tmp, sched->tmp_bytes, sched->trips, sched->keys_out,
+                                                    sched->order[sched->cur], sched->order[1 - sched->cur],
+                                                    sched->n_el, 0, 8, st);
+      if (e != cudaSuccess) return e;
+      sched->cur = 1 - sched->cur;
+    }
+    e = cudaMemsetAsync(sched->trips, 0, sizeof(int) * (size_t)sched->n_el, st);
+    if (e != cudaSuccess) return e;
+    sched->have_trips = true;
+    b.order = sched->order[sched->cur]; b.trips = sched->trips; b.n_el = sched->n_el;
+    ncta = (sched->n_el + EPC - 1) / EPC;
+  }
 #ifdef W3D_MM10F_HIST
   {
     int *hp = a.flags + 2;

@@ -17,7 +17,20 @@ struct CpArgs {
   double dt;
   int step, iter_0_extrapolate_off, asymmetric, ncrystals, nslip, num_hard;
   int ncta;                   // number of CTA descriptors (set by launch_mm10)
+  // k_mm10f with a schedule (Mm10Schedule): the element slots in the order they are taken, 16 per
+  // 128 threads; trips[position] receives the largest solver-loop trip count of the element
+  const int *order;
+  int *trips;
+  int n_el;
 };
+
+// Order in which k_mm10f takes the elements: by the trip count of the previous stress pass,
+// longest first (stable: equal counts keep their order, the first pass runs in block order).  A
+// CTA walks the solver loop in lock step and is as slow as its slowest point, so points of like
+// cost belong together; the result of a point does not depend on where it is computed.
+struct Mm10Schedule;
+cudaError_t mm10_schedule_create(const CtaDesc *host_cta, int ncta, Mm10Schedule **out);
+void mm10_schedule_destroy(Mm10Schedule *s);
 
 // Two instantiations of the shared core: up to 12 slip systems (fcc, bcc: the fast path, property
 // records staged in shared memory) and up to 48 (bcc48 and the other long tables of
@@ -37,7 +50,8 @@ bool mm10_fast_setup_props_host(const double *crystal_type_rec, const double *an
                                 double *props_out);
 int mm10_fast_consts_bytes();
 void mm10_fast_setup_consts_host(const double *crystal_type_rec, int angle_type, void *consts_out);
-cudaError_t launch_mm10_fast(const CpArgs &a, int ncta, const void *consts, bool taul, cudaStream_t st);
+cudaError_t launch_mm10_fast(const CpArgs &a, int ncta, const void *consts, bool taul, Mm10Schedule *sched,
+                             cudaStream_t st);
 // shared-memory opt-in of every instantiation on the current device (w3d_engine_create)
 cudaError_t mm10_prepare_device();
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st);

@@ -63,6 +63,7 @@ struct Segment {
   int ncrystals = 0, nslip = 0, num_hard = 0, o_gradfe = 0, o_Rp0 = 0;
   bool cp_fast = false, cp_taul = false;   // fast lattice-frame kernel (w3d_mm10_fast.h); k_0 != 0
   std::vector<char> cp_consts;             // its crystal-type table (host copy, uploaded per launch)
+  Mm10Schedule *cp_sched = nullptr;        // element order of k_mm10f (w3d_cp_kernel.h); W3D_MM10_SCHEDULE=0: block order
 };
 
 struct BlockInfo {
@@ -255,6 +256,7 @@ void free_all(w3d_engine *h) {
     cudaFree(s.rot_n); cudaFree(s.rot_n1); cudaFree(s.cep); cudaFree(s.hist_n);
     cudaFree(s.hist_n1); cudaFree(s.elem_vol); cudaFree(s.partials);
     cudaFree(s.d_cprops); cudaFree(s.scratch); cudaFree(s.d_mm03_active);
+    mm10_schedule_destroy(s.cp_sched); s.cp_sched = nullptr;
   }
   h->assembly.release();
   h->residual.release();
@@ -492,6 +494,8 @@ int create_impl(w3d_engine *h) {
         sg.cp_taul = c.crystal_types[36 + 288 + 5] != 0.0;      // k_o: geometric hardening
         sg.cp_consts.resize(mm10_fast_consts_bytes());
         mm10_fast_setup_consts_host(c.crystal_types, c.cp_angle_type, sg.cp_consts.data());
+        const char *sch = getenv("W3D_MM10_SCHEDULE");
+        if (!(sch && sch[0] == '0')) CUDA_TRY(mm10_schedule_create(cta.data(), sg.ncta, &sg.cp_sched));
       }
       const int pd = sg.cp_fast ? mm10_fast_props_doubles() : mm10_props_doubles(sg.nslip);
       sg.num_hard = (int)c.crystal_types[338];
@@ -691,7 +695,7 @@ int stress_resident(w3d_engine *h, int step, int iter, int extrapolated_du) {
       ca.iter_0_extrapolate_off = (iter == 0 && (!extrapolated_du || step == 1)) ? 1 : 0;   // rstgp1.f:4453-4457
       ca.asymmetric = c.asymmetric_assembly ? 1 : 0;
       ca.ncrystals = sg.ncrystals; ca.nslip = sg.nslip; ca.num_hard = sg.num_hard;
-      if (sg.cp_fast) CUDA_TRY(launch_mm10_fast(ca, sg.ncta, sg.cp_consts.data(), sg.cp_taul, h->stream));
+      if (sg.cp_fast) CUDA_TRY(launch_mm10_fast(ca, sg.ncta, sg.cp_consts.data(), sg.cp_taul, sg.cp_sched, h->stream));
       else CUDA_TRY(launch_mm10(ca, sg.ncta, h->stream));
       CUDA_TRY((launch_stress<10, 2>(sg, a, h->stream)));
       h->launches += 3;

@@ -424,7 +424,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
                                         double n_tt, double n_tt_rate, double dt,
                                         bool iter_0_extrapolate_off, bool asymmetric, bool init,
                                         const LayoutF &L, int c, const CHistF &hn, const HistF &h1,
-                                        PointSumsF &acc) {
+                                        PointSumsF &acc, unsigned &trips) {
   // state at n of this crystal, read where needed (mm10_copy_cc_hist / mm10_init_cc_hist0)
   auto n_stress = [&](int k) { return init ? in.urcs_n(k) : hn[L.c_stress(c) + k]; };
   auto n_D = [&](int k) { return init ? 0.0 : hn[L.c_D(c) + k]; };
@@ -585,8 +585,9 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   // the separate tangent trip exists only without TANGENT_AHEAD
 #define W3DF_TP (!TANGENT_AHEAD && ct.tangent_pass)
   // loop control packed into one register (each of these was a register or a spill slot of its own)
-  struct { unsigned cuts : 4, stage : 4, iter : 12, ls : 8, full : 1, tangent_pass : 1, failed : 1, begin_sub : 1; } ct;
-  ct.cuts = 0; ct.stage = 0; ct.iter = 0; ct.ls = 0;
+  // (iter <= miter + 1 <= 251: mm10_fast_eligible; ls <= mls + 1; trips saturates)
+  struct { unsigned cuts : 4, stage : 4, iter : 8, ls : 4, trips : 8, full : 1, tangent_pass : 1, failed : 1, begin_sub : 1; } ct;
+  ct.cuts = 0; ct.stage = 0; ct.iter = 0; ct.ls = 0; ct.trips = 0;
   ct.full = 0; ct.tangent_pass = 0; ct.failed = 0;
   double inR = 0.0, ls1 = 0.0, ls2 = 0.0, alpha = 1.0, nR = 0.0;
   W3DF_UNROLL
@@ -602,6 +603,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   for (;;) {
     if (!SYNC::any(!done)) break;
     if (done) continue;
+    if (ct.trips < 255u) ct.trips = ct.trips + 1;
 #ifdef W3D_MM10F_HIST
     ++w3df_trips;
 #endif
@@ -1117,6 +1119,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
 #if defined(W3D_MM10F_HIST) && defined(__CUDA_ARCH__)
   atomicAdd(&w3df_hist[w3df_trips < 61 ? w3df_trips : 61], 1);
 #endif
+  trips = trips + ct.trips;      // solver-loop trips of this point (the next pass is ordered by them)
   if (idle) return false;
   if (cut) return true;
   if (!elastic) {     // converged state back from the workspace (the tangent pass reused x)
@@ -1436,7 +1439,7 @@ template <bool TAUL, class SYNC, bool TANGENT_AHEAD = false, int RATE_E = -1>
 W3DF_HD inline bool gauss_point_update_fast(int step, int ncrystals, const FProps *props, const LayoutF &L,
                                             const CHistF &hn, const HistF &h1, const WorkF &W,
                                             const PointInF &in, double dt, bool iter_0_extrapolate_off,
-                                            bool asymmetric, double *cgn1) {
+                                            bool asymmetric, double *cgn1, unsigned *trips_out = nullptr) {
   // At step 1 the reference initialises its block-local copy of history at n and never writes
   // that copy back; the same values are substituted on the fly (mm10_init_cc_hist0 & co.)
   const bool init = (step == 1);
@@ -1447,6 +1450,7 @@ W3DF_HD inline bool gauss_point_update_fast(int step, int ncrystals, const FProp
   acc.t_work = 0.0; acc.p_work = 0.0; acc.p_strain = 0.0;
   for (int k = 0; k < ns; ++k) h1[L.o_sliphist() + k] = 0.0;
   bool cut = false;
+  unsigned trips = 0;
   for (int c = 0; c < ncrystals; ++c) {
     if (cut) {                      // a crystal asked for a step cut: only keep the CTA's loop barriers company
       while (SYNC::any(false)) {}
@@ -1455,8 +1459,9 @@ W3DF_HD inline bool gauss_point_update_fast(int step, int ncrystals, const FProp
     const double n_tt = init ? W3DF_CT.tau_y + 1.0e-5 : hn[L.c_tt(c)];      // mm10_init_voche
     const double n_tt_rate = init ? 0.0 : hn[L.c_rate(c)];
     cut = crystal_update_fast<TAUL, SYNC, TANGENT_AHEAD, RATE_E>(props[c], W, in, n_tt, n_tt_rate, dt, iter_0_extrapolate_off,
-                                          asymmetric, init, L, c, hn, h1, acc);
+                                          asymmetric, init, L, c, hn, h1, acc, trips);
   }
+  if (trips_out) *trips_out = trips;
   if (cut) return true;
   // mm10_a_crystal_avgs + mm10_a_store_crystal
   const double irn = 1.0 / (double)ncrystals;
