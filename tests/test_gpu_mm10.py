@@ -90,3 +90,40 @@ def test_bcc48_two_crystals_per_point():
     ct = dict(e=200000.0, nu=0.3, slip="bcc48", harden_n=5.0, tau_y=205.0, tau_v=5000.0, voche_m=1.0,
               theta_o=0.01, eps_dot_o_y=4.0e-05, alter_mode=True)
     assert _run(_model(2, 2, 2, ncrystals=2, crystal=ct), nsteps=3, strain=3.0e-3) > 0.0
+
+
+def test_geometric_hardening_from_the_lattice_curvature():
+    # k_0 /= 0: tau_l per slip system from grad Fe^-1 of the previous step (mm10_a.f:925-975) -- the
+    # k_mm10f instantiation with the tau_l column in its workspace.  k_0 is set large enough for
+    # the term to move the stresses by ~0.5 % on this mesh (the deck value of test74 is 10)
+    ct = dict(e=100000.0, nu=0.3, harden_n=20, tau_y=100.0, tau_v=50.0, theta_o=500.0, voche_m=1.0, k_o=1.0e7)
+    assert _run(_model(3, 2, 2, block_size=7, crystal=ct)) > 0.0
+
+
+def test_element_order_by_trip_count_does_not_change_a_single_bit(monkeypatch):
+    # k_mm10f takes the elements in the order of the previous pass's solver-loop trip counts
+    # (Mm10Schedule); every point is computed by the same instructions wherever it runs, so the state
+    # after several passes is bit-identical to the run in block order (W3D_MM10_SCHEDULE=0)
+    from warp3d_b200.engine import Engine
+    m = _model(5, 4, 3, block_size=13)
+    out = []
+    for sched in ("1", "0"):
+        monkeypatch.setenv("W3D_MM10_SCHEDULE", sched)
+        eng, st = Engine(m), new_state(m)
+        eng.push_state(st)
+        fs = []
+        for step, iters in load_path(m, nsteps=3, strain=2.5e-3):
+            for itr, u, du in iters:
+                f, sc = eng.drive_eps_sig_internal_forces(step, itr, u, du)
+                assert not sc["material_cut_step"]
+                fs.append(f.copy())
+            eng.update(); eng.adaptive_save()
+        eng.pull_state(st)
+        out.append((fs, st.history1.copy(), st.urcs_n1.copy()))
+        eng.close()
+    (fa, ha, ua), (fb, hb, ub) = out
+    assert ua.max() > 0.0 and np.abs(ha).max() > 0.0
+    for a, b in zip(fa, fb):
+        # ifv is summed with atomics (order not fixed, as in the reference's addifv): not bitwise
+        assert relerr(a, b) <= 1e-13
+    assert np.array_equal(ha, hb) and np.array_equal(ua, ub)
