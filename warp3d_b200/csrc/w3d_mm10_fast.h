@@ -47,9 +47,11 @@
 #endif
 // slip systems handled per trip of the (rolled) slip-system loops: the loops over the systems
 // stay rolled so that residual + Jacobian + LU -- the solver loop -- fit the instruction cache;
-// the systems of one trip are independent work for the FP64 pipe
+// the systems of one trip are independent work for the FP64 pipe.  Measured on the 1 M mesh
+// (stress pass): 1 per trip 30.1 ms, 2: 30.5, 4: 33.5 (one system's 6x6 and 3x6 updates already
+// fill the pipe; more per trip only lengthens the code)
 #ifndef W3DF_CHUNK
-#define W3DF_CHUNK 2
+#define W3DF_CHUNK 1
 #endif
 
 namespace w3d_mm10f {
@@ -1067,7 +1069,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     if (TANGENT_AHEAD && ct.full) {
       // tangent columns of this pass: leading block of J^-1 [C; 0] (mm10_tangent), c == 0
       if (jstop == 7) {
-        W3DF_ROLLED
+        W3DF_ROLLED      // (unrolled: 31.0 vs 30.5 ms)
         for (int cc = 0; cc < 6; ++cc) {
           double b[7];
           W3DF_UNROLL
