@@ -4,7 +4,7 @@ w3d_mm10_fast.h, from an ncu source-page CSV and nvdisasm -g of the SAME build.
 usage: ncu_regions_mm10f.py <source.csv> <nvdisasm -g output> [kernel substring]"""
 import collections, csv, re, sys
 src_csv, sass = sys.argv[1:3]
-kern = sys.argv[3] if len(sys.argv) > 3 else 'k_mm10fILb0ELb1'
+kern = sys.argv[3] if len(sys.argv) > 3 else 'k_mm10fILb0ELb1ELi19'
 cur = None; infn = False; off2 = {}
 for line in open(sass):
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', line)
