@@ -41,6 +41,10 @@ WORKLOADS = {
     "hex8_2m_mm01_beta05": ((200, 100, 100), "mm01", (64, 50, 50)),
     "hex8_1m_mm10": ((100, 100, 100), "mm10", (32, 25, 25)),   # BASELINE.json configs[4]: CP polycrystal
     "hex8_64k_mm10": ((40, 40, 40), "mm10", (32, 25, 25)),
+    # the same with geometric hardening from the lattice curvature (k_0 = 10 as in verification/test74):
+    # the k_mm10f instantiation that also keeps tau_l of the 12 systems per thread
+    "hex8_64k_mm10_k0": ((40, 40, 40), "mm10", (32, 25, 25)),
+    "hex8_1m_mm10_k0": ((100, 100, 100), "mm10", (32, 25, 25)),
     # mm05 cyclic plasticity, both options (the GP one with the reference's own deck values, ksi)
     "hex8_256k_mm05_fa": ((64, 64, 64), "mm05_fa", (32, 25, 25)),
     "hex8_256k_mm05_gp": ((64, 64, 64), "mm05_gp", (32, 25, 25)),
@@ -84,7 +88,8 @@ def make_workload(name, dims=None):
         m = build_structured_hex8(*dims, materials=[mat])
         return m, 0.5 * graded_stretch(m), 1      # yield strain 2e-3 for both, as for mm01
     m = build_structured_hex8(*dims, materials=[Material(mat_type=10)], dt=1.0)
-    attach_crystals(m, make_crystal_type(**MM10_CRYSTAL), ncrystals=1)
+    attach_crystals(m, make_crystal_type(**MM10_CRYSTAL, **(dict(k_o=10.0) if name.endswith("_k0") else {})),
+                    ncrystals=1)
     return m, 0.25 * graded_stretch(m, eps_lo=3.0e-3, eps_hi=9.0e-3), 2
 
 

@@ -59,7 +59,7 @@ extern "C" int mm10_point_both(const double *ct /*344*/, int ncrystals, const do
     using E19 = std::integral_constant<int, 19>;
     const bool single = (ncrystals == 1);
     const bool e19 = (g_host_ct->rate_ie == 19);
-    const bool cut = taul ? (single ? run(T{}, T{}, RT{}) : run(T{}, F{}, RT{}))
+    const bool cut = taul ? (single ? (e19 ? run(T{}, T{}, E19{}) : run(T{}, T{}, RT{})) : run(T{}, F{}, RT{}))
                           : (single ? (e19 ? run(F{}, T{}, E19{}) : run(F{}, T{}, RT{})) : run(F{}, F{}, RT{}));
     cuts[1] = cut ? 1 : 0;
   }

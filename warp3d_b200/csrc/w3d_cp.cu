@@ -125,12 +125,12 @@ typedef CtaSync Mm10fSync;
 #else
 typedef w3d_mm10f::NoSync Mm10fSync;
 #endif
-template <bool TAUL>
+template <bool TAUL, bool SINGLE>
 struct Mm10fShape {
   static constexpr int THREADS = TAUL ? TPB : W3D_MM10F_THREADS;
-  static constexpr int MIN_CTAS = TAUL ? 1 : (W3D_MM10F_THREADS > 128 ? 1 : W3D_MM10F_THREADS > 64 ? 2 : 4);
-  static constexpr int SMEM_BYTES =
-      (w3d_mm10f::WORK_DOUBLES + (TAUL ? w3d_mm10f::NSF : 0)) * THREADS * (int)sizeof(double);
+  // geometric hardening: 123 words per thread (one CTA per SM), 112 with one crystal per point
+  static constexpr int MIN_CTAS = TAUL ? (SINGLE ? 2 : 1) : (W3D_MM10F_THREADS > 128 ? 1 : W3D_MM10F_THREADS > 64 ? 2 : 4);
+  static constexpr int SMEM_BYTES = w3d_mm10f::work_doubles(TAUL, SINGLE) * THREADS * (int)sizeof(double);
 };
 
 // SINGLE: one crystal per element -- the tangent is stored ahead by the Newton passes
@@ -138,9 +138,9 @@ struct Mm10fShape {
 // RATE_E: rate exponent harden_n - 1 fixed at compile time (19: harden_n 20 of verification/test82
 // and test74), or -1 = read from the crystal table at run time
 template <bool TAUL, bool SINGLE, int RATE_E>
-__global__ void __launch_bounds__(Mm10fShape<TAUL>::THREADS, Mm10fShape<TAUL>::MIN_CTAS) k_mm10f(const CpArgs a) {
+__global__ void __launch_bounds__(Mm10fShape<TAUL, SINGLE>::THREADS, Mm10fShape<TAUL, SINGLE>::MIN_CTAS) k_mm10f(const CpArgs a) {
   extern __shared__ double sWork[];   // [word][thread]
-  constexpr int MM10F_THREADS = Mm10fShape<TAUL>::THREADS;
+  constexpr int MM10F_THREADS = Mm10fShape<TAUL, SINGLE>::THREADS;
   // a CTA takes THREADS / 128 whole 16-element groups, or (64 threads) half a group
   constexpr int GROUPS = MM10F_THREADS >= TPB ? MM10F_THREADS / TPB : 1;
   constexpr int SPLIT = MM10F_THREADS >= TPB ? 1 : TPB / MM10F_THREADS;
@@ -287,11 +287,12 @@ cudaError_t launch_mm10_fast(const CpArgs &a, int ncta, const void *consts, bool
   const bool single = (a.ncrystals == 1);
   const bool e19 = (static_cast<const w3d_mm10f::CrystalConsts *>(consts)->rate_ie == 19);
   if (taul) {
-    const int T = Mm10fShape<true>::THREADS, S = Mm10fShape<true>::SMEM_BYTES;
-    if (single) k_mm10f<true, true, -1><<<ncta, T, S, st>>>(b);
-    else k_mm10f<true, false, -1><<<ncta, T, S, st>>>(b);
+    constexpr int T = Mm10fShape<true, true>::THREADS;
+    if (single && e19) k_mm10f<true, true, 19><<<ncta, T, Mm10fShape<true, true>::SMEM_BYTES, st>>>(b);
+    else if (single) k_mm10f<true, true, -1><<<ncta, T, Mm10fShape<true, true>::SMEM_BYTES, st>>>(b);
+    else k_mm10f<true, false, -1><<<ncta, T, Mm10fShape<true, false>::SMEM_BYTES, st>>>(b);
   } else {
-    constexpr int T = Mm10fShape<false>::THREADS, S = Mm10fShape<false>::SMEM_BYTES;
+    constexpr int T = Mm10fShape<false, true>::THREADS, S = Mm10fShape<false, true>::SMEM_BYTES;
     const int grid = T >= TPB ? (ncta + T / TPB - 1) / (T / TPB) : ncta * (TPB / T);
     if (single && e19) k_mm10f<false, true, 19><<<grid, T, S, st>>>(b);
     else if (single) k_mm10f<false, true, -1><<<grid, T, S, st>>>(b);
@@ -344,11 +345,12 @@ cudaError_t mm10_prepare_device() {
   auto opt_in = [&](auto kernel, int bytes) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   };
-  opt_in(k_mm10f<false, false, -1>, Mm10fShape<false>::SMEM_BYTES);
-  opt_in(k_mm10f<false, true, -1>, Mm10fShape<false>::SMEM_BYTES);
-  opt_in(k_mm10f<false, true, 19>, Mm10fShape<false>::SMEM_BYTES);
-  opt_in(k_mm10f<true, false, -1>, Mm10fShape<true>::SMEM_BYTES);
-  opt_in(k_mm10f<true, true, -1>, Mm10fShape<true>::SMEM_BYTES);
+  opt_in(k_mm10f<false, false, -1>, Mm10fShape<false, false>::SMEM_BYTES);
+  opt_in(k_mm10f<false, true, -1>, Mm10fShape<false, true>::SMEM_BYTES);
+  opt_in(k_mm10f<false, true, 19>, Mm10fShape<false, true>::SMEM_BYTES);
+  opt_in(k_mm10f<true, false, -1>, Mm10fShape<true, false>::SMEM_BYTES);
+  opt_in(k_mm10f<true, true, -1>, Mm10fShape<true, true>::SMEM_BYTES);
+  opt_in(k_mm10f<true, true, 19>, Mm10fShape<true, true>::SMEM_BYTES);
   return e;
 }
 cudaError_t launch_mm10(const CpArgs &a, int ncta, cudaStream_t st) {

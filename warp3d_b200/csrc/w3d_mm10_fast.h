@@ -159,6 +159,30 @@ struct PointInF {
   W3DF_HD double urcs_n(int k) const { return cgn[(long long)k * stride]; }
 };
 constexpr int WORK_DOUBLES = 111;          // + NSF with geometric hardening (tau_l)
+// Geometric hardening with the tangent stored ahead (one crystal per point): tau_l of the 12
+// systems takes the 7 words of the previous iterate (not kept then), the words of the 4 cold
+// scalars (which go back to registers) and one more -- 112 words per thread, so that two CTAs
+// still fit an SM (123 words: one).
+template <bool PACKED>
+W3DF_HD inline int tl_word(int i) {
+  return PACKED ? (i < 7 ? O_XP + i : (i < 11 ? O_SC + (i - 7) : O_TL)) : O_TL + i;
+}
+constexpr int work_doubles(bool taul, bool tangent_ahead) {
+  return taul ? (tangent_ahead ? WORK_DOUBLES + 1 : WORK_DOUBLES + NSF) : WORK_DOUBLES;
+}
+// a cold scalar of the solver loop: a word of the column, or a plain variable
+template <bool IN_COLUMN>
+struct ColdScalar {
+  volatile double *p;
+  double v;
+  W3DF_HD explicit ColdScalar(volatile double *q) : p(q), v(0.0) {}
+  W3DF_HD operator double() const { return IN_COLUMN ? *p : v; }
+  W3DF_HD ColdScalar &operator=(double x) {
+    if (IN_COLUMN) *p = x;
+    else v = x;
+    return *this;
+  }
+};
 
 // ---- small dense helpers (mm10_a.f:1431 rt2rve, :1492 rt2rvw, mm10_b.f:1513 symsw) -------------
 W3DF_HD inline void rt2rve(const double (&rt)[3][3], double (&rv)[6][6]) {
@@ -522,7 +546,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       for (int i = 0; i < 3; ++i)
         tm[i] = 0.0 + 0.5 * (-curv[i][0][1] * cn[2] + curv[i][0][2] * cn[1] + curv[i][1][0] * cn[2] -
                              curv[i][1][2] * cn[0] - curv[i][2][0] * cn[1] + curv[i][2][1] * cn[0]);
-      W(O_TL + t) = cst * sqrt(tm[0] * tm[0] + tm[1] * tm[1] + tm[2] * tm[2]);
+      W(tl_word<TAUL && TANGENT_AHEAD>(t)) = cst * sqrt(tm[0] * tm[0] + tm[1] * tm[1] + tm[2] * tm[2]);
     }
   }
 
@@ -582,7 +606,8 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   // top of a trip (seven doubles fewer to keep live through the Jacobian)
   double dx[7], Rv[7];
   double tinc = dt, dg, tt_rate = 0.0;
-  volatile double &frac = W(O_SC + 0), &stepf = W(O_SC + 1), &ott = W(O_SC + 2), &inR1 = W(O_SC + 3);
+  constexpr bool SC_IN_COLUMN = !(TAUL && TANGENT_AHEAD);
+  ColdScalar<SC_IN_COLUMN> frac(&W(O_SC + 0)), stepf(&W(O_SC + 1)), ott(&W(O_SC + 2)), inR1(&W(O_SC + 3));
   frac = 0.0; stepf = 1.0; ott = x[6]; inR1 = 0.0;
   // the separate tangent trip exists only without TANGENT_AHEAD
 #define W3DF_TP (!TANGENT_AHEAD && ct.tangent_pass)
@@ -697,7 +722,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
             W3DF_UNROLL
             for (int k = 0; k < 3; ++k) a3[k] = a3[k] + f * W3DF_CT.qcr[i][k];
             if (TAUL) {
-              const double h_term = ht.a + W(O_TL + i) * ht.inv_d;
+              const double h_term = ht.a + W(tl_word<TAUL && TANGENT_AHEAD>(i)) * ht.inv_d;
               hsum = hsum + pow1(W3DF_CT.voche_ie, W3DF_CT.voche_m, fabs(h_term)) * sgn1(h_term) * fabs(si);
             } else {
               hsum = hsum + fabs(si);
@@ -900,7 +925,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
             for (int a = 0; a < 3; ++a) q3[a] = q3[a] + dgdh * W3DF_CT.qcr[i][a];
             double hp = hp0, sg = sg0, rx = rx0, tl = 0.0;
             if (TAUL) {
-              tl = W(O_TL + i);
+              tl = W(tl_word<TAUL && TANGENT_AHEAD>(i));
               const double h_term = ht.a + tl * ht.inv_d;
               hp = pow1(W3DF_CT.voche_ie, W3DF_CT.voche_m, fabs(h_term));
               sg = sgn1(h_term);
