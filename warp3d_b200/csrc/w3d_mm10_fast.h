@@ -301,6 +301,16 @@ W3DF_HD inline void pow_rate(double (&b)[CH], double (&r)[CH]) {
 }
 W3DF_HD inline double pow1(int ie, double e, double x) {
   if (ie < 0) return pow_general(x, e);
+  if (ie < 16) {
+    // the loop below for exponents under 16 without its branches: the same products in the same
+    // order, the multiplications by 1 left out by selects
+    const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+    double r = (ie & 1) ? x : 1.0;
+    r = (ie & 2) ? r * x2 : r;
+    r = (ie & 4) ? r * x4 : r;
+    r = (ie & 8) ? r * x8 : r;
+    return r;
+  }
   double r = 1.0, b = x;
   for (int k = ie; k != 0; k >>= 1) {
     if (k & 1) r = r * b;
