@@ -128,13 +128,13 @@ typedef w3d_mm10f::NoSync Mm10fSync;
 template <bool TAUL, bool SINGLE>
 struct Mm10fShape {
   static constexpr int THREADS = TAUL ? TPB : W3D_MM10F_THREADS;
-  // geometric hardening: 123 words per thread (one CTA per SM), 112 with one crystal per point
-  static constexpr int MIN_CTAS = TAUL ? (SINGLE ? 2 : 1) : (W3D_MM10F_THREADS > 128 ? 1 : W3D_MM10F_THREADS > 64 ? 2 : 4);
-  static constexpr int SMEM_BYTES = w3d_mm10f::work_doubles(TAUL, SINGLE) * THREADS * (int)sizeof(double);
+  // geometric hardening: 112 words per thread (w3d_mm10_fast.h, tl_word), still two CTAs per SM
+  static constexpr int MIN_CTAS = TAUL ? 2 : (W3D_MM10F_THREADS > 128 ? 1 : W3D_MM10F_THREADS > 64 ? 2 : 4);
+  static constexpr int SMEM_BYTES = w3d_mm10f::work_doubles(TAUL) * THREADS * (int)sizeof(double);
 };
 
-// SINGLE: one crystal per element -- the tangent is stored ahead by the Newton passes
-// (w3d_mm10_fast.h, TANGENT_AHEAD)
+// SINGLE: one crystal per element -- the tangent columns stored ahead by the Newton passes go
+// straight to their place (w3d_mm10_fast.h, crystal_update_fast: SINGLE)
 // RATE_E: rate exponent harden_n - 1 fixed at compile time (19: harden_n 20 of verification/test82
 // and test74), or -1 = read from the crystal table at run time
 template <bool TAUL, bool SINGLE, int RATE_E>

@@ -101,7 +101,7 @@ W3D5_HD inline int find_pos_lambda(double sigy, const double *sig_t, double *equ
                                    double gamma, double &lambda, double &k_np1, double Q, double b,
                                    double H_bar, double &lg, double g, const double *alpha_n,
                                    bool adaptive_possible, double &H_np1, double tol, double &aps_np1) {
-  const double zero = W3D5_K(0.0), one = W3D5_K(1.0);
+  const double zero = W3D5_K(0.0);
   const int sc_max = 4, bs_max = 10, nr_max = 10;
   double dk_np1, dH_np1, res_i, res_f, res;
   double lambda_i = zero;

@@ -159,17 +159,15 @@ struct PointInF {
   W3DF_HD double urcs_n(int k) const { return cgn[(long long)k * stride]; }
 };
 constexpr int WORK_DOUBLES = 111;          // + NSF with geometric hardening (tau_l)
-// Geometric hardening with the tangent stored ahead (one crystal per point): tau_l of the 12
-// systems takes the 7 words of the previous iterate (not kept then), the words of the 4 cold
-// scalars (which go back to registers) and one more -- 112 words per thread, so that two CTAs
-// still fit an SM (123 words: one).
-template <bool PACKED>
+// Geometric hardening: tau_l of the 12 systems takes the 7 words O_XP (free: the previous iterate
+// was only kept for a separate tangent trip), the words of the 4 cold scalars (which go back to
+// registers then) and one more -- 112 words per thread, so that two CTAs still fit an SM (with 12
+// words of its own: 123, one CTA).
+template <bool TAUL>
 W3DF_HD inline int tl_word(int i) {
-  return PACKED ? (i < 7 ? O_XP + i : (i < 11 ? O_SC + (i - 7) : O_TL)) : O_TL + i;
+  return i < 7 ? O_XP + i : (i < 11 ? O_SC + (i - 7) : O_TL);
 }
-constexpr int work_doubles(bool taul, bool tangent_ahead) {
-  return taul ? (tangent_ahead ? WORK_DOUBLES + 1 : WORK_DOUBLES + NSF) : WORK_DOUBLES;
-}
+constexpr int work_doubles(bool taul) { return taul ? WORK_DOUBLES + 1 : WORK_DOUBLES; }
 // a cold scalar of the solver loop: a word of the column, or a plain variable
 template <bool IN_COLUMN>
 struct ColdScalar {
@@ -450,12 +448,19 @@ W3DF_HD inline HardF hard_term(double tt) {
 // mm10_store_cryhist.  Returns true when the crystal asks for a global step cut.
 // n_* : state at n of this crystal; R: rot_blk_n1 (3x3); W: per-thread workspace column.
 // ------------------------------------------------------------------------------------------------
-// TANGENT_AHEAD (single crystal): every full Newton pass also solves for the tangent columns with
+// The tangent is stored ahead: every full Newton pass also solves for the tangent columns with
 // the factors it has in registers and stores them (unsymmetrised) in history at n+1; the pass that
-// turns out to be the last one has then left exactly what mm10_tangent forms from the Jacobian
-// of the last solver pass, and the separate trip that re-forms and re-factors that Jacobian is
-// not needed.  With several crystals the tangents are summed, so the separate trip stays.
-template <bool TAUL, class SYNC, bool TANGENT_AHEAD, int RATE_E>
+// turns out to be the last one has then left exactly what mm10_tangent forms from the Jacobian of
+// the last solver pass -- no trip that re-forms and re-factors that Jacobian.
+// SINGLE (one crystal per point): the columns go straight to the tangent's place and are
+// symmetrised there; otherwise the tangents of the crystals are summed, and the columns of crystal
+// c wait in words of its own history at n+1 that are only written after the solve (wait_word).
+// word k = 0..35 of the waiting tangent columns of crystal c: Euler angles + Rp (12 consecutive
+// words), eps (6), the user words (15), ep (3 of 6) -- none of them written before mm10_output
+W3DF_HD inline int wait_word(const LayoutF &L, int c, int k) {
+  return k < 12 ? L.c_euler(c) + k : (k < 18 ? L.c_eps(c) + (k - 12) : (k < 33 ? L.c_u(c) + (k - 18) : L.c_ep(c) + (k - 33)));
+}
+template <bool TAUL, class SYNC, bool SINGLE, int RATE_E>
 W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const PointInF &in,
                                         double n_tt, double n_tt_rate, double dt,
                                         bool iter_0_extrapolate_off, bool asymmetric, bool init,
@@ -556,7 +561,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       for (int i = 0; i < 3; ++i)
         tm[i] = 0.0 + 0.5 * (-curv[i][0][1] * cn[2] + curv[i][0][2] * cn[1] + curv[i][1][0] * cn[2] -
                              curv[i][1][2] * cn[0] - curv[i][2][0] * cn[1] + curv[i][2][1] * cn[0]);
-      W(tl_word<TAUL && TANGENT_AHEAD>(t)) = cst * sqrt(tm[0] * tm[0] + tm[1] * tm[1] + tm[2] * tm[2]);
+      W(tl_word<TAUL>(t)) = cst * sqrt(tm[0] * tm[0] + tm[1] * tm[1] + tm[2] * tm[2]);
     }
   }
 
@@ -616,16 +621,14 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   // top of a trip (seven doubles fewer to keep live through the Jacobian)
   double dx[7], Rv[7];
   double tinc = dt, dg, tt_rate = 0.0;
-  constexpr bool SC_IN_COLUMN = !(TAUL && TANGENT_AHEAD);
+  constexpr bool SC_IN_COLUMN = !TAUL;
   ColdScalar<SC_IN_COLUMN> frac(&W(O_SC + 0)), stepf(&W(O_SC + 1)), ott(&W(O_SC + 2)), inR1(&W(O_SC + 3));
   frac = 0.0; stepf = 1.0; ott = x[6]; inR1 = 0.0;
-  // the separate tangent trip exists only without TANGENT_AHEAD
-#define W3DF_TP (!TANGENT_AHEAD && ct.tangent_pass)
   // loop control packed into one register (each of these was a register or a spill slot of its own)
   // (iter <= miter + 1 <= 251: mm10_fast_eligible; ls <= mls + 1; trips saturates)
-  struct { unsigned cuts : 4, stage : 4, iter : 8, ls : 4, trips : 8, full : 1, tangent_pass : 1, failed : 1, begin_sub : 1; } ct;
+  struct { unsigned cuts : 4, stage : 4, iter : 8, ls : 4, trips : 8, full : 1, failed : 1, begin_sub : 1; } ct;
   ct.cuts = 0; ct.stage = 0; ct.iter = 0; ct.ls = 0; ct.trips = 0;
-  ct.full = 0; ct.tangent_pass = 0; ct.failed = 0;
+  ct.full = 0; ct.failed = 0;
   double inR = 0.0, ls1 = 0.0, ls2 = 0.0, alpha = 1.0, nR = 0.0;
   W3DF_UNROLL
   for (int k = 0; k < 6; ++k) W(O_OST + k) = x[k];
@@ -684,8 +687,8 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       ct.iter = 0;
     }
 
-    bool newton = W3DF_TP;
-    if (!W3DF_TP) {
+    bool newton = false;
+    {
       // ================= residual at xt (mm10_formR1, mm10_formR2) =================
       double dot;
       double xt[7];
@@ -732,7 +735,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
             W3DF_UNROLL
             for (int k = 0; k < 3; ++k) a3[k] = a3[k] + f * W3DF_CT.qcr[i][k];
             if (TAUL) {
-              const double h_term = ht.a + W(tl_word<TAUL && TANGENT_AHEAD>(i)) * ht.inv_d;
+              const double h_term = ht.a + W(tl_word<TAUL>(i)) * ht.inv_d;
               hsum = hsum + pow1(W3DF_CT.voche_ie, W3DF_CT.voche_m, fabs(h_term)) * sgn1(h_term) * fabs(si);
             } else {
               hsum = hsum + fabs(si);
@@ -824,12 +827,8 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
           frac = frac + stepf;
           if (frac < 1.0) {
             ct.begin_sub = true;
-          } else if (TANGENT_AHEAD) {
-            done = true;      // the last full Newton pass has stored the tangent columns
           } else {
-            // tangent of the last solver pass: re-form its Jacobian at the state it was formed at
-            ct.tangent_pass = true;
-            newton = true;
+            done = true;      // the last full Newton pass has stored the tangent columns
           }
         }
       }
@@ -849,19 +848,8 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
 
     // ================= Jacobian at x (mm10_formJ) and the Newton step =================
     // (the residual is parked in the workspace while the Jacobian is accumulated: registers)
-    if (!W3DF_TP) {
-      W3DF_UNROLL
-      for (int k = 0; k < 7; ++k) W(O_RV + k) = Rv[k];
-    }
-    // the state the Jacobian is formed at: x, or for the tangent the state of the last solver
-    // pass (the converged state stays in the workspace: O_OST and ott)
-    if (W3DF_TP) {
-      W3DF_UNROLL
-      for (int k = 0; k < 7; ++k) x[k] = W(O_XP + k);
-    } else if (ct.full && !TANGENT_AHEAD) {
-      W3DF_UNROLL
-      for (int k = 0; k < 7; ++k) W(O_XP + k) = x[k];
-    }
+    W3DF_UNROLL
+    for (int k = 0; k < 7; ++k) W(O_RV + k) = Rv[k];
     double (&xs)[7] = x;
     double A[7][7];
     {
@@ -935,7 +923,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
             for (int a = 0; a < 3; ++a) q3[a] = q3[a] + dgdh * W3DF_CT.qcr[i][a];
             double hp = hp0, sg = sg0, rx = rx0, tl = 0.0;
             if (TAUL) {
-              tl = W(tl_word<TAUL && TANGENT_AHEAD>(i));
+              tl = W(tl_word<TAUL>(i));
               const double h_term = ht.a + tl * ht.inv_d;
               hp = pow1(W3DF_CT.voche_ie, W3DF_CT.voche_m, fabs(h_term));
               sg = sgn1(h_term);
@@ -1040,7 +1028,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     }
     // here A holds J.  Line-search terms need trans(J) R before the factorisation destroys J.
     double jtr[7];
-    if (!W3DF_TP) {
+    {
       W3DF_UNROLL
       for (int k = 0; k < 7; ++k) Rv[k] = W(O_RV + k);
       double dotR = 0.0;
@@ -1060,49 +1048,11 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
       W3DF_UNROLL
       for (int cc = 0; cc < 7; ++cc) A[r][cc] = -A[r][cc];
     const int jstop = lu7_nopivot(A);
-    if (W3DF_TP) {
-      // mm10_tangent: JJ^-1 C = leading block of J^-1 [C; 0]
-      double JR[6][6];
-      if (jstop == 7) {
-        W3DF_UNROLL
-        for (int cc = 0; cc < 6; ++cc) {
-          double b[7];
-          W3DF_UNROLL
-          for (int r = 0; r < 6; ++r) b[r] = -P.C[r][cc];
-          b[6] = 0.0;
-          lu7_apply(A, b);
-          W3DF_UNROLL
-          for (int r = 0; r < 6; ++r) JR[r][cc] = b[r];
-        }
-      } else {
-        double Am[49], Bm[42];
-        W3DF_UNROLL
-        for (int r = 0; r < 7; ++r)
-          W3DF_UNROLL
-          for (int cc = 0; cc < 7; ++cc) Am[r * 7 + cc] = A[r][cc];
-        for (int r = 0; r < 7; ++r)
-          for (int cc = 0; cc < 6; ++cc) Bm[r * 6 + cc] = (r < 6) ? -P.C[r][cc] : 0.0;
-        lu7_slow(Am, jstop, Bm, 6);
-        W3DF_UNROLL
-        for (int r = 0; r < 6; ++r)
-          W3DF_UNROLL
-          for (int cc = 0; cc < 6; ++cc) JR[r][cc] = Bm[r * 6 + cc];
-      }
-      W3DF_UNROLL
-      for (int cc = 0; cc < 6; ++cc)
-        W3DF_UNROLL
-        for (int r = 0; r < 6; ++r) {
-          // mm10_a_make_symm_1 unless asymmetric assembly
-          const double t = asymmetric ? JR[r][cc] : (JR[r][cc] + JR[cc][r]) * 0.5;
-          h1[L.o_D() + cc * 6 + r] = (c == 0) ? t : h1[L.o_D() + cc * 6 + r] + t;
-        }
-      done = true;
-      continue;
-    }
     W3DF_UNROLL
     for (int k = 0; k < 7; ++k) dx[k] = Rv[k];
-    if (TANGENT_AHEAD && ct.full) {
-      // tangent columns of this pass: leading block of J^-1 [C; 0] (mm10_tangent), c == 0
+    auto tcol = [&](int k) { return SINGLE ? L.o_D() + k : wait_word(L, c, k); };
+    if (ct.full) {
+      // tangent columns of this pass: leading block of J^-1 [C; 0] (mm10_tangent)
       if (jstop == 7) {
         W3DF_ROLLED      // (unrolled: 31.0 vs 30.5 ms)
         for (int cc = 0; cc < 6; ++cc) {
@@ -1112,7 +1062,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
           b[6] = 0.0;
           lu7_apply(A, b);
           W3DF_UNROLL
-          for (int r = 0; r < 6; ++r) h1[L.o_D() + cc * 6 + r] = b[r];
+          for (int r = 0; r < 6; ++r) h1[tcol(cc * 6 + r)] = b[r];
         }
         lu7_apply(A, dx);
       } else {
@@ -1127,7 +1077,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
         }
         lu7_slow(Am, jstop, Bm, 7);
         for (int r = 0; r < 6; ++r)
-          for (int cc = 0; cc < 6; ++cc) h1[L.o_D() + cc * 6 + r] = Bm[r * 7 + cc];
+          for (int cc = 0; cc < 6; ++cc) h1[tcol(cc * 6 + r)] = Bm[r * 7 + cc];
         for (int k = 0; k < 7; ++k) dx[k] = Bm[k * 7 + 6];
       }
     } else if (jstop == 7) {
@@ -1193,7 +1143,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
     for (int k = 0; k < 6; ++k) bad = bad || (x[k] != x[k]);
     if (bad) return true;
   }
-  if (TANGENT_AHEAD && !asymmetric) {
+  if (SINGLE && !asymmetric) {
     // mm10_a_make_symm_1 on the columns the last full Newton pass stored
     W3DF_UNROLL
     for (int cc = 1; cc < 6; ++cc)
@@ -1202,6 +1152,19 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
         const double t = (h1[L.o_D() + cc * 6 + r] + h1[L.o_D() + r * 6 + cc]) * 0.5;
         h1[L.o_D() + cc * 6 + r] = t;
         h1[L.o_D() + r * 6 + cc] = t;
+      }
+  }
+  if (!SINGLE) {
+    // the columns of this crystal from where they waited, symmetrised unless asymmetric assembly,
+    // into the sum over the crystals (before the output below overwrites those words)
+    auto wcol = [&](int k) { return wait_word(L, c, k); };
+    W3DF_UNROLL
+    for (int cc = 0; cc < 6; ++cc)
+      W3DF_UNROLL
+      for (int r = 0; r < 6; ++r) {
+        const double jr = h1[wcol(cc * 6 + r)], jt = h1[wcol(r * 6 + cc)];
+        const double t = asymmetric ? jr : (jr + jt) * 0.5;
+        h1[L.o_D() + cc * 6 + r] = (c == 0) ? t : h1[L.o_D() + cc * 6 + r] + t;
       }
   }
   W3DF_UNROLL
@@ -1468,11 +1431,10 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   return false;
 }
 
-#undef W3DF_TP
 // mm10 (mm10_a.f:29): all crystals of one Gauss point.  hn / h1: history at n / n+1; props:
 // ncrystals consecutive FProps records of this element; Rur: rot_blk_n1 column-major 9; uddt:
 // un-rotated strain increment; cgn / cgn1: urcs at n / n+1 (9).  true = step cut requested.
-template <bool TAUL, class SYNC, bool TANGENT_AHEAD = false, int RATE_E = -1>
+template <bool TAUL, class SYNC, bool SINGLE = false, int RATE_E = -1>
 W3DF_HD inline bool gauss_point_update_fast(int step, int ncrystals, const FProps *props, const LayoutF &L,
                                             const CHistF &hn, const HistF &h1, const WorkF &W,
                                             const PointInF &in, double dt, bool iter_0_extrapolate_off,
@@ -1495,7 +1457,7 @@ W3DF_HD inline bool gauss_point_update_fast(int step, int ncrystals, const FProp
     }
     const double n_tt = init ? W3DF_CT.tau_y + 1.0e-5 : hn[L.c_tt(c)];      // mm10_init_voche
     const double n_tt_rate = init ? 0.0 : hn[L.c_rate(c)];
-    cut = crystal_update_fast<TAUL, SYNC, TANGENT_AHEAD, RATE_E>(props[c], W, in, n_tt, n_tt_rate, dt, iter_0_extrapolate_off,
+    cut = crystal_update_fast<TAUL, SYNC, SINGLE, RATE_E>(props[c], W, in, n_tt, n_tt_rate, dt, iter_0_extrapolate_off,
                                           asymmetric, init, L, c, hn, h1, acc, trips);
   }
   if (trips_out) *trips_out = trips;
