@@ -133,6 +133,12 @@ struct Mm10fShape {
   static constexpr int SMEM_BYTES = w3d_mm10f::work_doubles(TAUL) * THREADS * (int)sizeof(double);
 };
 
+// two CTAs of either shape per SM: 228 KB of shared memory less 1 KB reserved per CTA
+static_assert(Mm10fShape<false, true>::MIN_CTAS * (Mm10fShape<false, true>::SMEM_BYTES + 1024) <= 228 * 1024,
+              "k_mm10f workspace column too long for its CTAs per SM");
+static_assert(Mm10fShape<true, true>::MIN_CTAS * (Mm10fShape<true, true>::SMEM_BYTES + 1024) <= 228 * 1024,
+              "k_mm10f workspace column with tau_l too long for two CTAs per SM");
+
 // SINGLE: one crystal per element -- the tangent columns stored ahead by the Newton passes go
 // straight to their place (w3d_mm10_fast.h, crystal_update_fast: SINGLE)
 // RATE_E: rate exponent harden_n - 1 fixed at compile time (19: harden_n 20 of verification/test82
