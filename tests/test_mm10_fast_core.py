@@ -43,7 +43,7 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def _run_paths(ct, ncrystals=1, npoints=40, nsteps=4, strain=2.5e-3, dt=1.0, taul=False, seed=0, rot=0.02):
+def _run_paths(ct, ncrystals=1, npoints=40, nsteps=4, strain=2.5e-3, dt=1.0, taul=False, seed=0, rot=0.02, asym=0):
     L = _lib()
     rng = np.random.default_rng(seed)
     nslip = int(ct[337])
@@ -69,7 +69,7 @@ def _run_paths(ct, ncrystals=1, npoints=40, nsteps=4, strain=2.5e-3, dt=1.0, tau
                 c_lit, c_fast = np.zeros(9), np.zeros(9)
                 cuts = (C.c_int * 2)()
                 rc = L.mm10_point_both(_p(ct), ncrystals, _p(ang), 1, step, _p(hist), _p(Rur), _p(uddt),
-                                       C.c_double(dt), it0, 0, _p(cgn), int(taul), _p(h_lit), _p(c_lit),
+                                       C.c_double(dt), it0, asym, _p(cgn), int(taul), _p(h_lit), _p(c_lit),
                                        _p(h_fast), _p(c_fast), cuts)
                 assert rc == 0
                 assert cuts[0] == cuts[1], (pt, step, it0)
@@ -92,6 +92,9 @@ def _run_paths(ct, ncrystals=1, npoints=40, nsteps=4, strain=2.5e-3, dt=1.0, tau
                     u_l, u_f = h_lit[b + 31 + nslip:b + 46 + nslip], h_fast[b + 31 + nslip:b + 46 + nslip]
                     # u(7), u(8): integers (most active system, number of active systems) -- exact
                     assert u_l[6] == u_f[6] and u_l[7] == u_f[7], (pt, step, it0, u_l, u_f)
+                    # the user words nothing is stored in stay zero (several crystals per point: 12 of
+                    # them hold tangent columns during the solve)
+                    assert not u_l[[0, 1, 2, 3, 4, 8, 9]].any() and not u_f[[0, 1, 2, 3, 4, 8, 9]].any(), (pt, step, u_f)
                     for k in (5, 10, 11, 12, 13, 14):
                         if abs(u_l[k]) < 1e9:                # n_eff = 1e10 sentinel compared exactly below
                             groups[f"u{k}"] = (np.atleast_1d(u_l[k]), np.atleast_1d(u_f[k]))
@@ -118,7 +121,8 @@ FCC = dict(e=150000.0, nu=0.28, harden_n=20.0, voche_m=5.0, theta_o=400.0, tau_y
 
 
 @pytest.mark.parametrize("case", ["bench_fcc", "voche_m1", "bcc", "general_exponents", "polycrystal3",
-                                  "geometric_hardening", "alter_mode"])
+                                  "geometric_hardening", "alter_mode", "asymmetric_tangent",
+                                  "polycrystal3_asymmetric_tangent"])
 def test_fast_core_matches_literal_restatement(case):
     kw = dict(FCC)
     run = dict(strain=6.0e-3)
@@ -131,6 +135,10 @@ def test_fast_core_matches_literal_restatement(case):
         kw.update(harden_n=12.5, voche_m=1.7)
     elif case == "polycrystal3":
         run.update(ncrystals=3, npoints=15)
+    elif case == "asymmetric_tangent":            # asymmetric assembly: mm10_a_make_symm_1 skipped
+        run.update(asym=1, npoints=15)
+    elif case == "polycrystal3_asymmetric_tangent":
+        run.update(ncrystals=3, npoints=10, asym=1)
     elif case == "geometric_hardening":
         kw.update(k_o=1.0)
         run.update(taul=True)
