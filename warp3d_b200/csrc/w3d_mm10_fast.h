@@ -12,16 +12,19 @@
 //    from __constant__ memory, no per-element Schmid records, no per-thread arrays):
 //        rs_i = (B6^T T) . mc_i,   dbarp = B6 sum f_i mc_i,   M = B6 (sum g_i mc_i x mc_i) B6^T, ...
 //    The same numbers as the reference's per-system evaluation up to re-association (rounding).
-//  * One inlined copy of the residual and of the Jacobian: predictor, update, their line searches,
-//    the sub-increment restarts and the final tangent run through ONE flat loop, so the kernel is
-//    a few tens of KB of straight-line code instead of 290 KB.  The stress predictor is the 7x7
+//  * One inlined copy of the residual and of the Jacobian: predictor, update, their line searches
+//    and the sub-increment restarts run through ONE flat loop (the slip-system loops inside it
+//    stay rolled), so the loop body fits the instruction cache.  The stress predictor is the 7x7
 //    update with the hardening equation switched off (row / column 7 = identity), which is the
 //    same arithmetic as the reference's 6x6 system.
-//  * No per-thread stack: every loop has compile-time bounds and is unrolled; B6, C B6, B3 and the
-//    few vectors that must survive the Jacobian live in a per-thread shared-memory column.
+//  * Small per-thread state: the 7x7 system lives in registers (compile-time indices), B6, C B6,
+//    B3 and the few vectors that must survive the Jacobian in a per-thread shared-memory column;
+//    the stack serves only the out-of-line pivoting LU (lu7_slow), which the usual path never calls.
 //  * The tangent  T = JJ^-1 C,  JJ = J11 - J12 J22^-1 J21 (mm10_tangent) is the leading block of
-//    J^-1 [C; 0]: one more LU of the full Jacobian of the last solver pass (re-formed at the state
-//    it was formed at), no Schur complement.  C^-1 for the lattice strain comes from the host.
+//    J^-1 [C; 0] with J the Jacobian of the last solver pass, no Schur complement: every full
+//    Newton pass back-substitutes the six columns with the LU factors it holds and stores them,
+//    the last pass's columns are the tangent (crystal_update_fast).  C^-1 for the lattice strain
+//    comes from the host.
 //
 // Compiled by nvcc for the device and by g++ for the host-side point checks under tests/ (which
 // compare it with the independent statement-for-statement restatement kept with the tests).
@@ -1109,7 +1112,7 @@ W3DF_HD inline bool crystal_update_fast(const FProps &P, const WorkF &W, const P
   trips = trips + ct.trips;      // solver-loop trips of this point (the next pass is ordered by them)
   if (idle) return false;
   if (cut) return true;
-  if (!elastic) {     // converged state back from the workspace (the tangent pass reused x)
+  if (!elastic) {     // the converged state as kept in the workspace
     W3DF_UNROLL
     for (int k = 0; k < 6; ++k) x[k] = W(O_OST + k);
     x[6] = ott;
